@@ -1,0 +1,66 @@
+"""ctypes binding of the 15-function ``mpeg1_decoder_*`` C ABI (reference src/wasm/mpeg1.h:10-25).
+
+The same binding works for any shared library that exports that ABI: the product
+(``jsmpeg_b200/libjsmpeg_b200.so`` -- CUDA), and, in tests only, the compiled reference
+(``oracle/_ref/libjsmpeg_ref.so``) and our CPU restatement (``oracle/liboracle.so``).
+The product never loads anything from ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+BIT_BUFFER_MODE_EVICT = 1   # reference src/wasm/buffer.h:8-11
+BIT_BUFFER_MODE_EXPAND = 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_HERE, "libjsmpeg_b200.so")
+
+MPEG1_ABI = {
+    # name: (restype, argtypes)
+    "mpeg1_decoder_create": (ctypes.c_void_p, [ctypes.c_uint, ctypes.c_int]),
+    "mpeg1_decoder_destroy": (None, [ctypes.c_void_p]),
+    "mpeg1_decoder_get_write_ptr": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_uint]),
+    "mpeg1_decoder_get_index": (ctypes.c_int, [ctypes.c_void_p]),
+    "mpeg1_decoder_set_index": (None, [ctypes.c_void_p, ctypes.c_uint]),
+    "mpeg1_decoder_did_write": (None, [ctypes.c_void_p, ctypes.c_uint]),
+    "mpeg1_decoder_has_sequence_header": (ctypes.c_int, [ctypes.c_void_p]),
+    "mpeg1_decoder_get_frame_rate": (ctypes.c_float, [ctypes.c_void_p]),
+    "mpeg1_decoder_get_coded_size": (ctypes.c_int, [ctypes.c_void_p]),
+    "mpeg1_decoder_get_width": (ctypes.c_int, [ctypes.c_void_p]),
+    "mpeg1_decoder_get_height": (ctypes.c_int, [ctypes.c_void_p]),
+    "mpeg1_decoder_get_y_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "mpeg1_decoder_get_cr_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "mpeg1_decoder_get_cb_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "mpeg1_decoder_decode": (ctypes.c_bool, [ctypes.c_void_p]),
+}
+
+
+def bind_mpeg1_abi(lib):
+    for name, (res, args) in MPEG1_ABI.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def load_library(path):
+    """dlopen ``path`` with RTLD_LOCAL (all three libraries export the same symbol names)."""
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} is missing -- build it first (python -c 'import __graft_entry__ as g; g.build()')")
+    return bind_mpeg1_abi(ctypes.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW))
+
+
+_product = None
+
+
+def product_library():
+    """The CUDA product library.  Fails loudly when the extension has not been built: there is
+    no CPU fallback anywhere in the product path."""
+    global _product
+    if _product is None:
+        _product = load_library(PRODUCT_LIB)
+        from . import batch as _batch  # binds the batch-extension symbols on the same handle
+        _batch.bind_batch_abi(_product)
+    return _product

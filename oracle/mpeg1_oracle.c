@@ -1,0 +1,592 @@
+/*
+ * oracle/mpeg1_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A CPU restatement of the reference's MPEG-1 video decode path (reference src/mpeg1.js ==
+ * src/wasm/mpeg1.c, bit reader src/buffer.js == src/wasm/buffer.c), written in the SAME two-stage
+ * shape as the CUDA product so that it pins the stage-1 -> stage-2 record format as well:
+ *
+ *     oracle_parse_picture()   bitstream/VLC walk of one picture  -> mb_record_t[] + int16 coef[]
+ *     oracle_reconstruct()     records + forward planes           -> current planes
+ *
+ * and the reference's 15-function mpeg1_decoder_* ABI (src/wasm/mpeg1.h:10-25) on top of the two.
+ *
+ * Pinning: the reference has no tests or golden vectors, so this file is
+ * pinned by running the reference itself: tests/test_oracle_vs_reference.py compares every plane
+ * byte and every bit index against oracle/_ref/libjsmpeg_ref.so (the unmodified reference C,
+ * compiled in place) on FFmpeg-encoded clips and on the synthetic syntax-corner streams, and
+ * tests/golden/ holds plane checksums produced by that reference build.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library.
+ * It deliberately decodes VLCs a different way (bit-by-bit trie built from the ISO-form code
+ * lists) than the product (clz-indexed LUTs).
+ */
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../jsmpeg_b200/csrc/records.h"
+#include "vlc_tables_oracle.h"
+
+/* ------------------------------------------------------------------------------------------ */
+/* VLC tries                                                                                   */
+
+typedef struct { int16_t child[2]; int value; bool leaf; } trie_node_t;
+typedef struct { trie_node_t *nodes; int count; } trie_t;
+
+enum { T_MBA, T_TYPE_I, T_TYPE_P, T_CBP, T_MOTION, T_DC_LUMA, T_DC_CHROMA, T_DCT, T_COUNT };
+static trie_t g_trie[T_COUNT];
+static bool g_tries_ready = false;
+#define VLC_INVALID (-999999)
+
+static void trie_build(trie_t *t, const vlc_code_t *codes) {
+	int n = 0, total = 1;
+	for (const vlc_code_t *c = codes; c->code; c++) { n++; total += (int)strlen(c->code); }
+	t->nodes = (trie_node_t *)calloc(total, sizeof(trie_node_t));
+	t->count = 1;
+	for (const vlc_code_t *c = codes; c->code; c++) {
+		int at = 0;
+		for (const char *p = c->code; *p; p++) {
+			int b = *p - '0';
+			if (!t->nodes[at].child[b]) t->nodes[at].child[b] = (int16_t)t->count++;
+			at = t->nodes[at].child[b];
+		}
+		t->nodes[at].leaf = true;
+		t->nodes[at].value = c->value;
+	}
+}
+
+static void tries_init(void) {
+	if (g_tries_ready) return;
+	trie_build(&g_trie[T_MBA], ORACLE_MACROBLOCK_ADDRESS_INCREMENT);
+	trie_build(&g_trie[T_TYPE_I], ORACLE_MACROBLOCK_TYPE_INTRA);
+	trie_build(&g_trie[T_TYPE_P], ORACLE_MACROBLOCK_TYPE_PREDICTIVE);
+	trie_build(&g_trie[T_CBP], ORACLE_CODE_BLOCK_PATTERN);
+	trie_build(&g_trie[T_MOTION], ORACLE_MOTION);
+	trie_build(&g_trie[T_DC_LUMA], ORACLE_DCT_DC_SIZE_LUMINANCE);
+	trie_build(&g_trie[T_DC_CHROMA], ORACLE_DCT_DC_SIZE_CHROMINANCE);
+	trie_build(&g_trie[T_DCT], ORACLE_DCT_COEFF);
+	g_tries_ready = true;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Bit reader over a byte span (MSB first; buffer.js:152-187).  Bytes past the end read as 0,   */
+/* which is what a JS typed-array read past byteLength yields after `& mask`.                    */
+
+typedef struct { const uint8_t *bytes; uint32_t length; uint32_t index; /* in bits */ } bits_t;
+
+static inline int bit_at(const bits_t *b, uint32_t i) {
+	uint32_t byte = i >> 3;
+	return byte < b->length ? (b->bytes[byte] >> (7 - (i & 7))) & 1 : 0;
+}
+static int bits_read(bits_t *b, int count) {
+	int v = 0;
+	for (int k = 0; k < count; k++) v = (v << 1) | bit_at(b, b->index + k);
+	b->index += count;
+	return v;
+}
+static inline void bits_skip(bits_t *b, int count) { b->index += count; }
+
+/* buffer.js:115-128.  A start code needs its 4 bytes inside the buffer. */
+static int bits_find_next_start_code(bits_t *b) {
+	for (uint32_t i = (b->index + 7) >> 3; i + 3 < b->length; i++) {
+		if (b->bytes[i] == 0 && b->bytes[i + 1] == 0 && b->bytes[i + 2] == 1) {
+			b->index = (i + 4) << 3;
+			return b->bytes[i + 3];
+		}
+	}
+	b->index = b->length << 3;
+	return -1;
+}
+/* buffer.js:130-139 */
+static int bits_find_start_code(bits_t *b, int code) {
+	for (;;) {
+		int c = bits_find_next_start_code(b);
+		if (c == code || c == -1) return c;
+	}
+}
+/* buffer.js:141-150 */
+static bool bits_next_bytes_are_start_code(const bits_t *b) {
+	uint32_t i = (b->index + 7) >> 3;
+	if (i >= b->length) return true;
+	return i + 2 < b->length && b->bytes[i] == 0 && b->bytes[i + 1] == 0 && b->bytes[i + 2] == 1;
+}
+
+/* mpeg1.js:66-72 readHuffman, as a trie walk.  The reference has no defined result for an
+ * invalid code; we return VLC_INVALID and the caller abandons the slice. */
+static int read_vlc(bits_t *b, int which) {
+	const trie_t *t = &g_trie[which];
+	int at = 0;
+	for (;;) {
+		at = t->nodes[at].child[bits_read(b, 1)];
+		if (!at) return VLC_INVALID;
+		if (t->nodes[at].leaf) return t->nodes[at].value;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Stage 1: picture parse -> records                                                            */
+
+typedef struct {
+	int mb_width, mb_size;
+	uint8_t intra_q[64], non_intra_q[64]; /* de-zigzagged, mpeg1.js:100-116 */
+} seq_params_t;
+
+typedef struct {
+	bits_t bits;
+	const seq_params_t *seq;
+	picture_info_t *info;
+	mb_record_t *hdr;
+	int16_t *coef;
+	int picture_type, full_pel, r_size, f;
+	int qscale, mb_addr;
+	bool slice_begin;
+	int mv_h, mv_v, mv_h_prev, mv_v_prev;
+	int dc_pred[3]; /* Y, then the predictor used by block 4, then the one used by block 5 */
+} parse_t;
+
+static void reset_dc(parse_t *p) { p->dc_pred[0] = p->dc_pred[1] = p->dc_pred[2] = 128; }
+static void reset_mv(parse_t *p) { p->mv_h = p->mv_v = p->mv_h_prev = p->mv_v_prev = 0; }
+
+static int16_t sat16(int v) { return (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
+
+/* mpeg1.js:698-811 decodeBlock, bitstream part only.  Returns false on an invalid code. */
+static bool parse_block(parse_t *p, int mb, int block, bool intra, uint8_t *dc_only_mask) {
+	int16_t *out = p->coef + ((size_t)mb * 6 + block) * 64;
+	memset(out, 0, 64 * sizeof(int16_t));
+	int n = 0;
+	const uint8_t *q;
+	if (intra) {
+		/* mpeg1.js:705-751: DC size VLC, differential, predictor update.  Block 4 uses the
+		 * predictor the reference calls "Cr", block 5 the one it calls "Cb" (mpeg1.js:717,739-744). */
+		int *pred = &p->dc_pred[block < 4 ? 0 : block - 3];
+		int size = read_vlc(&p->bits, block < 4 ? T_DC_LUMA : T_DC_CHROMA);
+		if (size == VLC_INVALID) return false;
+		int dc = *pred;
+		if (size > 0) {
+			int diff = bits_read(&p->bits, size);
+			if (diff & (1 << (size - 1))) dc += diff;
+			else dc += (int)((~0u << size) | (uint32_t)(diff + 1));
+		}
+		*pred = dc;
+		out[0] = sat16(dc * 8); /* x PREMULTIPLIER[0]=32 in stage 2 gives dc<<8, mpeg1.js:747 */
+		q = p->seq->intra_q;
+		n = 1;
+	} else {
+		q = p->seq->non_intra_q;
+	}
+
+	for (;;) { /* mpeg1.js:757-811 */
+		int run, level;
+		int coeff = read_vlc(&p->bits, T_DCT);
+		if (coeff == VLC_INVALID) return false;
+		if (coeff == 0x0001 && n > 0 && bits_read(&p->bits, 1) == 0) break; /* EOB, mpeg1.js:763 */
+		if (coeff == 0xffff) { /* escape, mpeg1.js:767-780 */
+			run = bits_read(&p->bits, 6);
+			level = bits_read(&p->bits, 8);
+			if (level == 0) level = bits_read(&p->bits, 8);
+			else if (level == 128) level = bits_read(&p->bits, 8) - 256;
+			else if (level > 128) level -= 256;
+		} else {
+			run = coeff >> 8;
+			level = coeff & 0xff;
+			if (bits_read(&p->bits, 1)) level = -level;
+		}
+		n += run;
+		if (n > 63) { /* JS: ZIG_ZAG[n] is undefined, the store is a no-op (mpeg1.js:790-810) */
+			p->info->error = PARSE_ERR_COEF_INDEX;
+			n++;
+			continue;
+		}
+		int idx = ORACLE_ZIG_ZAG[n];
+		n++;
+		/* dequantise, oddify toward zero, clip (mpeg1.js:794-807) */
+		level *= 2;
+		if (!intra) level += level < 0 ? -1 : 1;
+		level = (level * p->qscale * q[idx]) >> 4; /* arithmetic shift: floors negatives */
+		if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
+		if (level > 2047) level = 2047;
+		else if (level < -2048) level = -2048;
+		out[idx] = (int16_t)level;
+	}
+	if (n == 1) *dc_only_mask |= (uint8_t)(0x20 >> block); /* mpeg1.js:838,850 */
+	p->info->n_coded_blocks++;
+	return true;
+}
+
+/* mpeg1.js:395-457, one component */
+static bool parse_motion_component(parse_t *p, int *prev, int *mv) {
+	int code = read_vlc(&p->bits, T_MOTION);
+	if (code == VLC_INVALID) return false;
+	int d = code;
+	if (code != 0 && p->f != 1) {
+		int r = bits_read(&p->bits, p->r_size);
+		d = ((abs(code) - 1) << p->r_size) + r + 1;
+		if (code < 0) d = -d;
+	}
+	*prev += d;
+	if (*prev > (p->f << 4) - 1) *prev -= p->f << 5;
+	else if (*prev < -(p->f << 4)) *prev += p->f << 5;
+	*mv = p->full_pel ? *prev * 2 : *prev;
+	return true;
+}
+
+static void emit_predicted(parse_t *p, int addr, uint8_t extra_flags) {
+	mb_record_t *r = &p->hdr[addr];
+	memset(r, 0, sizeof(*r));
+	r->mv_h = (int16_t)p->mv_h;
+	r->mv_v = (int16_t)p->mv_v;
+	r->flags = MBF_PRESENT | extra_flags;
+	r->qscale = (uint8_t)p->qscale;
+	r->bit_pos = p->bits.index;
+	p->info->n_present++;
+}
+
+/* mpeg1.js:294-392 decodeMacroblock.  Returns false when the slice walk must stop. */
+static bool parse_macroblock(parse_t *p) {
+	int increment = 0;
+	int t = read_vlc(&p->bits, T_MBA);
+	while (t == 34) t = read_vlc(&p->bits, T_MBA);                 /* stuffing */
+	while (t == 35) { increment += 33; t = read_vlc(&p->bits, T_MBA); } /* escape   */
+	if (t == VLC_INVALID) return false;
+	increment += t;
+
+	if (p->slice_begin) { /* mpeg1.js:312-317: first increment only positions the address */
+		p->slice_begin = false;
+		p->mb_addr += increment;
+	} else {
+		if (p->mb_addr + increment >= p->seq->mb_size) return true; /* mpeg1.js:319-322 (loop goes on) */
+		if (increment > 1) { /* mpeg1.js:323-334 */
+			reset_dc(p);
+			if (p->picture_type == 2) reset_mv(p);
+		}
+		while (increment > 1) { /* skipped macroblocks: predicted copy, mpeg1.js:336-346 */
+			p->mb_addr++;
+			emit_predicted(p, p->mb_addr, MBF_SKIPPED);
+			increment--;
+		}
+		p->mb_addr++;
+	}
+	int mb = p->mb_addr;
+	if (mb < 0 || mb >= p->seq->mb_size) return false; /* out of the picture: memory safety */
+
+	int type = read_vlc(&p->bits, p->picture_type == 1 ? T_TYPE_I : T_TYPE_P);
+	if (type == VLC_INVALID) return false;
+	bool intra = type & 0x01;
+	if (type & 0x10) p->qscale = bits_read(&p->bits, 5);
+
+	uint32_t mb_bit_pos = p->bits.index;
+	if (intra) {
+		reset_mv(p); /* mpeg1.js:363-367 */
+	} else {
+		reset_dc(p); /* mpeg1.js:370-372 */
+		if (type & 0x08) {
+			if (!parse_motion_component(p, &p->mv_h_prev, &p->mv_h)) return false;
+			if (!parse_motion_component(p, &p->mv_v_prev, &p->mv_v)) return false;
+		} else if (p->picture_type == 2) {
+			reset_mv(p); /* mpeg1.js:452-456 */
+		}
+	}
+
+	int cbp = (type & 0x02) ? read_vlc(&p->bits, T_CBP) : (intra ? 0x3f : 0);
+	if (cbp == VLC_INVALID) return false;
+
+	mb_record_t *r = &p->hdr[mb];
+	if (!(r->flags & MBF_PRESENT)) p->info->n_present++;
+	memset(r, 0, sizeof(*r));
+	r->mv_h = (int16_t)p->mv_h;
+	r->mv_v = (int16_t)p->mv_v;
+	r->flags = MBF_PRESENT | (intra ? MBF_INTRA : 0);
+	r->qscale = (uint8_t)p->qscale;
+	r->bit_pos = mb_bit_pos;
+	uint8_t dc_only = 0;
+	bool ok = true;
+	for (int block = 0; block < 6 && ok; block++) {
+		if (cbp & (0x20 >> block)) {
+			ok = parse_block(p, mb, block, intra, &dc_only);
+			if (ok) r->cbp |= (uint8_t)(0x20 >> block);
+		}
+	}
+	r->dc_only = dc_only;
+	return ok;
+}
+
+/* mpeg1.js:255-276 decodeSlice */
+static void parse_slice(parse_t *p, int slice) {
+	p->slice_begin = true;
+	p->mb_addr = (slice - 1) * p->seq->mb_width - 1;
+	reset_mv(p);
+	reset_dc(p);
+	p->qscale = bits_read(&p->bits, 5);
+	while (bits_read(&p->bits, 1)) bits_skip(&p->bits, 8);
+	do {
+		if (!parse_macroblock(p)) {
+			if (!p->info->error) p->info->error = PARSE_ERR_INVALID_VLC;
+			break;
+		}
+	} while (!bits_next_bytes_are_start_code(&p->bits));
+}
+
+/* mpeg1.js:174-247 decodePicture, bitstream part.  `index` enters just after the picture start
+ * code.  hdr[] must be zeroed by the caller (no MBF_PRESENT).  Exported for the tests. */
+void oracle_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t start_bit,
+                          const seq_params_t *seq, picture_info_t *info,
+                          mb_record_t *hdr, int16_t *coef) {
+	tries_init();
+	parse_t p;
+	memset(&p, 0, sizeof(p));
+	memset(info, 0, sizeof(*info));
+	p.bits.bytes = es; p.bits.length = es_len; p.bits.index = start_bit;
+	p.seq = seq; p.info = info; p.hdr = hdr; p.coef = coef;
+	info->start_byte = start_bit >> 3;
+
+	bits_skip(&p.bits, 10);
+	p.picture_type = bits_read(&p.bits, 3);
+	bits_skip(&p.bits, 16);
+	info->picture_type = p.picture_type;
+	info->status = PIC_IGNORED;
+	if (p.picture_type <= 0 || p.picture_type >= 3) { info->end_bit = p.bits.index; return; }
+	if (p.picture_type == 2) {
+		p.full_pel = bits_read(&p.bits, 1);
+		int f_code = bits_read(&p.bits, 3);
+		info->full_pel = p.full_pel; info->f_code = f_code;
+		if (f_code == 0) { info->end_bit = p.bits.index; return; }
+		p.r_size = f_code - 1;
+		p.f = 1 << p.r_size;
+	}
+	info->status = PIC_DECODED;
+
+	int code;
+	do { code = bits_find_next_start_code(&p.bits); } while (code == 0xB5 || code == 0xB2);
+	while (code >= 0x01 && code <= 0xAF) {
+		parse_slice(&p, code);
+		code = bits_find_next_start_code(&p.bits);
+	}
+	if (code != -1) p.bits.index -= 32; /* mpeg1.js:209-213 */
+	info->end_bit = p.bits.index;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Stage 2: records -> planes                                                                   */
+
+/* One 8-point pass of the reference's integer IDCT (mpeg1.js:925-947 / :952-981).  `s` is the
+ * element stride; shift = false for the column pass, true for the row pass ((v+128)>>8). */
+static void idct_pass(int *v, int s, bool shift) {
+	int b1 = v[4 * s];
+	int b3 = v[2 * s] + v[6 * s];
+	int b4 = v[5 * s] - v[3 * s];
+	int t1 = v[1 * s] + v[7 * s];
+	int t2 = v[3 * s] + v[5 * s];
+	int b6 = v[1 * s] - v[7 * s];
+	int b7 = t1 + t2;
+	int m0 = v[0];
+	int x4 = ((b6 * 473 - b4 * 196 + 128) >> 8) - b7;
+	int x0 = x4 - (((t1 - t2) * 362 + 128) >> 8);
+	int x1 = m0 - b1;
+	int x2 = (((v[2 * s] - v[6 * s]) * 362 + 128) >> 8) - b3;
+	int x3 = m0 + b1;
+	int y3 = x1 + x2, y4 = x3 + b3, y5 = x1 - x2, y6 = x3 - b3;
+	int y7 = -x0 - ((b4 * 473 + b6 * 196 + 128) >> 8);
+	int o[8] = { b7 + y4, x4 + y3, y5 - x0, y6 - y7, y6 + y7, x0 + y5, y3 - x4, y4 - b7 };
+	for (int k = 0; k < 8; k++) v[k * s] = shift ? (o[k] + 128) >> 8 : o[k];
+}
+
+static inline uint8_t clamp255(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+/* mpeg1.js:459-687 copyMacroblock for one plane: `size` x `size` block at (col,row) block units,
+ * vector (mh, mv) in half-pel units of that plane.  The source index is FLAT (a vector leaving
+ * the row wraps into the neighbouring row, mpeg1.js:479,567).  A tap outside the plane reads
+ * `undefined` in JS, the sum becomes NaN and `NaN >> k` is 0, so any out-of-plane tap zeroes the
+ * whole output pixel. */
+static void predict_plane(uint8_t *dst, const uint8_t *src, int stride, int plane_size,
+                          int row, int col, int size, int mh, int mv) {
+	int H = mh >> 1, V = mv >> 1, oh = mh & 1, ov = mv & 1;
+	int base = (row * size + V) * stride + col * size + H;
+	for (int y = 0; y < size; y++) {
+		for (int x = 0; x < size; x++) {
+			int i = base + y * stride + x;
+			int taps[4] = { i, i + 1, i + stride, i + stride + 1 };
+			int use[4] = { 1, oh, ov, oh && ov };
+			int sum = 0, n = 0; bool inside = true;
+			for (int k = 0; k < 4; k++) {
+				if (!use[k]) continue;
+				if (taps[k] < 0 || taps[k] >= plane_size) { inside = false; break; }
+				sum += src[taps[k]]; n++;
+			}
+			int v = !inside ? 0 : (n == 4 ? (sum + 2) >> 2 : (n == 2 ? (sum + 1) >> 1 : sum));
+			dst[(row * size + y) * stride + col * size + x] = (uint8_t)v;
+		}
+	}
+}
+
+typedef struct { uint8_t *y, *cr, *cb; } planes_t;
+
+void oracle_reconstruct(const seq_params_t *seq, int coded_width, int coded_height,
+                        const mb_record_t *hdr, const int16_t *coef,
+                        const planes_t *fwd, planes_t *cur) {
+	int cw = coded_width, hw = coded_width >> 1;
+	int ysize = coded_width * coded_height, csize = ysize >> 2;
+	for (int mb = 0; mb < seq->mb_size; mb++) {
+		const mb_record_t *r = &hdr[mb];
+		if (!(r->flags & MBF_PRESENT)) continue; /* untouched: keeps the 2-frames-old content */
+		int row = mb / seq->mb_width, col = mb % seq->mb_width;
+		bool intra = r->flags & MBF_INTRA;
+		if (!intra) {
+			predict_plane(cur->y, fwd->y, cw, ysize, row, col, 16, r->mv_h, r->mv_v);
+			/* chroma vector: (mv / 2) truncated toward zero, mpeg1.js:562-565 */
+			predict_plane(cur->cr, fwd->cr, hw, csize, row, col, 8, r->mv_h / 2, r->mv_v / 2);
+			predict_plane(cur->cb, fwd->cb, hw, csize, row, col, 8, r->mv_h / 2, r->mv_v / 2);
+		}
+		for (int block = 0; block < 6; block++) {
+			if (!(r->cbp & (0x20 >> block))) continue;
+			const int16_t *c = coef + ((size_t)mb * 6 + block) * 64;
+			uint8_t *dst; int stride;
+			if (block < 4) { /* mpeg1.js:819-828 */
+				stride = cw;
+				dst = cur->y + (row * 16 + (block & 2 ? 8 : 0)) * cw + col * 16 + (block & 1 ? 8 : 0);
+			} else {         /* block 4 -> Cb plane, block 5 -> Cr plane, mpeg1.js:829-834 */
+				stride = hw;
+				dst = (block == 4 ? cur->cb : cur->cr) + row * 8 * hw + col * 8;
+			}
+			int px[64];
+			if (r->dc_only & (0x20 >> block)) { /* mpeg1.js:838-841, 850-853 */
+				int v = (c[0] * ORACLE_PREMULTIPLIER[0] + 128) >> 8;
+				for (int k = 0; k < 64; k++) px[k] = v;
+			} else {
+				for (int k = 0; k < 64; k++) px[k] = c[k] * ORACLE_PREMULTIPLIER[k];
+				for (int k = 0; k < 8; k++) idct_pass(px + k, 8, false);
+				for (int k = 0; k < 8; k++) idct_pass(px + 8 * k, 1, true);
+			}
+			for (int y = 0; y < 8; y++)
+				for (int x = 0; x < 8; x++) {
+					uint8_t *d = dst + y * stride + x;
+					*d = clamp255(intra ? px[y * 8 + x] : *d + px[y * 8 + x]); /* mpeg1.js:864-914 */
+				}
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* The reference's 15-function ABI (src/wasm/mpeg1.h:10-25) on top of the two stages            */
+
+typedef struct mpeg1_decoder_t {
+	uint8_t *bytes; uint32_t capacity, length, index; int mode; /* bit buffer, buffer.c */
+	bool has_sequence_header;
+	float frame_rate;
+	int width, height, coded_width, coded_height, coded_size;
+	seq_params_t seq;
+	planes_t current, forward;
+	mb_record_t *hdr; int16_t *coef;
+	picture_info_t last;
+} mpeg1_decoder_t;
+
+mpeg1_decoder_t *mpeg1_decoder_create(unsigned int buffer_size, int mode) {
+	mpeg1_decoder_t *d = (mpeg1_decoder_t *)calloc(1, sizeof(*d));
+	d->bytes = (uint8_t *)malloc(buffer_size ? buffer_size : 1);
+	d->capacity = buffer_size; d->mode = mode;
+	tries_init();
+	return d;
+}
+
+static void free_planes(planes_t *p) { free(p->y); free(p->cr); free(p->cb); }
+
+void mpeg1_decoder_destroy(mpeg1_decoder_t *d) {
+	free(d->bytes);
+	if (d->has_sequence_header) { free_planes(&d->current); free_planes(&d->forward); free(d->hdr); free(d->coef); }
+	free(d);
+}
+
+/* buffer.c:48-65 get_write_ptr + :167-190 evict + :157-164 resize */
+void *mpeg1_decoder_get_write_ptr(mpeg1_decoder_t *d, unsigned int n) {
+	uint32_t avail = d->capacity - d->length;
+	if (n > avail) {
+		if (d->mode == 2) { /* EXPAND */
+			uint32_t cap = d->capacity * 2;
+			if (cap + avail < n) cap = n - avail;
+			d->bytes = (uint8_t *)realloc(d->bytes, cap);
+			d->capacity = cap;
+			if (d->index > d->length << 3) d->index = d->length << 3;
+		} else {            /* EVICT */
+			uint32_t pos = d->index >> 3;
+			if (pos == d->length || n > avail + pos) { d->length = 0; d->index = 0; }
+			else if (pos != 0) {
+				memmove(d->bytes, d->bytes + pos, d->length - pos);
+				d->length -= pos; d->index -= pos << 3;
+			}
+		}
+	}
+	return d->bytes + d->length;
+}
+
+int mpeg1_decoder_get_index(mpeg1_decoder_t *d) { return (int)d->index; }
+void mpeg1_decoder_set_index(mpeg1_decoder_t *d, unsigned int i) { d->index = i; }
+
+static planes_t alloc_planes(int ysize) {
+	planes_t p = { (uint8_t *)calloc(ysize, 1), (uint8_t *)calloc(ysize >> 2, 1), (uint8_t *)calloc(ysize >> 2, 1) };
+	return p;
+}
+
+/* mpeg1.js:78-153 decodeSequenceHeader + initBuffers */
+static void parse_sequence_header(mpeg1_decoder_t *d, bits_t *b) {
+	d->width = bits_read(b, 12);
+	d->height = bits_read(b, 12);
+	bits_skip(b, 4);
+	d->frame_rate = ORACLE_PICTURE_RATE[bits_read(b, 4)];
+	bits_skip(b, 18 + 1 + 10 + 1);
+	if (bits_read(b, 1)) { for (int i = 0; i < 64; i++) d->seq.intra_q[ORACLE_ZIG_ZAG[i]] = (uint8_t)bits_read(b, 8); }
+	else memcpy(d->seq.intra_q, ORACLE_DEFAULT_INTRA_QUANT, 64);
+	if (bits_read(b, 1)) { for (int i = 0; i < 64; i++) d->seq.non_intra_q[ORACLE_ZIG_ZAG[i]] = (uint8_t)bits_read(b, 8); }
+	else memset(d->seq.non_intra_q, 16, 64);
+	int mbw = (d->width + 15) >> 4, mbh = (d->height + 15) >> 4;
+	d->seq.mb_width = mbw; d->seq.mb_size = mbw * mbh;
+	d->coded_width = mbw << 4; d->coded_height = mbh << 4;
+	d->coded_size = d->coded_width * d->coded_height;
+	d->current = alloc_planes(d->coded_size);
+	d->forward = alloc_planes(d->coded_size);
+	d->hdr = (mb_record_t *)calloc(d->seq.mb_size, sizeof(mb_record_t));
+	d->coef = (int16_t *)calloc((size_t)d->seq.mb_size * MB_COEF_INT16, sizeof(int16_t));
+	d->has_sequence_header = true;
+}
+
+/* mpeg1.c:812-819 */
+void mpeg1_decoder_did_write(mpeg1_decoder_t *d, unsigned int n) {
+	d->length += n;
+	if (!d->has_sequence_header) {
+		bits_t b = { d->bytes, d->length, d->index };
+		if (bits_find_start_code(&b, 0xB3) != -1) parse_sequence_header(d, &b);
+		d->index = b.index;
+	}
+}
+
+int mpeg1_decoder_has_sequence_header(mpeg1_decoder_t *d) { return d->has_sequence_header; }
+float mpeg1_decoder_get_frame_rate(mpeg1_decoder_t *d) { return d->frame_rate; }
+int mpeg1_decoder_get_coded_size(mpeg1_decoder_t *d) { return d->coded_size; }
+int mpeg1_decoder_get_width(mpeg1_decoder_t *d) { return d->width; }
+int mpeg1_decoder_get_height(mpeg1_decoder_t *d) { return d->height; }
+/* most recently decoded picture = forward after the swap (mpeg1.c:841-851) */
+void *mpeg1_decoder_get_y_ptr(mpeg1_decoder_t *d) { return d->forward.y; }
+void *mpeg1_decoder_get_cr_ptr(mpeg1_decoder_t *d) { return d->forward.cr; }
+void *mpeg1_decoder_get_cb_ptr(mpeg1_decoder_t *d) { return d->forward.cb; }
+
+/* mpeg1.c:853-864 + decode_picture :947-995 */
+bool mpeg1_decoder_decode(mpeg1_decoder_t *d) {
+	if (!d->has_sequence_header) return false;
+	bits_t b = { d->bytes, d->length, d->index };
+	int found = bits_find_start_code(&b, 0x00);
+	d->index = b.index;
+	if (found == -1) return false;
+	memset(d->hdr, 0, (size_t)d->seq.mb_size * sizeof(mb_record_t));
+	oracle_parse_picture(d->bytes, d->length, d->index, &d->seq, &d->last, d->hdr, d->coef);
+	d->index = d->last.end_bit;
+	if (d->last.status == PIC_DECODED) {
+		oracle_reconstruct(&d->seq, d->coded_width, d->coded_height, d->hdr, d->coef, &d->forward, &d->current);
+		planes_t t = d->forward; d->forward = d->current; d->current = t;
+	}
+	return true;
+}
+
+/* test hooks */
+const picture_info_t *oracle_last_picture_info(mpeg1_decoder_t *d) { return &d->last; }
+const mb_record_t *oracle_last_mb_records(mpeg1_decoder_t *d) { return d->hdr; }
+const int16_t *oracle_last_coefficients(mpeg1_decoder_t *d) { return d->coef; }
+const seq_params_t *oracle_seq_params(mpeg1_decoder_t *d) { return &d->seq; }
