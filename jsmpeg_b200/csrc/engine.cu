@@ -1,0 +1,868 @@
+// engine.cu -- host side of libjsmpeg_b200.so: stream state, HBM residency, wave planning, and
+// the two C ABIs declared in include/jsmpeg_b200.h.
+//
+// What stays on the host is exactly what is bookkeeping in the reference too: the bit-buffer write
+// protocol (src/wasm/buffer.c:48-71, 157-190), the sequence header (src/mpeg1.js:78-153, parsed
+// once per stream) and the decode() state machine (src/wasm/mpeg1.c:853-864, 947-995: which
+// picture is next, where the bit index ends up, when planes swap).  All per-byte, per-bit and
+// per-pixel work runs in the three kernels (scan.cu, parse.cu, recon.cu).  There is no CPU
+// fallback: without a CUDA device every entry point aborts with the CUDA error.
+//
+// Wave model.  decode() on a stream needs (a) the next picture start code, (b) that picture's
+// records, (c) its reconstruction from the previous picture.  (a) comes from the start-code index
+// built when bytes become resident; (b) for MANY pictures (all streams x pictures ahead) is one
+// parse launch, one warp per picture; (c) is one launch per picture STEP covering every stream
+// that has a picture at that step.  The reference's serial semantics are re-established on the
+// host after the parse: picture j+1 of a stream is accepted only if its start code is the first
+// one at/after the bit index where picture j's parse ended (otherwise the look-ahead is discarded
+// and re-planned from there).
+#include <algorithm>
+#include <cstring>
+#include <deque>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/jsmpeg_b200.h"
+
+namespace {
+
+constexpr int HOST_RING = 4;
+constexpr uint32_t ES_PAD = 512;  // readable slack after the ES mirror (chunk prefetch reads ahead)
+
+template <typename T>
+T *dev_alloc(size_t n) {
+	T *p = nullptr;
+	CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+	return p;
+}
+template <typename T>
+T *pinned_alloc(size_t n) {
+	T *p = nullptr;
+	CUDA_CHECK(cudaHostAlloc(&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault));
+	return p;
+}
+
+struct Parsed {
+	uint32_t pos;           // byte position of the 00 00 01 00 start code
+	uint32_t len_at_parse;  // buffer length the parse saw
+	int slot;
+	picture_info_t info;
+};
+
+struct Stream {
+	// host bit buffer (pinned) -- src/wasm/buffer.c
+	uint8_t *h_bytes = nullptr;
+	uint32_t capacity = 0, length = 0, index = 0;
+	int mode = BIT_BUFFER_MODE_EXPAND;
+	// sequence header
+	bool has_seq = false;
+	float frame_rate = 0.f;
+	int width = 0, height = 0, coded_size = 0;
+	uint32_t seq_end_index = 0;  // bit index right after the sequence header
+	SeqParams seq{};
+	SeqParams *d_seq = nullptr;
+	// ES mirror in HBM + start-code index
+	uint8_t *d_es = nullptr;
+	uint32_t d_capacity = 0, d_valid = 0;
+	std::vector<uint32_t> pics;  // sorted byte positions of picture start codes
+	uint32_t scanned = 0;        // every start code with pos + 3 < scanned is in `pics`
+	uint32_t *d_scan = nullptr, *h_scan = nullptr;  // [0] = count, [1..] = positions
+	uint32_t scan_cap = 0, scan_from = 0;
+	bool scan_pending = false;
+	// planes: two sets in HBM (ping-pong like mpeg1.js:221-246), a host ring for OUT_HOST
+	uint8_t *d_planes[2] = {nullptr, nullptr};
+	int cur = 0;  // set written by the next I/P picture; forward = 1 - cur
+	uint8_t *h_planes[HOST_RING] = {};
+	int h_head = -1;
+	uint8_t *d_rgba = nullptr;
+	// parsed-ahead pictures, consecutive, front = next picture decode() consumes
+	std::deque<Parsed> cache;
+};
+
+}  // namespace
+
+struct jsmpeg_b200_batch_t {
+	int device = 0;
+	std::vector<Stream> streams;
+	cudaStream_t st_main = nullptr, st_copy = nullptr;
+	cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_step = nullptr, ev_copied[2] = {nullptr, nullptr};
+	// record slots
+	unsigned max_slots_req = 0;
+	int slot_mb = 0, n_slots = 0;
+	mb_record_t *d_hdr = nullptr;
+	int16_t *d_coef = nullptr;
+	picture_info_t *d_info = nullptr, *h_info = nullptr;
+	std::vector<int> free_slots;
+	int lookahead = 1;
+	// task staging
+	ParseTask *h_ptasks = nullptr, *d_ptasks = nullptr;
+	int ptask_cap = 0;
+	ReconTask *h_rtasks = nullptr, *d_rtasks = nullptr;
+	int rtask_cap = 0;
+	bool copies_outstanding[2] = {false, false};
+	jsmpeg_b200_stats_t stats{};
+};
+
+namespace {
+
+using Batch = jsmpeg_b200_batch_t;
+
+void use_device(Batch *b) { CUDA_CHECK(cudaSetDevice(b->device)); }
+
+void release_slot(Batch *b, int slot) { b->free_slots.push_back(slot); }
+
+void flush_cache(Batch *b, Stream &s) {
+	for (auto &p : s.cache) release_slot(b, p.slot);
+	s.cache.clear();
+}
+
+void forget_index(Batch *b, Stream &s) {
+	flush_cache(b, s);
+	s.pics.clear();
+	s.scanned = 0;
+	s.d_valid = 0;
+}
+
+// ---- bit buffer (host) ------------------------------------------------------------------------
+
+void host_resize(Stream &s, uint32_t cap) {
+	uint8_t *n = pinned_alloc<uint8_t>(cap);
+	if (s.h_bytes) {
+		memcpy(n, s.h_bytes, std::min(s.length, cap));
+		CUDA_CHECK(cudaFreeHost(s.h_bytes));
+	}
+	s.h_bytes = n;
+	s.capacity = cap;
+	if (s.index > (s.length << 3)) s.index = s.length << 3;  // buffer.c:160-163
+}
+
+// src/wasm/buffer.c:48-65 get_write_ptr, :167-190 evict
+void *stream_get_write_ptr(Batch *b, Stream &s, uint32_t n) {
+	uint32_t avail = s.capacity - s.length;
+	if (n > avail) {
+		if (s.mode == BIT_BUFFER_MODE_EXPAND) {
+			uint32_t cap = s.capacity * 2;
+			if (cap + avail < n) cap = n - avail;
+			host_resize(s, cap);
+		} else {
+			uint32_t pos = s.index >> 3;
+			if (pos == s.length || n > avail + pos) {  // nothing unread, or emergency evacuation
+				s.length = 0;
+				s.index = 0;
+				forget_index(b, s);
+			} else if (pos != 0) {
+				memmove(s.h_bytes, s.h_bytes + pos, s.length - pos);
+				s.length -= pos;
+				s.index -= pos << 3;
+				forget_index(b, s);
+			}
+		}
+	}
+	return s.h_bytes + s.length;
+}
+
+// MSB-first reader for the (tiny, once-per-stream) sequence header on the host
+struct HostBits {
+	const uint8_t *p;
+	uint32_t len, idx;
+	uint32_t read(int n) {
+		uint32_t v = 0;
+		for (int i = 0; i < n; i++, idx++) {
+			uint32_t byte = idx >> 3;
+			v = (v << 1) | (byte < len ? (p[byte] >> (7 - (idx & 7))) & 1u : 0u);
+		}
+		return v;
+	}
+};
+
+const float kPictureRate[16] = {0.f, 23.976f, 24.f, 25.f, 29.97f, 30.f, 50.f, 59.94f, 60.f, 0, 0, 0, 0, 0, 0, 0};
+const uint8_t kZigZag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48,
+                             41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22,
+                             15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+const uint8_t kDefaultIntraQ[64] = {8, 16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37,
+                                    19, 22, 26, 27, 29, 34, 34, 38, 22, 22, 26, 27, 29, 34, 37, 40,
+                                    22, 26, 27, 29, 32, 35, 40, 48, 26, 27, 29, 32, 35, 40, 48, 58,
+                                    26, 27, 29, 34, 38, 46, 56, 69, 27, 29, 35, 38, 46, 56, 69, 83};
+
+// src/mpeg1.js:78-153 decodeSequenceHeader + initBuffers (first header only, mpeg1.c:812-819)
+void parse_sequence_header(Batch *b, Stream &s, uint32_t bit_index) {
+	HostBits hb{s.h_bytes, s.length, bit_index};
+	s.width = (int)hb.read(12);
+	s.height = (int)hb.read(12);
+	hb.read(4);
+	s.frame_rate = kPictureRate[hb.read(4)];
+	hb.read(18 + 1 + 10 + 1);
+	if (hb.read(1)) { for (int i = 0; i < 64; i++) s.seq.intra_q[kZigZag[i]] = (uint8_t)hb.read(8); }
+	else memcpy(s.seq.intra_q, kDefaultIntraQ, 64);
+	if (hb.read(1)) { for (int i = 0; i < 64; i++) s.seq.non_intra_q[kZigZag[i]] = (uint8_t)hb.read(8); }
+	else memset(s.seq.non_intra_q, 16, 64);
+	s.index = hb.idx;
+	s.seq_end_index = hb.idx;
+	s.seq.mb_width = (s.width + 15) >> 4;
+	s.seq.mb_height = (s.height + 15) >> 4;
+	s.seq.mb_size = s.seq.mb_width * s.seq.mb_height;
+	s.seq.coded_width = s.seq.mb_width << 4;
+	s.seq.coded_height = s.seq.mb_height << 4;
+	s.coded_size = s.seq.coded_width * s.seq.coded_height;
+	s.has_seq = true;
+
+	const size_t plane_bytes = (size_t)s.coded_size * 3 / 2;
+	s.d_seq = dev_alloc<SeqParams>(1);
+	CUDA_CHECK(cudaMemcpyAsync(s.d_seq, &s.seq, sizeof(SeqParams), cudaMemcpyHostToDevice, b->st_main));
+	for (int i = 0; i < 2; i++) {
+		s.d_planes[i] = dev_alloc<uint8_t>(plane_bytes + 64);
+		CUDA_CHECK(cudaMemsetAsync(s.d_planes[i], 0, plane_bytes + 64, b->st_main));  // JS typed arrays start zeroed
+	}
+	for (int i = 0; i < HOST_RING; i++) {
+		s.h_planes[i] = pinned_alloc<uint8_t>(plane_bytes);
+		memset(s.h_planes[i], 0, plane_bytes);
+	}
+	CUDA_CHECK(cudaStreamSynchronize(b->st_main));  // s.seq is read by the async copy
+}
+
+// src/wasm/mpeg1.c:812-819 did_write
+void stream_did_write(Batch *b, Stream &s, uint32_t n) {
+	s.length += n;
+	if (!s.has_seq) {
+		// findStartCode(SEQUENCE): serial host scan of the not-yet-consumed head of the stream
+		uint32_t i = (s.index + 7) >> 3;
+		bool found = false;
+		for (; i + 3 < s.length; i++) {
+			if (s.h_bytes[i] == 0 && s.h_bytes[i + 1] == 0 && s.h_bytes[i + 2] == 1) {
+				if (s.h_bytes[i + 3] == 0xB3) { found = true; break; }
+				i += 3;  // index jumps past the code (buffer.js:121-123)
+			}
+		}
+		if (found) parse_sequence_header(b, s, (i + 4) << 3);
+		else s.index = s.length << 3;
+	}
+}
+
+// ---- residency: H2D of new bytes + start-code scan -----------------------------------------------
+
+void begin_upload(Batch *b, Stream &s) {
+	s.scan_pending = false;
+	if (s.d_valid >= s.length && s.scanned >= s.length) return;
+	if (s.length + ES_PAD > s.d_capacity) {
+		uint32_t cap = std::max<uint32_t>(s.length + ES_PAD, s.d_capacity * 2);
+		cap = (cap + 255u) & ~255u;
+		uint8_t *n = dev_alloc<uint8_t>(cap);
+		if (s.d_es) CUDA_CHECK(cudaFree(s.d_es));  // stream-ordered work on it is complete: every call ends synchronised
+		s.d_es = n;
+		s.d_capacity = cap;
+		s.d_valid = 0;
+	}
+	if (s.d_valid < s.length) {
+		uint32_t from = s.d_valid & ~15u;
+		CUDA_CHECK(cudaMemcpyAsync(s.d_es + from, s.h_bytes + from, s.length - from, cudaMemcpyHostToDevice, b->st_main));
+		b->stats.h2d_bytes += s.length - from;
+		s.d_valid = s.length;
+	}
+	if (s.scanned < s.length) {
+		uint32_t from = s.scanned >= 3 ? s.scanned - 3 : 0;
+		uint32_t want = (s.length - from) / 4 + 16;  // start codes cannot overlap
+		want = std::min<uint32_t>(want, 1u << 20);
+		if (want + 1 > s.scan_cap) {
+			if (s.d_scan) CUDA_CHECK(cudaFree(s.d_scan));
+			if (s.h_scan) CUDA_CHECK(cudaFreeHost(s.h_scan));
+			s.scan_cap = want + 1;
+			s.d_scan = dev_alloc<uint32_t>(s.scan_cap);
+			s.h_scan = pinned_alloc<uint32_t>(s.scan_cap);
+		}
+		CUDA_CHECK(cudaMemsetAsync(s.d_scan, 0, sizeof(uint32_t), b->st_main));
+		launch_scan_start_codes(s.d_es, from, s.length, s.d_scan + 1, s.scan_cap - 1, s.d_scan, b->st_main);
+		b->stats.kernel_launches++;
+		s.scan_from = from;
+		s.scan_pending = true;
+	}
+}
+
+long upload_all(Batch *b) {
+	CUDA_CHECK(cudaEventRecord(b->ev_a, b->st_main));
+	bool any = false;
+	for (auto &s : b->streams) {
+		begin_upload(b, s);
+		if (s.scan_pending) {
+			any = true;
+			CUDA_CHECK(cudaMemcpyAsync(s.h_scan, s.d_scan, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->st_main));
+		}
+	}
+	if (any) {
+		CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
+		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+		float ms = 0;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_b));
+		b->stats.scan_ms += ms;
+		for (auto &s : b->streams) {
+			if (!s.scan_pending) continue;
+			if (s.h_scan[0] > s.scan_cap - 1) {
+				fprintf(stderr, "jsmpeg_b200: start-code index overflow (%u > %u)\n", s.h_scan[0], s.scan_cap - 1);
+				abort();
+			}
+			if (s.h_scan[0]) {
+				CUDA_CHECK(cudaMemcpyAsync(s.h_scan + 1, s.d_scan + 1, s.h_scan[0] * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->st_main));
+				b->stats.d2h_bytes += s.h_scan[0] * sizeof(uint32_t);
+			}
+		}
+		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+		for (auto &s : b->streams) {
+			if (!s.scan_pending) continue;
+			const uint32_t n = s.h_scan[0];
+			std::sort(s.h_scan + 1, s.h_scan + 1 + n);
+			// the rescanned window starts 3 bytes before the old frontier, so nothing is reported twice
+			for (uint32_t i = 1; i <= n; i++) s.pics.push_back(s.h_scan[i]);
+			s.scanned = s.length;
+			s.scan_pending = false;
+		}
+	}
+	long total = 0;
+	for (auto &s : b->streams) total += (long)s.pics.size();
+	return total;
+}
+
+// ---- record slots ----------------------------------------------------------------------------------
+
+void ensure_pool(Batch *b) {
+	int need_mb = 0, active = 0;
+	for (auto &s : b->streams) if (s.has_seq) { need_mb = std::max(need_mb, s.seq.mb_size); active++; }
+	if (need_mb <= b->slot_mb || need_mb == 0) return;
+	for (auto &s : b->streams) flush_cache(b, s);
+	if (b->d_hdr) { CUDA_CHECK(cudaFree(b->d_hdr)); CUDA_CHECK(cudaFree(b->d_coef)); CUDA_CHECK(cudaFree(b->d_info)); CUDA_CHECK(cudaFreeHost(b->h_info)); }
+	const size_t slot_bytes = (size_t)need_mb * (sizeof(mb_record_t) + MB_COEF_INT16 * sizeof(int16_t));
+	size_t n = b->max_slots_req;
+	if (n == 0) {
+		size_t free_b = 0, total_b = 0;
+		CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+		n = (size_t)(0.45 * (double)free_b) / slot_bytes;
+		n = std::min<size_t>(n, 4096);
+	}
+	n = std::max<size_t>(n, 2);
+	b->slot_mb = need_mb;
+	b->n_slots = (int)n;
+	b->d_hdr = dev_alloc<mb_record_t>(n * need_mb);
+	b->d_coef = dev_alloc<int16_t>(n * need_mb * MB_COEF_INT16);
+	b->d_info = dev_alloc<picture_info_t>(n);
+	b->h_info = pinned_alloc<picture_info_t>(n);
+	b->free_slots.clear();
+	for (int i = (int)n - 1; i >= 0; i--) b->free_slots.push_back(i);
+}
+
+void ensure_task_caps(Batch *b, int n_parse, int n_recon) {
+	if (n_parse > b->ptask_cap) {
+		if (b->h_ptasks) { CUDA_CHECK(cudaFreeHost(b->h_ptasks)); CUDA_CHECK(cudaFree(b->d_ptasks)); }
+		b->ptask_cap = std::max(n_parse, b->ptask_cap * 2);
+		b->h_ptasks = pinned_alloc<ParseTask>(b->ptask_cap);
+		b->d_ptasks = dev_alloc<ParseTask>(b->ptask_cap);
+	}
+	if (n_recon > b->rtask_cap) {
+		if (b->h_rtasks) { CUDA_CHECK(cudaFreeHost(b->h_rtasks)); CUDA_CHECK(cudaFree(b->d_rtasks)); }
+		b->rtask_cap = std::max(n_recon, b->rtask_cap * 2);
+		b->h_rtasks = pinned_alloc<ReconTask>(b->rtask_cap);
+		b->d_rtasks = dev_alloc<ReconTask>(b->rtask_cap);
+	}
+}
+
+PlaneSet plane_set(const Stream &s, uint8_t *base) {
+	PlaneSet p;
+	p.y = base;
+	p.cr = base + s.coded_size;
+	p.cb = base + s.coded_size + (s.coded_size >> 2);
+	return p;
+}
+
+bool entry_stale(const Stream &s, const Parsed &e) {
+	// a parse that ran into the end of the data it saw must be redone once more data is there
+	return e.len_at_parse != s.length && (uint64_t)e.info.end_bit + 64 >= (uint64_t)e.len_at_parse * 8;
+}
+
+// One chunk: parse ahead what is missing (one wave), then consume up to want[s] pictures per stream.
+// Returns pictures consumed; `progress[s]` gets the per-stream count, `more[s]` whether the stream
+// may have further pictures.
+long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &progress, std::vector<char> &more, int flags) {
+	const int S = (int)b->streams.size();
+	// ---- 1. plan the parse wave
+	struct NewParse { int stream; size_t cache_idx; };
+	std::vector<NewParse> fresh;
+	for (int si = 0; si < S; si++) {
+		Stream &s = b->streams[si];
+		progress[si] = 0;
+		if (!s.has_seq || want[si] <= 0) { more[si] = 0; continue; }
+		const uint32_t from_byte = (s.index + 7) >> 3;
+		auto it = std::lower_bound(s.pics.begin(), s.pics.end(), from_byte);
+		if (!s.cache.empty() && (it == s.pics.end() || s.cache.front().pos != *it)) flush_cache(b, s);
+		for (size_t j = 0; j < s.cache.size(); j++) {
+			if (entry_stale(s, s.cache[j])) {
+				while (s.cache.size() > j) { release_slot(b, s.cache.back().slot); s.cache.pop_back(); }
+				break;
+			}
+		}
+		if ((int)s.cache.size() >= want[si]) continue;
+		int target = std::max(want[si], b->lookahead);
+		auto next = it + (ptrdiff_t)s.cache.size();
+		// `it` may be end(); cache is then empty
+		while ((int)s.cache.size() < target && next < s.pics.end() && !b->free_slots.empty()) {
+			Parsed p{};
+			p.pos = *next;
+			p.len_at_parse = s.length;
+			p.slot = b->free_slots.back();
+			b->free_slots.pop_back();
+			s.cache.push_back(p);
+			fresh.push_back({si, s.cache.size() - 1});
+			++next;
+		}
+	}
+	// ---- 2. parse wave
+	if (!fresh.empty()) {
+		ensure_task_caps(b, (int)fresh.size(), 0);
+		for (size_t i = 0; i < fresh.size(); i++) {
+			Stream &s = b->streams[fresh[i].stream];
+			Parsed &p = s.cache[fresh[i].cache_idx];
+			ParseTask &t = b->h_ptasks[i];
+			t.es = s.d_es;
+			t.es_len = s.length;
+			t.start_byte = p.pos + 4;
+			t.seq = s.d_seq;
+			t.hdr = b->d_hdr + (size_t)p.slot * b->slot_mb;
+			t.coef = b->d_coef + (size_t)p.slot * b->slot_mb * MB_COEF_INT16;
+			t.info = b->d_info + i;
+		}
+		CUDA_CHECK(cudaMemcpyAsync(b->d_ptasks, b->h_ptasks, fresh.size() * sizeof(ParseTask), cudaMemcpyHostToDevice, b->st_main));
+		CUDA_CHECK(cudaEventRecord(b->ev_a, b->st_main));
+		launch_parse_pictures(b->d_ptasks, (int)fresh.size(), b->st_main);
+		CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
+		CUDA_CHECK(cudaMemcpyAsync(b->h_info, b->d_info, fresh.size() * sizeof(picture_info_t), cudaMemcpyDeviceToHost, b->st_main));
+		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+		float ms = 0;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_b));
+		b->stats.parse_ms += ms;
+		b->stats.kernel_launches++;
+		b->stats.h2d_bytes += fresh.size() * sizeof(ParseTask);
+		b->stats.d2h_bytes += fresh.size() * sizeof(picture_info_t);
+		for (size_t i = 0; i < fresh.size(); i++) {
+			Parsed &p = b->streams[fresh[i].stream].cache[fresh[i].cache_idx];
+			p.info = b->h_info[i];
+			if (p.info.error == PARSE_ERR_INVALID_VLC) b->stats.parse_errors++;
+		}
+	}
+	// ---- 3. consume in decode() order per stream; step j of a stream -> recon launch j
+	std::vector<std::vector<ReconTask>> steps;
+	std::vector<std::vector<int>> step_streams;
+	long consumed = 0;
+	for (int si = 0; si < S; si++) {
+		Stream &s = b->streams[si];
+		if (!s.has_seq || want[si] <= 0) continue;
+		more[si] = 1;
+		int step = 0;
+		for (int j = 0; j < want[si]; j++) {
+			const uint32_t from_byte = (s.index + 7) >> 3;
+			auto it = std::lower_bound(s.pics.begin(), s.pics.end(), from_byte);
+			if (it == s.pics.end()) {  // findStartCode(PICTURE) == -1: index parks at the end (buffer.js:126-127)
+				s.index = s.length << 3;
+				more[si] = 0;
+				break;
+			}
+			if (s.cache.empty() || s.cache.front().pos != *it || entry_stale(s, s.cache.front())) {
+				flush_cache(b, s);  // look-ahead does not match the serial order: re-plan next chunk
+				break;
+			}
+			const Parsed e = s.cache.front();
+			s.cache.pop_front();
+			s.index = e.info.end_bit;
+			progress[si]++;
+			consumed++;
+			b->stats.pictures++;
+			b->stats.es_bytes += (e.info.end_bit >> 3) - e.pos;
+			if (e.info.status == PIC_DECODED) {
+				ReconTask t{};
+				t.hdr = b->d_hdr + (size_t)e.slot * b->slot_mb;
+				t.coef = b->d_coef + (size_t)e.slot * b->slot_mb * MB_COEF_INT16;
+				t.cur = plane_set(s, s.d_planes[s.cur]);
+				t.fwd = plane_set(s, s.d_planes[1 - s.cur]);
+				t.mb_width = s.seq.mb_width;
+				t.mb_size = s.seq.mb_size;
+				t.coded_width = s.seq.coded_width;
+				t.coded_height = s.seq.coded_height;
+				t.width = s.width;
+				t.height = s.height;
+				t.rgba = nullptr;
+				if (flags & JSMPEG_B200_OUT_RGBA) {
+					if (!s.d_rgba) s.d_rgba = dev_alloc<uint8_t>((size_t)s.width * s.height * 4);
+					t.rgba = s.d_rgba;
+				}
+				if ((int)steps.size() <= step) { steps.emplace_back(); step_streams.emplace_back(); }
+				steps[step].push_back(t);
+				step_streams[step].push_back(si);
+				step++;
+				s.cur ^= 1;  // mpeg1.js:221-246: the picture just decoded becomes `forward`
+				b->stats.pictures_decoded++;
+				b->stats.coded_blocks += e.info.n_coded_blocks;
+				b->stats.macroblocks += e.info.n_present;
+				const uint64_t planes = (uint64_t)s.coded_size * 3 / 2;
+				b->stats.algorithmic_bytes += planes + (e.info.picture_type == 2 ? planes : 0) +
+				                              (uint64_t)s.seq.mb_size * sizeof(mb_record_t) + (uint64_t)e.info.n_coded_blocks * 128;
+			}
+			release_slot(b, e.slot);  // stream order: the next parse launch runs after this chunk's recon launches
+		}
+	}
+	// ---- 4. reconstruction, one launch per step
+	if (!steps.empty()) {
+		size_t total = 0;
+		for (auto &v : steps) total += v.size();
+		ensure_task_caps(b, 0, (int)total);
+		size_t off = 0;
+		for (auto &v : steps) { memcpy(b->h_rtasks + off, v.data(), v.size() * sizeof(ReconTask)); off += v.size(); }
+		CUDA_CHECK(cudaMemcpyAsync(b->d_rtasks, b->h_rtasks, total * sizeof(ReconTask), cudaMemcpyHostToDevice, b->st_main));
+		b->stats.h2d_bytes += total * sizeof(ReconTask);
+		for (int i = 0; i < 2; i++)  // planes of the previous chunk may still be on their way out
+			if (b->copies_outstanding[i]) CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_copied[i], 0));
+		CUDA_CHECK(cudaEventRecord(b->ev_c, b->st_main));
+		off = 0;
+		for (size_t f = 0; f < steps.size(); f++) {
+			int max_mb = 0;
+			for (auto &t : steps[f]) max_mb = std::max(max_mb, t.mb_size);
+			// step f overwrites the plane set that step f-2 produced: its copy-out must be done
+			if ((flags & JSMPEG_B200_OUT_HOST) && f >= 2) CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_copied[f & 1], 0));
+			launch_reconstruct(b->d_rtasks + off, (int)steps[f].size(), max_mb, b->st_main);
+			b->stats.kernel_launches++;
+			b->stats.recon_launches++;
+			if (flags & JSMPEG_B200_OUT_RGBA) {
+				int mw = 0, mh = 0;
+				for (auto &t : steps[f]) { mw = std::max(mw, t.width); mh = std::max(mh, t.height); }
+				launch_rgba(b->d_rtasks + off, (int)steps[f].size(), mw, mh, b->st_main);
+				b->stats.kernel_launches++;
+			}
+			if (flags & JSMPEG_B200_OUT_HOST) {
+				// copy this step's pictures out on the copy stream while the next step reconstructs
+				CUDA_CHECK(cudaEventRecord(b->ev_step, b->st_main));
+				CUDA_CHECK(cudaStreamWaitEvent(b->st_copy, b->ev_step, 0));
+				for (size_t i = 0; i < steps[f].size(); i++) {
+					Stream &s = b->streams[step_streams[f][i]];
+					s.h_head = (s.h_head + 1) % HOST_RING;
+					const size_t bytes = (size_t)s.coded_size * 3 / 2;
+					CUDA_CHECK(cudaMemcpyAsync(s.h_planes[s.h_head], steps[f][i].cur.y, bytes, cudaMemcpyDeviceToHost, b->st_copy));
+					b->stats.d2h_bytes += bytes;
+				}
+				CUDA_CHECK(cudaEventRecord(b->ev_copied[f & 1], b->st_copy));
+				b->copies_outstanding[f & 1] = true;
+			}
+			off += steps[f].size();
+		}
+		CUDA_CHECK(cudaEventRecord(b->ev_d, b->st_main));
+		CUDA_CHECK(cudaEventSynchronize(b->ev_d));
+		float ms = 0;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_c, b->ev_d));
+		b->stats.recon_ms += ms;
+	}
+	return consumed;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI, part 2 (batch)
+
+extern "C" {
+
+const char *jsmpeg_b200_version(void) { return "jsmpeg_b200 0.1 (sm_100a)"; }
+
+jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigned int max_slots) {
+	Batch *b = new Batch();
+	b->device = device;
+	use_device(b);
+	b->streams.resize(std::max(n_streams, 1));
+	b->max_slots_req = max_slots;
+	CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
+	CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
+	cudaEvent_t *evs[] = {&b->ev_a, &b->ev_b, &b->ev_c, &b->ev_d};
+	for (auto e : evs) CUDA_CHECK(cudaEventCreate(e));
+	CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_step, cudaEventDisableTiming));
+	for (auto &e : b->ev_copied) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	return b;
+}
+
+void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
+	if (!b) return;
+	use_device(b);
+	CUDA_CHECK(cudaDeviceSynchronize());
+	for (auto &s : b->streams) {
+		if (s.h_bytes) cudaFreeHost(s.h_bytes);
+		if (s.d_seq) cudaFree(s.d_seq);
+		if (s.d_es) cudaFree(s.d_es);
+		if (s.d_scan) cudaFree(s.d_scan);
+		if (s.h_scan) cudaFreeHost(s.h_scan);
+		if (s.d_rgba) cudaFree(s.d_rgba);
+		for (auto p : s.d_planes) if (p) cudaFree(p);
+		for (auto p : s.h_planes) if (p) cudaFreeHost(p);
+	}
+	if (b->d_hdr) { cudaFree(b->d_hdr); cudaFree(b->d_coef); cudaFree(b->d_info); cudaFreeHost(b->h_info); }
+	if (b->h_ptasks) { cudaFreeHost(b->h_ptasks); cudaFree(b->d_ptasks); }
+	if (b->h_rtasks) { cudaFreeHost(b->h_rtasks); cudaFree(b->d_rtasks); }
+	cudaEvent_t evs[] = {b->ev_a, b->ev_b, b->ev_c, b->ev_d, b->ev_step, b->ev_copied[0], b->ev_copied[1]};
+	for (auto e : evs) cudaEventDestroy(e);
+	cudaStreamDestroy(b->st_main);
+	cudaStreamDestroy(b->st_copy);
+	delete b;
+}
+
+void *jsmpeg_b200_batch_get_write_ptr(jsmpeg_b200_batch_t *b, int stream, unsigned int byte_size) {
+	use_device(b);
+	return stream_get_write_ptr(b, b->streams[stream], byte_size);
+}
+
+void jsmpeg_b200_batch_did_write(jsmpeg_b200_batch_t *b, int stream, unsigned int byte_size) {
+	use_device(b);
+	stream_did_write(b, b->streams[stream], byte_size);
+}
+
+int jsmpeg_b200_batch_get_index(jsmpeg_b200_batch_t *b, int stream) { return (int)b->streams[stream].index; }
+
+void jsmpeg_b200_batch_set_index(jsmpeg_b200_batch_t *b, int stream, unsigned int index) {
+	Stream &s = b->streams[stream];
+	s.index = index;
+	flush_cache(b, s);
+}
+
+int jsmpeg_b200_batch_stream_info(jsmpeg_b200_batch_t *b, int stream, int *width, int *height, int *coded_size, float *frame_rate) {
+	const Stream &s = b->streams[stream];
+	if (width) *width = s.width;
+	if (height) *height = s.height;
+	if (coded_size) *coded_size = s.coded_size;
+	if (frame_rate) *frame_rate = s.frame_rate;
+	return s.has_seq ? 1 : 0;
+}
+
+long jsmpeg_b200_batch_upload(jsmpeg_b200_batch_t *b) {
+	use_device(b);
+	return upload_all(b);
+}
+
+void jsmpeg_b200_batch_rewind(jsmpeg_b200_batch_t *b) {
+	use_device(b);
+	for (auto &s : b->streams) {
+		flush_cache(b, s);
+		s.pics.clear();
+		s.scanned = 0;
+		s.index = s.has_seq ? s.seq_end_index : 0;  // where did_write left it (mpeg1.c:812-819)
+	}
+}
+
+void jsmpeg_b200_batch_reset(jsmpeg_b200_batch_t *b) {
+	use_device(b);
+	for (auto &s : b->streams) {
+		forget_index(b, s);
+		s.length = 0;
+		s.index = 0;
+		s.cur = 0;
+		s.h_head = -1;
+		if (s.has_seq)
+			for (auto p : s.d_planes) CUDA_CHECK(cudaMemsetAsync(p, 0, (size_t)s.coded_size * 3 / 2, b->st_main));
+	}
+	CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+}
+
+long jsmpeg_b200_batch_decode(jsmpeg_b200_batch_t *b, int n_pictures, int flags) {
+	use_device(b);
+	upload_all(b);
+	ensure_pool(b);
+	const int S = (int)b->streams.size();
+	std::vector<int> remaining(S, n_pictures), want(S), progress(S);
+	std::vector<char> more(S, 1);
+	long total = 0;
+	int idle_rounds = 0;
+	for (;;) {
+		int active = 0;
+		for (int i = 0; i < S; i++) if (more[i] && remaining[i] > 0 && b->streams[i].has_seq) active++;
+		if (!active) break;
+		// share the record slots between the active streams
+		int cached = 0;
+		for (auto &s : b->streams) cached += (int)s.cache.size();
+		const int per_stream = std::max(1, (int)(b->free_slots.size() + cached) / active);
+		for (int i = 0; i < S; i++)
+			want[i] = (more[i] && b->streams[i].has_seq) ? std::min(remaining[i], per_stream) : 0;
+		const long got = decode_chunk(b, want, progress, more, flags);
+		total += got;
+		bool replanned = false;
+		for (int i = 0; i < S; i++) {
+			remaining[i] -= progress[i];
+			if (want[i] > 0 && progress[i] < want[i] && more[i]) replanned = true;
+		}
+		if (got == 0 && (!replanned || ++idle_rounds > 2)) break;
+		if (got) idle_rounds = 0;
+	}
+	for (int i = 0; i < 2; i++) {
+		if (b->copies_outstanding[i]) CUDA_CHECK(cudaEventSynchronize(b->ev_copied[i]));
+		b->copies_outstanding[i] = false;
+	}
+	CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+	return total;
+}
+
+int jsmpeg_b200_batch_get_planes(jsmpeg_b200_batch_t *b, int stream, void **y, void **cr, void **cb) {
+	const Stream &s = b->streams[stream];
+	if (!s.has_seq) return -1;
+	PlaneSet p = plane_set(s, s.d_planes[1 - s.cur]);  // most recent picture = forward (mpeg1.c:841-851)
+	if (y) *y = p.y;
+	if (cr) *cr = p.cr;
+	if (cb) *cb = p.cb;
+	return 0;
+}
+
+int jsmpeg_b200_batch_get_host_planes(jsmpeg_b200_batch_t *b, int stream, void **y, void **cr, void **cb) {
+	const Stream &s = b->streams[stream];
+	if (!s.has_seq) return -1;
+	PlaneSet p = plane_set(s, s.h_planes[s.h_head < 0 ? 0 : s.h_head]);
+	if (y) *y = p.y;
+	if (cr) *cr = p.cr;
+	if (cb) *cb = p.cb;
+	return 0;
+}
+
+int jsmpeg_b200_batch_get_rgba(jsmpeg_b200_batch_t *b, int stream, void **rgba) {
+	const Stream &s = b->streams[stream];
+	if (!s.has_seq || !s.d_rgba) return -1;
+	*rgba = s.d_rgba;
+	return 0;
+}
+
+int jsmpeg_b200_batch_read_planes(jsmpeg_b200_batch_t *b, int stream, void *y, void *cr, void *cb) {
+	use_device(b);
+	const Stream &s = b->streams[stream];
+	if (!s.has_seq) return -1;
+	PlaneSet p = plane_set(s, s.d_planes[1 - s.cur]);
+	if (y) CUDA_CHECK(cudaMemcpy(y, p.y, s.coded_size, cudaMemcpyDeviceToHost));
+	if (cr) CUDA_CHECK(cudaMemcpy(cr, p.cr, s.coded_size >> 2, cudaMemcpyDeviceToHost));
+	if (cb) CUDA_CHECK(cudaMemcpy(cb, p.cb, s.coded_size >> 2, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+int jsmpeg_b200_batch_read_rgba(jsmpeg_b200_batch_t *b, int stream, void *rgba) {
+	use_device(b);
+	const Stream &s = b->streams[stream];
+	if (!s.has_seq || !s.d_rgba) return -1;
+	CUDA_CHECK(cudaMemcpy(rgba, s.d_rgba, (size_t)s.width * s.height * 4, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+void jsmpeg_b200_batch_get_stats(jsmpeg_b200_batch_t *b, jsmpeg_b200_stats_t *out) { *out = b->stats; }
+void jsmpeg_b200_batch_reset_stats(jsmpeg_b200_batch_t *b) { b->stats = jsmpeg_b200_stats_t{}; }
+
+// ================================================================================================
+// C ABI, part 1 (reference ABI): one stream, synchronous, host-visible planes
+
+struct mpeg1_decoder_t {
+	jsmpeg_b200_batch_t *b;
+};
+
+mpeg1_decoder_t *mpeg1_decoder_create(unsigned int buffer_size, bit_buffer_mode_t buffer_mode) {
+	const char *dev = getenv("JSMPEG_B200_DEVICE");
+	const char *slots = getenv("JSMPEG_B200_LOOKAHEAD");
+	int lookahead = slots ? atoi(slots) : 16;
+	if (lookahead < 1) lookahead = 1;
+	mpeg1_decoder_t *d = new mpeg1_decoder_t();
+	d->b = jsmpeg_b200_batch_create(1, dev ? atoi(dev) : 0, (unsigned)lookahead + 1);
+	d->b->lookahead = lookahead;
+	Stream &s = d->b->streams[0];
+	s.mode = buffer_mode;
+	host_resize(s, buffer_size ? buffer_size : 1);
+	return d;
+}
+
+void mpeg1_decoder_destroy(mpeg1_decoder_t *self) {
+	jsmpeg_b200_batch_destroy(self->b);
+	delete self;
+}
+
+void *mpeg1_decoder_get_write_ptr(mpeg1_decoder_t *self, unsigned int byte_size) {
+	return jsmpeg_b200_batch_get_write_ptr(self->b, 0, byte_size);
+}
+int mpeg1_decoder_get_index(mpeg1_decoder_t *self) { return jsmpeg_b200_batch_get_index(self->b, 0); }
+void mpeg1_decoder_set_index(mpeg1_decoder_t *self, unsigned int index) { jsmpeg_b200_batch_set_index(self->b, 0, index); }
+void mpeg1_decoder_did_write(mpeg1_decoder_t *self, unsigned int byte_size) { jsmpeg_b200_batch_did_write(self->b, 0, byte_size); }
+int mpeg1_decoder_has_sequence_header(mpeg1_decoder_t *self) { return self->b->streams[0].has_seq ? 1 : 0; }
+float mpeg1_decoder_get_frame_rate(mpeg1_decoder_t *self) { return self->b->streams[0].frame_rate; }
+int mpeg1_decoder_get_coded_size(mpeg1_decoder_t *self) { return self->b->streams[0].coded_size; }
+int mpeg1_decoder_get_width(mpeg1_decoder_t *self) { return self->b->streams[0].width; }
+int mpeg1_decoder_get_height(mpeg1_decoder_t *self) { return self->b->streams[0].height; }
+
+static void *host_plane(mpeg1_decoder_t *self, int which) {
+	void *p[3] = {nullptr, nullptr, nullptr};
+	if (jsmpeg_b200_batch_get_host_planes(self->b, 0, &p[0], &p[1], &p[2]) != 0) return nullptr;
+	return p[which];
+}
+void *mpeg1_decoder_get_y_ptr(mpeg1_decoder_t *self) { return host_plane(self, 0); }
+void *mpeg1_decoder_get_cr_ptr(mpeg1_decoder_t *self) { return host_plane(self, 1); }
+void *mpeg1_decoder_get_cb_ptr(mpeg1_decoder_t *self) { return host_plane(self, 2); }
+
+bool mpeg1_decoder_decode(mpeg1_decoder_t *self) {
+	if (!self->b->streams[0].has_seq) return false;
+	return jsmpeg_b200_batch_decode(self->b, 1, JSMPEG_B200_OUT_HOST) > 0;
+}
+
+// ================================================================================================
+// test hooks
+
+int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t start_byte, int mb_width,
+                                    int mb_height, const uint8_t *intra_q, const uint8_t *non_intra_q,
+                                    void *info_out, void *hdr_out, void *coef_out) {
+	SeqParams sp{};
+	sp.mb_width = mb_width; sp.mb_height = mb_height; sp.mb_size = mb_width * mb_height;
+	sp.coded_width = mb_width * 16; sp.coded_height = mb_height * 16;
+	memcpy(sp.intra_q, intra_q, 64);
+	memcpy(sp.non_intra_q, non_intra_q, 64);
+	const size_t n_mb = sp.mb_size;
+	uint8_t *d_es = dev_alloc<uint8_t>(es_len + ES_PAD);
+	SeqParams *d_seq = dev_alloc<SeqParams>(1);
+	mb_record_t *d_hdr = dev_alloc<mb_record_t>(n_mb);
+	int16_t *d_coef = dev_alloc<int16_t>(n_mb * MB_COEF_INT16);
+	picture_info_t *d_info = dev_alloc<picture_info_t>(1);
+	ParseTask *d_task = dev_alloc<ParseTask>(1);
+	CUDA_CHECK(cudaMemcpy(d_es, es, es_len, cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(d_seq, &sp, sizeof(sp), cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemset(d_coef, 0, n_mb * MB_COEF_INT16 * sizeof(int16_t)));
+	ParseTask t{d_es, es_len, start_byte, d_seq, d_hdr, d_coef, d_info};
+	CUDA_CHECK(cudaMemcpy(d_task, &t, sizeof(t), cudaMemcpyHostToDevice));
+	launch_parse_pictures(d_task, 1, 0);
+	CUDA_CHECK(cudaGetLastError());
+	CUDA_CHECK(cudaDeviceSynchronize());
+	CUDA_CHECK(cudaMemcpy(info_out, d_info, sizeof(picture_info_t), cudaMemcpyDeviceToHost));
+	CUDA_CHECK(cudaMemcpy(hdr_out, d_hdr, n_mb * sizeof(mb_record_t), cudaMemcpyDeviceToHost));
+	CUDA_CHECK(cudaMemcpy(coef_out, d_coef, n_mb * MB_COEF_INT16 * sizeof(int16_t), cudaMemcpyDeviceToHost));
+	cudaFree(d_es); cudaFree(d_seq); cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_info); cudaFree(d_task);
+	return 0;
+}
+
+int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, const void *coef,
+                                  const uint8_t *fwd_y, const uint8_t *fwd_cr, const uint8_t *fwd_cb,
+                                  uint8_t *cur_y, uint8_t *cur_cr, uint8_t *cur_cb) {
+	const size_t n_mb = (size_t)mb_width * mb_height;
+	const size_t ysz = n_mb * 256, csz = ysz / 4, total = ysz + 2 * csz;
+	mb_record_t *d_hdr = dev_alloc<mb_record_t>(n_mb);
+	int16_t *d_coef = dev_alloc<int16_t>(n_mb * MB_COEF_INT16);
+	uint8_t *d_fwd = dev_alloc<uint8_t>(total + 64), *d_cur = dev_alloc<uint8_t>(total + 64);
+	ReconTask *d_task = dev_alloc<ReconTask>(1);
+	CUDA_CHECK(cudaMemcpy(d_hdr, hdr, n_mb * sizeof(mb_record_t), cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(d_coef, coef, n_mb * MB_COEF_INT16 * sizeof(int16_t), cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(d_fwd, fwd_y, ysz, cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(d_fwd + ysz, fwd_cr, csz, cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(d_fwd + ysz + csz, fwd_cb, csz, cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(d_cur, cur_y, ysz, cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(d_cur + ysz, cur_cr, csz, cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(d_cur + ysz + csz, cur_cb, csz, cudaMemcpyHostToDevice));
+	ReconTask t{};
+	t.hdr = d_hdr; t.coef = d_coef;
+	t.cur = PlaneSet{d_cur, d_cur + ysz, d_cur + ysz + csz};
+	t.fwd = PlaneSet{d_fwd, d_fwd + ysz, d_fwd + ysz + csz};
+	t.mb_width = mb_width; t.mb_size = (int)n_mb;
+	t.coded_width = mb_width * 16; t.coded_height = mb_height * 16;
+	CUDA_CHECK(cudaMemcpy(d_task, &t, sizeof(t), cudaMemcpyHostToDevice));
+	launch_reconstruct(d_task, 1, (int)n_mb, 0);
+	CUDA_CHECK(cudaGetLastError());
+	CUDA_CHECK(cudaDeviceSynchronize());
+	CUDA_CHECK(cudaMemcpy(cur_y, d_cur, ysz, cudaMemcpyDeviceToHost));
+	CUDA_CHECK(cudaMemcpy(cur_cr, d_cur + ysz, csz, cudaMemcpyDeviceToHost));
+	CUDA_CHECK(cudaMemcpy(cur_cb, d_cur + ysz + csz, csz, cudaMemcpyDeviceToHost));
+	cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_fwd); cudaFree(d_cur); cudaFree(d_task);
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle, bit-exact.
+
+Every test here needs a B200 (``-m gpu``).  The oracle (oracle/liboracle.so, our CPU restatement
+pinned to the reference by tests/test_oracle_vs_reference.py) and, when it was built in the
+build container, the compiled reference itself (oracle/_ref) are the checkers.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import assert_frames_equal, clip_packets, decode_all, oracle_lib, ref_lib
+from jsmpeg_b200 import capi
+from jsmpeg_b200.batch import OUT_DEVICE, OUT_HOST, BatchDecoder
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(320, 240, 24), (1280, 720, 14)]
+
+
+def _oracle_pictures(packets, n):
+    """Decode n pictures with the oracle and capture, per picture, its records and planes."""
+    lib = oracle_lib()
+    from jsmpeg_b200 import decoder
+    d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=lib)
+    for pts, p in packets:
+        d.write(pts, [p])
+    seq = lib.oracle_seq_params(d.decoder).contents
+    mb_size = seq.mb_size
+    out = []
+    while len(out) < n:
+        start_index = d.bufferGetIndex()
+        if not d.decode():
+            break
+        info = lib.oracle_last_picture_info(d.decoder).contents
+        hdr = np.ctypeslib.as_array(ctypes.cast(lib.oracle_last_mb_records(d.decoder), ctypes.POINTER(ctypes.c_uint8)),
+                                    shape=(mb_size * 16,)).copy()
+        coef = np.ctypeslib.as_array(ctypes.cast(lib.oracle_last_coefficients(d.decoder), ctypes.POINTER(ctypes.c_int16)),
+                                     shape=(mb_size * 384,)).copy()
+        planes = tuple(p.copy() for p in d.planes())
+        out.append(dict(start_byte=info.start_byte, end_bit=info.end_bit, status=info.status,
+                        type=info.picture_type, n_coded=info.n_coded_blocks, n_present=info.n_present,
+                        hdr=hdr, coef=coef, planes=planes))
+    return d, seq, out
+
+
+def _coded_mask(hdr, mb_size):
+    """Boolean mask over the int16 coefficient plane: blocks whose cbp bit is set."""
+    h = hdr.reshape(mb_size, 16)
+    present = (h[:, 4] & 1).astype(bool)
+    cbp = h[:, 5]
+    mask = np.zeros((mb_size, 6, 64), bool)
+    for blk in range(6):
+        mask[:, blk, :] = (present & ((cbp & (0x20 >> blk)) != 0))[:, None]
+    return mask.reshape(-1)
+
+
+@pytest.mark.parametrize("w,h,n", SIZES)
+def test_stage1_parse_matches_oracle_records(w, h, n):
+    packets = clip_packets(w, h, n)
+    es = b"".join(p for _, p in packets)
+    d, seq, pics = _oracle_pictures(packets, n)
+    lib = capi.product_library()
+    mbw, mbh = (w + 15) // 16, (h + 15) // 16
+    mb_size = mbw * mbh
+    iq = bytes(seq.intra_q)
+    nq = bytes(seq.non_intra_q)
+    for k, pic in enumerate(pics):
+        info = helpers.PictureInfo()
+        hdr = np.zeros(mb_size * 16, np.uint8)
+        coef = np.zeros(mb_size * 384, np.int16)
+        rc = lib.jsmpeg_b200_debug_parse_picture(es, len(es), pic["start_byte"], mbw, mbh, iq, nq,
+                                                 ctypes.addressof(info), hdr.ctypes.data, coef.ctypes.data)
+        assert rc == 0
+        assert (info.status, info.picture_type, info.end_bit) == (pic["status"], pic["type"], pic["end_bit"]), k
+        assert info.error == 0
+        assert info.n_coded_blocks == pic["n_coded"] and info.n_present == pic["n_present"]
+        # header bytes 0..7 are the contract (mv, flags, cbp, dc_only, qscale); 8.. are diagnostics
+        got = hdr.reshape(mb_size, 16)[:, :8]
+        exp = pic["hdr"].reshape(mb_size, 16)[:, :8]
+        assert np.array_equal(got, exp), f"picture {k}: macroblock headers differ at {np.nonzero((got != exp).any(1))[0][:8]}"
+        m = _coded_mask(pic["hdr"], mb_size)
+        assert np.array_equal(coef[m], pic["coef"][m]), f"picture {k}: coefficients differ"
+    d.destroy()
+
+
+@pytest.mark.parametrize("w,h,n", SIZES)
+def test_stage2_reconstruct_matches_oracle_planes(w, h, n):
+    packets = clip_packets(w, h, n)
+    d, seq, pics = _oracle_pictures(packets, n)
+    lib = capi.product_library()
+    mbw, mbh = (w + 15) // 16, (h + 15) // 16
+    ysz = mbw * mbh * 256
+    fwd = (np.zeros(ysz, np.uint8), np.zeros(ysz // 4, np.uint8), np.zeros(ysz // 4, np.uint8))
+    prev2 = tuple(p.copy() for p in fwd)
+    for k, pic in enumerate(pics):
+        cur = tuple(p.copy() for p in prev2)  # ping-pong: the set written now held picture k-2
+        rc = lib.jsmpeg_b200_debug_reconstruct(mbw, mbh, pic["hdr"].ctypes.data, pic["coef"].ctypes.data,
+                                               fwd[0].ctypes.data, fwd[1].ctypes.data, fwd[2].ctypes.data,
+                                               cur[0].ctypes.data, cur[1].ctypes.data, cur[2].ctypes.data)
+        assert rc == 0
+        assert_frames_equal([cur], [pic["planes"]], f"stage 2, picture {k}")
+        prev2, fwd = fwd, cur
+    d.destroy()
+
+
+@pytest.mark.parametrize("w,h,n", SIZES + [(1920, 1080, 5)])
+def test_reference_abi_whole_clip_bit_exact(w, h, n):
+    """write everything, decode() until false: planes and bit indices identical to the oracle
+    (and to the compiled reference when oracle/_ref is present)."""
+    packets = clip_packets(w, h, n)
+    exp_frames, exp_idx, od = decode_all(oracle_lib(), packets)
+    got_frames, got_idx, gd = decode_all(capi.product_library(), packets)
+    assert got_idx == exp_idx
+    assert_frames_equal(got_frames, exp_frames, "CUDA vs oracle")
+    assert (gd.width, gd.height, gd.codedSize, gd.frameRate) == (od.width, od.height, od.codedSize, od.frameRate)
+    assert abs(gd.decodedTime - od.decodedTime) < 1e-9
+    ref = ref_lib()
+    if ref is not None:
+        ref_frames, ref_idx, rd = decode_all(ref, packets)
+        assert got_idx == ref_idx
+        assert_frames_equal(got_frames, ref_frames, "CUDA vs compiled reference")
+        rd.destroy()
+    od.destroy()
+    gd.destroy()
+
+
+def test_batch_streams_are_independent_and_bit_exact():
+    """4 streams (different seeds and sizes) decoded together, device-resident, against the oracle."""
+    specs = [(320, 240, 12, 1), (320, 240, 12, 2), (352, 288, 10, 3), (640, 368, 8, 4)]
+    clips = [clip_packets(w, h, n, seed=s) for (w, h, n, s) in specs]
+    bd = BatchDecoder(len(specs))
+    for i, packets in enumerate(clips):
+        bd.write(i, b"".join(p for _, p in packets))
+    expected = [decode_all(oracle_lib(), packets)[0] for packets in clips]
+    step = 0
+    while True:
+        got = bd.decode(1, OUT_DEVICE)
+        if got == 0:
+            break
+        for i, frames in enumerate(expected):
+            if step < len(frames):
+                assert_frames_equal([bd.read_planes(i)], [frames[step]], f"stream {i} picture {step}")
+        step += 1
+    assert step == max(len(f) for f in expected)
+    st = bd.stats()
+    assert st["pictures"] == sum(len(f) for f in expected)
+    assert st["parse_errors"] == 0
+    bd.close()
+
+
+def test_batch_multi_picture_steps_and_host_output():
+    """decode(n>1): several pictures per call, copied out to the host ring; the last picture of
+    every call is checked, and a rewind reproduces the same pictures."""
+    packets = clip_packets(320, 240, 24)
+    exp, _, od = decode_all(oracle_lib(), packets)
+    bd = BatchDecoder(2)
+    es = b"".join(p for _, p in packets)
+    bd.write(0, es)
+    bd.write(1, es)
+    for rnd in range(2):
+        done = 0
+        for n in (1, 3, 5, 24):
+            got = bd.decode(n, OUT_HOST)
+            assert got % 2 == 0
+            done += got // 2
+            if got:
+                for s in range(2):
+                    assert_frames_equal([tuple(p.copy() for p in bd.host_planes(s))], [exp[done - 1]], f"round {rnd} picture {done - 1}")
+        assert done == len(exp)
+        bd.rewind()
+    od.destroy()
+    bd.close()
