@@ -19,7 +19,7 @@ class Stats(ctypes.Structure):
         ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
         ("kernel_launches", ctypes.c_uint64), ("recon_launches", ctypes.c_uint64),
         ("parse_ms", ctypes.c_double), ("recon_ms", ctypes.c_double), ("scan_ms", ctypes.c_double),
-        ("parse_errors", ctypes.c_uint64),
+        ("parse_errors", ctypes.c_uint64), ("walk_ms", ctypes.c_double),
     ]
 
     def as_dict(self):

@@ -55,6 +55,7 @@ struct ReconTask {
 // kernel launchers (defined in scan.cu / parse.cu / recon.cu)
 void launch_scan_start_codes(const uint8_t *es, uint32_t from, uint32_t len, uint32_t *positions,
                              uint32_t capacity, uint32_t *count, cudaStream_t stream);
-void launch_parse_pictures(const ParseTask *tasks, int n_tasks, cudaStream_t stream);
+void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream,
+                           cudaEvent_t between_kernels = nullptr);
 void launch_reconstruct(const ReconTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream);
 void launch_rgba(const ReconTask *tasks, int n_tasks, int max_width, int max_height, cudaStream_t stream);

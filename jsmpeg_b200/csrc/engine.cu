@@ -85,7 +85,7 @@ struct jsmpeg_b200_batch_t {
 	int device = 0;
 	std::vector<Stream> streams;
 	cudaStream_t st_main = nullptr, st_copy = nullptr;
-	cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_step = nullptr, ev_copied[2] = {nullptr, nullptr};
+	cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_mid = nullptr, ev_step = nullptr, ev_copied[2] = {nullptr, nullptr};
 	// record slots
 	unsigned max_slots_req = 0;
 	int slot_mb = 0, n_slots = 0;
@@ -381,7 +381,7 @@ bool entry_stale(const Stream &s, const Parsed &e) {
 long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &progress, std::vector<char> &more, int flags) {
 	const int S = (int)b->streams.size();
 	// ---- 1. plan the parse wave
-	struct NewParse { int stream; size_t cache_idx; };
+	struct NewParse { int stream; size_t cache_idx; uint32_t bytes; };
 	std::vector<NewParse> fresh;
 	for (int si = 0; si < S; si++) {
 		Stream &s = b->streams[si];
@@ -407,12 +407,14 @@ long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			p.slot = b->free_slots.back();
 			b->free_slots.pop_back();
 			s.cache.push_back(p);
-			fresh.push_back({si, s.cache.size() - 1});
 			++next;
+			fresh.push_back({si, s.cache.size() - 1, (next < s.pics.end() ? *next : s.length) - p.pos});
 		}
 	}
-	// ---- 2. parse wave
+	// ---- 2. parse wave.  Longest pictures first: a CTA's warps, and consecutive CTAs (which land on
+	// different SMs), then carry similar amounts of work and the wave ends without a long tail.
 	if (!fresh.empty()) {
+		std::stable_sort(fresh.begin(), fresh.end(), [](const NewParse &a, const NewParse &b) { return a.bytes > b.bytes; });
 		ensure_task_caps(b, (int)fresh.size(), 0);
 		for (size_t i = 0; i < fresh.size(); i++) {
 			Stream &s = b->streams[fresh[i].stream];
@@ -428,14 +430,16 @@ long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 		}
 		CUDA_CHECK(cudaMemcpyAsync(b->d_ptasks, b->h_ptasks, fresh.size() * sizeof(ParseTask), cudaMemcpyHostToDevice, b->st_main));
 		CUDA_CHECK(cudaEventRecord(b->ev_a, b->st_main));
-		launch_parse_pictures(b->d_ptasks, (int)fresh.size(), b->st_main);
+		launch_parse_pictures(b->d_ptasks, (int)fresh.size(), b->slot_mb, b->st_main, b->ev_mid);
 		CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
 		CUDA_CHECK(cudaMemcpyAsync(b->h_info, b->d_info, fresh.size() * sizeof(picture_info_t), cudaMemcpyDeviceToHost, b->st_main));
 		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
 		float ms = 0;
 		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_b));
 		b->stats.parse_ms += ms;
-		b->stats.kernel_launches++;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_mid));
+		b->stats.walk_ms += ms;
+		b->stats.kernel_launches += 2;  // walk + expand
 		b->stats.h2d_bytes += fresh.size() * sizeof(ParseTask);
 		b->stats.d2h_bytes += fresh.size() * sizeof(picture_info_t);
 		for (size_t i = 0; i < fresh.size(); i++) {
@@ -565,6 +569,7 @@ extern "C" {
 
 const char *jsmpeg_b200_version(void) { return "jsmpeg_b200 0.1 (sm_100a)"; }
 
+
 jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigned int max_slots) {
 	Batch *b = new Batch();
 	b->device = device;
@@ -573,7 +578,7 @@ jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigne
 	b->max_slots_req = max_slots;
 	CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
 	CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
-	cudaEvent_t *evs[] = {&b->ev_a, &b->ev_b, &b->ev_c, &b->ev_d};
+	cudaEvent_t *evs[] = {&b->ev_a, &b->ev_b, &b->ev_c, &b->ev_d, &b->ev_mid};
 	for (auto e : evs) CUDA_CHECK(cudaEventCreate(e));
 	CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_step, cudaEventDisableTiming));
 	for (auto &e : b->ev_copied) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -597,7 +602,7 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 	if (b->d_hdr) { cudaFree(b->d_hdr); cudaFree(b->d_coef); cudaFree(b->d_info); cudaFreeHost(b->h_info); }
 	if (b->h_ptasks) { cudaFreeHost(b->h_ptasks); cudaFree(b->d_ptasks); }
 	if (b->h_rtasks) { cudaFreeHost(b->h_rtasks); cudaFree(b->d_rtasks); }
-	cudaEvent_t evs[] = {b->ev_a, b->ev_b, b->ev_c, b->ev_d, b->ev_step, b->ev_copied[0], b->ev_copied[1]};
+	cudaEvent_t evs[] = {b->ev_a, b->ev_b, b->ev_c, b->ev_d, b->ev_mid, b->ev_step, b->ev_copied[0], b->ev_copied[1]};
 	for (auto e : evs) cudaEventDestroy(e);
 	cudaStreamDestroy(b->st_main);
 	cudaStreamDestroy(b->st_copy);
@@ -821,7 +826,7 @@ int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t
 	CUDA_CHECK(cudaMemset(d_coef, 0, n_mb * MB_COEF_INT16 * sizeof(int16_t)));
 	ParseTask t{d_es, es_len, start_byte, d_seq, d_hdr, d_coef, d_info};
 	CUDA_CHECK(cudaMemcpy(d_task, &t, sizeof(t), cudaMemcpyHostToDevice));
-	launch_parse_pictures(d_task, 1, 0);
+	launch_parse_pictures(d_task, 1, sp.mb_size, 0);
 	CUDA_CHECK(cudaGetLastError());
 	CUDA_CHECK(cudaDeviceSynchronize());
 	CUDA_CHECK(cudaMemcpy(info_out, d_info, sizeof(picture_info_t), cudaMemcpyDeviceToHost));

@@ -1,20 +1,33 @@
-// parse.cu -- stage 1: bitstream / VLC parse, one warp per picture (sm_100a).
+// parse.cu -- stage 1: bitstream / VLC parse (sm_100a), in two kernels.
 //
 // Replaces, for the bitstream half, the reference's decodePicture / decodeSlice / decodeMacroblock /
 // decodeMotionVectors / decodeBlock (src/mpeg1.js:174-457, 698-811) and its bit reader
-// (src/buffer.js:115-187).  A picture is an inherently serial VLC walk (DC and motion-vector
-// predictors, quantiser scale, run/level positions), so the unit of parallelism is the PICTURE:
-// every picture starts at a byte-aligned start code and resets all of that state in its slice
-// headers, and nothing in the parse depends on decoded pixels.  One warp owns one picture:
-//   * the 32 lanes run the walk in lock-step (warp-uniform control flow, no divergence),
-//   * the bitstream is fetched 128 B at a time, one word per lane, double buffered, and handed to
-//     the 64-bit bit window with a shuffle,
-//   * the 64 coefficients of the block being decoded live in the warp's registers (two int16 per
-//     lane) and leave as ONE coalesced 128-byte store per coded block,
-//   * VLCs are decoded with clz-indexed look-up tables in shared memory (tools/gen_tables.py)
-//     instead of the reference's one-bit-per-step tree walk (src/mpeg1.js:66-72); the tables are
-//     pinned to the reference's trees by tests/test_vlc_tables.py.
+// (src/buffer.js:115-187).
+//
+// A picture is an inherently serial VLC walk: where symbol k+1 starts is only known once symbol k
+// has been decoded.  Everything ELSE the reference does per symbol (run/level bookkeeping,
+// zig-zag, dequantisation, oddification, clipping, the store) does not feed that chain.  So:
+//
+//   1a  walk_pictures_kernel    one warp per PICTURE (every picture starts at a byte-aligned start
+//       code and resets all predictor state in its slice headers, and nothing in the parse depends
+//       on decoded pixels, so all buffered pictures of all streams are walked concurrently).
+//       The walk does the minimum that is serial: macroblock headers (address increment, type,
+//       quantiser, motion vectors with their predictors, coded block pattern), intra DC
+//       differentials with their predictors, and for the AC coefficients only LUT -> code length
+//       -> shift.  It emits the 16-byte macroblock record and, per coded block, the bit offset of
+//       its first coefficient code (parked in the block's own 128-byte coefficient slot).
+//   1b  expand_blocks_kernel    one thread per coded BLOCK, all blocks of all pictures at once:
+//       re-reads the block's codes from its bit offset, does run/level -> zig-zag -> dequantise ->
+//       oddify -> clip (src/mpeg1.js:757-811) into a shared-memory tile and writes the 64 x int16
+//       block record with 16-byte stores.
+//
+// VLCs are decoded with clz-indexed look-up tables in shared memory (tools/gen_tables.py; pinned
+// to the reference's trees by tests/test_vlc_tables.py) instead of the reference's one-bit-per-step
+// tree walk (src/mpeg1.js:66-72).  Bit window: 64-bit, MSB first, refilled one prefetched 32-bit
+// word at a time.
 // Output: mb_record_t per macroblock address + dequantised int16 coefficient blocks (records.h).
+#include <vector>
+
 #include "common.cuh"
 
 #define VLC_TABLE_QUALIFIER static __device__ const
@@ -22,78 +35,85 @@
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 4;
-constexpr unsigned FULL = 0xffffffffu;
+constexpr int CTA_THREADS = 128;       // expand kernel
+constexpr int WALK_THREADS = 256;      // walk kernel: 8 pictures per CTA share one 16 KB multi-symbol table
+constexpr int MS_BITS = 13;            // multi-symbol table is indexed by the next 13 bits
+constexpr uint32_t OFF_MS = 4096;      // uint16[1 << MS_BITS], after the per-symbol tables
 
-struct Luts {
-	uint16_t dct[(VLC_DCT_MAX_Z + 1) * 32];
-	uint16_t mba[(VLC_MBA_MAX_Z + 1) * 32];
-	uint16_t cbp[(VLC_CBP_MAX_Z + 1) * 32];
-	uint16_t motion[(VLC_MOTION_MAX_Z + 1) * 32];
-	uint16_t dc_luma[128];
-	uint16_t dc_chroma[256];
-	uint16_t type_i[4];
-	uint16_t type_p[64];
-	uint8_t zigzag[64];
-};
+// shared-memory layout (byte offsets from the dynamic shared base)
+constexpr uint32_t OFF_DCT = 0;                                        // uint16[384]
+constexpr uint32_t OFF_MBA = OFF_DCT + (VLC_DCT_MAX_Z + 1) * 64;       // uint16[256]
+constexpr uint32_t OFF_CBP = OFF_MBA + (VLC_MBA_MAX_Z + 1) * 64;       // uint16[256]
+constexpr uint32_t OFF_MOTION = OFF_CBP + (VLC_CBP_MAX_Z + 1) * 64;    // uint16[224]
+constexpr uint32_t OFF_DC_LUMA = OFF_MOTION + (VLC_MOTION_MAX_Z + 1) * 64;  // uint16[128]
+constexpr uint32_t OFF_DC_CHROMA = OFF_DC_LUMA + 256;                  // uint16[256]
+constexpr uint32_t OFF_TYPE_I = OFF_DC_CHROMA + 512;                   // uint16[4]
+constexpr uint32_t OFF_TYPE_P = OFF_TYPE_I + 8;                        // uint16[64]
+constexpr uint32_t OFF_ZIGZAG = OFF_TYPE_P + 128;                      // uint8[64]
+constexpr uint32_t OFF_BLOCKS = (OFF_ZIGZAG + 64 + 127) & ~127u;       // int16[64] per group
 
-struct WarpShared {
-	uint8_t intra_q[64];
-	uint8_t non_intra_q[64];
-};
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+	uint16_t v;
+	asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+	uint32_t v;
+	asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void sts_s16(uint32_t addr, int v) {
+	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_v4_zero(uint32_t addr) {
+	asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0) : "memory");
+}
 
-// MSB-first bit window over a byte span (src/buffer.js:152-187), warp-uniform.
+// MSB-first bit window over a byte span (src/buffer.js:152-187); one copy per thread.
 struct BitReader {
 	const uint32_t *words;
 	const uint8_t *bytes;
-	uint32_t len;         // valid bytes; everything past it reads as zero
-	uint32_t wpos;        // next word to shift into the window
-	uint32_t chunk_base;  // word index held by lane 0 of `chunk`
-	uint32_t chunk, chunk_next;
-	uint64_t win;         // left-aligned window
-	int nbits;            // valid bits in win (>= 32 between calls)
-	int lane;
+	uint32_t len;    // valid bytes; everything past it reads as zero (JS typed-array semantics)
+	uint32_t wpos;   // index of the word held in `nextw` (the next one to enter the window)
+	uint32_t nextw;  // prefetched
+	uint64_t win;    // left-aligned window
+	int nbits;       // valid bits in win, >= 32 between calls
 
 	__device__ __forceinline__ uint32_t load_word(uint32_t w) const {
-		uint32_t byte = w * 4u;
+		const uint32_t byte = w * 4u;
 		if (byte >= len) return 0u;
 		uint32_t v = __byte_perm(__ldg(words + w), 0, 0x0123);  // first byte -> MSB
-		uint32_t left = len - byte;
+		const uint32_t left = len - byte;
 		if (left < 4u) v &= 0xffffffffu << (8u * (4u - left));
 		return v;
 	}
-	__device__ __forceinline__ uint32_t fetch(uint32_t w) {
-		if (w >= chunk_base + 32u) {  // warp-uniform
-			chunk = chunk_next;
-			chunk_base += 32u;
-			chunk_next = load_word(chunk_base + 32u + lane);
-		}
-		return __shfl_sync(FULL, chunk, (int)(w - chunk_base));
-	}
 	__device__ __forceinline__ void seek_byte(uint32_t byte_pos) {
-		wpos = byte_pos >> 2;
-		chunk_base = wpos & ~31u;
-		chunk = load_word(chunk_base + lane);
-		chunk_next = load_word(chunk_base + 32u + lane);
-		uint32_t hi = fetch(wpos++);
-		uint32_t lo = fetch(wpos++);
-		win = ((uint64_t)hi << 32) | lo;
+		const uint32_t w = byte_pos >> 2;
+		win = ((uint64_t)load_word(w) << 32) | load_word(w + 1);
+		wpos = w + 2;
+		nextw = load_word(wpos);
 		nbits = 64;
-		int drop = (int)(byte_pos & 3u) * 8;
+		const int drop = (int)(byte_pos & 3u) * 8;
 		if (drop) consume(drop);
 	}
 	__device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(win >> 32); }
-	__device__ __forceinline__ void consume(int n) {
+	__device__ __forceinline__ void consume(int n) {  // 0 <= n <= 32
 		win <<= n;
 		nbits -= n;
 		if (nbits < 32) {
-			uint32_t w = fetch(wpos++);
-			win |= (uint64_t)w << (32 - nbits);
+			win |= (uint64_t)nextw << (32 - nbits);
 			nbits += 32;
+			wpos++;
+			nextw = load_word(wpos);
 		}
 	}
 	__device__ __forceinline__ uint32_t read(int n) {  // 1 <= n <= 32
-		uint32_t v = peek32() >> (32 - n);
+		const uint32_t v = peek32() >> (32 - n);
 		consume(n);
 		return v;
 	}
@@ -101,34 +121,30 @@ struct BitReader {
 
 	// src/buffer.js:141-150 nextBytesAreStartCode
 	__device__ __forceinline__ bool next_bytes_are_start_code() const {
-		uint32_t bp = bitpos();
-		uint32_t i = (bp + 7u) >> 3;
+		const uint32_t bp = bitpos();
+		const uint32_t i = (bp + 7u) >> 3;
 		if (i >= len) return true;
-		int skip = (int)((8u - (bp & 7u)) & 7u);
+		const int skip = (int)((8u - (bp & 7u)) & 7u);
 		// bytes past `len` are zero in the window, so a code straddling the end cannot match
 		return (uint32_t)((win << skip) >> 40) == 0x000001u && i + 2u < len;
 	}
-	// src/buffer.js:115-128 findNextStartCode: lanes test 32 byte positions per step.
-	// Returns the code (and leaves the reader after it) or -1 (reader parked at the end).
+	// src/buffer.js:115-128 findNextStartCode.  Returns the code (reader left just after it) or -1
+	// (reader parked at the end of the data).  A start code needs its 4 bytes inside the buffer.
 	__device__ int find_next_start_code() {
 		uint32_t i = (bitpos() + 7u) >> 3;
-		while (i + 3u < len) {
-			uint32_t j = i + (uint32_t)lane;
-			bool hit = false;
-			if (j + 3u < len) hit = bytes[j] == 0 && bytes[j + 1] == 0 && bytes[j + 2] == 1;
-			unsigned m = __ballot_sync(FULL, hit);
-			if (m) {
-				uint32_t at = i + (uint32_t)(__ffs(m) - 1);
-				int code = bytes[at + 3];
-				seek_byte(at + 4u);
+		for (; i + 3u < len; i++) {
+			if (bytes[i + 2] > 1) { i += 2; continue; }  // 00 00 01 cannot end at i+2, i+3 or i+4
+			if (bytes[i] == 0 && bytes[i + 1] == 0 && bytes[i + 2] == 1) {
+				const int code = bytes[i + 3];
+				seek_byte(i + 4u);
 				return code;
 			}
-			i += 32u;
 		}
 		seek_byte(len);
 		return -1;
 	}
 };
+
 
 struct PictureState {
 	int picture_type, full_pel, r_size, f;
@@ -139,105 +155,102 @@ struct PictureState {
 	int n_present, n_coded, error;
 };
 
-__device__ __forceinline__ int clz_lut(const uint16_t *lut, uint32_t w, int max_z) {
-	int z = __clz((int)w);
-	if (z > max_z) return 0;
-	return lut[(z << 5) | ((w << (z + 1)) >> 27)];
+// The shared-window address of the dynamic shared memory, made opaque so that the compiler keeps
+// it in a register instead of re-deriving it (S2R + LEA) at every table access.
+__device__ __forceinline__ uint32_t smem_base(const void *p) {
+	uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+	asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+	return r;
 }
 
-// One coded block: src/mpeg1.js:698-811.  Returns false on an invalid code.
-__device__ __forceinline__ bool parse_block(BitReader &br, const Luts &L, const uint8_t *quant,
-                                            PictureState &ps, bool intra, int block,
-                                            uint32_t *coef_out /* 32 words */, bool &dc_only) {
-	const int lane = br.lane;
-	uint32_t acc = 0;  // coefficients 2*lane (low half) and 2*lane+1 (high half)
+__device__ __forceinline__ uint32_t clz_lut(uint32_t table_addr, uint32_t w, int max_z) {
+	const int z = __clz((int)w);
+	if (z > max_z) return 0;
+	return lds_u16(table_addr + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+}
+
+// ==================================================================================================
+// 1a: the serial walk
+
+// walk-table entry derived from the DCT table: bits 0..4 = bits to consume (code + sign),
+// bits 5..10 = run + 1, bits 11..12 = 1 end_of_block / 2 escape; 0 = invalid code.
+__device__ __forceinline__ uint16_t walk_entry(uint16_t e) {
+	const int len = e & 31, run = (e >> 5) & 31, level = e >> 10;
+	if (len == 0) return 0;
+	if (level == 0) return run ? (uint16_t)(2 | (1 << 11)) : (uint16_t)(6 | (2 << 11));
+	return (uint16_t)((len + 1) | ((run + 1) << 5));
+}
+
+// One coded block (bitstream side of src/mpeg1.js:698-811): intra DC with its predictor, then only
+// code lengths.  Leaves {bit offset of the first coefficient code, dc * 8} in the block's slot.
+__device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
+                                           uint32_t *__restrict__ slot, int lane, bool &dc_only) {
 	int n = 0;
+	int dc8 = 0;
 	if (intra) {
 		// DC size VLC + differential + predictor (mpeg1.js:705-751)
-		uint32_t w = br.peek32();
-		int e = block < 4 ? L.dc_luma[w >> 25] : L.dc_chroma[w >> 24];
-		int len = e & 31, size = e >> 5;
+		const uint32_t w = br.peek32();
+		const uint32_t e = block < 4 ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
+		                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
+		const int len = e & 31, size = e >> 5;
 		if (len == 0) return false;
 		br.consume(len);
 		int *pred = block < 4 ? &ps.dc_y : (block == 4 ? &ps.dc_b4 : &ps.dc_b5);
 		int dc = *pred;
 		if (size > 0) {
-			int diff = (int)br.read(size);
+			const int diff = (int)br.read(size);
 			dc += (diff & (1 << (size - 1))) ? diff : (int)((0xffffffffu << size) | (uint32_t)(diff + 1));
 		}
 		*pred = dc;
-		int v = max(-32768, min(32767, dc * 8));
-		if (lane == 0) acc = (uint32_t)v & 0xffffu;
+		dc8 = max(-32768, min(32767, dc * 8));  // x PREMULTIPLIER[0] = dc << 8 in stage 2 (mpeg1.js:747)
 		n = 1;
 	}
-	const int qs = ps.qscale;
-	for (;;) {  // mpeg1.js:757-811
-		uint32_t w = br.peek32();
-		int run, level;
-		if (w >> 31) {
-			if (n == 0) {               // dct_coeff_first: '1s' = (0, +-1)
-				run = 0;
-				level = (w & 0x40000000u) ? -1 : 1;
-				br.consume(2);
-			} else if (!(w & 0x40000000u)) {  // '10' end_of_block (mpeg1.js:763)
-				br.consume(2);
-				break;
-			} else {                    // '11s'
-				run = 0;
-				level = (w & 0x20000000u) ? -1 : 1;
-				br.consume(3);
-			}
-		} else {
-			int e = clz_lut(L.dct, w, VLC_DCT_MAX_Z);
-			int len = e & 31;
-			if (len == 0) return false;
-			int payload = e >> 5;
-			if (payload == 0) {         // escape (mpeg1.js:767-780): 6 + 6 + 8 (+ 8) bits
-				run = (w >> 20) & 63;
-				int l8 = (w >> 12) & 255;
-				if (l8 == 0) { level = (w >> 4) & 255; br.consume(28); }
-				else if (l8 == 128) { level = (int)((w >> 4) & 255) - 256; br.consume(28); }
-				else { level = l8 > 128 ? l8 - 256 : l8; br.consume(20); }
-			} else {
-				run = payload & 31;
-				level = payload >> 5;
-				if ((w >> (31 - len)) & 1u) level = -level;
-				br.consume(len + 1);
-			}
-		}
-		n += run;
-		if (n > 63) {  // JS: ZIG_ZAG[n] undefined -> the store is a no-op
-			ps.error = PARSE_ERR_COEF_INDEX;
-			n++;
+	if (lane == 0) *reinterpret_cast<uint2 *>(slot) = make_uint2(br.bitpos(), (uint32_t)dc8 & 0xffffu);
+	if (!intra && (br.peek32() >> 31)) {  // dct_coeff_first: a leading '1' is (0, +-1), never end_of_block
+		br.consume(2);
+		n = 1;
+	}
+	for (;;) {
+		const uint32_t w = br.peek32();
+		// as many complete codes as fit in the next 13 bits, in one look-up
+		const uint32_t m = lds_u16(sbase + OFF_MS + (w >> (32 - MS_BITS)) * 2u);
+		if (m & 15u) {
+			n += (int)((m >> 4) & 63u);
+			br.consume((int)(m & 15u));
+			if (m & 0x400u) break;  // the last code consumed was end_of_block
 			continue;
 		}
-		int idx = L.zigzag[n];
-		n++;
-		// dequantise, oddify toward zero, clip (mpeg1.js:794-807)
-		level <<= 1;
-		if (!intra) level += level < 0 ? -1 : 1;
-		level = (level * qs * (int)quant[idx]) >> 4;
-		if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
-		level = max(-2048, min(2047, level));
-		if (lane == (idx >> 1)) acc |= ((uint32_t)level & 0xffffu) << ((idx & 1) * 16);
+		// long code or escape: one symbol through the clz-indexed table
+		const int z = __clz((int)w);
+		if (z > VLC_DCT_MAX_Z) return false;
+		const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+		if (e >> 11) {
+			// escape (mpeg1.js:767-780): 6-bit code, 6-bit run, 8 (+8) bit level.  (end_of_block is
+			// two bits and always resolved by the multi-symbol table.)
+			n += (int)((w >> 20) & 63u) + 1;
+			br.consume((w & 0x0007f000u) ? 20 : 28);  // level byte 0 or 128 -> a second byte follows
+			continue;
+		}
+		if (e == 0) return false;  // hole in the code space
+		n += (int)(e >> 5);
+		br.consume((int)(e & 31u));
 	}
+	if (n > 64) ps.error = PARSE_ERR_COEF_INDEX;  // some run pushed the index past 63 (stores dropped, like JS)
 	dc_only = (n == 1);  // mpeg1.js:838, 850
-	coef_out[lane] = acc;  // one coalesced 128-byte store
 	ps.n_coded++;
 	return true;
 }
 
 // mpeg1.js:395-457, one component
-__device__ __forceinline__ bool parse_motion(BitReader &br, const Luts &L, const PictureState &ps,
-                                             int &prev, int &mv) {
-	int e = clz_lut(L.motion, br.peek32(), VLC_MOTION_MAX_Z);
-	int len = e & 31;
+__device__ __forceinline__ bool parse_motion(BitReader &br, uint32_t sbase, const PictureState &ps, int &prev, int &mv) {
+	const uint32_t e = clz_lut(sbase + OFF_MOTION, br.peek32(), VLC_MOTION_MAX_Z);
+	const int len = e & 31;
 	if (len == 0) return false;
 	br.consume(len);
-	int code = (e >> 5) - 16;
+	const int code = (int)(e >> 5) - 16;
 	int d = code;
 	if (code != 0 && ps.f != 1) {
-		int r = (int)br.read(ps.r_size);
+		const int r = (int)br.read(ps.r_size);
 		d = ((abs(code) - 1) << ps.r_size) + r + 1;
 		if (code < 0) d = -d;
 	}
@@ -248,16 +261,15 @@ __device__ __forceinline__ bool parse_motion(BitReader &br, const Luts &L, const
 	return true;
 }
 
-__device__ __forceinline__ int read_mba(BitReader &br, const Luts &L) {
-	int e = clz_lut(L.mba, br.peek32(), VLC_MBA_MAX_Z);
-	int len = e & 31;
+__device__ __forceinline__ int read_mba(BitReader &br, uint32_t sbase) {
+	const uint32_t e = clz_lut(sbase + OFF_MBA, br.peek32(), VLC_MBA_MAX_Z);
+	const int len = e & 31;
 	if (len == 0) return -1;
 	br.consume(len);
-	return e >> 5;
+	return (int)(e >> 5);
 }
 
-__device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int cbp, int dc_only,
-                                             int qscale, uint32_t bit_pos) {
+__device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int cbp, int dc_only, int qscale, uint32_t bit_pos) {
 	uint4 r;
 	r.x = ((uint32_t)mv_h & 0xffffu) | ((uint32_t)mv_v << 16);
 	r.y = (uint32_t)flags | ((uint32_t)cbp << 8) | ((uint32_t)dc_only << 16) | ((uint32_t)qscale << 24);
@@ -267,13 +279,11 @@ __device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int 
 }
 
 // mpeg1.js:294-392 decodeMacroblock.  false = stop walking this slice.
-__device__ bool parse_macroblock(BitReader &br, const Luts &L, const WarpShared &ws,
-                                 PictureState &ps, const ParseTask &t, int mb_size) {
-	const int lane = br.lane;
+__device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
 	int increment = 0;
-	int v = read_mba(br, L);
-	while (v == 34) v = read_mba(br, L);                       // macroblock_stuffing
-	while (v == 35) { increment += 33; v = read_mba(br, L); }  // macroblock_escape
+	int v = read_mba(br, sbase);
+	while (v == 34) v = read_mba(br, sbase);                       // macroblock_stuffing
+	while (v == 35) { increment += 33; v = read_mba(br, sbase); }  // macroblock_escape
 	if (v < 0) return false;
 	increment += v;
 
@@ -286,10 +296,9 @@ __device__ bool parse_macroblock(BitReader &br, const Luts &L, const WarpShared 
 			ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;
 			if (ps.picture_type == 2) ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;
 			// skipped macroblocks: predicted copy with the current vector (mpeg1.js:336-346)
-			int n_skip = increment - 1;
-			uint4 rec = pack_record(ps.mv_h, ps.mv_v, MBF_PRESENT | MBF_SKIPPED, 0, 0, ps.qscale, br.bitpos());
-			for (int k = lane; k < n_skip; k += 32)
-				reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
+			const int n_skip = increment - 1;
+			const uint4 rec = pack_record(ps.mv_h, ps.mv_v, MBF_PRESENT | MBF_SKIPPED, 0, 0, ps.qscale, br.bitpos());
+			for (int k = lane; k < n_skip; k += 32) reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
 			ps.n_present += n_skip;
 			ps.mb_addr += n_skip;
 		}
@@ -298,8 +307,9 @@ __device__ bool parse_macroblock(BitReader &br, const Luts &L, const WarpShared 
 	const int mb = ps.mb_addr;
 	if (mb < 0 || mb >= mb_size) return false;  // outside the picture: never write there
 
-	uint32_t w = br.peek32();
-	int e = ps.picture_type == 1 ? L.type_i[w >> 30] : L.type_p[w >> 26];
+	const uint32_t w = br.peek32();
+	const uint32_t e = ps.picture_type == 1 ? lds_u16(sbase + OFF_TYPE_I + (w >> 30) * 2u)
+	                                        : lds_u16(sbase + OFF_TYPE_P + (w >> 26) * 2u);
 	if ((e & 31) == 0) return false;
 	br.consume(e & 31);
 	const int type = e >> 5;
@@ -312,8 +322,8 @@ __device__ bool parse_macroblock(BitReader &br, const Luts &L, const WarpShared 
 	} else {
 		ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;                  // mpeg1.js:370-372
 		if (type & 0x08) {
-			if (!parse_motion(br, L, ps, ps.mv_h_prev, ps.mv_h)) return false;
-			if (!parse_motion(br, L, ps, ps.mv_v_prev, ps.mv_v)) return false;
+			if (!parse_motion(br, sbase, ps, ps.mv_h_prev, ps.mv_h)) return false;
+			if (!parse_motion(br, sbase, ps, ps.mv_v_prev, ps.mv_v)) return false;
 		} else if (ps.picture_type == 2) {
 			ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:452-456
 		}
@@ -321,14 +331,13 @@ __device__ bool parse_macroblock(BitReader &br, const Luts &L, const WarpShared 
 
 	int cbp = intra ? 0x3f : 0;
 	if (type & 0x02) {
-		int c = clz_lut(L.cbp, br.peek32(), VLC_CBP_MAX_Z);
-		if ((c & 31) == 0) return false;
-		br.consume(c & 31);
-		cbp = c >> 5;
+		const uint32_t ce = clz_lut(sbase + OFF_CBP, br.peek32(), VLC_CBP_MAX_Z);
+		if ((ce & 31) == 0) return false;
+		br.consume(ce & 31);
+		cbp = ce >> 5;
 	}
 
 	const int mv_h = ps.mv_h, mv_v = ps.mv_v, qscale = ps.qscale;
-	const uint8_t *quant = intra ? ws.intra_q : ws.non_intra_q;
 	uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)mb * (MB_COEF_INT16 / 2);
 	int done = 0, dc_mask = 0;
 	bool ok = true;
@@ -336,7 +345,7 @@ __device__ bool parse_macroblock(BitReader &br, const Luts &L, const WarpShared 
 	for (int block = 0; block < 6; block++) {
 		if (cbp & (0x20 >> block)) {
 			bool dc_only;
-			ok = parse_block(br, L, quant, ps, intra, block, coef_mb + block * 32, dc_only);
+			ok = walk_block(br, sbase, ps, intra, block, coef_mb + block * 32, lane, dc_only);
 			if (!ok) break;
 			done |= 0x20 >> block;
 			if (dc_only) dc_mask |= 0x20 >> block;
@@ -349,32 +358,29 @@ __device__ bool parse_macroblock(BitReader &br, const Luts &L, const WarpShared 
 	return ok;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-parse_pictures_kernel(const ParseTask *__restrict__ tasks, int n_tasks) {
-	__shared__ Luts L;
-	__shared__ WarpShared wsh[WARPS_PER_CTA];
-
-	for (int i = threadIdx.x; i < (int)(sizeof(L.dct) / 2); i += blockDim.x) L.dct[i] = VLC_DCT_COEFF[i];
-	for (int i = threadIdx.x; i < (int)(sizeof(L.mba) / 2); i += blockDim.x) L.mba[i] = VLC_MBA[i];
-	for (int i = threadIdx.x; i < (int)(sizeof(L.cbp) / 2); i += blockDim.x) L.cbp[i] = VLC_CBP[i];
-	for (int i = threadIdx.x; i < (int)(sizeof(L.motion) / 2); i += blockDim.x) L.motion[i] = VLC_MOTION[i];
-	for (int i = threadIdx.x; i < 128; i += blockDim.x) L.dc_luma[i] = VLC_DC_SIZE_LUMA[i];
-	for (int i = threadIdx.x; i < 256; i += blockDim.x) L.dc_chroma[i] = VLC_DC_SIZE_CHROMA[i];
-	for (int i = threadIdx.x; i < 4; i += blockDim.x) L.type_i[i] = VLC_MBTYPE_I[i];
-	for (int i = threadIdx.x; i < 64; i += blockDim.x) L.type_p[i] = VLC_MBTYPE_P[i];
-	for (int i = threadIdx.x; i < 64; i += blockDim.x) L.zigzag[i] = TBL_ZIG_ZAG[i];
+__global__ void __launch_bounds__(WALK_THREADS)
+walk_pictures_kernel(const ParseTask *__restrict__ tasks, int n_tasks, const uint4 *__restrict__ ms_table) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	{
+		uint16_t *s16 = reinterpret_cast<uint16_t *>(smem);
+		for (int i = threadIdx.x; i < (VLC_DCT_MAX_Z + 1) * 32; i += WALK_THREADS) s16[OFF_DCT / 2 + i] = walk_entry(VLC_DCT_COEFF[i]);
+		for (int i = threadIdx.x; i < (VLC_MBA_MAX_Z + 1) * 32; i += WALK_THREADS) s16[OFF_MBA / 2 + i] = VLC_MBA[i];
+		for (int i = threadIdx.x; i < (VLC_CBP_MAX_Z + 1) * 32; i += WALK_THREADS) s16[OFF_CBP / 2 + i] = VLC_CBP[i];
+		for (int i = threadIdx.x; i < (VLC_MOTION_MAX_Z + 1) * 32; i += WALK_THREADS) s16[OFF_MOTION / 2 + i] = VLC_MOTION[i];
+		for (int i = threadIdx.x; i < 128; i += WALK_THREADS) s16[OFF_DC_LUMA / 2 + i] = VLC_DC_SIZE_LUMA[i];
+		for (int i = threadIdx.x; i < 256; i += WALK_THREADS) s16[OFF_DC_CHROMA / 2 + i] = VLC_DC_SIZE_CHROMA[i];
+		for (int i = threadIdx.x; i < 4; i += WALK_THREADS) s16[OFF_TYPE_I / 2 + i] = VLC_MBTYPE_I[i];
+		for (int i = threadIdx.x; i < 64; i += WALK_THREADS) s16[OFF_TYPE_P / 2 + i] = VLC_MBTYPE_P[i];
+		uint4 *ms = reinterpret_cast<uint4 *>(smem + OFF_MS);
+		for (int i = threadIdx.x; i < (2 << MS_BITS) / 16; i += WALK_THREADS) ms[i] = __ldg(ms_table + i);
+	}
 	__syncthreads();
 
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int task_id = blockIdx.x * WARPS_PER_CTA + warp;
+	const int lane = threadIdx.x & 31;
+	const int task_id = blockIdx.x * (WALK_THREADS / 32) + (threadIdx.x >> 5);
 	if (task_id >= n_tasks) return;
 	const ParseTask t = tasks[task_id];
-	WarpShared &ws = wsh[warp];
-	for (int i = lane; i < 64; i += 32) {
-		ws.intra_q[i] = t.seq->intra_q[i];
-		ws.non_intra_q[i] = t.seq->non_intra_q[i];
-	}
-	__syncwarp();
+	const uint32_t sbase = smem_base(smem);
 	const int mb_width = t.seq->mb_width, mb_size = t.seq->mb_size;
 
 	// no macroblock is present until the walk reaches it (an address no slice covers keeps the
@@ -386,7 +392,6 @@ parse_pictures_kernel(const ParseTask *__restrict__ tasks, int n_tasks) {
 	br.words = reinterpret_cast<const uint32_t *>(t.es);
 	br.bytes = t.es;
 	br.len = t.es_len;
-	br.lane = lane;
 	br.seek_byte(t.start_byte);
 
 	PictureState ps;
@@ -422,7 +427,7 @@ parse_pictures_kernel(const ParseTask *__restrict__ tasks, int n_tasks) {
 			ps.qscale = (int)br.read(5);
 			while (br.read(1)) br.consume(8);
 			do {
-				if (!parse_macroblock(br, L, ws, ps, t, mb_size)) {
+				if (!walk_macroblock(br, sbase, ps, t, mb_size, lane)) {
 					if (!ps.error) ps.error = PARSE_ERR_INVALID_VLC;
 					break;
 				}
@@ -448,10 +453,163 @@ parse_pictures_kernel(const ParseTask *__restrict__ tasks, int n_tasks) {
 	}
 }
 
+// ==================================================================================================
+// 1b: expand every coded block (one thread per block slot)
+
+__global__ void __launch_bounds__(CTA_THREADS)
+expand_blocks_kernel(const ParseTask *__restrict__ tasks) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	{
+		uint16_t *s16 = reinterpret_cast<uint16_t *>(smem);
+		for (int i = threadIdx.x; i < (VLC_DCT_MAX_Z + 1) * 32; i += CTA_THREADS) s16[OFF_DCT / 2 + i] = VLC_DCT_COEFF[i];
+		for (int i = threadIdx.x; i < 64; i += CTA_THREADS) smem[OFF_ZIGZAG + i] = TBL_ZIG_ZAG[i];
+		uint32_t *blocks = reinterpret_cast<uint32_t *>(smem + OFF_BLOCKS);
+		for (int i = threadIdx.x; i < CTA_THREADS * 32; i += CTA_THREADS) blocks[i] = 0u;
+	}
+	__syncthreads();
+
+	const ParseTask &t = tasks[blockIdx.y];
+	const int mb_size = t.seq->mb_size;
+	const int slot_id = blockIdx.x * CTA_THREADS + threadIdx.x;  // mb * 6 + block
+	if (slot_id >= mb_size * 6) return;
+	if (t.info->status != PIC_DECODED) return;
+	const int mb = slot_id / 6, block = slot_id - mb * 6;
+	const uint32_t rec = reinterpret_cast<const uint32_t *>(t.hdr + mb)[1];
+	if (!(rec & MBF_PRESENT) || !((rec >> 8) & (0x20u >> block))) return;
+	const bool intra = rec & MBF_INTRA;
+	const int qs = (int)(rec >> 24);
+	const uint8_t *__restrict__ quant = intra ? t.seq->intra_q : t.seq->non_intra_q;
+
+	uint4 *slot = reinterpret_cast<uint4 *>(t.coef) + (size_t)slot_id * 8;
+	const uint2 parked = *reinterpret_cast<const uint2 *>(slot);  // left by the walk
+	const uint32_t sbase = smem_base(smem);
+	// this thread's 64 x int16 tile; 16-byte chunks swizzled by thread so that the lanes of a warp
+	// writing the same coefficient index hit different banks
+	const uint32_t sblock = sbase + OFF_BLOCKS + threadIdx.x * 128u;
+	const uint32_t swz = threadIdx.x & 7u;
+
+	BitReader br;
+	br.words = reinterpret_cast<const uint32_t *>(t.es);
+	br.bytes = t.es;
+	br.len = t.es_len;
+	br.seek_byte(parked.x >> 3);
+	if (parked.x & 7u) br.consume((int)(parked.x & 7u));
+
+	int n = 0;
+	if (intra) {
+		sts_s16(sblock + (swz << 4), (int)(int16_t)(parked.y & 0xffffu));  // coefficient 0
+		n = 1;
+	}
+	bool first = !intra;
+	for (;;) {  // mpeg1.js:757-811; the walk has already validated every code of this block
+		const uint32_t w = br.peek32();
+		const int z = min(__clz((int)w), VLC_DCT_MAX_Z);
+		const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+		int len = e & 31;
+		int run = (e >> 5) & 31;
+		int level = e >> 10;
+		if (first && z == 0) {  // '1s'
+			len = 1;
+			run = 0;
+			level = 1;
+		}
+		first = false;
+		if (level == 0) {
+			if (run != 0 || len == 0) break;  // end_of_block (or, defensively, an invalid code)
+			// escape (mpeg1.js:767-780)
+			run = (w >> 20) & 63;
+			const int l8 = (w >> 12) & 255;
+			if ((l8 & 127) == 0) {
+				level = (int)((w >> 4) & 255) - (l8 << 1);  // l8 == 128: second byte - 256
+				br.consume(28);
+			} else {
+				level = l8 > 128 ? l8 - 256 : l8;
+				br.consume(20);
+			}
+		} else {
+			if ((w >> (31 - len)) & 1u) level = -level;
+			br.consume(len + 1);
+		}
+		n += run;
+		if (n > 63) {  // JS: ZIG_ZAG[n] undefined -> the store is a no-op (the walk flagged the picture)
+			if (n > 4096) break;
+			n++;
+			continue;
+		}
+		const uint32_t idx = lds_u8(sbase + OFF_ZIGZAG + (uint32_t)n);
+		n++;
+		// dequantise, oddify toward zero, clip (mpeg1.js:794-807)
+		level <<= 1;
+		if (!intra) level += level < 0 ? -1 : 1;
+		level = (level * qs * (int)__ldg(quant + idx)) >> 4;
+		if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
+		level = max(-2048, min(2047, level));
+		sts_s16(sblock + ((((idx >> 3) ^ swz) << 4) | ((idx & 7u) << 1)), level);
+	}
+	// the finished block: 8 x 16 B to HBM, tile cleared for the next use
+#pragma unroll
+	for (uint32_t i = 0; i < 8; i++) {
+		const uint32_t a = sblock + ((i ^ swz) << 4);
+		slot[i] = lds_v4(a);
+		sts_v4_zero(a);
+	}
+}
+
 }  // namespace
 
-void launch_parse_pictures(const ParseTask *tasks, int n_tasks, cudaStream_t stream) {
+// Multi-symbol walk table: for every 13-bit prefix, the complete dct_coeff_next codes (with their
+// sign bits) that fit, greedily.  Entry: bits 0..3 = bits to consume (0 = first code does not fit
+// or is an escape: take the single-symbol path), bits 4..9 = sum of (run + 1), bit 10 = the last
+// code consumed was end_of_block.  Built once per device from the same generated DCT table.
+static const uint16_t *ms_table_for_current_device() {
+	static uint16_t *tables[64] = {};
+	int dev = 0;
+	CUDA_CHECK(cudaGetDevice(&dev));
+	if (tables[dev]) return tables[dev];
+	std::vector<uint16_t> dct((VLC_DCT_MAX_Z + 1) * 32);
+	CUDA_CHECK(cudaMemcpyFromSymbol(dct.data(), VLC_DCT_COEFF, dct.size() * sizeof(uint16_t)));
+	std::vector<uint16_t> ms(1u << MS_BITS);
+	for (uint32_t prefix = 0; prefix < (1u << MS_BITS); prefix++) {
+		const uint32_t w = prefix << (32 - MS_BITS);
+		int pos = 0, n = 0, eob = 0;
+		for (;;) {
+			const uint32_t v = w << pos;  // bits beyond the prefix read as 0 and are never trusted: lengths are checked
+			int z = 0;
+			while (z < 32 && !((v << z) & 0x80000000u)) z++;
+			if (z > VLC_DCT_MAX_Z) break;
+			const uint16_t e = dct[(z << 5) | ((z + 1 < 32 ? (v << (z + 1)) : 0u) >> 27)];
+			const int len = e & 31, run = (e >> 5) & 31, level = e >> 10;
+			if (len == 0) break;
+			if (level == 0) {
+				if (run == 1 && pos + 2 <= MS_BITS) { pos += 2; eob = 1; }
+				break;  // escape: single-symbol path
+			}
+			if (pos + len + 1 > MS_BITS) break;
+			pos += len + 1;
+			n += run + 1;
+		}
+		ms[prefix] = (uint16_t)(pos | (n << 4) | (eob << 10));
+	}
+	uint16_t *d = nullptr;
+	CUDA_CHECK(cudaMalloc(&d, ms.size() * sizeof(uint16_t)));
+	CUDA_CHECK(cudaMemcpy(d, ms.data(), ms.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+	tables[dev] = d;
+	return d;
+}
+
+void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream, cudaEvent_t between_kernels) {
 	if (n_tasks <= 0) return;
-	int grid = (n_tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-	parse_pictures_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(tasks, n_tasks);
+	const uint16_t *ms = ms_table_for_current_device();
+	const int per_cta = WALK_THREADS / 32;
+	const size_t walk_smem = OFF_MS + (2u << MS_BITS);
+	static bool attr_set = false;
+	if (!attr_set) {
+		CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+		attr_set = true;
+	}
+	walk_pictures_kernel<<<(n_tasks + per_cta - 1) / per_cta, WALK_THREADS, walk_smem, stream>>>(
+	    tasks, n_tasks, reinterpret_cast<const uint4 *>(ms));
+	if (between_kernels) CUDA_CHECK(cudaEventRecord(between_kernels, stream));
+	dim3 grid((max_mb_size * 6 + CTA_THREADS - 1) / CTA_THREADS, n_tasks);
+	expand_blocks_kernel<<<grid, CTA_THREADS, OFF_BLOCKS + CTA_THREADS * 128, stream>>>(tasks);
 }
