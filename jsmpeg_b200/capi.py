@@ -1,9 +1,8 @@
 """ctypes binding of the 15-function ``mpeg1_decoder_*`` C ABI (reference src/wasm/mpeg1.h:10-25).
 
 The same binding works for any shared library that exports that ABI: the product
-(``jsmpeg_b200/libjsmpeg_b200.so`` -- CUDA), and, in tests only, the compiled reference
-(``oracle/_ref/libjsmpeg_ref.so``) and our CPU restatement (``oracle/liboracle.so``).
-The product never loads anything from ``oracle/``.
+(``jsmpeg_b200/libjsmpeg_b200.so`` -- CUDA) and, in tests only, the CPU checkers the test suite
+builds (the compiled reference and our restatement of it).  Nothing in this package loads those.
 """
 from __future__ import annotations
 
