@@ -57,5 +57,6 @@ void launch_scan_start_codes(const uint8_t *es, uint32_t from, uint32_t len, uin
                              uint32_t capacity, uint32_t *count, cudaStream_t stream);
 void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream,
                            cudaEvent_t between_kernels = nullptr);
-void launch_reconstruct(const ReconTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream);
+// `tasks_host` is read on the host at launch time: the table travels in the kernel parameters
+void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream);
 void launch_rgba(const ReconTask *tasks, int n_tasks, int max_width, int max_height, cudaStream_t stream);

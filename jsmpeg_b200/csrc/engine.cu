@@ -515,18 +515,18 @@ long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 		ensure_task_caps(b, 0, (int)total);
 		size_t off = 0;
 		for (auto &v : steps) { memcpy(b->h_rtasks + off, v.data(), v.size() * sizeof(ReconTask)); off += v.size(); }
-		CUDA_CHECK(cudaMemcpyAsync(b->d_rtasks, b->h_rtasks, total * sizeof(ReconTask), cudaMemcpyHostToDevice, b->st_main));
-		b->stats.h2d_bytes += total * sizeof(ReconTask);
+		if (flags & JSMPEG_B200_OUT_RGBA) {  // only the RGBA epilogue reads the task table from HBM
+			CUDA_CHECK(cudaMemcpyAsync(b->d_rtasks, b->h_rtasks, total * sizeof(ReconTask), cudaMemcpyHostToDevice, b->st_main));
+			b->stats.h2d_bytes += total * sizeof(ReconTask);
+		}
 		for (int i = 0; i < 2; i++)  // planes of the previous chunk may still be on their way out
 			if (b->copies_outstanding[i]) CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_copied[i], 0));
 		CUDA_CHECK(cudaEventRecord(b->ev_c, b->st_main));
 		off = 0;
 		for (size_t f = 0; f < steps.size(); f++) {
-			int max_mb = 0;
-			for (auto &t : steps[f]) max_mb = std::max(max_mb, t.mb_size);
 			// step f overwrites the plane set that step f-2 produced: its copy-out must be done
 			if ((flags & JSMPEG_B200_OUT_HOST) && f >= 2) CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_copied[f & 1], 0));
-			launch_reconstruct(b->d_rtasks + off, (int)steps[f].size(), max_mb, b->st_main);
+			launch_reconstruct(b->h_rtasks + off, (int)steps[f].size(), b->st_main);
 			b->stats.kernel_launches++;
 			b->stats.recon_launches++;
 			if (flags & JSMPEG_B200_OUT_RGBA) {
@@ -844,7 +844,6 @@ int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, 
 	mb_record_t *d_hdr = dev_alloc<mb_record_t>(n_mb);
 	int16_t *d_coef = dev_alloc<int16_t>(n_mb * MB_COEF_INT16);
 	uint8_t *d_fwd = dev_alloc<uint8_t>(total + 64), *d_cur = dev_alloc<uint8_t>(total + 64);
-	ReconTask *d_task = dev_alloc<ReconTask>(1);
 	CUDA_CHECK(cudaMemcpy(d_hdr, hdr, n_mb * sizeof(mb_record_t), cudaMemcpyHostToDevice));
 	CUDA_CHECK(cudaMemcpy(d_coef, coef, n_mb * MB_COEF_INT16 * sizeof(int16_t), cudaMemcpyHostToDevice));
 	CUDA_CHECK(cudaMemcpy(d_fwd, fwd_y, ysz, cudaMemcpyHostToDevice));
@@ -859,14 +858,13 @@ int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, 
 	t.fwd = PlaneSet{d_fwd, d_fwd + ysz, d_fwd + ysz + csz};
 	t.mb_width = mb_width; t.mb_size = (int)n_mb;
 	t.coded_width = mb_width * 16; t.coded_height = mb_height * 16;
-	CUDA_CHECK(cudaMemcpy(d_task, &t, sizeof(t), cudaMemcpyHostToDevice));
-	launch_reconstruct(d_task, 1, (int)n_mb, 0);
+	launch_reconstruct(&t, 1, 0);
 	CUDA_CHECK(cudaGetLastError());
 	CUDA_CHECK(cudaDeviceSynchronize());
 	CUDA_CHECK(cudaMemcpy(cur_y, d_cur, ysz, cudaMemcpyDeviceToHost));
 	CUDA_CHECK(cudaMemcpy(cur_cr, d_cur + ysz, csz, cudaMemcpyDeviceToHost));
 	CUDA_CHECK(cudaMemcpy(cur_cb, d_cur + ysz + csz, csz, cudaMemcpyDeviceToHost));
-	cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_fwd); cudaFree(d_cur); cudaFree(d_task);
+	cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_fwd); cudaFree(d_cur);
 	return 0;
 }
 

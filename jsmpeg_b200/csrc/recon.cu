@@ -3,80 +3,112 @@
 // Replaces the pixel half of the reference's decodeMacroblock/decodeBlock: copyMacroblock
 // (src/mpeg1.js:459-687), IDCT (:916-983) and Copy/Add{Block,Value}ToDestination (:864-914).
 // Every macroblock of a picture reads only the PREVIOUS picture's planes and writes only its own
-// 16x16 / 8x8 / 8x8 pixels, so all macroblocks of a picture (and of all streams) are independent.
+// 16x16 / 8x8 / 8x8 pixels, so all blocks of a picture (and of all streams) are independent.
 //
-// Mapping: a CTA reconstructs MBS_PER_CTA = 4 consecutive macroblocks = 24 blocks of 8x8 with
-// 192 threads; thread (blk, k) owns line k of block blk:
-//   A  one 16-byte load = row k of the block's 64 int16 coefficients (coalesced 128 B per block),
-//      x PREMULTIPLIER (src/mpeg1.js:810, 1026-1035) in int32 -> shared memory
-//   B  column k of the block: 8-point pass without final shift (mpeg1.js:925-947)
-//   C  row k: 8-point pass with (v+128)>>8 (mpeg1.js:952-981) -> 8 residuals in registers
-//   D  row k of the prediction: unaligned 9(+9) byte fetch from the forward plane as aligned
-//      32-bit words, packed-byte half-pel averaging, + residual, saturate, one 8-byte store.
-// Blocks that take the reference's DC-only shortcut (mpeg1.js:838-841, 850-853) skip B and C.
-// The block tile in shared memory is padded to 72 words and the two 4-word halves of rows 4..7
-// are swapped, so that A/C (128-bit row accesses) and B (stride-8 column accesses) are all
-// bank-conflict free.
+// Mapping: ONE THREAD PER 8x8 BLOCK, the whole block in registers.
+//   * the block's 128-byte coefficient record is fetched by ONE instruction per lane: a TMA 1-D
+//     bulk copy (cp.async.bulk global -> shared, SASS UBLKCP) into a 144-byte-pitched row of
+//     the warp's staging area, completion counted on a per-warp mbarrier; the lane then reads
+//     its row back with eight conflict-free LDS.128.  (Eight per-lane LDG.128 at a 128-byte
+//     stride cost 32 L1 wavefronts per instruction and made the kernel L1TEX-bound.)
+//     The coefficients are multiplied by PREMULTIPLIER (src/mpeg1.js:810, 1026-1035) -- compile-time immediates,
+//     the loops are fully unrolled -- and go through the 8 column passes (mpeg1.js:925-947) and
+//     the 8 row passes with (v+128)>>8 (mpeg1.js:952-981) without leaving the register file:
+//     no shared memory, no barriers, all per-thread overhead amortised over 64 samples;
+//   * blocks are numbered so that the 32 lanes of a warp hold 32 horizontally adjacent blocks of
+//     one plane row ([luma top | luma bottom | Cb | Cr] per macroblock row): every row of the
+//     output is one 8-byte store per lane = 256 contiguous bytes per warp, and the forward-plane
+//     fetches of neighbouring lanes (similar vectors) fall into the same sectors;
+//   * prediction: 9 (+9) samples per row as three aligned 32-bit words + funnel shifts,
+//     packed-byte half-pel averaging (exact (a+b+1)>>1 / (a+b+c+d+2)>>2, mpeg1.js:481-556),
+//     + residual, saturate, store.
+// Blocks taking the reference's DC-only shortcut (mpeg1.js:838-841, 850-853) skip the IDCT.
+// The per-launch task table (pointers + sizes per stream) travels in the kernel parameters
+// (constant bank), so the first global access of a thread is already its macroblock header.
+// A vector whose footprint leaves the plane (non-conforming) takes a per-tap
+// bounds-checked path.
 //
 // HBM roofline accounting: per macroblock 16 B header + 128 B per coded block +
 // 384 B written + 384 B of forward-plane samples (P pictures), each counted once.
 #include "common.cuh"
 
-#define VLC_TABLE_QUALIFIER static __device__ const
-#include "vlc_tables.h"
-
 namespace {
 
-constexpr int MBS_PER_CTA = 4;
-constexpr int BLOCKS_PER_CTA = MBS_PER_CTA * 6;
-constexpr int THREADS = BLOCKS_PER_CTA * 8;  // 192
-constexpr int TILE = 72;                     // padded words per 8x8 block
+constexpr int THREADS = 128;
+constexpr int ROW_PITCH = 144;                       // bytes per staged block: 128 + 16 (bank spread)
+constexpr int WARP_STAGE = 32 * ROW_PITCH + 16;      // + the warp's mbarrier
+constexpr int MAX_TASKS = 80;  // per launch; (80 * 48 B) + 16 < 4 KB of kernel parameters
 
-// One 8-point pass of the reference IDCT.  Column pass: no scaling; row pass: (v + 128) >> 8.
-template <bool ROW>
-__device__ __forceinline__ void idct8(int (&v)[8]) {
-	const int b1 = v[4];
-	const int b3 = v[2] + v[6];
-	const int b4 = v[5] - v[3];
-	const int t1 = v[1] + v[7];
-	const int t2 = v[3] + v[5];
-	const int b6 = v[1] - v[7];
+struct CompactTask {
+	const mb_record_t *hdr;
+	const int16_t *coef;
+	uint8_t *cur;        // Y at 0, Cr at coded_size, Cb at coded_size * 5 / 4
+	const uint8_t *fwd;
+	int32_t mb_width, mb_height;
+	int32_t pad[2];
+};
+
+struct ReconParams {
+	CompactTask t[MAX_TASKS];
+};
+
+// PREMULTIPLIER_MATRIX (src/mpeg1.js:1026-1035) = outer product of these AAN scales, rounded as the
+// reference's table is; kept as a constexpr so that every use folds into an immediate.
+__device__ constexpr int PM[64] = {
+    32, 44, 42, 38, 32, 25, 17, 9,  44, 62, 58, 52, 44, 35, 24, 12, 42, 58, 55, 49, 42, 33, 23, 12,
+    38, 52, 49, 44, 38, 30, 20, 10, 32, 44, 42, 38, 32, 25, 17, 9,  25, 35, 33, 30, 25, 20, 14, 7,
+    17, 24, 23, 20, 17, 14, 9,  5,  9,  12, 12, 10, 9,  7,  5,  2};
+
+// One 8-point pass of the reference IDCT on v[o], v[o+s], ... v[o+7s].
+// Column pass: no scaling; row pass: (v + 128) >> 8.
+template <bool ROW, int O, int S>
+__device__ __forceinline__ void idct8(int (&v)[64]) {
+	const int b1 = v[O + 4 * S];
+	const int b3 = v[O + 2 * S] + v[O + 6 * S];
+	const int b4 = v[O + 5 * S] - v[O + 3 * S];
+	const int t1 = v[O + 1 * S] + v[O + 7 * S];
+	const int t2 = v[O + 3 * S] + v[O + 5 * S];
+	const int b6 = v[O + 1 * S] - v[O + 7 * S];
 	const int b7 = t1 + t2;
-	const int m0 = v[0];
+	const int m0 = v[O];
 	const int x4 = ((b6 * 473 - b4 * 196 + 128) >> 8) - b7;
 	const int x0 = x4 - (((t1 - t2) * 362 + 128) >> 8);
 	const int x1 = m0 - b1;
-	const int x2 = (((v[2] - v[6]) * 362 + 128) >> 8) - b3;
+	const int x2 = (((v[O + 2 * S] - v[O + 6 * S]) * 362 + 128) >> 8) - b3;
 	const int x3 = m0 + b1;
 	const int y3 = x1 + x2, y4 = x3 + b3, y5 = x1 - x2, y6 = x3 - b3;
 	const int y7 = -x0 - ((b4 * 473 + b6 * 196 + 128) >> 8);
 	if (ROW) {
-		v[0] = (b7 + y4 + 128) >> 8; v[1] = (x4 + y3 + 128) >> 8;
-		v[2] = (y5 - x0 + 128) >> 8; v[3] = (y6 - y7 + 128) >> 8;
-		v[4] = (y6 + y7 + 128) >> 8; v[5] = (x0 + y5 + 128) >> 8;
-		v[6] = (y3 - x4 + 128) >> 8; v[7] = (y4 - b7 + 128) >> 8;
+		v[O] = (b7 + y4 + 128) >> 8;         v[O + 1 * S] = (x4 + y3 + 128) >> 8;
+		v[O + 2 * S] = (y5 - x0 + 128) >> 8; v[O + 3 * S] = (y6 - y7 + 128) >> 8;
+		v[O + 4 * S] = (y6 + y7 + 128) >> 8; v[O + 5 * S] = (x0 + y5 + 128) >> 8;
+		v[O + 6 * S] = (y3 - x4 + 128) >> 8; v[O + 7 * S] = (y4 - b7 + 128) >> 8;
 	} else {
-		v[0] = b7 + y4; v[1] = x4 + y3; v[2] = y5 - x0; v[3] = y6 - y7;
-		v[4] = y6 + y7; v[5] = x0 + y5; v[6] = y3 - x4; v[7] = y4 - b7;
+		v[O] = b7 + y4;         v[O + 1 * S] = x4 + y3; v[O + 2 * S] = y5 - x0; v[O + 3 * S] = y6 - y7;
+		v[O + 4 * S] = y6 + y7; v[O + 5 * S] = x0 + y5; v[O + 6 * S] = y3 - x4; v[O + 7 * S] = y4 - b7;
 	}
 }
 
-// 12 bytes starting at flat index i of a plane, as three packed little-endian words whose byte 0
-// is sample i.  `p` is 4-byte aligned at index 0.  Caller guarantees [i, i+12) is readable.
-__device__ __forceinline__ void load12(const uint8_t *__restrict__ p, int i, uint32_t &a, uint32_t &b, uint32_t &c) {
-	const uint32_t *w = reinterpret_cast<const uint32_t *>(p) + (i >> 2);
-	const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
-	const uint32_t sh = (uint32_t)(i & 3) * 8u;
-	a = __funnelshift_r(w0, w1, sh);
-	b = __funnelshift_r(w1, w2, sh);
-	c = __funnelshift_r(w2, w3, sh);
+template <int I>
+__device__ __forceinline__ void idct_columns(int (&v)[64]) {
+	if constexpr (I < 8) {
+		idct8<false, I, 8>(v);
+		idct_columns<I + 1>(v);
+	}
+}
+template <int I>
+__device__ __forceinline__ void idct_rows(int (&v)[64]) {
+	if constexpr (I < 8) {
+		idct8<true, I * 8, 1>(v);
+		idct_rows<I + 1>(v);
+	}
 }
 
 // (a + b + c + d + 2) >> 2 per byte, exact (mpeg1.js:481-500)
 __device__ __forceinline__ uint32_t avg4_u8x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
 	const uint32_t M = 0x00ff00ffu;
-	uint32_t lo = (a & M) + (b & M) + (c & M) + (d & M) + 0x00020002u;
-	uint32_t hi = ((a >> 8) & M) + ((b >> 8) & M) + ((c >> 8) & M) + ((d >> 8) & M) + 0x00020002u;
+	const uint32_t lo = (a & M) + (b & M) + (c & M) + (d & M) + 0x00020002u;
+	const uint32_t hi = ((a >> 8) & M) + ((b >> 8) & M) + ((c >> 8) & M) + ((d >> 8) & M) + 0x00020002u;
 	return ((lo >> 2) & M) | (((hi >> 2) & M) << 8);
 }
 
@@ -89,163 +121,240 @@ __device__ __forceinline__ uint32_t pack_sat_u8x4(int a, int b, int c, int d) {
 	return r;
 }
 
-__global__ void __launch_bounds__(THREADS)
-reconstruct_kernel(const ReconTask *__restrict__ tasks) {
-	__shared__ int tile[BLOCKS_PER_CTA * TILE];
-	__shared__ int premult[64];
+// packed predicted samples p (4 per word) + 4 residuals -> 4 saturated output samples
+__device__ __forceinline__ uint32_t add_sat4(uint32_t p, int r0, int r1, int r2, int r3) {
+	return pack_sat_u8x4((int)(p & 255u) + r0, (int)((p >> 8) & 255u) + r1, (int)((p >> 16) & 255u) + r2, (int)(p >> 24) + r3);
+}
 
-	if (threadIdx.x < 64) premult[threadIdx.x] = TBL_PREMULTIPLIER[threadIdx.x];
+// 9 consecutive samples starting at flat index i of a plane whose base is 4-byte aligned:
+// a = samples 0..3, b = 4..7, c (low byte) = sample 8.
+__device__ __forceinline__ void row9(const uint8_t *__restrict__ plane, int i, uint32_t &a, uint32_t &b, uint32_t &c) {
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(plane) + (i >> 2);
+	const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+	const uint32_t sh = (uint32_t)(i & 3) * 8u;
+	a = __funnelshift_r(w0, w1, sh);
+	b = __funnelshift_r(w1, w2, sh);
+	c = w2 >> sh;
+}
 
-	const ReconTask &t = tasks[blockIdx.y];
-	const int blk = threadIdx.x >> 3;   // 0..23
-	const int k = threadIdx.x & 7;      // line within the block
-	const int mb = blockIdx.x * MBS_PER_CTA + blk / 6;
-	const int b = blk % 6;              // block within the macroblock
-	const bool mb_valid = mb < t.mb_size;
-
-	uint32_t rec_y = 0;
-	int mv_h = 0, mv_v = 0;
-	if (mb_valid) {
-		const uint2 r = __ldg(reinterpret_cast<const uint2 *>(t.hdr + mb));
-		mv_h = (int)(int16_t)(r.x & 0xffffu);
-		mv_v = (int)(int16_t)(r.x >> 16);
-		rec_y = r.y;
+// Prediction of the 8 rows of one block + residual.  The four half-pel cases of the reference
+// (copy, (a+b+1)>>1 horizontally or vertically, (a+b+c+d+2)>>2; src/mpeg1.js:481-556) are ONE
+// formula when the unused taps are replaced by duplicates of the used ones:
+//     (A + B' + C' + D' + 2) >> 2   with  B' = oh ? B : A,  C' = ov ? C : A,  D' = ov ? (oh ? D : C) : B'
+// ((4A+2)>>2 = A, (2A+2B+2)>>2 = (A+B+1)>>1).  The lanes of a warp hold blocks of different
+// macroblocks, i.e. different parities: one branch-free path keeps them converged.
+// FULLPEL (warp-uniform: no lane has a half-pel component) is the plain copy.
+template <bool FULLPEL>
+__device__ __forceinline__ void predict_rows(const uint8_t *__restrict__ splane, int src, int stride, bool oh, bool ov,
+                                             bool coded, const int (&v)[64], uint8_t *__restrict__ dst) {
+	uint32_t a0, a1, a2;
+	row9(splane, src, a0, a1, a2);
+#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		uint32_t p0, p1, c0 = 0, c1 = 0, c2 = 0;
+		if (FULLPEL) {
+			p0 = a0; p1 = a1;
+			if (r < 7) row9(splane, src + (r + 1) * stride, c0, c1, c2);
+		} else {
+			row9(splane, src + (r + 1) * stride, c0, c1, c2);  // row 8 is inside the plane (checked by the caller)
+			const uint32_t b0 = oh ? __funnelshift_r(a0, a1, 8) : a0, b1 = oh ? __funnelshift_r(a1, a2, 8) : a1;
+			const uint32_t d0 = oh ? __funnelshift_r(c0, c1, 8) : c0, d1 = oh ? __funnelshift_r(c1, c2, 8) : c1;
+			p0 = avg4_u8x4(a0, b0, ov ? c0 : a0, ov ? d0 : b0);
+			p1 = avg4_u8x4(a1, b1, ov ? c1 : a1, ov ? d1 : b1);
+		}
+		uint2 out;
+		if (coded) {
+			out.x = add_sat4(p0, v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
+			out.y = add_sat4(p1, v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+		} else {
+			out.x = p0; out.y = p1;
+		}
+		*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+		a0 = c0; a1 = c1; a2 = c2;
 	}
-	const int flags = rec_y & 0xff;
-	const int bit = 0x20 >> b;
-	const bool present = flags & MBF_PRESENT;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(THREADS, 5)
+reconstruct_kernel(const __grid_constant__ ReconParams params) {
+	__shared__ __align__(16) uint8_t stage[(THREADS / 32) * WARP_STAGE];
+
+	const CompactTask &t = params.t[blockIdx.y];
+	const int W = t.mb_width;
+	const int slots_per_row = 6 * W;
+	const int slot = blockIdx.x * THREADS + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const bool in_picture = slot < slots_per_row * t.mb_height;
+	const int mb_row = in_picture ? slot / slots_per_row : 0;
+	const int s = in_picture ? slot - mb_row * slots_per_row : 0;
+	// [luma top 2W | luma bottom 2W | Cb W | Cr W]
+	int b, mb_col;
+	if (s < 4 * W) {
+		const int by = s >= 2 * W;
+		const int bx = s - by * 2 * W;
+		mb_col = bx >> 1;
+		b = by * 2 + (bx & 1);
+	} else {
+		const int c = s - 4 * W;
+		const int second = c >= W;
+		mb_col = c - second * W;
+		b = 4 + second;  // block 4 -> Cb plane, block 5 -> Cr plane (mpeg1.js:829-834)
+	}
+	const int mb = mb_row * W + mb_col;
+
+	uint2 rec = make_uint2(0, 0);
+	if (in_picture) rec = __ldg(reinterpret_cast<const uint2 *>(t.hdr + mb));
+	const int flags = rec.y & 0xff;
+	const bool present = flags & MBF_PRESENT;  // an untouched macroblock keeps the two-pictures-old content
 	const bool intra = flags & MBF_INTRA;
-	const bool coded = present && (((rec_y >> 8) & 0xff) & bit);
-	const bool dc_only = coded && (((rec_y >> 16) & 0xff) & bit);
+	const int bit = 0x20 >> b;
+	const bool coded = present && ((rec.y >> 8) & bit);
+	const bool dc_only = coded && ((rec.y >> 16) & bit);
 	const bool full = coded && !dc_only;
 
-	// ---- A: coefficients -> premultiplied int32 tile
+	// ---- coefficient records of the warp's blocks: one TMA bulk copy per lane
+	uint8_t *wstage = stage + (threadIdx.x >> 5) * WARP_STAGE;
+	const uint32_t mbar = smem_u32(wstage + 32 * ROW_PITCH);
+	const uint32_t my_row = smem_u32(wstage + lane * ROW_PITCH);
 	const int16_t *cblk = t.coef + ((size_t)mb * 6 + b) * 64;
-	int res[8];
-	int *my = tile + blk * TILE;
-	__syncthreads();  // premult visible
-	if (full) {
-		const uint4 q = __ldg(reinterpret_cast<const uint4 *>(cblk) + k);
-		const int *pm = premult + k * 8;
-		int4 lo, hi;
-		lo.x = (int)(int16_t)(q.x & 0xffffu) * pm[0]; lo.y = ((int)q.x >> 16) * pm[1];
-		lo.z = (int)(int16_t)(q.y & 0xffffu) * pm[2]; lo.w = ((int)q.y >> 16) * pm[3];
-		hi.x = (int)(int16_t)(q.z & 0xffffu) * pm[4]; hi.y = ((int)q.z >> 16) * pm[5];
-		hi.z = (int)(int16_t)(q.w & 0xffffu) * pm[6]; hi.w = ((int)q.w >> 16) * pm[7];
-		*reinterpret_cast<int4 *>(my + k * 8 + (k & 4)) = lo;
-		*reinterpret_cast<int4 *>(my + k * 8 + ((k & 4) ^ 4)) = hi;
-	} else if (dc_only) {
-		const int c0 = (int)__ldg(cblk);
-		const int v = (c0 * premult[0] + 128) >> 8;  // mpeg1.js:838-841, 850-853
-#pragma unroll
-		for (int j = 0; j < 8; j++) res[j] = v;
-	} else {
-#pragma unroll
-		for (int j = 0; j < 8; j++) res[j] = 0;
-	}
-	__syncthreads();
-
-	// ---- B: column pass
-	if (full) {
-		int v[8];
-#pragma unroll
-		for (int j = 0; j < 8; j++) v[j] = my[j * 8 + (j < 4 ? k : k ^ 4)];
-		idct8<false>(v);
-#pragma unroll
-		for (int j = 0; j < 8; j++) my[j * 8 + (j < 4 ? k : k ^ 4)] = v[j];
-	}
-	__syncthreads();
-
-	// ---- C: row pass
-	if (full) {
-		const int4 lo = *reinterpret_cast<const int4 *>(my + k * 8 + (k & 4));
-		const int4 hi = *reinterpret_cast<const int4 *>(my + k * 8 + ((k & 4) ^ 4));
-		res[0] = lo.x; res[1] = lo.y; res[2] = lo.z; res[3] = lo.w;
-		res[4] = hi.x; res[5] = hi.y; res[6] = hi.z; res[7] = hi.w;
-		idct8<true>(res);
-	}
-	if (!present) return;  // untouched macroblock keeps the two-pictures-old content
-
-	// ---- D: prediction + residual -> 8 output samples of line k
-	uint8_t *dplane;
-	const uint8_t *splane;
-	int stride, plane_size, origin, mh, mv;
-	const int mb_row = mb / t.mb_width, mb_col = mb - mb_row * t.mb_width;
-	if (b < 4) {
-		dplane = t.cur.y; splane = t.fwd.y;
-		stride = t.coded_width;
-		plane_size = t.coded_width * t.coded_height;
-		origin = (mb_row * 16 + (b >> 1) * 8 + k) * stride + mb_col * 16 + (b & 1) * 8;
-		mh = mv_h; mv = mv_v;
-	} else {
-		// block 4 -> Cb plane, block 5 -> Cr plane (mpeg1.js:829-834)
-		dplane = b == 4 ? t.cur.cb : t.cur.cr;
-		splane = b == 4 ? t.fwd.cb : t.fwd.cr;
-		stride = t.coded_width >> 1;
-		plane_size = (t.coded_width * t.coded_height) >> 2;
-		origin = (mb_row * 8 + k) * stride + mb_col * 8;
-		mh = mv_h / 2; mv = mv_v / 2;  // truncation toward zero (mpeg1.js:562-565)
-	}
-
-	uint32_t p0 = 0, p1 = 0;  // predicted samples 0..3, 4..7
-	if (!intra) {
-		const int oh = mh & 1, ov = mv & 1;
-		const int src = origin + (mv >> 1) * stride + (mh >> 1);  // flat index (mpeg1.js:479, 567)
-		const int last = src + 8 + stride;                        // furthest tap that may be used
-		if (src >= 0 && last + 16 < plane_size) {
-			uint32_t a0, a1, a2;
-			load12(splane, src, a0, a1, a2);
-			if (!ov) {
-				if (!oh) { p0 = a0; p1 = a1; }
-				else {
-					p0 = __vavgu4(a0, __funnelshift_r(a0, a1, 8));
-					p1 = __vavgu4(a1, __funnelshift_r(a1, a2, 8));
-				}
-			} else {
-				uint32_t c0, c1, c2;
-				load12(splane, src + stride, c0, c1, c2);
-				if (!oh) { p0 = __vavgu4(a0, c0); p1 = __vavgu4(a1, c1); }
-				else {
-					p0 = avg4_u8x4(a0, __funnelshift_r(a0, a1, 8), c0, __funnelshift_r(c0, c1, 8));
-					p1 = avg4_u8x4(a1, __funnelshift_r(a1, a2, 8), c1, __funnelshift_r(c1, c2, 8));
-				}
-			}
-		} else {
-			// vector leaves the plane: per-tap bounds check, any outside tap zeroes the sample
-			for (int x = 0; x < 8; x++) {
-				const int i = src + x;
-				const int taps[4] = {i, i + 1, i + stride, i + stride + 1};
-				const bool use[4] = {true, (bool)oh, (bool)ov, oh && ov};
-				int sum = 0, n = 0;
-				bool inside = true;
-				for (int q = 0; q < 4; q++) {
-					if (!use[q]) continue;
-					if (taps[q] < 0 || taps[q] >= plane_size) { inside = false; continue; }
-					sum += splane[taps[q]];
-					n++;
-				}
-				const int v = !inside ? 0 : (n == 4 ? (sum + 2) >> 2 : (n == 2 ? (sum + 1) >> 1 : sum));
-				if (x < 4) p0 |= (uint32_t)v << (8 * x);
-				else p1 |= (uint32_t)v << (8 * (x - 4));
-			}
+	const unsigned full_mask = __ballot_sync(0xffffffffu, full);
+	if (full_mask) {  // warp-uniform
+		if (lane == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(128u * (uint32_t)__popc(full_mask)) : "memory");
 		}
+		__syncwarp();
+		if (full)
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];"
+			             ::"r"(my_row), "l"(cblk), "r"(mbar) : "memory");
 	}
-	uint2 out;
-	if (coded) {
-		out.x = pack_sat_u8x4((int)(p0 & 255u) + res[0], (int)((p0 >> 8) & 255u) + res[1],
-		                      (int)((p0 >> 16) & 255u) + res[2], (int)(p0 >> 24) + res[3]);
-		out.y = pack_sat_u8x4((int)(p1 & 255u) + res[4], (int)((p1 >> 8) & 255u) + res[5],
-		                      (int)((p1 >> 16) & 255u) + res[6], (int)(p1 >> 24) + res[7]);
+
+	const int stride_y = W * 16;
+	const int ysize = stride_y * t.mb_height * 16;
+	int stride, plane_off, plane_size, origin;
+	if (b < 4) {
+		stride = stride_y; plane_off = 0; plane_size = ysize;
+		origin = (mb_row * 16 + (b >> 1) * 8) * stride + mb_col * 16 + (b & 1) * 8;
 	} else {
-		out.x = p0; out.y = p1;
+		stride = stride_y >> 1; plane_size = ysize >> 2;
+		plane_off = b == 4 ? ysize + plane_size : ysize;  // Cb is the third plane, Cr the second
+		origin = mb_row * 8 * stride + mb_col * 8;
 	}
-	*reinterpret_cast<uint2 *>(dplane + origin) = out;
+
+	if (full_mask) {  // wait for the warp's copies (phase 0 of a barrier used once)
+		uint32_t done = 0;
+		while (!done)
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+			             : "=r"(done) : "r"(mbar) : "memory");
+	}
+	// motion vector of this block's plane, and whether ANY lane of the warp needs half-pel taps
+	int mh = (int)(int16_t)(rec.x & 0xffffu), mv = (int)(int16_t)(rec.x >> 16);
+	if (b >= 4) { mh /= 2; mv /= 2; }  // truncation toward zero (mpeg1.js:562-565)
+	const bool oh = mh & 1, ov = mv & 1;
+	const bool warp_halfpel = __any_sync(0xffffffffu, present && !intra && (oh || ov));
+	if (!present) return;
+
+	// ---- residual: 64 values in registers
+	int v[64];
+	if (full) {
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			uint4 q;
+			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(my_row + i * 16));
+			v[i * 8 + 0] = (int)(int16_t)(q.x & 0xffffu) * PM[i * 8 + 0]; v[i * 8 + 1] = ((int)q.x >> 16) * PM[i * 8 + 1];
+			v[i * 8 + 2] = (int)(int16_t)(q.y & 0xffffu) * PM[i * 8 + 2]; v[i * 8 + 3] = ((int)q.y >> 16) * PM[i * 8 + 3];
+			v[i * 8 + 4] = (int)(int16_t)(q.z & 0xffffu) * PM[i * 8 + 4]; v[i * 8 + 5] = ((int)q.z >> 16) * PM[i * 8 + 5];
+			v[i * 8 + 6] = (int)(int16_t)(q.w & 0xffffu) * PM[i * 8 + 6]; v[i * 8 + 7] = ((int)q.w >> 16) * PM[i * 8 + 7];
+		}
+		idct_columns<0>(v);
+		idct_rows<0>(v);
+	} else {
+		int dc = 0;
+		if (coded) dc = ((int)__ldg(cblk) * PM[0] + 128) >> 8;  // mpeg1.js:838-841, 850-853
+#pragma unroll
+		for (int i = 0; i < 64; i++) v[i] = dc;
+	}
+
+	uint8_t *dst = t.cur + plane_off + origin;
+	if (intra) {
+#pragma unroll
+		for (int r = 0; r < 8; r++) {
+			uint2 out;
+			out.x = pack_sat_u8x4(v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
+			out.y = pack_sat_u8x4(v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+			*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+		}
+		return;
+	}
+
+	// ---- prediction from the forward picture + residual
+	const int src = origin + (mv >> 1) * stride + (mh >> 1);  // flat index (mpeg1.js:479, 567)
+	const uint8_t *splane = t.fwd + plane_off;
+	if (src >= 0 && src + 8 * stride + 8 < plane_size) {
+		if (warp_halfpel) predict_rows<false>(splane, src, stride, oh, ov, coded, v, dst);
+		else predict_rows<true>(splane, src, stride, false, false, coded, v, dst);
+		return;
+	}
+	// vector leaves the plane: per-tap bounds check, any outside tap zeroes the sample
+#pragma unroll 1
+	for (int r = 0; r < 8; r++) {
+		uint32_t p[2] = {0, 0};
+		for (int x = 0; x < 8; x++) {
+			const int i = src + r * stride + x;
+			const int taps[4] = {i, i + 1, i + stride, i + stride + 1};
+			const bool use[4] = {true, (bool)oh, (bool)ov, oh && ov};
+			int sum = 0, n = 0;
+			bool inside = true;
+			for (int k = 0; k < 4; k++) {
+				if (!use[k]) continue;
+				if (taps[k] < 0 || taps[k] >= plane_size) { inside = false; continue; }
+				sum += splane[taps[k]];
+				n++;
+			}
+			const int px = !inside ? 0 : (n == 4 ? (sum + 2) >> 2 : (n == 2 ? (sum + 1) >> 1 : sum));
+			p[x >> 2] |= (uint32_t)px << (8 * (x & 3));
+		}
+		// v[] is indexed dynamically only on this rare path (spills to local memory are fine here)
+		int rr[8];
+#pragma unroll
+		for (int x = 0; x < 8; x++) {
+			int acc = 0;
+#pragma unroll
+			for (int q = 0; q < 8; q++) acc = (q == r) ? v[q * 8 + x] : acc;
+			rr[x] = acc;
+		}
+		uint2 out;
+		if (coded) {
+			out.x = add_sat4(p[0], rr[0], rr[1], rr[2], rr[3]);
+			out.y = add_sat4(p[1], rr[4], rr[5], rr[6], rr[7]);
+		} else {
+			out.x = p[0]; out.y = p[1];
+		}
+		*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+	}
 }
 
 }  // namespace
 
-void launch_reconstruct(const ReconTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream) {
-	if (n_tasks <= 0 || max_mb_size <= 0) return;
-	dim3 grid((max_mb_size + MBS_PER_CTA - 1) / MBS_PER_CTA, n_tasks);
-	reconstruct_kernel<<<grid, THREADS, 0, stream>>>(tasks);
+void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream) {
+	for (int first = 0; first < n_tasks; first += MAX_TASKS) {
+		const int n = n_tasks - first < MAX_TASKS ? n_tasks - first : MAX_TASKS;
+		ReconParams p;
+		int max_slots = 0;
+		for (int i = 0; i < n; i++) {
+			const ReconTask &t = tasks_host[first + i];
+			p.t[i].hdr = t.hdr;
+			p.t[i].coef = t.coef;
+			p.t[i].cur = t.cur.y;   // planes are contiguous: Y | Cr | Cb (engine.cu plane_set)
+			p.t[i].fwd = t.fwd.y;
+			p.t[i].mb_width = t.mb_width;
+			p.t[i].mb_height = t.mb_size / t.mb_width;
+			p.t[i].pad[0] = p.t[i].pad[1] = 0;
+			max_slots = max_slots > t.mb_size * 6 ? max_slots : t.mb_size * 6;
+		}
+		dim3 grid((max_slots + THREADS - 1) / THREADS, n);
+		reconstruct_kernel<<<grid, THREADS, 0, stream>>>(p);
+	}
 }
