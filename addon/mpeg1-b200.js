@@ -1,0 +1,76 @@
+// JSMpeg.Decoder.MPEG1VideoB200 -- the reference-side binding for libjsmpeg_b200.so.
+//
+// NOT RUN IN THIS REPOSITORY'S IMAGE (no Node / JS engine; see INTEGRATION.md).  It has the surface
+// of JSMpeg.Decoder.MPEG1Video / MPEG1VideoWASM (reference src/mpeg1.js:6-64, src/mpeg1-wasm.js):
+// the player picks it exactly where it picks the WASM decoder (src/player.js:35-38), e.g.
+//     options.decoderB200 ? new JSMpeg.Decoder.MPEG1VideoB200(options) : ...
+// Everything except the five native calls is inherited from JSMpeg.Decoder.Base
+// (src/decoder.js): PTS table, seek, advanceDecodedTime, currentTime.
+// The host-side mirror that IS tested here is jsmpeg_b200/decoder.py (same logic, Python).
+
+JSMpeg.Decoder.MPEG1VideoB200 = (function(){ "use strict";
+
+var native = require('./jsmpeg_b200.node');
+
+var MPEG1B200 = function(options) {
+	JSMpeg.Decoder.Base.call(this, options);
+	this.onDecodeCallback = options.onVideoDecode;
+	var bufferSize = options.videoBufferSize || 512*1024;
+	var bufferMode = options.streaming ? 1 /* EVICT */ : 2 /* EXPAND */;
+	this.decoder = native.create(bufferSize, bufferMode);
+	this.decodeFirstFrame = options.decodeFirstFrame !== false;
+	this.hasSequenceHeader = false;
+};
+
+MPEG1B200.prototype = Object.create(JSMpeg.Decoder.Base.prototype);
+MPEG1B200.prototype.constructor = MPEG1B200;
+
+MPEG1B200.prototype.destroy = function() { native.destroy(this.decoder); };
+MPEG1B200.prototype.bufferGetIndex = function() { return native.getIndex(this.decoder); };
+MPEG1B200.prototype.bufferSetIndex = function(index) { native.setIndex(this.decoder, index); };
+
+MPEG1B200.prototype.bufferWrite = function(buffers) {
+	var total = 0;
+	for (var i = 0; i < buffers.length; i++) {
+		total += native.write(this.decoder, buffers[i]);
+	}
+	return total;
+};
+
+MPEG1B200.prototype.write = function(pts, buffers) {
+	JSMpeg.Decoder.Base.prototype.write.call(this, pts, buffers);
+	if (!this.hasSequenceHeader && native.hasSequenceHeader(this.decoder)) {
+		this.hasSequenceHeader = true;
+		this.frameRate = native.getFrameRate(this.decoder);
+		this.codedSize = native.getCodedSize(this.decoder);
+		this.width = native.getWidth(this.decoder);
+		this.height = native.getHeight(this.decoder);
+		if (this.destination) {
+			this.destination.resize(this.width, this.height);
+		}
+		if (this.decodeFirstFrame) {
+			this.decode();
+		}
+	}
+};
+
+MPEG1B200.prototype.decode = function() {
+	var startTime = JSMpeg.Now();
+	if (!native.decode(this.decoder)) {
+		return false;
+	}
+	if (this.destination) {
+		var p = native.planes(this.decoder);
+		this.currentY = p.y; this.currentCr = p.cr; this.currentCb = p.cb;
+		this.destination.render(p.y, p.cr, p.cb, false);
+	}
+	this.advanceDecodedTime(1/this.frameRate);
+	if (this.onDecodeCallback) {
+		this.onDecodeCallback(this, JSMpeg.Now() - startTime);
+	}
+	return true;
+};
+
+return MPEG1B200;
+
+})();

@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
         return OUT
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = [nvcc_path(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC",
-           "-Xptxas", "-v" if verbose else "-O3",
+           "-Xptxas", "-v" if verbose else "-O3", *os.environ.get("JSMPEG_B200_NVCC_FLAGS", "").split(),
            "-o", OUT, *srcs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -13,7 +13,7 @@ BIT_BUFFER_MODE_EVICT = 1   # reference src/wasm/buffer.h:8-11
 BIT_BUFFER_MODE_EXPAND = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(_HERE, "libjsmpeg_b200.so")
+PRODUCT_LIB = os.environ.get("JSMPEG_B200_LIB", os.path.join(_HERE, "libjsmpeg_b200.so"))  # override: kernel-tuning experiments
 
 MPEG1_ABI = {
     # name: (restype, argtypes)

@@ -257,6 +257,8 @@ void begin_upload(Batch *b, Stream &s) {
 		CUDA_CHECK(cudaMemcpyAsync(s.d_es + from, s.h_bytes + from, s.length - from, cudaMemcpyHostToDevice, b->st_main));
 		b->stats.h2d_bytes += s.length - from;
 		s.d_valid = s.length;
+		// the kernels rely on zeros right after the data (bytes past the end read as 0, like JS)
+		CUDA_CHECK(cudaMemsetAsync(s.d_es + s.length, 0, ES_PAD, b->st_main));
 	}
 	if (s.scanned < s.length) {
 		uint32_t from = s.scanned >= 3 ? s.scanned - 3 : 0;
@@ -822,6 +824,7 @@ int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t
 	picture_info_t *d_info = dev_alloc<picture_info_t>(1);
 	ParseTask *d_task = dev_alloc<ParseTask>(1);
 	CUDA_CHECK(cudaMemcpy(d_es, es, es_len, cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemset(d_es + es_len, 0, ES_PAD));
 	CUDA_CHECK(cudaMemcpy(d_seq, &sp, sizeof(sp), cudaMemcpyHostToDevice));
 	CUDA_CHECK(cudaMemset(d_coef, 0, n_mb * MB_COEF_INT16 * sizeof(int16_t)));
 	ParseTask t{d_es, es_len, start_byte, d_seq, d_hdr, d_coef, d_info};
