@@ -220,6 +220,8 @@ __device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, Pictur
 	}
 	for (;;) {
 		const uint32_t w = br.peek32();
+		// (Resolving '10' / '11s' arithmetically before the look-up was measured 8 % SLOWER: it defeats the
+		// combining of several codes per look-up.)
 		// as many complete codes as fit in the next 13 bits, in one look-up
 		const uint32_t m = lds_u16(sbase + OFF_MS + (w >> (32 - MS_BITS)) * 2u);
 		if (m & 15u) {
