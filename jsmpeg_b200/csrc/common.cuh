@@ -55,8 +55,15 @@ struct ReconTask {
 // kernel launchers (defined in scan.cu / parse.cu / recon.cu)
 void launch_scan_start_codes(const uint8_t *es, uint32_t from, uint32_t len, uint32_t *positions,
                              uint32_t capacity, uint32_t *count, cudaStream_t stream);
+// Helper streams/events with which stage 1 forks the (size-sorted) wave into groups: the expand of
+// a group of small pictures runs while the walk of the bigger pictures is still going.
+constexpr int PARSE_GROUPS = 4;
+struct ParseFork {
+	cudaStream_t side[PARSE_GROUPS];
+	cudaEvent_t fork, join[PARSE_GROUPS];
+};
 void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream,
-                           cudaEvent_t between_kernels = nullptr);
+                           cudaEvent_t walk_done = nullptr, const ParseFork *fork = nullptr);
 // `tasks_host` is read on the host at launch time: the table travels in the kernel parameters
 void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream);
 void launch_rgba(const ReconTask *tasks, int n_tasks, int max_width, int max_height, cudaStream_t stream);

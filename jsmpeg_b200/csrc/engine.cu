@@ -100,6 +100,7 @@ struct jsmpeg_b200_batch_t {
 	ReconTask *h_rtasks = nullptr, *d_rtasks = nullptr;
 	int rtask_cap = 0;
 	bool copies_outstanding[2] = {false, false};
+	ParseFork fork{};
 	jsmpeg_b200_stats_t stats{};
 };
 
@@ -432,7 +433,7 @@ long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 		}
 		CUDA_CHECK(cudaMemcpyAsync(b->d_ptasks, b->h_ptasks, fresh.size() * sizeof(ParseTask), cudaMemcpyHostToDevice, b->st_main));
 		CUDA_CHECK(cudaEventRecord(b->ev_a, b->st_main));
-		launch_parse_pictures(b->d_ptasks, (int)fresh.size(), b->slot_mb, b->st_main, b->ev_mid);
+		launch_parse_pictures(b->d_ptasks, (int)fresh.size(), b->slot_mb, b->st_main, b->ev_mid, &b->fork);
 		CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
 		CUDA_CHECK(cudaMemcpyAsync(b->h_info, b->d_info, fresh.size() * sizeof(picture_info_t), cudaMemcpyDeviceToHost, b->st_main));
 		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
@@ -441,7 +442,7 @@ long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 		b->stats.parse_ms += ms;
 		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_mid));
 		b->stats.walk_ms += ms;
-		b->stats.kernel_launches += 2;  // walk + expand
+		b->stats.kernel_launches += 2 * (fresh.size() >= 64 * PARSE_GROUPS ? PARSE_GROUPS : 1);  // walk + expand per size group
 		b->stats.h2d_bytes += fresh.size() * sizeof(ParseTask);
 		b->stats.d2h_bytes += fresh.size() * sizeof(picture_info_t);
 		for (size_t i = 0; i < fresh.size(); i++) {
@@ -584,6 +585,11 @@ jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigne
 	for (auto e : evs) CUDA_CHECK(cudaEventCreate(e));
 	CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_step, cudaEventDisableTiming));
 	for (auto &e : b->ev_copied) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	CUDA_CHECK(cudaEventCreateWithFlags(&b->fork.fork, cudaEventDisableTiming));
+	for (int i = 0; i < PARSE_GROUPS; i++) {
+		CUDA_CHECK(cudaStreamCreateWithFlags(&b->fork.side[i], cudaStreamNonBlocking));
+		CUDA_CHECK(cudaEventCreateWithFlags(&b->fork.join[i], cudaEventDisableTiming));
+	}
 	return b;
 }
 
@@ -606,6 +612,8 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 	if (b->h_rtasks) { cudaFreeHost(b->h_rtasks); cudaFree(b->d_rtasks); }
 	cudaEvent_t evs[] = {b->ev_a, b->ev_b, b->ev_c, b->ev_d, b->ev_mid, b->ev_step, b->ev_copied[0], b->ev_copied[1]};
 	for (auto e : evs) cudaEventDestroy(e);
+	cudaEventDestroy(b->fork.fork);
+	for (int i = 0; i < PARSE_GROUPS; i++) { cudaEventDestroy(b->fork.join[i]); cudaStreamDestroy(b->fork.side[i]); }
 	cudaStreamDestroy(b->st_main);
 	cudaStreamDestroy(b->st_copy);
 	delete b;

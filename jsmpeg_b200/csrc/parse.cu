@@ -607,7 +607,8 @@ static const uint16_t *ms_table_for_current_device() {
 	return d;
 }
 
-void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream, cudaEvent_t between_kernels) {
+void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream,
+                           cudaEvent_t walk_done, const ParseFork *fork) {
 	if (n_tasks <= 0) return;
 	const uint16_t *ms = ms_table_for_current_device();
 	const int per_cta = WALK_THREADS / 32;
@@ -617,9 +618,25 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 		CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
 		attr_set = true;
 	}
-	walk_pictures_kernel<<<(n_tasks + per_cta - 1) / per_cta, WALK_THREADS, walk_smem, stream>>>(
-	    tasks, n_tasks, reinterpret_cast<const uint4 *>(ms));
-	if (between_kernels) CUDA_CHECK(cudaEventRecord(between_kernels, stream));
-	dim3 grid((max_mb_size * 6 + CTA_THREADS - 1) / CTA_THREADS, n_tasks);
-	expand_blocks_kernel<<<grid, CTA_THREADS, OFF_BLOCKS + CTA_THREADS * 128, stream>>>(tasks);
+	// The wave arrives sorted by picture size, largest first.  Group 0 (largest pictures) stays on
+	// `stream`; the other groups go to side streams, each walk followed by its own expand.
+	const int groups = (fork && n_tasks >= 64 * PARSE_GROUPS) ? PARSE_GROUPS : 1;
+	if (groups > 1) CUDA_CHECK(cudaEventRecord(fork->fork, stream));
+	for (int g = 0; g < groups; g++) {
+		// equal quarters measured best (53.9 ms vs 55.0 ms with a small first group, 59.8 ms unforked)
+		const int lo = (int)((long)n_tasks * g / groups), hi = (int)((long)n_tasks * (g + 1) / groups);
+		const int n = hi - lo;
+		if (n <= 0) continue;
+		cudaStream_t st = g == 0 ? stream : fork->side[g];
+		if (g > 0) CUDA_CHECK(cudaStreamWaitEvent(st, fork->fork, 0));
+		walk_pictures_kernel<<<(n + per_cta - 1) / per_cta, WALK_THREADS, walk_smem, st>>>(
+		    tasks + lo, n, reinterpret_cast<const uint4 *>(ms));
+		if (g == 0 && walk_done) CUDA_CHECK(cudaEventRecord(walk_done, st));
+		dim3 grid((max_mb_size * 6 + CTA_THREADS - 1) / CTA_THREADS, n);
+		expand_blocks_kernel<<<grid, CTA_THREADS, OFF_BLOCKS + CTA_THREADS * 128, st>>>(tasks + lo);
+		if (g > 0) {
+			CUDA_CHECK(cudaEventRecord(fork->join[g], st));
+			CUDA_CHECK(cudaStreamWaitEvent(stream, fork->join[g], 0));
+		}
+	}
 }
