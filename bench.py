@@ -49,7 +49,7 @@ STREAMS_PER_GPU = int(os.environ.get("BENCH_STREAMS", 64))
 PICTURES = int(os.environ.get("BENCH_PICTURES", 60))
 DISTINCT = int(os.environ.get("BENCH_DISTINCT", 8))
 NOISE = 9
-E2E_GROUPS = int(os.environ.get("BENCH_E2E_GROUPS", 8))
+E2E_GROUPS = int(os.environ.get("BENCH_E2E_GROUPS", 16))
 
 
 def env_int(name, default):
@@ -287,15 +287,18 @@ def main():
         for j, i in enumerate(g):
             dec.write(j, streams[i])
 
-    def step_e2e():
+    def run_e2e(n_steps):
+        """n_steps whole-workload steps: every group's thread runs its n_steps back to back (no
+        per-step join), so one group's PCIe copy-out overlaps the others' write + parse."""
         counts = [0] * E2E_GROUPS
 
         def work(k):
             dec = e2e_decoders[k]
-            dec.reset()
-            for j, i in enumerate(groups[k]):
-                dec.write(j, streams[i])
-            counts[k] = dec.decode(PICTURES, OUT_HOST)
+            for _ in range(n_steps):
+                dec.reset()
+                for j, i in enumerate(groups[k]):
+                    dec.write(j, streams[i])
+                counts[k] += dec.decode(PICTURES, OUT_HOST)
 
         threads = [threading.Thread(target=work, args=(k,)) for k in range(E2E_GROUPS)]
         for th in threads:
@@ -304,19 +307,17 @@ def main():
             th.join()
         return sum(counts)
 
-    def timed(step, steps, warmup, decoders):
+    def timed(run, steps, warmup, decoders):
+        """run(n) performs n steps and returns the pictures decoded."""
         sampler = ClockSampler(local_rank)
         sampler.start()  # started before the warm-up so that it is already streaming samples
-        for _ in range(warmup):
-            step()
+        run(warmup)
         barrier()
         for d in decoders:
             d.reset_stats()
         sampler.mark()
         t0 = time.perf_counter()
-        frames = 0
-        for _ in range(steps):
-            frames += step()
+        frames = run(steps)
         barrier()
         dt = time.perf_counter() - t0
         clocks = sampler.stop()
@@ -332,9 +333,12 @@ def main():
             dt, frames = float(t.item()), int(fr.item())
         return frames, dt, st, clocks
 
-    frames, dt, st, clocks = timed(step_device, args.steps, args.warmup, [bd])
-    e_steps = max(1, min(args.steps, 3))
-    e_frames, e_dt, e_st, e_clocks = timed(step_e2e, e_steps, 3, e2e_decoders)
+    def run_device(n_steps):
+        return sum(step_device() for _ in range(n_steps))
+
+    frames, dt, st, clocks = timed(run_device, args.steps, args.warmup, [bd])
+    e_steps = args.steps
+    e_frames, e_dt, e_st, e_clocks = timed(run_e2e, e_steps, 3, e2e_decoders)
 
     if rank != 0:
         if world > 1:

@@ -101,6 +101,9 @@ struct jsmpeg_b200_batch_t {
 	int rtask_cap = 0;
 	bool copies_outstanding[2] = {false, false};
 	ParseFork fork{};
+	std::vector<void *> copy_dst, copy_src;
+	std::vector<size_t> copy_size;
+	bool batch_copy_ok = true;
 	jsmpeg_b200_stats_t stats{};
 };
 
@@ -542,13 +545,32 @@ long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 				// copy this step's pictures out on the copy stream while the next step reconstructs
 				CUDA_CHECK(cudaEventRecord(b->ev_step, b->st_main));
 				CUDA_CHECK(cudaStreamWaitEvent(b->st_copy, b->ev_step, 0));
-				for (size_t i = 0; i < steps[f].size(); i++) {
+				// all pictures of the step leave in ONE batched copy call (cudaMemcpyBatchAsync, CUDA 12.8+)
+				const size_t n_copy = steps[f].size();
+				b->copy_dst.resize(n_copy);
+				b->copy_src.resize(n_copy);
+				b->copy_size.resize(n_copy);
+				for (size_t i = 0; i < n_copy; i++) {
 					Stream &s = b->streams[step_streams[f][i]];
 					s.h_head = (s.h_head + 1) % HOST_RING;
-					const size_t bytes = (size_t)s.coded_size * 3 / 2;
-					CUDA_CHECK(cudaMemcpyAsync(s.h_planes[s.h_head], steps[f][i].cur.y, bytes, cudaMemcpyDeviceToHost, b->st_copy));
-					b->stats.d2h_bytes += bytes;
+					b->copy_dst[i] = s.h_planes[s.h_head];
+					b->copy_src[i] = steps[f][i].cur.y;
+					b->copy_size[i] = (size_t)s.coded_size * 3 / 2;
+					b->stats.d2h_bytes += b->copy_size[i];
 				}
+				bool batched = false;
+				if (b->batch_copy_ok && n_copy > 1) {
+					cudaMemcpyAttributes attr{};
+					attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+					size_t attr_idx = 0, fail_idx = 0;
+					cudaError_t e = cudaMemcpyBatchAsync(b->copy_dst.data(), b->copy_src.data(), b->copy_size.data(), n_copy,
+					                                     &attr, &attr_idx, 1, &fail_idx, b->st_copy);
+					if (e == cudaSuccess) batched = true;
+					else { (void)cudaGetLastError(); b->batch_copy_ok = false; }  // older driver: plain copies from now on
+				}
+				if (!batched)
+					for (size_t i = 0; i < n_copy; i++)
+						CUDA_CHECK(cudaMemcpyAsync(b->copy_dst[i], b->copy_src[i], b->copy_size[i], cudaMemcpyDeviceToHost, b->st_copy));
 				CUDA_CHECK(cudaEventRecord(b->ev_copied[f & 1], b->st_copy));
 				b->copies_outstanding[f & 1] = true;
 			}
