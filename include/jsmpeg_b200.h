@@ -15,6 +15,7 @@
 #define JSMPEG_B200_H
 
 #include <stdbool.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -99,6 +100,17 @@ void jsmpeg_b200_batch_set_index(jsmpeg_b200_batch_t *b, int stream, unsigned in
 /* returns has_sequence_header */
 int jsmpeg_b200_batch_stream_info(jsmpeg_b200_batch_t *b, int stream, int *width, int *height,
                                   int *coded_size, float *frame_rate);
+
+/* MPEG-TS in, demultiplexed on the GPU (mirror of the reference's host demuxer src/ts.js for a
+ * buffer of whole 188-byte packets): the payload of every PES packet with stream id `stream_id`
+ * (0xE0 = first video stream, ts.js:213-224) is appended to `stream` exactly as if it had been
+ * written with get_write_ptr/did_write.  Returns the number of elementary-stream bytes appended,
+ * or -1 when the buffer is not a clean sequence of packets starting with the sync byte (use the
+ * host demuxer, which resyncs).  pts_out / offset_out (capacity n_max, may be NULL) receive, per
+ * PES packet in stream order, its PTS in 90 kHz ticks (0 if absent) and the byte offset of its
+ * payload in the stream's buffer -- the table Decoder.Base.write keeps (src/decoder.js:36-47). */
+long jsmpeg_b200_batch_write_ts(jsmpeg_b200_batch_t *b, int stream, const uint8_t *ts, size_t n_bytes, int stream_id,
+                                uint64_t *pts_out, uint32_t *offset_out, int n_max, int *n_pes);
 
 /* Make everything written so far resident in HBM and indexed (H2D copy of new bytes + start-code
  * scan).  Called implicitly by decode; exposed so that a benchmark can separate it.  Returns the

@@ -37,6 +37,8 @@ _BATCH_ABI = {
     "jsmpeg_b200_batch_stream_info": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                                      ctypes.POINTER(ctypes.c_float)]),
+    "jsmpeg_b200_batch_write_ts": (ctypes.c_long, [_VP, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                                   _VP, _VP, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "jsmpeg_b200_batch_upload": (ctypes.c_long, [_VP]),
     "jsmpeg_b200_batch_rewind": (None, [_VP]),
     "jsmpeg_b200_batch_reset": (None, [_VP]),
@@ -85,6 +87,20 @@ class BatchDecoder:
         ptr = self.lib.jsmpeg_b200_batch_get_write_ptr(self.handle, stream, len(data))
         ctypes.memmove(ptr, data, len(data))
         self.lib.jsmpeg_b200_batch_did_write(self.handle, stream, len(data))
+
+    def write_ts(self, stream, ts_bytes, stream_id=0xE0):
+        """MPEG-TS in, demultiplexed on the GPU.  Returns (ES bytes appended, [(payload byte offset,
+        pts seconds), ...] per PES packet) or raises ValueError when the buffer is not packet aligned."""
+        ts_bytes = bytes(ts_bytes)
+        n_max = len(ts_bytes) // 188 + 1
+        pts = np.zeros(n_max, np.uint64)
+        off = np.zeros(n_max, np.uint32)
+        n = ctypes.c_int()
+        total = self.lib.jsmpeg_b200_batch_write_ts(self.handle, stream, ts_bytes, len(ts_bytes), stream_id,
+                                                    pts.ctypes.data, off.ctypes.data, n_max, ctypes.byref(n))
+        if total < 0:
+            raise ValueError("not a clean sequence of 188-byte TS packets (use jsmpeg_b200.ts.TS, which resyncs)")
+        return total, [(int(off[i]), float(pts[i]) / 90000.0) for i in range(n.value)]
 
     def get_index(self, stream):
         return self.lib.jsmpeg_b200_batch_get_index(self.handle, stream)

@@ -67,3 +67,11 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 // `tasks_host` is read on the host at launch time: the table travels in the kernel parameters
 void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream);
 void launch_rgba(const ReconTask *tasks, int n_tasks, int max_width, int max_height, cudaStream_t stream);
+
+// device MPEG-TS demux (tsdemux.cu)
+struct TsScratch;
+TsScratch *ts_scratch_create();
+void ts_scratch_destroy(TsScratch *s);
+long ts_demux_measure(TsScratch *s, const uint8_t *ts_host, size_t ts_bytes, int stream_id, uint8_t *bound, cudaStream_t st);
+int ts_demux_gather(TsScratch *s, size_t ts_bytes, uint8_t *es, uint32_t es_base, uint64_t *pts_out,
+                    uint32_t *offset_out, int n_max, cudaStream_t st);

@@ -75,6 +75,7 @@ struct Stream {
 	uint8_t *h_planes[HOST_RING] = {};
 	int h_head = -1;
 	uint8_t *d_rgba = nullptr;
+	std::vector<uint8_t> ts_bound;  // device TS demux: PIDs already bound to the stream id (ts.js pidsToStreamIds)
 	// parsed-ahead pictures, consecutive, front = next picture decode() consumes
 	std::deque<Parsed> cache;
 };
@@ -104,6 +105,7 @@ struct jsmpeg_b200_batch_t {
 	std::vector<void *> copy_dst, copy_src;
 	std::vector<size_t> copy_size;
 	bool batch_copy_ok = true;
+	TsScratch *ts = nullptr;
 	jsmpeg_b200_stats_t stats{};
 };
 
@@ -244,18 +246,25 @@ void stream_did_write(Batch *b, Stream &s, uint32_t n) {
 
 // ---- residency: H2D of new bytes + start-code scan -----------------------------------------------
 
+// Room for `need` ES bytes (+ pad) in the HBM mirror; what is already resident stays resident.
+void reserve_device_es(Batch *b, Stream &s, uint32_t need) {
+	if (need + ES_PAD <= s.d_capacity) return;
+	uint32_t cap = std::max<uint32_t>(need + ES_PAD, s.d_capacity * 2);
+	cap = (cap + 255u) & ~255u;
+	uint8_t *n = dev_alloc<uint8_t>(cap);
+	if (s.d_es) {
+		if (s.d_valid) CUDA_CHECK(cudaMemcpyAsync(n, s.d_es, s.d_valid, cudaMemcpyDeviceToDevice, b->st_main));
+		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+		CUDA_CHECK(cudaFree(s.d_es));
+	}
+	s.d_es = n;
+	s.d_capacity = cap;
+}
+
 void begin_upload(Batch *b, Stream &s) {
 	s.scan_pending = false;
 	if (s.d_valid >= s.length && s.scanned >= s.length) return;
-	if (s.length + ES_PAD > s.d_capacity) {
-		uint32_t cap = std::max<uint32_t>(s.length + ES_PAD, s.d_capacity * 2);
-		cap = (cap + 255u) & ~255u;
-		uint8_t *n = dev_alloc<uint8_t>(cap);
-		if (s.d_es) CUDA_CHECK(cudaFree(s.d_es));  // stream-ordered work on it is complete: every call ends synchronised
-		s.d_es = n;
-		s.d_capacity = cap;
-		s.d_valid = 0;
-	}
+	reserve_device_es(b, s, s.length);
 	if (s.d_valid < s.length) {
 		uint32_t from = s.d_valid & ~15u;
 		CUDA_CHECK(cudaMemcpyAsync(s.d_es + from, s.h_bytes + from, s.length - from, cudaMemcpyHostToDevice, b->st_main));
@@ -632,6 +641,7 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 	if (b->d_hdr) { cudaFree(b->d_hdr); cudaFree(b->d_coef); cudaFree(b->d_info); cudaFreeHost(b->h_info); }
 	if (b->h_ptasks) { cudaFreeHost(b->h_ptasks); cudaFree(b->d_ptasks); }
 	if (b->h_rtasks) { cudaFreeHost(b->h_rtasks); cudaFree(b->d_rtasks); }
+	ts_scratch_destroy(b->ts);
 	cudaEvent_t evs[] = {b->ev_a, b->ev_b, b->ev_c, b->ev_d, b->ev_mid, b->ev_step, b->ev_copied[0], b->ev_copied[1]};
 	for (auto e : evs) cudaEventDestroy(e);
 	cudaEventDestroy(b->fork.fork);
@@ -770,6 +780,44 @@ int jsmpeg_b200_batch_read_planes(jsmpeg_b200_batch_t *b, int stream, void *y, v
 	if (cr) CUDA_CHECK(cudaMemcpy(cr, p.cr, s.coded_size >> 2, cudaMemcpyDeviceToHost));
 	if (cb) CUDA_CHECK(cudaMemcpy(cb, p.cb, s.coded_size >> 2, cudaMemcpyDeviceToHost));
 	return 0;
+}
+
+long jsmpeg_b200_batch_write_ts(jsmpeg_b200_batch_t *b, int stream, const uint8_t *ts, size_t n_bytes, int stream_id,
+                                uint64_t *pts_out, uint32_t *offset_out, int n_max, int *n_pes) {
+	use_device(b);
+	Stream &s = b->streams[stream];
+	if (!b->ts) b->ts = ts_scratch_create();
+	if (n_pes) *n_pes = 0;
+	if (s.ts_bound.empty()) s.ts_bound.assign(8192, 0);
+	const long total = ts_demux_measure(b->ts, ts, n_bytes, stream_id, s.ts_bound.data(), b->st_main);
+	if (total <= 0) return total;
+	// room in the host bit buffer (the reference's write protocol, may expand or evict) and in HBM
+	uint8_t *hdst = static_cast<uint8_t *>(stream_get_write_ptr(b, s, (uint32_t)total));
+	reserve_device_es(b, s, s.length + (uint32_t)total);
+	if (s.d_valid < s.length) {  // bytes written the ordinary way that are not resident yet
+		CUDA_CHECK(cudaMemcpyAsync(s.d_es + s.d_valid, s.h_bytes + s.d_valid, s.length - s.d_valid, cudaMemcpyHostToDevice, b->st_main));
+		b->stats.h2d_bytes += s.length - s.d_valid;
+		s.d_valid = s.length;
+	}
+	const int count = ts_demux_gather(b->ts, n_bytes, s.d_es, s.length, pts_out, offset_out, n_max, b->st_main);
+	b->stats.kernel_launches += 4;
+	b->stats.h2d_bytes += n_bytes;
+	// the host keeps a mirror of the ES (sequence header parse, EVICT bookkeeping): copy the new bytes back
+	CUDA_CHECK(cudaMemcpyAsync(hdst, s.d_es + s.length, (size_t)total, cudaMemcpyDeviceToHost, b->st_main));
+	CUDA_CHECK(cudaMemsetAsync(s.d_es + s.length + total, 0, ES_PAD, b->st_main));
+	CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+	b->stats.d2h_bytes += (uint64_t)total;
+	stream_did_write(b, s, (uint32_t)total);
+	s.d_valid = s.length;
+	if (n_pes) *n_pes = count;
+	if (pts_out && offset_out && count > 1) {  // the device appends PES starts unordered: sort by offset
+		const int m = std::min(count, n_max);
+		std::vector<std::pair<uint32_t, uint64_t>> v(m);
+		for (int i = 0; i < m; i++) v[i] = {offset_out[i], pts_out[i]};
+		std::sort(v.begin(), v.end());
+		for (int i = 0; i < m; i++) { offset_out[i] = v[i].first; pts_out[i] = v[i].second; }
+	}
+	return total;
 }
 
 int jsmpeg_b200_batch_read_rgba(jsmpeg_b200_batch_t *b, int stream, void *rgba) {

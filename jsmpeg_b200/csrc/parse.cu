@@ -26,6 +26,7 @@
 // tree walk (src/mpeg1.js:66-72).  Bit window: 64-bit, MSB first, refilled one prefetched 32-bit
 // word at a time.
 // Output: mb_record_t per macroblock address + dequantised int16 coefficient blocks (records.h).
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -573,9 +574,13 @@ expand_blocks_kernel(const ParseTask *__restrict__ tasks) {
 // code consumed was end_of_block.  Built once per device from the same generated DCT table.
 static const uint16_t *ms_table_for_current_device() {
 	static uint16_t *tables[64] = {};
+	static std::mutex lock;  // decoders may be driven from several host threads
+	std::lock_guard<std::mutex> guard(lock);
 	int dev = 0;
 	CUDA_CHECK(cudaGetDevice(&dev));
 	if (tables[dev]) return tables[dev];
+	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                (int)(OFF_MS + (2u << MS_BITS))));  // per device, once
 	std::vector<uint16_t> dct((VLC_DCT_MAX_Z + 1) * 32);
 	CUDA_CHECK(cudaMemcpyFromSymbol(dct.data(), VLC_DCT_COEFF, dct.size() * sizeof(uint16_t)));
 	std::vector<uint16_t> ms(1u << MS_BITS);
@@ -613,11 +618,6 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 	const uint16_t *ms = ms_table_for_current_device();
 	const int per_cta = WALK_THREADS / 32;
 	const size_t walk_smem = OFF_MS + (2u << MS_BITS);
-	static bool attr_set = false;
-	if (!attr_set) {
-		CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
-		attr_set = true;
-	}
 	// The wave arrives sorted by picture size, largest first.  Group 0 (largest pictures) stays on
 	// `stream`; the other groups go to side streams, each walk followed by its own expand.
 	const int groups = (fork && n_tasks >= 64 * PARSE_GROUPS) ? PARSE_GROUPS : 1;

@@ -285,3 +285,51 @@ def test_rgba_epilogue_matches_canvas2d_formula(name):
         n += 1
     assert n >= 6
     bd.close()
+
+
+# ---- MPEG-TS demux on the device ---------------------------------------
+
+def test_device_ts_demux_matches_host_demuxer_and_decodes_bit_exact():
+    """jsmpeg_b200_batch_write_ts against the host mirror of src/ts.js (jsmpeg_b200/ts.py): same
+    elementary stream, same PES table (offsets + PTS), and the decoded pictures equal the oracle's."""
+    import gen_streams
+    from jsmpeg_b200 import ts
+    data = gen_streams.make_clip_ts(320, 240, 24, seed=1234, noise=9)
+    packets = ts.demux_video_es(data)
+    es = b"".join(p for _, p in packets)
+    bd = BatchDecoder(2)
+    total, pes = bd.write_ts(0, data)
+    assert total == len(es)
+    # stream 1: the same clip in two pieces, the second after an ordinary write (mixed residency)
+    cut = (len(data) // 188 // 2) * 188
+    first_pes = [p for p in ts.demux_video_es(data[:cut])]
+    t1, pes1 = bd.write_ts(1, data[:cut])
+    t2, pes2 = bd.write_ts(1, data[cut:])
+    assert t1 + t2 == len(es)
+    # PES table: offsets are the running payload sizes, PTS as the host demuxer reports them
+    offsets, acc = [], 0
+    for _, p in packets:
+        offsets.append(acc)
+        acc += len(p)
+    assert [o for o, _ in pes] == offsets
+    assert all(abs(a - b) < 1e-9 for (_, a), (b, _) in zip(pes, packets))
+    assert [o for o, _ in pes1 + pes2][:len(first_pes)] == offsets[:len(first_pes)]
+    exp_frames, exp_idx, od = decode_all(oracle_lib(), packets)
+    n = 0
+    while bd.decode(1, OUT_DEVICE):
+        for s in range(2):
+            assert_frames_equal([bd.read_planes(s)], [exp_frames[n]], f"TS stream {s} picture {n}")
+        n += 1
+    assert n == len(exp_frames)
+    assert bd.get_index(0) == exp_idx[-1] == bd.get_index(1)
+    od.destroy()
+    bd.close()
+
+
+def test_device_ts_demux_rejects_unaligned_input():
+    import gen_streams
+    data = gen_streams.make_clip_ts(176, 144, 6, seed=3, noise=4)
+    bd = BatchDecoder(1)
+    with pytest.raises(ValueError):
+        bd.write_ts(0, b"\x00\x01\x02" + data)
+    bd.close()
