@@ -50,6 +50,7 @@ PICTURES = int(os.environ.get("BENCH_PICTURES", 60))
 DISTINCT = int(os.environ.get("BENCH_DISTINCT", 8))
 NOISE = 9
 E2E_GROUPS = int(os.environ.get("BENCH_E2E_GROUPS", 16))
+VALUE_GROUPS = int(os.environ.get("BENCH_VALUE_GROUPS", 1))
 
 
 def env_int(name, default):
@@ -200,9 +201,24 @@ def run_reference_cpu(clips, threads, loops):
     return sum(counts), time.perf_counter() - t0, "port"
 
 
-def cpu_sample(clips, threads):
+def truncate_pictures(es, n_pictures):
+    """The first n_pictures pictures of an elementary stream (cut at the next picture start code)."""
+    pos, count = 0, 0
+    while True:
+        pos = es.find(b"\x00\x00\x01\x00", pos)
+        if pos < 0:
+            return es
+        if count == n_pictures:
+            return es[:pos]
+        count += 1
+        pos += 4
+
+
+def cpu_sample(clips, threads, pictures=None):
     """Bounded sample for the reference timing: one clip per host thread (replicated round-robin
-    from the distinct clips)."""
+    from the distinct clips), optionally only its first `pictures` pictures."""
+    if pictures is not None:
+        clips = [truncate_pictures(c, pictures) for c in clips]
     return [clips[i % len(clips)] for i in range(threads)]
 
 
@@ -232,7 +248,8 @@ def main():
             return 0
         clips = load_streams(0, 1)
         threads = os.cpu_count() or 1
-        sample = cpu_sample(clips, threads)
+        ref_pictures = min(PICTURES, env_int("BENCH_REF_PICTURES", 30))  # bounded sample: keeps a step at ~5 s
+        sample = cpu_sample(clips, threads, ref_pictures)
         for _ in range(min(args.warmup, 1)):
             run_reference_cpu(sample[:threads], threads, 1)
         frames = 0
@@ -243,7 +260,8 @@ def main():
             frames += f
             seconds += s
         fps = frames / seconds
-        desc = f"{threads} threads x 1 clip x {PICTURES} pictures per step ({len(clips)} distinct clips)"
+        desc = (f"{threads} threads x 1 clip x first {ref_pictures} of {PICTURES} pictures per step "
+                f"({len(clips)} distinct {WIDTH}x{HEIGHT} clips, same streams as the GPU arm)")
         print(json.dumps({
             "impl": "reference", "metric": "MPEG-1 video decode frames/s", "value": fps, "unit": "frames/s",
             "gpix_per_s": fps * pix / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -265,10 +283,15 @@ def main():
 
     clips = load_streams(rank, world)
     streams = [clips[(i + rank) % len(clips)] for i in range(STREAMS_PER_GPU)]
-    bd = BatchDecoder(STREAMS_PER_GPU, device=local_rank, max_slots=STREAMS_PER_GPU * PICTURES + 8)
-    for i, es in enumerate(streams):
-        bd.write(i, es)
-    bd.upload()  # elementary streams resident in HBM before the timed region
+    # value: VALUE_GROUPS decoders share the 64 streams; with more than one, each is driven by its own
+    # host thread and the groups run free (one group's reconstruct/expand overlaps another's walk)
+    vgroups = [list(range(g, STREAMS_PER_GPU, VALUE_GROUPS)) for g in range(VALUE_GROUPS)]
+    value_decoders = [BatchDecoder(len(g), device=local_rank, max_slots=len(g) * PICTURES + 8) for g in vgroups]
+    for dec, g in zip(value_decoders, vgroups):
+        for j, i in enumerate(g):
+            dec.write(j, streams[i])
+        dec.upload()  # elementary streams resident in HBM before the timed region
+    bd = value_decoders[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -334,9 +357,24 @@ def main():
         return frames, dt, st, clocks
 
     def run_device(n_steps):
-        return sum(step_device() for _ in range(n_steps))
+        if VALUE_GROUPS == 1:
+            return sum(step_device() for _ in range(n_steps))
+        counts = [0] * VALUE_GROUPS
 
-    frames, dt, st, clocks = timed(run_device, args.steps, args.warmup, [bd])
+        def work(k):
+            dec = value_decoders[k]
+            for _ in range(n_steps):
+                dec.rewind()
+                counts[k] += dec.decode(PICTURES, OUT_DEVICE)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(VALUE_GROUPS)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        return sum(counts)
+
+    frames, dt, st, clocks = timed(run_device, args.steps, args.warmup, value_decoders)
     e_steps = args.steps
     e_frames, e_dt, e_st, e_clocks = timed(run_e2e, e_steps, 3, e2e_decoders)
 
@@ -364,7 +402,7 @@ def main():
                 "d2h_bytes_per_step": e_st["d2h_bytes"] // e_steps,
                 "ms_per_step": 1e3 * e_dt / e_steps, "steps": e_steps, "warmup": 3,
                 "host_threads": E2E_GROUPS, "clocks": e_clocks},
-        "gpu_launches": st["kernel_launches"],
+        "gpu_launches": st["kernel_launches"], "value_host_threads": VALUE_GROUPS,
         "roofline": {
             "kernel": "reconstruct_kernel (stage 2: IDCT + motion compensation + add/clamp)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -384,7 +422,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         sample = cpu_sample(clips, threads)
-        loops = 2
+        loops = 1
         f, s, kind = run_reference_cpu(sample, threads, loops)
         out["cpu_baseline"] = {"value": f / s, "unit": "frames/s", "gpix_per_s": f / s * pix / 1e9, "cores": threads,
                                "kind": kind,

@@ -91,8 +91,8 @@ struct BitReader {
 	uint64_t win;    // left-aligned window
 	int nbits;       // valid bits in win, >= 32 between calls
 
-	// (A branch-free variant that relies on the zero pad after the data was measured 17 % slower on
-	// the 3840-picture wave; the bounds check below is predicated and cheap.)
+	// (Measured and rejected on the 3840-picture wave: a branch-free variant relying on the zero pad
+	// after the data, 17 % slower; a software prefetch 256 B ahead at every refill, 7 % slower.)
 	__device__ __forceinline__ uint32_t load_word(uint32_t w) const {
 		const uint32_t byte = w * 4u;
 		if (byte >= len) return 0u;
