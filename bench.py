@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="value leg only (used for the ncu launch list)")
     args = ap.parse_args()
 
     rank = env_int("RANK", 0)
@@ -376,7 +377,10 @@ def main():
 
     frames, dt, st, clocks = timed(run_device, args.steps, args.warmup, value_decoders)
     e_steps = args.steps
-    e_frames, e_dt, e_st, e_clocks = timed(run_e2e, e_steps, 3, e2e_decoders)
+    if args.no_e2e:
+        e_frames, e_dt, e_st, e_clocks = 0, 1.0, {"h2d_bytes": 0, "d2h_bytes": 0}, None
+    else:
+        e_frames, e_dt, e_st, e_clocks = timed(run_e2e, e_steps, 3, e2e_decoders)
 
     if rank != 0:
         if world > 1:
