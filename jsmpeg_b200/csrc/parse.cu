@@ -73,15 +73,6 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 __device__ __forceinline__ void sts_s16(uint32_t addr, int v) {
 	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
 }
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
-	uint4 v;
-	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-	return v;
-}
-__device__ __forceinline__ void sts_v4_zero(uint32_t addr) {
-	asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0) : "memory");
-}
-
 // MSB-first bit window over a byte span (src/buffer.js:152-187); one copy per thread.
 struct BitReader {
 	const uint32_t *words;

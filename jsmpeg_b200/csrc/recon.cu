@@ -19,9 +19,12 @@
 //     one plane row ([luma top | luma bottom | Cb | Cr] per macroblock row): every row of the
 //     output is one 8-byte store per lane = 256 contiguous bytes per warp, and the forward-plane
 //     fetches of neighbouring lanes (similar vectors) fall into the same sectors;
-//   * prediction: 9 (+9) samples per row as three aligned 32-bit words + funnel shifts,
-//     packed-byte half-pel averaging (exact (a+b+1)>>1 / (a+b+c+d+2)>>2, mpeg1.js:481-556),
-//     + residual, saturate, store.
+//   * prediction: 9 (+9) samples per row as three aligned 32-bit words + funnel shifts; per
+//     output sample one PRMT gathers the four taps and one dp4a applies the lane's half-pel tap
+//     weights (exact (a+b+1)>>1 / (a+b+c+d+2)>>2, mpeg1.js:481-556, for every parity with the
+//     same instruction stream); + residual, saturate (cvt.pack.sat), store.
+//   * the kernel is bound by the integer ALU pipe, so multiplies/byte selects go to the dot-product
+//     unit where possible: dp2a for coefficient x premultiplier, dp4a for the taps.
 // Blocks taking the reference's DC-only shortcut (mpeg1.js:838-841, 850-853) skip the IDCT.
 // The per-launch task table (pointers + sizes per stream) travels in the kernel parameters
 // (constant bank), so the first global access of a thread is already its macroblock header.
@@ -104,14 +107,6 @@ __device__ __forceinline__ void idct_rows(int (&v)[64]) {
 	}
 }
 
-// (a + b + c + d + 2) >> 2 per byte, exact (mpeg1.js:481-500)
-__device__ __forceinline__ uint32_t avg4_u8x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-	const uint32_t M = 0x00ff00ffu;
-	const uint32_t lo = (a & M) + (b & M) + (c & M) + (d & M) + 0x00020002u;
-	const uint32_t hi = ((a >> 8) & M) + ((b >> 8) & M) + ((c >> 8) & M) + ((d >> 8) & M) + 0x00020002u;
-	return ((lo >> 2) & M) | (((hi >> 2) & M) << 8);
-}
-
 __device__ __forceinline__ uint32_t pack_sat_u8x4(int a, int b, int c, int d) {
 	// PTX: d[7:0] = sat(b_op), d[15:8] = sat(a_op), d[31:16] = c_op[15:0]
 	uint32_t hi, r;
@@ -137,38 +132,59 @@ __device__ __forceinline__ void row9(const uint8_t *__restrict__ plane, int i, u
 	c = w2 >> sh;
 }
 
+// dp4a with unsigned bytes in `a` and signed bytes in `b`: sum_i a.b[i] * b.b[i] + c (integer dot
+// product unit, off the ALU pipe that bounds this kernel)
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+	int d;
+	asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+
 // Prediction of the 8 rows of one block + residual.  The four half-pel cases of the reference
 // (copy, (a+b+1)>>1 horizontally or vertically, (a+b+c+d+2)>>2; src/mpeg1.js:481-556) are ONE
-// formula when the unused taps are replaced by duplicates of the used ones:
-//     (A + B' + C' + D' + 2) >> 2   with  B' = oh ? B : A,  C' = ov ? C : A,  D' = ov ? (oh ? D : C) : B'
-// ((4A+2)>>2 = A, (2A+2B+2)>>2 = (A+B+1)>>1).  The lanes of a warp hold blocks of different
-// macroblocks, i.e. different parities: one branch-free path keeps them converged.
-// FULLPEL (warp-uniform: no lane has a half-pel component) is the plain copy.
+// formula with per-thread tap weights:
+//     (wA*A + wB*B + wC*C + wD*D + 2) >> 2,   (wA,wB,wC,wD) = (4,0,0,0) | (2,2,0,0) | (2,0,2,0) | (1,1,1,1)
+// ((4A+2)>>2 = A, (2A+2B+2)>>2 = (A+B+1)>>1).  Per output sample: one PRMT gathers the four taps
+// into a word, one dp4a applies the weights (accumulator preloaded with the rounding 2).
+// The lanes of a warp hold blocks of different macroblocks, i.e. different parities: the weights
+// are data, the instruction stream is the same for every lane.
+// FULLPEL (warp-uniform: no lane has a half-pel component) is the plain copy: one dp4a per sample
+// selects the byte and adds the residual.
 template <bool FULLPEL>
-__device__ __forceinline__ void predict_rows(const uint8_t *__restrict__ splane, int src, int stride, bool oh, bool ov,
+__device__ __forceinline__ void predict_rows(const uint8_t *__restrict__ splane, int src, int stride, uint32_t weights,
                                              bool coded, const int (&v)[64], uint8_t *__restrict__ dst) {
 	uint32_t a0, a1, a2;
 	row9(splane, src, a0, a1, a2);
 #pragma unroll
 	for (int r = 0; r < 8; r++) {
-		uint32_t p0, p1, c0 = 0, c1 = 0, c2 = 0;
+		uint32_t c0 = 0, c1 = 0, c2 = 0;
+		int s[8];
 		if (FULLPEL) {
-			p0 = a0; p1 = a1;
 			if (r < 7) row9(splane, src + (r + 1) * stride, c0, c1, c2);
+#pragma unroll
+			for (int x = 0; x < 4; x++) {
+				s[x] = dp4a_us(a0, 1u << (8 * x), coded ? v[r * 8 + x] : 0);
+				s[4 + x] = dp4a_us(a1, 1u << (8 * x), coded ? v[r * 8 + 4 + x] : 0);
+			}
 		} else {
 			row9(splane, src + (r + 1) * stride, c0, c1, c2);  // row 8 is inside the plane (checked by the caller)
-			const uint32_t b0 = oh ? __funnelshift_r(a0, a1, 8) : a0, b1 = oh ? __funnelshift_r(a1, a2, 8) : a1;
-			const uint32_t d0 = oh ? __funnelshift_r(c0, c1, 8) : c0, d1 = oh ? __funnelshift_r(c1, c2, 8) : c1;
-			p0 = avg4_u8x4(a0, b0, ov ? c0 : a0, ov ? d0 : b0);
-			p1 = avg4_u8x4(a1, b1, ov ? c1 : a1, ov ? d1 : b1);
+			const uint32_t sa0 = __funnelshift_r(a0, a1, 8), sa1 = __funnelshift_r(a1, a2, 8);  // samples 1..4, 5..8
+			const uint32_t sc0 = __funnelshift_r(c0, c1, 8), sc1 = __funnelshift_r(c1, c2, 8);
+			// taps (A, B, C, D) = (row[x], row[x+1], next[x], next[x+1]) as one word per sample
+			s[0] = dp4a_us(__byte_perm(a0, c0, 0x5410), weights, 2);
+			s[1] = dp4a_us(__byte_perm(a0, c0, 0x6521), weights, 2);
+			s[2] = dp4a_us(__byte_perm(a0, c0, 0x7632), weights, 2);
+			s[3] = dp4a_us(__byte_perm(sa0, sc0, 0x7632), weights, 2);
+			s[4] = dp4a_us(__byte_perm(a1, c1, 0x5410), weights, 2);
+			s[5] = dp4a_us(__byte_perm(a1, c1, 0x6521), weights, 2);
+			s[6] = dp4a_us(__byte_perm(a1, c1, 0x7632), weights, 2);
+			s[7] = dp4a_us(__byte_perm(sa1, sc1, 0x7632), weights, 2);
+#pragma unroll
+			for (int x = 0; x < 8; x++) s[x] = (s[x] >> 2) + (coded ? v[r * 8 + x] : 0);
 		}
 		uint2 out;
-		if (coded) {
-			out.x = add_sat4(p0, v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
-			out.y = add_sat4(p1, v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
-		} else {
-			out.x = p0; out.y = p1;
-		}
+		out.x = pack_sat_u8x4(s[0], s[1], s[2], s[3]);
+		out.y = pack_sat_u8x4(s[4], s[5], s[6], s[7]);
 		*reinterpret_cast<uint2 *>(dst + r * stride) = out;
 		a0 = c0; a1 = c1; a2 = c2;
 	}
@@ -263,10 +279,11 @@ reconstruct_kernel(const __grid_constant__ ReconParams params) {
 		for (int i = 0; i < 8; i++) {
 			uint4 q;
 			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(my_row + i * 16));
-			v[i * 8 + 0] = (int)(int16_t)(q.x & 0xffffu) * PM[i * 8 + 0]; v[i * 8 + 1] = ((int)q.x >> 16) * PM[i * 8 + 1];
-			v[i * 8 + 2] = (int)(int16_t)(q.y & 0xffffu) * PM[i * 8 + 2]; v[i * 8 + 3] = ((int)q.y >> 16) * PM[i * 8 + 3];
-			v[i * 8 + 4] = (int)(int16_t)(q.z & 0xffffu) * PM[i * 8 + 4]; v[i * 8 + 5] = ((int)q.z >> 16) * PM[i * 8 + 5];
-			v[i * 8 + 6] = (int)(int16_t)(q.w & 0xffffu) * PM[i * 8 + 6]; v[i * 8 + 7] = ((int)q.w >> 16) * PM[i * 8 + 7];
+			// dp2a: (lo16 * b0 + hi16 * b1): one instruction per coefficient, no unpacking on the ALU pipe
+			v[i * 8 + 0] = __dp2a_lo((int)q.x, PM[i * 8 + 0], 0); v[i * 8 + 1] = __dp2a_lo((int)q.x, PM[i * 8 + 1] << 8, 0);
+			v[i * 8 + 2] = __dp2a_lo((int)q.y, PM[i * 8 + 2], 0); v[i * 8 + 3] = __dp2a_lo((int)q.y, PM[i * 8 + 3] << 8, 0);
+			v[i * 8 + 4] = __dp2a_lo((int)q.z, PM[i * 8 + 4], 0); v[i * 8 + 5] = __dp2a_lo((int)q.z, PM[i * 8 + 5] << 8, 0);
+			v[i * 8 + 6] = __dp2a_lo((int)q.w, PM[i * 8 + 6], 0); v[i * 8 + 7] = __dp2a_lo((int)q.w, PM[i * 8 + 7] << 8, 0);
 		}
 		idct_columns<0>(v);
 		idct_rows<0>(v);
@@ -293,8 +310,10 @@ reconstruct_kernel(const __grid_constant__ ReconParams params) {
 	const int src = origin + (mv >> 1) * stride + (mh >> 1);  // flat index (mpeg1.js:479, 567)
 	const uint8_t *splane = t.fwd + plane_off;
 	if (src >= 0 && src + 8 * stride + 8 < plane_size) {
-		if (warp_halfpel) predict_rows<false>(splane, src, stride, oh, ov, coded, v, dst);
-		else predict_rows<true>(splane, src, stride, false, false, coded, v, dst);
+		// tap weights of this lane: bytes (wA, wB, wC, wD)
+		const uint32_t weights = oh ? (ov ? 0x01010101u : 0x00000202u) : (ov ? 0x00020002u : 0x00000004u);
+		if (warp_halfpel) predict_rows<false>(splane, src, stride, weights, coded, v, dst);
+		else predict_rows<true>(splane, src, stride, weights, coded, v, dst);
 		return;
 	}
 	// vector leaves the plane: per-tap bounds check, any outside tap zeroes the sample
