@@ -44,7 +44,8 @@ for p in (ROOT, os.path.join(ROOT, "tools")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-WIDTH, HEIGHT = 1920, 1080
+WIDTH = int(os.environ.get("BENCH_WIDTH", 1920))    # the env overrides exist for the CPU smoke test of this file
+HEIGHT = int(os.environ.get("BENCH_HEIGHT", 1080))
 STREAMS_PER_GPU = int(os.environ.get("BENCH_STREAMS", 64))
 PICTURES = int(os.environ.get("BENCH_PICTURES", 60))
 DISTINCT = int(os.environ.get("BENCH_DISTINCT", 8))
