@@ -333,3 +333,31 @@ def test_device_ts_demux_rejects_unaligned_input():
     with pytest.raises(ValueError):
         bd.write_ts(0, b"\x00\x01\x02" + data)
     bd.close()
+
+
+# ---- robustness: garbage in must be memory-safe and must terminate -------------
+
+@pytest.mark.parametrize("seed", range(4))
+def test_corrupted_streams_terminate_and_stay_in_bounds(seed):
+    """Random byte corruption after the sequence header.  The reference gives no defined output for
+    such streams (undefined table reads), so only the contract is checked:
+    decode() keeps returning (no hang, no fault), one call per picture start code at most, and a
+    following clean stream on the same GPU still decodes bit-exactly."""
+    rng = np.random.default_rng(100 + seed)
+    es = bytearray(golden.load_case(["ffmpeg_176x144_ip", "rows_ip", "fcodes_fullpel", "skips_stuffing_escape_mba"][seed])[0])
+    n_flip = max(8, len(es) // 200)
+    for pos in rng.integers(64, len(es), n_flip):
+        es[pos] = int(rng.integers(0, 256))
+    if seed == 1:
+        es = es[:len(es) // 2]  # and a truncated tail
+    es = bytes(es)
+    starts = es.count(b"\x00\x00\x01\x00")
+    bd = BatchDecoder(1)
+    bd.write(0, es)
+    calls = 0
+    while bd.decode(1, OUT_HOST):
+        calls += 1
+        assert calls <= starts + 1
+    assert bd.get_index(0) <= len(es) * 8
+    bd.close()
+    golden.check_against_golden(capi.product_library(), "rows_ip")
