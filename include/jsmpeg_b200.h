@@ -33,8 +33,9 @@ typedef enum {
 	BIT_BUFFER_MODE_EXPAND = 2
 } bit_buffer_mode_t;
 
-/* mpeg1.h:12 / mpeg1.c:777-782.  Never fails (aborts on a CUDA error).  Uses the CUDA device
- * named by the environment variable JSMPEG_B200_DEVICE (default 0). */
+/* mpeg1.h:12 / mpeg1.c:777-782.  Never fails (aborts on a CUDA error).  Uses the CUDA device set
+ * with jsmpeg_b200_set_default_device, else the one named by the environment variable
+ * JSMPEG_B200_DEVICE, else device 0. */
 mpeg1_decoder_t *mpeg1_decoder_create(unsigned int buffer_size, bit_buffer_mode_t buffer_mode);
 /* mpeg1.h:13 / mpeg1.c:784-798 */
 void mpeg1_decoder_destroy(mpeg1_decoder_t *self);
@@ -156,6 +157,10 @@ int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t
 int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, const void *coef,
                                   const uint8_t *fwd_y, const uint8_t *fwd_cr, const uint8_t *fwd_cb,
                                   uint8_t *cur_y, uint8_t *cur_cr, uint8_t *cur_cb);
+
+/* CUDA device for decoders created through the reference ABI from now on (the reference ABI has no
+ * device argument; the JS/Python class passes its `device` option here). */
+void jsmpeg_b200_set_default_device(int device);
 
 const char *jsmpeg_b200_version(void);
 

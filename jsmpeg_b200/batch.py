@@ -53,6 +53,7 @@ _BATCH_ABI = {
     "jsmpeg_b200_debug_parse_picture": (ctypes.c_int, [_VP, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                                        _VP, _VP, _VP, _VP, _VP]),
     "jsmpeg_b200_debug_reconstruct": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "jsmpeg_b200_set_default_device": (None, [ctypes.c_int]),
     "jsmpeg_b200_version": (ctypes.c_char_p, []),
 }
 

@@ -838,13 +838,16 @@ struct mpeg1_decoder_t {
 	jsmpeg_b200_batch_t *b;
 };
 
+static int g_default_device = -1;  // -1: JSMPEG_B200_DEVICE or 0
+void jsmpeg_b200_set_default_device(int device) { g_default_device = device; }
+
 mpeg1_decoder_t *mpeg1_decoder_create(unsigned int buffer_size, bit_buffer_mode_t buffer_mode) {
 	const char *dev = getenv("JSMPEG_B200_DEVICE");
 	const char *slots = getenv("JSMPEG_B200_LOOKAHEAD");
 	int lookahead = slots ? atoi(slots) : 16;
 	if (lookahead < 1) lookahead = 1;
 	mpeg1_decoder_t *d = new mpeg1_decoder_t();
-	d->b = jsmpeg_b200_batch_create(1, dev ? atoi(dev) : 0, (unsigned)lookahead + 1);
+	d->b = jsmpeg_b200_batch_create(1, g_default_device >= 0 ? g_default_device : (dev ? atoi(dev) : 0), (unsigned)lookahead + 1);
 	d->b->lookahead = lookahead;
 	Stream &s = d->b->streams[0];
 	s.mode = buffer_mode;

@@ -4,6 +4,7 @@
 (reference src/decoder.js:3-106, src/mpeg1.js:6-64, src/mpeg1-wasm.js:1-132):
 
     ctor(options)  keys: videoBufferSize, streaming, decodeFirstFrame, onVideoDecode
+                   (+ our extension `device`: CUDA device index)
     connect(destination) / destroy()
     bufferGetIndex() / bufferSetIndex(i) / bufferWrite(buffers)
     write(pts, buffers) / seek(time) / decode() -> bool
@@ -52,6 +53,8 @@ class MPEG1Video:
         self.height = 0
         self.currentY = self.currentCr = self.currentCb = None
         self.functions = lib if lib is not None else capi.product_library()
+        if options.get("device") is not None and hasattr(self.functions, "jsmpeg_b200_set_default_device"):
+            self.functions.jsmpeg_b200_set_default_device(int(options["device"]))
         self.decoder = self.functions.mpeg1_decoder_create(self.bufferSize, self.bufferMode)
 
     # ---- src/decoder.js:19-35 / src/mpeg1-wasm.js:32-50
