@@ -57,7 +57,7 @@ void launch_scan_start_codes(const uint8_t *es, uint32_t from, uint32_t len, uin
                              uint32_t capacity, uint32_t *count, cudaStream_t stream);
 // Helper streams/events with which stage 1 forks the (size-sorted) wave into groups: the expand of
 // a group of small pictures runs while the walk of the bigger pictures is still going.
-constexpr int PARSE_GROUPS = 4;
+constexpr int PARSE_GROUPS = 8;
 struct ParseFork {
 	cudaStream_t side[PARSE_GROUPS];
 	cudaEvent_t fork, join[PARSE_GROUPS];
