@@ -611,7 +611,14 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 	const size_t walk_smem = OFF_MS + (2u << MS_BITS);
 	// The wave arrives sorted by picture size, largest first.  Group 0 (largest pictures) stays on
 	// `stream`; the other groups go to side streams, each walk followed by its own expand.
-	const int groups = (fork && n_tasks >= 64 * PARSE_GROUPS) ? PARSE_GROUPS : 1;
+	// JSMPEG_B200_PARSE_GROUPS=1 keeps stage 1 on one stream (used for the ncu launch list: ncu
+	// serialises concurrent kernels, so only the unforked run has comparable shares)
+	static const int max_groups = [] {
+		const char *e = getenv("JSMPEG_B200_PARSE_GROUPS");
+		const int g = e ? atoi(e) : PARSE_GROUPS;
+		return g < 1 ? 1 : (g > PARSE_GROUPS ? PARSE_GROUPS : g);
+	}();
+	const int groups = (fork && n_tasks >= 64 * max_groups) ? max_groups : 1;
 	if (groups > 1) CUDA_CHECK(cudaEventRecord(fork->fork, stream));
 	for (int g = 0; g < groups; g++) {
 		// equal groups; measured on the 3840-picture wave: unforked 59.8 ms, 4 groups 52.4, 8 groups 50.5,
