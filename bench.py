@@ -275,6 +275,9 @@ def main():
         }))
         return 0
 
+    # NCCL is used for the barrier / counter reduction only; keep its banner off stdout (one JSON line)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     if world > 1:
