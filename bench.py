@@ -268,7 +268,7 @@ def main():
             "impl": "reference", "metric": "MPEG-1 video decode frames/s", "value": fps, "unit": "frames/s",
             "gpix_per_s": fps * pix / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * seconds / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": base_config,
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": base_config,
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": desc},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -402,7 +402,7 @@ def main():
         "gpix_per_s": fps * pix / 1e9,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": base_config,
         "clocks": clocks,
         "e2e": {"value": e_fps, "unit": "frames/s", "gpix_per_s": e_fps * pix / 1e9,
