@@ -1,0 +1,890 @@
+// walk.cuh -- stage 1a, the walk of one picture's bitstream (sm_100a device code).
+//
+// Included by parse.cu (the kernels, the tables' upload and the launcher live there).  The same text
+// compiles for the host when JSMPEG_WALK_EMU is defined and the including file supplies the few CUDA
+// intrinsics it uses (tests/emu/walk_emu.cpp runs a "warp" as 32 host threads): that is how the
+// lane-parallel walk is checked against the serial one on machines without a GPU.  Nothing in the
+// product library is built that way.
+#pragma once
+#include "common.cuh"
+
+#ifndef VLC_TABLE_QUALIFIER
+#define VLC_TABLE_QUALIFIER static __device__ const
+#endif
+#include "vlc_tables.h"
+
+namespace {
+
+#ifndef JSMPEG_MS_BITS
+#define JSMPEG_MS_BITS 13
+#endif
+#ifndef JSMPEG_WALK_THREADS
+#define JSMPEG_WALK_THREADS 256
+#endif
+constexpr int WALK_THREADS = JSMPEG_WALK_THREADS;  // walk kernel: the pictures of a CTA share one multi-symbol table
+constexpr int MS_BITS = JSMPEG_MS_BITS;            // multi-symbol table is indexed by the next MS_BITS bits (2 << MS_BITS bytes)
+constexpr uint32_t OFF_MS = 4096;      // uint16[1 << MS_BITS], after the per-symbol tables
+
+// shared-memory layout (byte offsets from the dynamic shared base)
+constexpr uint32_t OFF_DCT = 0;                                        // uint16[384]
+constexpr uint32_t OFF_MBA = OFF_DCT + (VLC_DCT_MAX_Z + 1) * 64;       // uint16[256]
+constexpr uint32_t OFF_CBP = OFF_MBA + (VLC_MBA_MAX_Z + 1) * 64;       // uint16[256]
+constexpr uint32_t OFF_MOTION = OFF_CBP + (VLC_CBP_MAX_Z + 1) * 64;    // uint16[224]
+constexpr uint32_t OFF_DC_LUMA = OFF_MOTION + (VLC_MOTION_MAX_Z + 1) * 64;  // uint16[128]
+constexpr uint32_t OFF_DC_CHROMA = OFF_DC_LUMA + 256;                  // uint16[256]
+constexpr uint32_t OFF_TYPE_I = OFF_DC_CHROMA + 512;                   // uint16[4]
+constexpr uint32_t OFF_TYPE_P = OFF_TYPE_I + 8;                        // uint16[64]
+constexpr uint32_t OFF_ZIGZAG = OFF_TYPE_P + 128;                      // uint8[64]
+constexpr uint32_t OFF_BLOCKS = (OFF_ZIGZAG + 64 + 127) & ~127u;       // int16[64] per group
+
+#ifndef JSMPEG_WALK_EMU
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+	uint16_t v;
+	asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+	uint32_t v;
+	asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void sts_s16(uint32_t addr, int v) {
+	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+#else
+// host emulation (tests only): `emu_smem` stands in for the CTA's shared memory, addresses are offsets into it
+static uint8_t emu_smem[OFF_MS + (2u << MS_BITS)];
+static inline uint32_t lds_u16(uint32_t addr) { uint16_t v; memcpy(&v, emu_smem + addr, 2); return v; }
+static inline uint32_t lds_u8(uint32_t addr) { return emu_smem[addr]; }
+#endif
+// MSB-first bit window over a byte span (src/buffer.js:152-187); one copy per thread.
+struct BitReader {
+	const uint32_t *words;
+	const uint8_t *bytes;
+	uint32_t len;    // valid bytes; everything past it reads as zero (JS typed-array semantics)
+	uint32_t wpos;   // index of the word held in `nextw` (the next one to enter the window)
+	uint32_t nextw;  // prefetched
+	uint64_t win;    // left-aligned window
+	int nbits;       // valid bits in win, >= 32 between calls
+
+	// (Measured and rejected on the 3840-picture wave: a branch-free variant relying on the zero pad
+	// after the data, 17 % slower; a software prefetch 256 B ahead at every refill, 7 % slower.)
+	__device__ __forceinline__ uint32_t load_word(uint32_t w) const {
+		const uint32_t byte = w * 4u;
+		if (byte >= len) return 0u;
+		uint32_t v = __byte_perm(__ldg(words + w), 0, 0x0123);  // first byte -> MSB
+		const uint32_t left = len - byte;
+		if (left < 4u) v &= 0xffffffffu << (8u * (4u - left));
+		return v;
+	}
+	__device__ __forceinline__ void seek_byte(uint32_t byte_pos) {
+		const uint32_t w = byte_pos >> 2;
+		win = ((uint64_t)load_word(w) << 32) | load_word(w + 1);
+		wpos = w + 2;
+		nextw = load_word(wpos);
+		nbits = 64;
+		const int drop = (int)(byte_pos & 3u) * 8;
+		if (drop) consume(drop);
+	}
+	__device__ __forceinline__ void seek_bit(uint32_t bit_pos) {
+		seek_byte(bit_pos >> 3);
+		if (bit_pos & 7u) consume((int)(bit_pos & 7u));
+	}
+	__device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(win >> 32); }
+	__device__ __forceinline__ void consume(int n) {  // 0 <= n <= 32
+		win <<= n;
+		nbits -= n;
+		if (nbits < 32) {
+			win |= (uint64_t)nextw << (32 - nbits);
+			nbits += 32;
+			wpos++;
+			nextw = load_word(wpos);
+		}
+	}
+	__device__ __forceinline__ uint32_t read(int n) {  // 1 <= n <= 32
+		const uint32_t v = peek32() >> (32 - n);
+		consume(n);
+		return v;
+	}
+	__device__ __forceinline__ uint32_t bitpos() const { return wpos * 32u - (uint32_t)nbits; }
+
+	// src/buffer.js:141-150 nextBytesAreStartCode
+	__device__ __forceinline__ bool next_bytes_are_start_code() const {
+		const uint32_t bp = bitpos();
+		const uint32_t i = (bp + 7u) >> 3;
+		if (i >= len) return true;
+		const int skip = (int)((8u - (bp & 7u)) & 7u);
+		// bytes past `len` are zero in the window, so a code straddling the end cannot match
+		return (uint32_t)((win << skip) >> 40) == 0x000001u && i + 2u < len;
+	}
+	// src/buffer.js:115-128 findNextStartCode.  Returns the code (reader left just after it) or -1
+	// (reader parked at the end of the data).  A start code needs its 4 bytes inside the buffer.
+	__device__ int find_next_start_code() {
+		uint32_t i = (bitpos() + 7u) >> 3;
+		for (; i + 3u < len; i++) {
+			if (bytes[i + 2] > 1) { i += 2; continue; }  // 00 00 01 cannot end at i+2, i+3 or i+4
+			if (bytes[i] == 0 && bytes[i + 1] == 0 && bytes[i + 2] == 1) {
+				const int code = bytes[i + 3];
+				seek_byte(i + 4u);
+				return code;
+			}
+		}
+		seek_byte(len);
+		return -1;
+	}
+};
+
+
+struct PictureState {
+	int picture_type, full_pel, r_size, f;
+	int qscale, mb_addr;
+	bool slice_begin;
+	int mv_h, mv_v, mv_h_prev, mv_v_prev;
+	int dc_y, dc_b4, dc_b5;  // block 4 / block 5 predictors (the reference's "Cr"/"Cb", mpeg1.js:717)
+	int n_present, n_coded, error;
+	// lane-parallel walk only: which parts of a RELATIVE state no longer depend on the state the lane
+	// started from, and whether a case outside the lane-parallel walk's domain was met
+	bool qs_set, dc_abs, mv_abs, anomaly;
+	int sync_rounds;  // rounds of pass B over all slices (diagnostic, info.reserved[1])
+};
+
+#ifndef JSMPEG_WALK_EMU
+// The shared-window address of the dynamic shared memory, made opaque so that the compiler keeps
+// it in a register instead of re-deriving it (S2R + LEA) at every table access.
+__device__ __forceinline__ uint32_t smem_base(const void *p) {
+	uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+	asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+	return r;
+}
+#else
+static inline uint32_t smem_base(const void *) { return 0; }
+#endif
+
+__device__ __forceinline__ uint32_t clz_lut(uint32_t table_addr, uint32_t w, int max_z) {
+	const int z = __clz((int)w);
+	if (z > max_z) return 0;
+	return lds_u16(table_addr + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+}
+
+// ==================================================================================================
+// 1a: the serial walk
+
+// walk-table entry derived from the DCT table: bits 0..4 = bits to consume (code + sign),
+// bits 5..10 = run + 1, bits 11..12 = 1 end_of_block / 2 escape; 0 = invalid code.
+__device__ __forceinline__ uint16_t walk_entry(uint16_t e) {
+	const int len = e & 31, run = (e >> 5) & 31, level = e >> 10;
+	if (len == 0) return 0;
+	if (level == 0) return run ? (uint16_t)(2 | (1 << 11)) : (uint16_t)(6 | (2 << 11));
+	return (uint16_t)((len + 1) | ((run + 1) << 5));
+}
+
+// One coded block (bitstream side of src/mpeg1.js:698-811): intra DC with its predictor, then only
+// code lengths.  Leaves {bit offset of the first coefficient code, dc * 8} in the block's slot.
+__device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
+                                           uint32_t *__restrict__ slot, bool store, bool &dc_only) {
+	int n = 0;
+	int dc8 = 0;
+	if (intra) {
+		// DC size VLC + differential + predictor (mpeg1.js:705-751)
+		const uint32_t w = br.peek32();
+		const uint32_t e = block < 4 ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
+		                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
+		const int len = e & 31, size = e >> 5;
+		if (len == 0) return false;
+		br.consume(len);
+		int *pred = block < 4 ? &ps.dc_y : (block == 4 ? &ps.dc_b4 : &ps.dc_b5);
+		int dc = *pred;
+		if (size > 0) {
+			const int diff = (int)br.read(size);
+			dc += (diff & (1 << (size - 1))) ? diff : (int)((0xffffffffu << size) | (uint32_t)(diff + 1));
+		}
+		*pred = dc;
+		dc8 = max(-32768, min(32767, dc * 8));  // x PREMULTIPLIER[0] = dc << 8 in stage 2 (mpeg1.js:747)
+		n = 1;
+	}
+	if (store) *reinterpret_cast<uint2 *>(slot) = make_uint2(br.bitpos(), (uint32_t)dc8 & 0xffffu);
+	if (!intra && (br.peek32() >> 31)) {  // dct_coeff_first: a leading '1' is (0, +-1), never end_of_block
+		br.consume(2);
+		n = 1;
+	}
+	for (;;) {
+		const uint32_t w = br.peek32();
+		// (Resolving '10' / '11s' arithmetically before the look-up was measured 8 % SLOWER: it defeats the
+		// combining of several codes per look-up.)
+		// as many complete codes as fit in the next 13 bits, in one look-up
+		const uint32_t m = lds_u16(sbase + OFF_MS + (w >> (32 - MS_BITS)) * 2u);
+		if (m & 15u) {
+			n += (int)((m >> 4) & 63u);
+			br.consume((int)(m & 15u));
+			if (m & 0x400u) break;  // the last code consumed was end_of_block
+			continue;
+		}
+		// long code or escape: one symbol through the clz-indexed table
+		const int z = __clz((int)w);
+		if (z > VLC_DCT_MAX_Z) return false;
+		const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+		if (e >> 11) {
+			// escape (mpeg1.js:767-780): 6-bit code, 6-bit run, 8 (+8) bit level.  (end_of_block is
+			// two bits and always resolved by the multi-symbol table.)
+			n += (int)((w >> 20) & 63u) + 1;
+			br.consume((w & 0x0007f000u) ? 20 : 28);  // level byte 0 or 128 -> a second byte follows
+			continue;
+		}
+		if (e == 0) return false;  // hole in the code space
+		n += (int)(e >> 5);
+		br.consume((int)(e & 31u));
+	}
+	if (n > 64) ps.error = PARSE_ERR_COEF_INDEX;  // some run pushed the index past 63 (stores dropped, like JS)
+	dc_only = (n == 1);  // mpeg1.js:838, 850
+	ps.n_coded++;
+	return true;
+}
+
+// mpeg1.js:395-457, one component
+__device__ __forceinline__ bool parse_motion(BitReader &br, uint32_t sbase, const PictureState &ps, int &prev, int &mv) {
+	const uint32_t e = clz_lut(sbase + OFF_MOTION, br.peek32(), VLC_MOTION_MAX_Z);
+	const int len = e & 31;
+	if (len == 0) return false;
+	br.consume(len);
+	const int code = (int)(e >> 5) - 16;
+	int d = code;
+	if (code != 0 && ps.f != 1) {
+		const int r = (int)br.read(ps.r_size);
+		d = ((abs(code) - 1) << ps.r_size) + r + 1;
+		if (code < 0) d = -d;
+	}
+	prev += d;
+	if (prev > (ps.f << 4) - 1) prev -= ps.f << 5;
+	else if (prev < -(ps.f << 4)) prev += ps.f << 5;
+	mv = ps.full_pel ? prev * 2 : prev;
+	return true;
+}
+
+__device__ __forceinline__ int read_mba(BitReader &br, uint32_t sbase) {
+	const uint32_t e = clz_lut(sbase + OFF_MBA, br.peek32(), VLC_MBA_MAX_Z);
+	const int len = e & 31;
+	if (len == 0) return -1;
+	br.consume(len);
+	return (int)(e >> 5);
+}
+
+__device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int cbp, int dc_only, int qscale, uint32_t bit_pos) {
+	uint4 r;
+	r.x = ((uint32_t)mv_h & 0xffffu) | ((uint32_t)mv_v << 16);
+	r.y = (uint32_t)flags | ((uint32_t)cbp << 8) | ((uint32_t)dc_only << 16) | ((uint32_t)qscale << 24);
+	r.z = bit_pos;
+	r.w = 0;
+	return r;
+}
+
+// How a macroblock is walked:
+//   WALK_SERIAL  the whole warp walks the same macroblock redundantly, lane 0 stores (one warp = one chain)
+//   WALK_REL     one lane walks it, nothing is stored and no address is checked: the state is RELATIVE to the
+//                unknown state at the lane's first macroblock (summary pass of the lane-parallel walk)
+//   WALK_ABS     one lane walks it with the true state and stores; cases the lane-parallel walk leaves to
+//                the serial walk set ps.anomaly
+enum { WALK_SERIAL = 0, WALK_REL = 1, WALK_ABS = 2 };
+
+// mpeg1.js:294-392 decodeMacroblock.  false = stop walking this slice.
+template <int MODE>
+__device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
+	int increment = 0;
+	int v = read_mba(br, sbase);
+	while (v == 34) v = read_mba(br, sbase);                       // macroblock_stuffing
+	while (v == 35) { increment += 33; v = read_mba(br, sbase); }  // macroblock_escape
+	if (v < 0) return false;
+	increment += v;
+
+	if (ps.slice_begin) {  // mpeg1.js:312-317
+		ps.slice_begin = false;
+		ps.mb_addr += increment;
+	} else {
+		if (MODE == WALK_SERIAL && ps.mb_addr + increment >= mb_size) return true;  // mpeg1.js:319-322
+		if (MODE == WALK_ABS && ps.mb_addr + increment >= mb_size) { ps.anomaly = true; return false; }
+		if (increment > 1) {  // mpeg1.js:323-334
+			ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;
+			if (MODE == WALK_REL) ps.dc_abs = true;
+			if (ps.picture_type == 2) {
+				ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;
+				if (MODE == WALK_REL) ps.mv_abs = true;
+			}
+			// skipped macroblocks: predicted copy with the current vector (mpeg1.js:336-346)
+			const int n_skip = increment - 1;
+			const uint4 rec = pack_record(ps.mv_h, ps.mv_v, MBF_PRESENT | MBF_SKIPPED, 0, 0, ps.qscale, br.bitpos());
+			if (MODE == WALK_SERIAL)
+				for (int k = lane; k < n_skip; k += 32) reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
+			if (MODE == WALK_ABS)
+				for (int k = 0; k < n_skip; k++) reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
+			ps.n_present += n_skip;
+			ps.mb_addr += n_skip;
+		}
+		ps.mb_addr++;
+	}
+	const int mb = ps.mb_addr;
+	if (MODE != WALK_REL && (mb < 0 || mb >= mb_size)) {  // outside the picture: never write there
+		if (MODE == WALK_ABS) ps.anomaly = true;
+		return false;
+	}
+
+	const uint32_t w = br.peek32();
+	const uint32_t e = ps.picture_type == 1 ? lds_u16(sbase + OFF_TYPE_I + (w >> 30) * 2u)
+	                                        : lds_u16(sbase + OFF_TYPE_P + (w >> 26) * 2u);
+	if ((e & 31) == 0) return false;
+	br.consume(e & 31);
+	const int type = e >> 5;
+	const bool intra = type & 0x01;
+	if (type & 0x10) {
+		ps.qscale = (int)br.read(5);
+		if (MODE == WALK_REL) ps.qs_set = true;
+	}
+	const uint32_t mb_bit_pos = br.bitpos();
+
+	if (intra) {
+		ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:363-367
+		if (MODE == WALK_REL) ps.mv_abs = true;
+	} else {
+		ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;                  // mpeg1.js:370-372
+		if (MODE == WALK_REL) ps.dc_abs = true;
+		if (type & 0x08) {
+			if (!parse_motion(br, sbase, ps, ps.mv_h_prev, ps.mv_h)) return false;
+			if (!parse_motion(br, sbase, ps, ps.mv_v_prev, ps.mv_v)) return false;
+		} else if (ps.picture_type == 2) {
+			ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:452-456
+			if (MODE == WALK_REL) ps.mv_abs = true;
+		}
+	}
+
+	int cbp = intra ? 0x3f : 0;
+	if (type & 0x02) {
+		const uint32_t ce = clz_lut(sbase + OFF_CBP, br.peek32(), VLC_CBP_MAX_Z);
+		if ((ce & 31) == 0) return false;
+		br.consume(ce & 31);
+		cbp = ce >> 5;
+	}
+
+	const int mv_h = ps.mv_h, mv_v = ps.mv_v, qscale = ps.qscale;
+	uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)(MODE == WALK_REL ? 0 : mb) * (MB_COEF_INT16 / 2);
+	const bool store = MODE == WALK_ABS || (MODE == WALK_SERIAL && lane == 0);
+	int done = 0, dc_mask = 0;
+	bool ok = true;
+#pragma unroll 1
+	for (int block = 0; block < 6; block++) {
+		if (cbp & (0x20 >> block)) {
+			bool dc_only;
+			ok = walk_block(br, sbase, ps, intra, block, coef_mb + block * 32, store, dc_only);
+			if (!ok) break;
+			done |= 0x20 >> block;
+			if (dc_only) dc_mask |= 0x20 >> block;
+		}
+	}
+	if (store)
+		reinterpret_cast<uint4 *>(t.hdr)[mb] =
+		    pack_record(mv_h, mv_v, MBF_PRESENT | (intra ? MBF_INTRA : 0), done, dc_mask, qscale, mb_bit_pos);
+	ps.n_present++;
+	return ok;
+}
+
+// ==================================================================================================
+// 1a, lane-parallel: 32 lanes walk 32 sub-sequences of ONE slice
+//
+// The serial walk spends 31 of 32 lanes re-executing lane 0's chain.  Here the bits of a slice are cut
+// into up to 32 equal sub-sequences, one per lane, and the chain is recovered by self-synchronisation
+// (the property of variable-length codes that a decoder started at a wrong position or in a wrong
+// syntax state falls into step with the true one after a while; Klein & Wiseman 2003, and
+// Weissenberger & Schmidt 2018/2021 for Huffman/JPEG on GPUs):
+//
+//   A  every lane > 0 starts at the first bit of its sub-sequence in a GUESSED syntax state and runs a
+//      syntax-only automaton (code lengths and the state machine of mpeg1.js:294-392/698-790, no
+//      values) to the first code boundary at or beyond the end of its sub-sequence; lane 0 starts in
+//      the true state.  The (bit position, syntax state) reached is the sub-sequence's exit state.
+//   B  every lane keeps going through the NEXT sub-sequence and compares the exit state it reaches
+//      with the one the owner of that sub-sequence found.  Equal: the two chains have merged, the lane
+//      stops.  Different: it replaces the stored exit state and goes on to the following sub-sequence.
+//      Lane 0 carries the truth, so when all lanes have stopped every stored exit state is the true
+//      chain's (normally after ONE round: sub-sequences are thousands of bits long, chains merge
+//      within a few macroblocks).
+//   C  every lane starts from the true entry state of its sub-sequence, finds the first macroblock
+//      that STARTS in it and walks the macroblocks starting in it with full semantics but RELATIVE
+//      predictors (WALK_REL) -- a summary: address advance, last quantiser scale, DC and motion
+//      predictors as "absolute after a reset" or "delta".  A warp scan of the summaries (an
+//      associative composition) gives every lane the absolute state at its first macroblock.
+//   D  every lane walks its macroblocks again with the absolute state and stores (WALK_ABS).
+//
+// Anything outside the clean domain -- an invalid code on the true chain, an address outside the
+// picture, a slice that does not end exactly at the next start code -- makes the warp discard the
+// attempt and walk the whole picture with the serial code, which defines the behaviour there.
+
+enum { PH_MBA = 0, PH_MBA_STUFF, PH_MBA_ESC, PH_TYPE, PH_MV_H, PH_MV_V, PH_CBP, PH_DC, PH_AC_FIRST, PH_AC, PH_END, PH_ERR };
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr uint32_t MIN_SUBSEQ_BITS = 2048;  // below this a sub-sequence is too short for chains to merge in it
+
+struct SliceConst {
+	int picture_type, r_size, f;
+	uint32_t end_byte;  // byte index of the start code prefix that ends the slice (or the end of the data)
+};
+
+// syntax state: phase | blocks still to come (mask, current block = highest bit) << 4 | macroblock type bits << 10
+__device__ __forceinline__ uint32_t syn_make(int phase, uint32_t rem, uint32_t type) { return (uint32_t)phase | rem << 4 | type << 10; }
+__device__ __forceinline__ uint32_t syn_blocks(uint32_t rem, uint32_t type) {
+	if (rem == 0) return PH_MBA;
+	return syn_make((type & 1u) ? PH_DC : PH_AC_FIRST, rem, type & 1u);
+}
+__device__ __forceinline__ uint32_t syn_after_mv(uint32_t type) {
+	if (type & 2u) return syn_make(PH_CBP, 0, type & 3u);
+	return syn_blocks((type & 1u) ? 0x3fu : 0u, type);
+}
+__device__ __forceinline__ uint32_t syn_block_end(uint32_t st) {
+	uint32_t rem = (st >> 4) & 63u;
+	rem &= ~(0x80000000u >> __clz((int)rem));  // a block is being walked, so rem != 0
+	return syn_blocks(rem, st >> 10);
+}
+
+// The state a chain assumes where it knows nothing: inside the coefficients of the last block of a
+// macroblock.  After the next end_of_block it tries a macroblock header; a true end_of_block is a
+// true macroblock start often enough.
+__device__ __forceinline__ uint32_t syn_guess(const SliceConst &sc) { return syn_make(PH_AC, 1u, sc.picture_type == 1 ? 1u : 0u); }
+
+// Runs the syntax-only automaton from the reader's position in state `st` until the first code
+// boundary at or beyond bit `limit` (or END; or, if asked, the first macroblock start).
+// An invalid code does not stop a chain: it drops one bit and guesses again (a chain that dies can
+// never merge, and every sub-sequence behind a dead lane costs the lanes before it a round).  If it
+// is the TRUE chain that meets an invalid code, pass C/D meet it too, with full semantics, and the
+// picture goes to the serial walk.
+// Several coefficient codes are taken per look-up only while that cannot jump over `limit`, so that
+// the boundary reached depends on the chain alone, not on where a lane joined it.
+__device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, uint32_t limit, uint32_t &st, bool stop_at_mb_start) {
+	for (;;) {
+		const int ph = (int)(st & 15u);
+		if (ph >= PH_END) return;
+		if (stop_at_mb_start && ph == PH_MBA) return;
+		const uint32_t pos = br.bitpos();
+		if (pos >= limit) return;
+		const uint32_t w = br.peek32();
+		if (ph == PH_AC) {
+			if (pos + MS_BITS <= limit) {
+				const uint32_t m = lds_u16(sbase + OFF_MS + (w >> (32 - MS_BITS)) * 2u);
+				if (m & 15u) {
+					br.consume((int)(m & 15u));
+					if (m & 0x400u) st = syn_block_end(st);
+					continue;
+				}
+			}
+			const int z = __clz((int)w);
+			if (z > VLC_DCT_MAX_Z) { br.consume(1); st = syn_guess(sc); continue; }
+			const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+			if (e >> 11) {
+				if ((e >> 11) == 1u) {  // end_of_block
+					br.consume(2);
+					st = syn_block_end(st);
+				} else {
+					br.consume((w & 0x0007f000u) ? 20 : 28);  // escape (mpeg1.js:767-780)
+				}
+				continue;
+			}
+			if (e == 0) { br.consume(1); st = syn_guess(sc); continue; }
+			br.consume((int)(e & 31u));
+			continue;
+		}
+		switch (ph) {
+		case PH_MBA:  // mpeg1.js:276 (nextBytesAreStartCode after every macroblock), then :295-310
+			if (((pos + 7u) >> 3) >= sc.end_byte) { st = PH_END; return; }
+			// fall through
+		case PH_MBA_STUFF:
+		case PH_MBA_ESC: {
+			const uint32_t e = clz_lut(sbase + OFF_MBA, w, VLC_MBA_MAX_Z);
+			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
+			br.consume((int)(e & 31u));
+			const uint32_t v = e >> 5;
+			if (v == 35u) st = PH_MBA_ESC;
+			else if (v == 34u && ph != PH_MBA_ESC) st = PH_MBA_STUFF;  // after an escape, 34 is an increment (mpeg1.js:297-306)
+			else st = PH_TYPE;
+			break;
+		}
+		case PH_TYPE: {
+			const uint32_t e = sc.picture_type == 1 ? lds_u16(sbase + OFF_TYPE_I + (w >> 30) * 2u)
+			                                        : lds_u16(sbase + OFF_TYPE_P + (w >> 26) * 2u);
+			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
+			const uint32_t type = e >> 5;
+			br.consume((int)(e & 31u) + ((type & 0x10u) ? 5 : 0));
+			if (!(type & 1u) && (type & 8u)) st = syn_make(PH_MV_H, 0, type & 3u);
+			else st = syn_after_mv(type);
+			break;
+		}
+		case PH_MV_H:
+		case PH_MV_V: {
+			const uint32_t e = clz_lut(sbase + OFF_MOTION, w, VLC_MOTION_MAX_Z);
+			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
+			const int code = (int)(e >> 5) - 16;
+			br.consume((int)(e & 31u) + ((code != 0 && sc.f != 1) ? sc.r_size : 0));
+			st = ph == PH_MV_H ? syn_make(PH_MV_V, 0, st >> 10) : syn_after_mv(st >> 10);
+			break;
+		}
+		case PH_CBP: {
+			const uint32_t e = clz_lut(sbase + OFF_CBP, w, VLC_CBP_MAX_Z);
+			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
+			br.consume((int)(e & 31u));
+			st = syn_blocks(e >> 5, st >> 10);
+			break;
+		}
+		case PH_DC: {
+			const uint32_t rem = (st >> 4) & 63u;  // blocks 0..3 are the mask bits 0x20..0x04
+			const uint32_t e = rem >= 4u ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
+			                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
+			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
+			br.consume((int)(e & 31u) + (int)(e >> 5));
+			st = (st & ~15u) | PH_AC;
+			break;
+		}
+		default:  // PH_AC_FIRST: a leading '1' is (0, +-1), never end_of_block (mpeg1.js:757-760)
+			if (w >> 31) br.consume(2);
+			st = (st & ~15u) | PH_AC;
+			break;
+		}
+	}
+}
+
+// What the macroblocks a lane owns do to the slice state, relative to the state they start from.
+struct LaneSum {
+	int d_addr, qs, dcy, dc4, dc5, mvh, mvv;
+	uint32_t flags;  // 1 quantiser scale set, 2 DC predictors absolute, 4 motion predictors absolute
+};
+__device__ __forceinline__ int wrap_mv(int v, int f) {  // mpeg1.js:413-419: arithmetic modulo 32 f in [-16 f, 16 f)
+	if (v > (f << 4) - 1) v -= f << 5;
+	else if (v < -(f << 4)) v += f << 5;
+	return v;
+}
+__device__ __forceinline__ LaneSum compose(const LaneSum &a, const LaneSum &b, int f) {  // a, then b (associative)
+	LaneSum r;
+	r.d_addr = a.d_addr + b.d_addr;
+	r.qs = (b.flags & 1u) ? b.qs : a.qs;
+	const bool dabs = b.flags & 2u, mabs = b.flags & 4u;
+	r.dcy = dabs ? b.dcy : a.dcy + b.dcy;
+	r.dc4 = dabs ? b.dc4 : a.dc4 + b.dc4;
+	r.dc5 = dabs ? b.dc5 : a.dc5 + b.dc5;
+	r.mvh = mabs ? b.mvh : wrap_mv(a.mvh + b.mvh, f);
+	r.mvv = mabs ? b.mvv : wrap_mv(a.mvv + b.mvv, f);
+	r.flags = a.flags | b.flags;
+	return r;
+}
+__device__ __forceinline__ LaneSum shfl_up_sum(const LaneSum &s, int d) {
+	LaneSum r;
+	r.d_addr = __shfl_up_sync(FULL_MASK, s.d_addr, d);
+	r.qs = __shfl_up_sync(FULL_MASK, s.qs, d);
+	r.dcy = __shfl_up_sync(FULL_MASK, s.dcy, d);
+	r.dc4 = __shfl_up_sync(FULL_MASK, s.dc4, d);
+	r.dc5 = __shfl_up_sync(FULL_MASK, s.dc5, d);
+	r.mvh = __shfl_up_sync(FULL_MASK, s.mvh, d);
+	r.mvv = __shfl_up_sync(FULL_MASK, s.mvv, d);
+	r.flags = __shfl_up_sync(FULL_MASK, s.flags, d);
+	return r;
+}
+
+// The byte index of the first start code prefix (00 00 01) at or after `from`, or len: where
+// nextBytesAreStartCode (buffer.js:141-150) first becomes true.  The warp scans 128 bytes per step.
+__device__ uint32_t find_slice_end(const BitReader &br, uint32_t from, int lane) {
+	const uint32_t len = br.len;
+	for (uint32_t base = from >> 2; base * 4u < len; base += 32u) {
+		const uint32_t wi = base + (uint32_t)lane;
+		const uint64_t x = ((uint64_t)br.load_word(wi) << 32) | br.load_word(wi + 1u);  // bytes 4 wi .. 4 wi + 7
+		uint32_t hit = 0xffffffffu;
+#pragma unroll
+		for (int k = 3; k >= 0; k--) {
+			const uint32_t p = wi * 4u + (uint32_t)k;
+			if (((uint32_t)(x >> (40 - 8 * k)) & 0xffffffu) == 1u && p >= from && p + 2u < len) hit = p;
+		}
+		const unsigned any = __ballot_sync(FULL_MASK, hit != 0xffffffffu);
+		if (any) return __shfl_sync(FULL_MASK, hit, __ffs((int)any) - 1);
+	}
+	return len;
+}
+
+// The macroblocks that START in [reader position, limit), walked in MODE.  Returns 0 when the lane
+// reached `limit`, 1 when the slice ended cleanly at the start code, 2 on anything else.
+template <int MODE>
+__device__ __forceinline__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const ParseTask &t, int mb_size,
+                                          uint32_t limit, uint32_t end_byte, int lane) {
+	for (;;) {
+		if (!walk_macroblock<MODE>(br, sbase, ls, t, mb_size, lane)) return 2;
+		const uint32_t pos = br.bitpos();
+		const uint32_t i = (pos + 7u) >> 3;
+		if (i >= end_byte) return i == end_byte ? 1 : 2;
+		if (pos >= limit) return 0;
+	}
+}
+
+// One slice: the reader is at its first macroblock (bit p_start), `ps` holds the picture constants and
+// the slice's initial state (mb_addr, qscale).  true: records stored, ps totals updated, reader at the
+// start code prefix that ended the slice.  false: outside the clean domain, nothing is to be trusted.
+__device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
+	const uint32_t p_start = br.bitpos();
+	const uint32_t end_byte = find_slice_end(br, (p_start + 7u) >> 3, lane);
+	if (((p_start + 7u) >> 3) >= end_byte) return false;
+	const uint32_t end_bit = end_byte * 8u;
+	const uint32_t total = end_bit - p_start;
+	uint32_t L = (total + 31u) >> 5;
+	if (L < MIN_SUBSEQ_BITS) L = MIN_SUBSEQ_BITS;
+	const int K = (int)((total + L - 1u) / L);  // 1..32 sub-sequences
+	const bool active = lane < K;
+	const uint32_t s_lo = active ? p_start + (uint32_t)lane * L : end_bit;
+	const uint32_t s_hi = (active && lane < K - 1) ? s_lo + L : end_bit;
+	SliceConst sc;
+	sc.picture_type = ps.picture_type; sc.r_size = ps.r_size; sc.f = ps.f; sc.end_byte = end_byte;
+
+	// ---- A: own sub-sequence, from a guessed state (lane 0: the true one)
+	uint32_t my_pos = end_bit, my_st = PH_END;
+	if (active) {
+		br.seek_bit(s_lo);
+		my_st = lane == 0 ? (uint32_t)PH_MBA : syn_guess(sc);
+		syntax_run(br, sbase, sc, s_hi, my_st, false);
+		my_pos = br.bitpos();
+	}
+	uint32_t e_pos = my_pos, e_st = my_st;  // exit state of sub-sequence `lane`, as known so far
+
+	// ---- B: run on into the following sub-sequences until the chains have merged
+	bool merged = !active || lane >= K - 1 || (my_st & 15u) >= PH_END;
+	for (int round = 0; round < K - 1; round++) {
+		if (!__any_sync(FULL_MASK, !merged)) break;
+		ps.sync_rounds++;
+		const int idx = lane + 1 + round;  // the sub-sequence this lane walks in this round
+		if (idx >= K) merged = true;
+		const bool arrive = !merged;
+		if (arrive) {
+			const uint32_t lim = idx < K - 1 ? p_start + (uint32_t)(idx + 1) * L : end_bit;
+			syntax_run(br, sbase, sc, lim, my_st, false);
+			my_pos = br.bitpos();
+		}
+		__syncwarp();
+		const int src = lane - 1 - round;  // the lane that arrives at the end of sub-sequence `lane` in this round
+		const uint32_t v_pos = __shfl_sync(FULL_MASK, my_pos, src & 31), v_st = __shfl_sync(FULL_MASK, my_st, src & 31);
+		const int v_arrive = __shfl_sync(FULL_MASK, (int)arrive, src & 31);
+		int same = 0;
+		if (src >= 0 && v_arrive) {
+			same = v_pos == e_pos && v_st == e_st;
+			e_pos = v_pos;
+			e_st = v_st;
+		}
+		const int got = __shfl_sync(FULL_MASK, same, idx & 31);
+		if (arrive && (got || (my_st & 15u) >= PH_END)) merged = true;  // a dead chain stops: it must not overwrite further exit states
+	}
+
+	// ---- C: first macroblock starting in the sub-sequence, then the relative summary of the owned macroblocks
+	uint32_t in_pos = __shfl_up_sync(FULL_MASK, e_pos, 1), in_st = __shfl_up_sync(FULL_MASK, e_st, 1);
+	if (lane == 0) { in_pos = p_start; in_st = PH_MBA; }
+	bool bad = false, owns = false;
+	uint32_t q = 0;
+	if (active) {
+		if ((in_st & 15u) == PH_ERR) bad = true;
+		else if ((in_st & 15u) != PH_END) {
+			br.seek_bit(in_pos);
+			uint32_t st = in_st;
+			syntax_run(br, sbase, sc, s_hi, st, true);
+			q = br.bitpos();
+			if ((st & 15u) == PH_ERR) bad = true;
+			else if ((st & 15u) == PH_MBA && q < s_hi && ((q + 7u) >> 3) < end_byte) owns = true;
+		}
+	}
+	PictureState ls = ps;  // picture constants; the rest is set per pass
+	LaneSum sum;
+	sum.d_addr = 0; sum.qs = 0; sum.dcy = sum.dc4 = sum.dc5 = 0; sum.mvh = sum.mvv = 0; sum.flags = 0;
+	int how = 0;
+	if (owns) {
+		ls.mb_addr = 0; ls.qscale = 0; ls.slice_begin = lane == 0;
+		ls.mv_h = ls.mv_v = ls.mv_h_prev = ls.mv_v_prev = 0;
+		ls.dc_y = ls.dc_b4 = ls.dc_b5 = 0;
+		ls.qs_set = ls.dc_abs = ls.mv_abs = ls.anomaly = false;
+		ls.n_present = ls.n_coded = ls.error = 0;
+		how = walk_owned<WALK_REL>(br, sbase, ls, t, mb_size, s_hi, end_byte, lane);
+		if (how == 2) bad = true;
+		sum.d_addr = ls.mb_addr; sum.qs = ls.qscale;
+		sum.dcy = ls.dc_y; sum.dc4 = ls.dc_b4; sum.dc5 = ls.dc_b5;
+		sum.mvh = ls.mv_h_prev; sum.mvv = ls.mv_v_prev;
+		sum.flags = (ls.qs_set ? 1u : 0u) | (ls.dc_abs ? 2u : 0u) | (ls.mv_abs ? 4u : 0u);
+	}
+	__syncwarp();
+	if (__any_sync(FULL_MASK, bad)) return false;
+	const unsigned enders = __ballot_sync(FULL_MASK, how == 1);
+	if (__popc(enders) != 1) return false;  // exactly one lane sees the slice end at its start code
+
+	// inclusive scan of the summaries, then the absolute state at each lane's first macroblock
+	for (int d = 1; d < 32; d <<= 1) {
+		const LaneSum o = shfl_up_sum(sum, d);
+		if (lane >= d) sum = compose(o, sum, ps.f);
+	}
+	LaneSum x0;
+	x0.d_addr = ps.mb_addr; x0.qs = ps.qscale; x0.dcy = x0.dc4 = x0.dc5 = 128; x0.mvh = x0.mvv = 0; x0.flags = 7u;
+	const LaneSum before = shfl_up_sum(sum, 1);
+	const LaneSum x = lane == 0 ? x0 : compose(x0, before, ps.f);
+
+	// ---- D: the owned macroblocks again, absolute, storing
+	ls.n_present = ls.n_coded = ls.error = 0;
+	ls.anomaly = false;
+	if (owns) {
+		br.seek_bit(q);
+		ls.mb_addr = x.d_addr; ls.qscale = x.qs; ls.slice_begin = lane == 0;
+		ls.dc_y = x.dcy; ls.dc_b4 = x.dc4; ls.dc_b5 = x.dc5;
+		ls.mv_h_prev = x.mvh; ls.mv_v_prev = x.mvv;
+		ls.mv_h = ps.full_pel ? x.mvh * 2 : x.mvh;
+		ls.mv_v = ps.full_pel ? x.mvv * 2 : x.mvv;
+		const int how_abs = walk_owned<WALK_ABS>(br, sbase, ls, t, mb_size, s_hi, end_byte, lane);
+		if (how_abs != how) bad = true;
+	}
+	__syncwarp();
+	if (__any_sync(FULL_MASK, bad)) return false;
+	int n_present = ls.n_present, n_coded = ls.n_coded, error = ls.error;
+	for (int d = 16; d > 0; d >>= 1) {
+		n_present += __shfl_xor_sync(FULL_MASK, n_present, d);
+		n_coded += __shfl_xor_sync(FULL_MASK, n_coded, d);
+		error = max(error, __shfl_xor_sync(FULL_MASK, error, d));
+	}
+	ps.n_present += n_present;
+	ps.n_coded += n_coded;
+	if (error) ps.error = error;
+	br.seek_byte(end_byte);
+	return true;
+}
+
+// ==================================================================================================
+// one picture = one warp
+
+// the shared-memory tables of the walk; `ms_table` is the device's multi-symbol table (build_ms_table)
+__device__ __forceinline__ void walk_tables_init(uint8_t *smem, int tid, int nthreads, const uint4 *__restrict__ ms_table) {
+	uint16_t *s16 = reinterpret_cast<uint16_t *>(smem);
+	for (int i = tid; i < (VLC_DCT_MAX_Z + 1) * 32; i += nthreads) s16[OFF_DCT / 2 + i] = walk_entry(VLC_DCT_COEFF[i]);
+	for (int i = tid; i < (VLC_MBA_MAX_Z + 1) * 32; i += nthreads) s16[OFF_MBA / 2 + i] = VLC_MBA[i];
+	for (int i = tid; i < (VLC_CBP_MAX_Z + 1) * 32; i += nthreads) s16[OFF_CBP / 2 + i] = VLC_CBP[i];
+	for (int i = tid; i < (VLC_MOTION_MAX_Z + 1) * 32; i += nthreads) s16[OFF_MOTION / 2 + i] = VLC_MOTION[i];
+	for (int i = tid; i < 128; i += nthreads) s16[OFF_DC_LUMA / 2 + i] = VLC_DC_SIZE_LUMA[i];
+	for (int i = tid; i < 256; i += nthreads) s16[OFF_DC_CHROMA / 2 + i] = VLC_DC_SIZE_CHROMA[i];
+	for (int i = tid; i < 4; i += nthreads) s16[OFF_TYPE_I / 2 + i] = VLC_MBTYPE_I[i];
+	for (int i = tid; i < 64; i += nthreads) s16[OFF_TYPE_P / 2 + i] = VLC_MBTYPE_P[i];
+	uint4 *ms = reinterpret_cast<uint4 *>(smem + OFF_MS);
+	for (int i = tid; i < (2 << MS_BITS) / 16; i += nthreads) ms[i] = __ldg(ms_table + i);
+}
+
+// decodePicture (mpeg1.js:174-247), bitstream side.  LANES: every slice is first tried with the
+// lane-parallel walk; the first slice outside its domain makes the warp start the picture over with
+// the serial walk (info.reserved[0] tells which one produced the records).
+template <bool LANES>
+__device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
+	const int mb_width = t.seq->mb_width, mb_size = t.seq->mb_size;
+	bool lanes = LANES;
+	for (;;) {
+		// no macroblock is present until the walk reaches it (an address no slice covers keeps the
+		// two-pictures-old samples)
+		for (int i = lane; i < mb_size; i += 32) reinterpret_cast<uint4 *>(t.hdr)[i] = make_uint4(0, 0, 0, 0);
+		__syncwarp();
+
+		BitReader br;
+		br.words = reinterpret_cast<const uint32_t *>(t.es);
+		br.bytes = t.es;
+		br.len = t.es_len;
+		br.seek_byte(t.start_byte);
+
+		PictureState ps;
+		ps.n_present = ps.n_coded = ps.error = 0;
+		ps.full_pel = 0; ps.r_size = 0; ps.f = 1;
+		ps.qs_set = ps.dc_abs = ps.mv_abs = ps.anomaly = false;
+		ps.sync_rounds = 0;
+		int f_code = 0;
+		int status = PIC_IGNORED;
+
+		// picture header (mpeg1.js:174-196)
+		br.consume(10);
+		ps.picture_type = (int)br.read(3);
+		br.consume(16);
+		bool go = ps.picture_type == 1 || ps.picture_type == 2;
+		if (ps.picture_type == 2) {
+			ps.full_pel = (int)br.read(1);
+			f_code = (int)br.read(3);
+			if (f_code == 0) go = false;
+			else { ps.r_size = f_code - 1; ps.f = 1 << ps.r_size; }
+		}
+		uint32_t end_bit;
+		bool again = false;
+		if (!go) {
+			end_bit = br.bitpos();
+		} else {
+			status = PIC_DECODED;
+			int code;
+			do { code = br.find_next_start_code(); } while (code == 0xB5 || code == 0xB2);  // mpeg1.js:198-201
+			while (code >= 0x01 && code <= 0xAF) {
+				// slice (mpeg1.js:255-276)
+				ps.slice_begin = true;
+				ps.mb_addr = (code - 1) * mb_width - 1;
+				ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;
+				ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;
+				ps.qscale = (int)br.read(5);
+				while (br.read(1)) br.consume(8);
+				if (LANES && lanes) {
+					if (!walk_slice_lanes(br, sbase, ps, t, mb_size, lane)) {
+						again = true;
+						break;
+					}
+				} else {
+					do {
+						if (!walk_macroblock<WALK_SERIAL>(br, sbase, ps, t, mb_size, lane)) {
+							if (!ps.error) ps.error = PARSE_ERR_INVALID_VLC;
+							break;
+						}
+					} while (!br.next_bytes_are_start_code());
+				}
+				code = br.find_next_start_code();
+			}
+			end_bit = br.bitpos();
+			if (code != -1) end_bit -= 32;  // mpeg1.js:209-213
+		}
+		if (LANES && again) {
+			lanes = false;
+			__syncwarp();
+			continue;
+		}
+		if (lane == 0) {
+			picture_info_t info;
+			info.start_byte = t.start_byte;
+			info.end_bit = end_bit;
+			info.status = status;
+			info.picture_type = ps.picture_type;
+			info.full_pel = ps.full_pel;
+			info.f_code = f_code;
+			info.n_present = ps.n_present;
+			info.n_coded_blocks = ps.n_coded;
+			info.error = ps.error;
+			info.reserved[0] = (LANES && lanes && go) ? 1 : 0;
+			info.reserved[1] = (LANES && lanes) ? ps.sync_rounds : 0;
+			info.reserved[2] = 0;
+			*t.info = info;
+		}
+		return;
+	}
+}
+
+// Multi-symbol walk table: for every MS_BITS-bit prefix, the complete dct_coeff_next codes (with their
+// sign bits) that fit, greedily.  Entry: bits 0..3 = bits to consume (0 = first code does not fit
+// or is an escape: take the single-symbol path), bits 4..9 = sum of (run + 1), bit 10 = the last
+// code consumed was end_of_block.  `dct` is the generated clz-indexed DCT table (VLC_DCT_COEFF).
+static inline void build_ms_table(const uint16_t *dct, uint16_t *ms) {
+	for (uint32_t prefix = 0; prefix < (1u << MS_BITS); prefix++) {
+		const uint32_t w = prefix << (32 - MS_BITS);
+		int pos = 0, n = 0, eob = 0;
+		for (;;) {
+			const uint32_t v = w << pos;  // bits beyond the prefix read as 0 and are never trusted: lengths are checked
+			int z = 0;
+			while (z < 32 && !((v << z) & 0x80000000u)) z++;
+			if (z > VLC_DCT_MAX_Z) break;
+			const uint16_t e = dct[(z << 5) | ((z + 1 < 32 ? (v << (z + 1)) : 0u) >> 27)];
+			const int len = e & 31, run = (e >> 5) & 31, level = e >> 10;
+			if (len == 0) break;
+			if (level == 0) {
+				if (run == 1 && pos + 2 <= MS_BITS) { pos += 2; eob = 1; }
+				break;  // escape: single-symbol path
+			}
+			if (pos + len + 1 > MS_BITS) break;
+			pos += len + 1;
+			n += run + 1;
+		}
+		ms[prefix] = (uint16_t)(pos | (n << 4) | (eob << 10));
+	}
+}
+
+}  // namespace

@@ -1,0 +1,107 @@
+// walk_emu.cpp -- TEST INFRASTRUCTURE, not part of the product library.
+//
+// Compiles jsmpeg_b200/csrc/walk.cuh (the stage-1a walk, device code) for the HOST and runs one "warp"
+// as 32 host threads: the warp collectives become barrier + exchange, shared memory becomes a static
+// array.  tests/test_walk_emu.py uses it to check, on machines without a GPU, that the lane-parallel
+// walk produces exactly the records of the serial walk (the GPU parity tests then check both against
+// the oracle).  Build: g++ -O2 -std=c++17 -shared -fPIC -pthread -I/usr/local/cuda/include.
+#define JSMPEG_WALK_EMU 1
+#include <string.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>  // vector types only
+
+using std::max;
+using std::min;
+
+// ---- a reusable barrier for the 32 "lanes"
+namespace emu {
+struct Barrier {
+	std::mutex m;
+	std::condition_variable cv;
+	int waiting = 0, generation = 0;
+	void wait() {
+		std::unique_lock<std::mutex> lk(m);
+		const int gen = generation;
+		if (++waiting == 32) {
+			waiting = 0;
+			generation++;
+			cv.notify_all();
+		} else {
+			cv.wait(lk, [&] { return gen != generation; });
+		}
+	}
+};
+static Barrier bar;
+static uint64_t slots[32];
+static thread_local int lane;
+
+template <class T>
+static T exchange(T v, int src) {
+	uint64_t raw = 0;
+	memcpy(&raw, &v, sizeof(T));
+	slots[lane] = raw;
+	bar.wait();
+	T r;
+	memcpy(&r, &slots[src & 31], sizeof(T));
+	bar.wait();
+	return r;
+}
+}  // namespace emu
+
+// ---- the CUDA intrinsics walk.cuh uses
+static inline void __syncwarp() { emu::bar.wait(); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu::exchange(v, src); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu::exchange(v, emu::lane - d >= 0 ? emu::lane - d : emu::lane); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::exchange(v, emu::lane ^ m); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+	emu::slots[emu::lane] = pred ? 1 : 0;
+	emu::bar.wait();
+	unsigned r = 0;
+	for (int l = 0; l < 32; l++) r |= (unsigned)emu::slots[l] << l;
+	emu::bar.wait();
+	return r;
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline uint32_t __byte_perm(uint32_t a, uint32_t, uint32_t sel) {
+	if (sel != 0x0123) abort();  // the only selector the walk uses: byte swap
+	return __builtin_bswap32(a);
+}
+template <class T> static inline T __ldg(const T *p) { return *p; }
+
+#define VLC_TABLE_QUALIFIER static const
+#include "../../jsmpeg_b200/csrc/walk.cuh"
+
+extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t start_byte, int mb_width, int mb_height,
+                                mb_record_t *hdr, int16_t *coef, picture_info_t *info, int lanes) {
+	static std::once_flag once;
+	static std::vector<uint16_t> ms(1u << MS_BITS);
+	std::call_once(once, [] {
+		build_ms_table(VLC_DCT_COEFF, ms.data());
+		walk_tables_init(emu_smem, 0, 1, reinterpret_cast<const uint4 *>(ms.data()));
+	});
+	SeqParams seq;
+	memset(&seq, 0, sizeof(seq));
+	seq.mb_width = mb_width;
+	seq.mb_height = mb_height;
+	seq.mb_size = mb_width * mb_height;
+	ParseTask t;
+	t.es = es; t.es_len = es_len; t.start_byte = start_byte; t.seq = &seq; t.hdr = hdr; t.coef = coef; t.info = info;
+	std::vector<std::thread> warp;
+	for (int l = 0; l < 32; l++)
+		warp.emplace_back([&, l] {
+			emu::lane = l;
+			if (lanes) walk_picture<true>(t, 0, l);
+			else walk_picture<false>(t, 0, l);
+		});
+	for (auto &th : warp) th.join();
+	return 0;
+}

@@ -1,0 +1,114 @@
+"""Lane-parallel walk == serial walk, record for record, WITHOUT a GPU.
+
+tests/emu/walk_emu.cpp compiles the device code of jsmpeg_b200/csrc/walk.cuh for the host and runs a
+warp as 32 threads.  The serial walk is the one the GPU parity tests pin to the oracle; here every
+picture of the golden streams, of the syntax-level generator's cases and of encoder-made clips is
+walked both ways and the outputs must be identical: macroblock records, the parked
+{bit offset, dc} of every coded block, and the picture info (end_bit, counts, error).
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers  # noqa: F401  (adds tools/ to sys.path)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_SRC = os.path.join(HERE, "emu", "walk_emu.cpp")
+EMU_LIB = os.path.join(HERE, "emu", "libwalk_emu.so")
+CSRC = os.path.join(HERE, "..", "jsmpeg_b200", "csrc")
+
+
+def emu_lib():
+    deps = [EMU_SRC] + [os.path.join(CSRC, f) for f in ("walk.cuh", "common.cuh", "records.h", "vlc_tables.h")]
+    if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-attributes",
+                               "-Wno-unknown-pragmas", "-I/usr/local/cuda/include", "-o", EMU_LIB, EMU_SRC])
+    lib = ctypes.CDLL(EMU_LIB)
+    lib.emu_walk_picture.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    return lib
+
+
+def stream_geometry(es):
+    i = es.find(b"\x00\x00\x01\xb3")
+    assert i >= 0
+    w = (es[i + 4] << 4) | (es[i + 5] >> 4)
+    h = ((es[i + 5] & 15) << 8) | es[i + 6]
+    return (w + 15) >> 4, (h + 15) >> 4
+
+
+def picture_starts(es):
+    out, i = [], 0
+    while True:
+        i = es.find(b"\x00\x00\x01\x00", i)
+        if i < 0:
+            return out
+        out.append(i + 4)
+        i += 4
+
+
+def walk(lib, buf, n, start, mbw, mbh, lanes):
+    mb = mbw * mbh
+    hdr = np.zeros(mb * 4, dtype=np.uint32)
+    coef = np.full(mb * 6 * 32, 0xDEADBEEF, dtype=np.uint32)  # the walk parks 8 bytes per coded block
+    info = np.zeros(12, dtype=np.int32)
+    lib.emu_walk_picture(buf.ctypes.data, n, start, mbw, mbh, hdr.ctypes.data, coef.ctypes.data, info.ctypes.data, lanes)
+    return hdr.reshape(mb, 4), coef.reshape(mb * 6, 32)[:, :2].copy(), info
+
+
+def check_stream(lib, es, what, expect_lanes=None):
+    mbw, mbh = stream_geometry(es)
+    buf = np.frombuffer(es + b"\0" * 16, dtype=np.uint8).copy()  # 4-byte aligned base, padded like the ES mirror
+    used = 0
+    starts = picture_starts(es)
+    for k, s in enumerate(starts):
+        h0, c0, i0 = walk(lib, buf, len(es), s, mbw, mbh, 0)
+        h1, c1, i1 = walk(lib, buf, len(es), s, mbw, mbh, 1)
+        used += int(i1[9])
+        assert np.array_equal(i0[:9], i1[:9]), f"{what}: picture {k}: info {i0[:9]} vs {i1[:9]}"
+        assert np.array_equal(h0, h1), f"{what}: picture {k}: records differ at mb {np.nonzero((h0 != h1).any(axis=1))[0][:8]}"
+        assert np.array_equal(c0, c1), f"{what}: picture {k}: parked block data differ at slot {np.nonzero((c0 != c1).any(axis=1))[0][:8]}"
+    if expect_lanes is not None:
+        assert used >= expect_lanes, f"{what}: lane-parallel walk used for {used} of {len(starts)} pictures"
+    return used, len(starts)
+
+
+GOLDEN = sorted(f[:-3] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".es"))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_streams(name):
+    es = open(os.path.join(HERE, "golden", name + ".es"), "rb").read()
+    check_stream(emu_lib(), es, name)
+
+
+def test_synth_cases():
+    import synth_es
+    lib = emu_lib()
+    for name in synth_es.CASES:
+        check_stream(lib, synth_es.make_case(name), name)
+
+
+@pytest.mark.parametrize("size,frames", [((320, 240), 14), ((1280, 720), 4), ((1920, 1080), 3)])
+def test_encoder_clips_use_the_lane_walk(size, frames):
+    pytest.importorskip("cv2")
+    es = b"".join(p for _, p in helpers.clip_packets(size[0], size[1], frames))
+    used, n = check_stream(emu_lib(), es, f"clip {size}")
+    assert used == n, f"lane-parallel walk fell back on {n - used} of {n} clean pictures"
+
+
+def test_truncated_and_corrupt_streams_fall_back_identically():
+    pytest.importorskip("cv2")
+    es = b"".join(p for _, p in helpers.clip_packets(320, 240, 6))
+    lib = emu_lib()
+    check_stream(lib, es[: len(es) * 2 // 3], "truncated")
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        bad = bytearray(es)
+        for pos in rng.integers(200, len(es), size=4):
+            bad[pos] ^= 1 << int(rng.integers(0, 8))
+        check_stream(lib, bytes(bad), f"corrupt {trial}")
