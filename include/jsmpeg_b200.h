@@ -85,7 +85,8 @@ typedef struct jsmpeg_b200_stats_t {
 	uint64_t recon_launches;
 	double parse_ms, recon_ms, scan_ms; /* CUDA-event device time on the launching stream       */
 	uint64_t parse_errors;        /* pictures whose slice walk hit an invalid code              */
-	double walk_ms;               /* part of parse_ms spent in the serial walk kernel (1a)      */
+	double walk_ms;               /* part of parse_ms spent in the walk kernel (1a)             */
+	uint64_t lane_walk_pictures;  /* pictures walked by the lane-parallel walk (JSMPEG_B200_WALK=lanes), not its serial fall-back */
 } jsmpeg_b200_stats_t;
 
 /* n_streams decoders on CUDA device `device`.  max_slots bounds the pictures parsed ahead

@@ -20,6 +20,7 @@ class Stats(ctypes.Structure):
         ("kernel_launches", ctypes.c_uint64), ("recon_launches", ctypes.c_uint64),
         ("parse_ms", ctypes.c_double), ("recon_ms", ctypes.c_double), ("scan_ms", ctypes.c_double),
         ("parse_errors", ctypes.c_uint64), ("walk_ms", ctypes.c_double),
+        ("lane_walk_pictures", ctypes.c_uint64),
     ]
 
     def as_dict(self):

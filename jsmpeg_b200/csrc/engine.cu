@@ -461,6 +461,7 @@ long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			Parsed &p = b->streams[fresh[i].stream].cache[fresh[i].cache_idx];
 			p.info = b->h_info[i];
 			if (p.info.error == PARSE_ERR_INVALID_VLC) b->stats.parse_errors++;
+			if (p.info.reserved[0]) b->stats.lane_walk_pictures++;
 		}
 	}
 	// ---- 3. consume in decode() order per stream; step j of a stream -> recon launch j

@@ -180,12 +180,12 @@ __device__ __forceinline__ uint16_t walk_entry(uint16_t e) {
 
 // One coded block (bitstream side of src/mpeg1.js:698-811): intra DC with its predictor, then only
 // code lengths.  Leaves {bit offset of the first coefficient code, dc * 8} in the block's slot.
-__device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
-                                           uint32_t *__restrict__ slot, bool store, bool &dc_only) {
-	int n = 0;
+// head: DC size VLC + differential + predictor (mpeg1.js:705-751), the parked pair, dct_coeff_first
+__device__ __forceinline__ bool walk_block_head(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
+                                                uint32_t *__restrict__ slot, bool store, int &n) {
+	n = 0;
 	int dc8 = 0;
 	if (intra) {
-		// DC size VLC + differential + predictor (mpeg1.js:705-751)
 		const uint32_t w = br.peek32();
 		const uint32_t e = block < 4 ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
 		                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
@@ -207,6 +207,17 @@ __device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, Pictur
 		br.consume(2);
 		n = 1;
 	}
+	return true;
+}
+__device__ __forceinline__ void walk_block_tail(PictureState &ps, int n, bool &dc_only) {
+	if (n > 64) ps.error = PARSE_ERR_COEF_INDEX;  // some run pushed the index past 63 (stores dropped, like JS)
+	dc_only = (n == 1);  // mpeg1.js:838, 850
+	ps.n_coded++;
+}
+__device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
+                                           uint32_t *__restrict__ slot, bool store, bool &dc_only) {
+	int n;
+	if (!walk_block_head(br, sbase, ps, intra, block, slot, store, n)) return false;
 	for (;;) {
 		const uint32_t w = br.peek32();
 		// (Resolving '10' / '11s' arithmetically before the look-up was measured 8 % SLOWER: it defeats the
@@ -234,10 +245,38 @@ __device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, Pictur
 		n += (int)(e >> 5);
 		br.consume((int)(e & 31u));
 	}
-	if (n > 64) ps.error = PARSE_ERR_COEF_INDEX;  // some run pushed the index past 63 (stores dropped, like JS)
-	dc_only = (n == 1);  // mpeg1.js:838, 850
-	ps.n_coded++;
+	walk_block_tail(ps, n, dc_only);
 	return true;
+}
+// The same loop, one look-up per call (the lane-parallel walk votes between look-ups so that the lanes
+// stay in step): 0 = go on, 1 = end_of_block consumed, 2 = invalid code.  `combine` = several codes
+// may be taken at once.
+__device__ __forceinline__ int ac_step(BitReader &br, uint32_t sbase, int &n, bool combine) {
+	const uint32_t w = br.peek32();
+	if (combine) {
+		const uint32_t m = lds_u16(sbase + OFF_MS + (w >> (32 - MS_BITS)) * 2u);
+		if (m & 15u) {
+			n += (int)((m >> 4) & 63u);
+			br.consume((int)(m & 15u));
+			return (m & 0x400u) ? 1 : 0;
+		}
+	}
+	const int z = __clz((int)w);
+	if (z > VLC_DCT_MAX_Z) return 2;
+	const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+	if (e == 0) return 2;
+	if ((e >> 11) == 1u) {  // end_of_block
+		br.consume(2);
+		return 1;
+	}
+	if (e >> 11) {  // escape
+		n += (int)((w >> 20) & 63u) + 1;
+		br.consume((w & 0x0007f000u) ? 20 : 28);
+		return 0;
+	}
+	n += (int)(e >> 5);
+	br.consume((int)(e & 31u));
+	return 0;
 }
 
 // mpeg1.js:395-457, one component
@@ -285,22 +324,29 @@ __device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int 
 //                the serial walk set ps.anomaly
 enum { WALK_SERIAL = 0, WALK_REL = 1, WALK_ABS = 2 };
 
-// mpeg1.js:294-392 decodeMacroblock.  false = stop walking this slice.
+struct MbHead {
+	int mb, cbp, mv_h, mv_v, qscale;
+	bool intra;
+	uint32_t bit_pos;
+};
+
+// mpeg1.js:294-384, decodeMacroblock up to the blocks.  0: the blocks of h.cbp follow; 1: nothing more
+// to do for this macroblock, the slice goes on; 2: stop walking this slice.
 template <int MODE>
-__device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
+__device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane, MbHead &h) {
 	int increment = 0;
 	int v = read_mba(br, sbase);
 	while (v == 34) v = read_mba(br, sbase);                       // macroblock_stuffing
 	while (v == 35) { increment += 33; v = read_mba(br, sbase); }  // macroblock_escape
-	if (v < 0) return false;
+	if (v < 0) return 2;
 	increment += v;
 
 	if (ps.slice_begin) {  // mpeg1.js:312-317
 		ps.slice_begin = false;
 		ps.mb_addr += increment;
 	} else {
-		if (MODE == WALK_SERIAL && ps.mb_addr + increment >= mb_size) return true;  // mpeg1.js:319-322
-		if (MODE == WALK_ABS && ps.mb_addr + increment >= mb_size) { ps.anomaly = true; return false; }
+		if (MODE == WALK_SERIAL && ps.mb_addr + increment >= mb_size) return 1;  // mpeg1.js:319-322
+		if (MODE == WALK_ABS && ps.mb_addr + increment >= mb_size) { ps.anomaly = true; return 2; }
 		if (increment > 1) {  // mpeg1.js:323-334
 			ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;
 			if (MODE == WALK_REL) ps.dc_abs = true;
@@ -321,23 +367,25 @@ __device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps,
 		ps.mb_addr++;
 	}
 	const int mb = ps.mb_addr;
+	h.mb = mb;
 	if (MODE != WALK_REL && (mb < 0 || mb >= mb_size)) {  // outside the picture: never write there
 		if (MODE == WALK_ABS) ps.anomaly = true;
-		return false;
+		return 2;
 	}
 
 	const uint32_t w = br.peek32();
 	const uint32_t e = ps.picture_type == 1 ? lds_u16(sbase + OFF_TYPE_I + (w >> 30) * 2u)
 	                                        : lds_u16(sbase + OFF_TYPE_P + (w >> 26) * 2u);
-	if ((e & 31) == 0) return false;
+	if ((e & 31) == 0) return 2;
 	br.consume(e & 31);
 	const int type = e >> 5;
 	const bool intra = type & 0x01;
+	h.intra = intra;
 	if (type & 0x10) {
 		ps.qscale = (int)br.read(5);
 		if (MODE == WALK_REL) ps.qs_set = true;
 	}
-	const uint32_t mb_bit_pos = br.bitpos();
+	h.bit_pos = br.bitpos();
 
 	if (intra) {
 		ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:363-367
@@ -346,8 +394,8 @@ __device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps,
 		ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;                  // mpeg1.js:370-372
 		if (MODE == WALK_REL) ps.dc_abs = true;
 		if (type & 0x08) {
-			if (!parse_motion(br, sbase, ps, ps.mv_h_prev, ps.mv_h)) return false;
-			if (!parse_motion(br, sbase, ps, ps.mv_v_prev, ps.mv_v)) return false;
+			if (!parse_motion(br, sbase, ps, ps.mv_h_prev, ps.mv_h)) return 2;
+			if (!parse_motion(br, sbase, ps, ps.mv_v_prev, ps.mv_v)) return 2;
 		} else if (ps.picture_type == 2) {
 			ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:452-456
 			if (MODE == WALK_REL) ps.mv_abs = true;
@@ -357,29 +405,39 @@ __device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps,
 	int cbp = intra ? 0x3f : 0;
 	if (type & 0x02) {
 		const uint32_t ce = clz_lut(sbase + OFF_CBP, br.peek32(), VLC_CBP_MAX_Z);
-		if ((ce & 31) == 0) return false;
+		if ((ce & 31) == 0) return 2;
 		br.consume(ce & 31);
 		cbp = ce >> 5;
 	}
 
-	const int mv_h = ps.mv_h, mv_v = ps.mv_v, qscale = ps.qscale;
-	uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)(MODE == WALK_REL ? 0 : mb) * (MB_COEF_INT16 / 2);
-	const bool store = MODE == WALK_ABS || (MODE == WALK_SERIAL && lane == 0);
+	h.cbp = cbp;
+	h.mv_h = ps.mv_h; h.mv_v = ps.mv_v; h.qscale = ps.qscale;
+	return 0;
+}
+
+// mpeg1.js:294-392 decodeMacroblock, serial.  false = stop walking this slice.
+__device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
+	MbHead h;
+	const int r = walk_mb_header<WALK_SERIAL>(br, sbase, ps, t, mb_size, lane, h);
+	if (r) return r == 1;
+	const int mb = h.mb, cbp = h.cbp;
+	const bool intra = h.intra;
+	uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)mb * (MB_COEF_INT16 / 2);
 	int done = 0, dc_mask = 0;
 	bool ok = true;
 #pragma unroll 1
 	for (int block = 0; block < 6; block++) {
 		if (cbp & (0x20 >> block)) {
 			bool dc_only;
-			ok = walk_block(br, sbase, ps, intra, block, coef_mb + block * 32, store, dc_only);
+			ok = walk_block(br, sbase, ps, intra, block, coef_mb + block * 32, lane == 0, dc_only);
 			if (!ok) break;
 			done |= 0x20 >> block;
 			if (dc_only) dc_mask |= 0x20 >> block;
 		}
 	}
-	if (store)
+	if (lane == 0)
 		reinterpret_cast<uint4 *>(t.hdr)[mb] =
-		    pack_record(mv_h, mv_v, MBF_PRESENT | (intra ? MBF_INTRA : 0), done, dc_mask, qscale, mb_bit_pos);
+		    pack_record(h.mv_h, h.mv_v, MBF_PRESENT | (intra ? MBF_INTRA : 0), done, dc_mask, h.qscale, h.bit_pos);
 	ps.n_present++;
 	return ok;
 }
@@ -414,7 +472,7 @@ __device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps,
 // picture, a slice that does not end exactly at the next start code -- makes the warp discard the
 // attempt and walk the whole picture with the serial code, which defines the behaviour there.
 
-enum { PH_MBA = 0, PH_MBA_STUFF, PH_MBA_ESC, PH_TYPE, PH_MV_H, PH_MV_V, PH_CBP, PH_DC, PH_AC_FIRST, PH_AC, PH_END, PH_ERR };
+enum { PH_MBA = 0, PH_MBA_STUFF, PH_MBA_ESC, PH_TYPE, PH_MV_H, PH_MV_V, PH_CBP, PH_DC, PH_AC_FIRST, PH_AC, PH_END };
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr uint32_t MIN_SUBSEQ_BITS = 2048;  // below this a sub-sequence is too short for chains to merge in it
@@ -426,20 +484,6 @@ struct SliceConst {
 
 // syntax state: phase | blocks still to come (mask, current block = highest bit) << 4 | macroblock type bits << 10
 __device__ __forceinline__ uint32_t syn_make(int phase, uint32_t rem, uint32_t type) { return (uint32_t)phase | rem << 4 | type << 10; }
-__device__ __forceinline__ uint32_t syn_blocks(uint32_t rem, uint32_t type) {
-	if (rem == 0) return PH_MBA;
-	return syn_make((type & 1u) ? PH_DC : PH_AC_FIRST, rem, type & 1u);
-}
-__device__ __forceinline__ uint32_t syn_after_mv(uint32_t type) {
-	if (type & 2u) return syn_make(PH_CBP, 0, type & 3u);
-	return syn_blocks((type & 1u) ? 0x3fu : 0u, type);
-}
-__device__ __forceinline__ uint32_t syn_block_end(uint32_t st) {
-	uint32_t rem = (st >> 4) & 63u;
-	rem &= ~(0x80000000u >> __clz((int)rem));  // a block is being walked, so rem != 0
-	return syn_blocks(rem, st >> 10);
-}
-
 // The state a chain assumes where it knows nothing: inside the coefficients of the last block of a
 // macroblock.  After the next end_of_block it tries a macroblock header; a true end_of_block is a
 // true macroblock start often enough.
@@ -453,95 +497,123 @@ __device__ __forceinline__ uint32_t syn_guess(const SliceConst &sc) { return syn
 // picture goes to the serial walk.
 // Several coefficient codes are taken per look-up only while that cannot jump over `limit`, so that
 // the boundary reached depends on the chain alone, not on where a lane joined it.
-__device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, uint32_t limit, uint32_t &st, bool stop_at_mb_start) {
-	for (;;) {
-		const int ph = (int)(st & 15u);
-		if (ph >= PH_END) return;
-		if (stop_at_mb_start && ph == PH_MBA) return;
-		const uint32_t pos = br.bitpos();
-		if (pos >= limit) return;
-		const uint32_t w = br.peek32();
-		if (ph == PH_AC) {
-			if (pos + MS_BITS <= limit) {
-				const uint32_t m = lds_u16(sbase + OFF_MS + (w >> (32 - MS_BITS)) * 2u);
-				if (m & 15u) {
-					br.consume((int)(m & 15u));
-					if (m & 0x400u) st = syn_block_end(st);
-					continue;
-				}
+//
+// WARP-SYNCHRONOUS: all 32 lanes call it together (`live` = this lane has something to run).  The
+// automaton is written in the order of the syntax, one macroblock per trip of the outer loop and one
+// look-up per trip of the coefficient loop, and both loops are closed by a warp vote: the lanes run
+// the same stage at the same time.  (Left to themselves, lanes that leave a loop early never wait for
+// the others: measured on B200, the first version ran with 4 of 32 lanes active on average and its
+// per-lane macroblock loops with ONE.)
+__device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, bool live, uint32_t limit, uint32_t &st, bool stop_at_mb_start) {
+	int ph = (int)(st & 15u);
+	uint32_t rem = (st >> 4) & 63u, ty = st >> 10;
+	const uint32_t guess_ty = sc.picture_type == 1 ? 1u : 0u;
+	bool run = live && ph < PH_END;
+#define SYN_RESYNC() do { br.consume(1); ph = PH_AC; rem = 1u; ty = guess_ty; } while (0)
+	while (__any_sync(FULL_MASK, run)) {
+		if (run) do {  // the stages before the blocks; `break` leaves them
+			// ---- macroblock_address_increment (mpeg1.js:295-310), after the slice-end test of mpeg1.js:276
+			while (run && ph <= PH_MBA_ESC) {
+				if (stop_at_mb_start && ph == PH_MBA) { run = false; break; }
+				const uint32_t pos = br.bitpos();
+				if (pos >= limit) { run = false; break; }
+				if (ph == PH_MBA && ((pos + 7u) >> 3) >= sc.end_byte) { ph = PH_END; run = false; break; }
+				const uint32_t e = clz_lut(sbase + OFF_MBA, br.peek32(), VLC_MBA_MAX_Z);
+				if ((e & 31u) == 0) { SYN_RESYNC(); break; }
+				br.consume((int)(e & 31u));
+				const uint32_t v = e >> 5;
+				if (v == 35u) ph = PH_MBA_ESC;
+				else if (v == 34u && ph != PH_MBA_ESC) ph = PH_MBA_STUFF;  // after an escape, 34 is an increment (mpeg1.js:297-306)
+				else ph = PH_TYPE;
 			}
-			const int z = __clz((int)w);
-			if (z > VLC_DCT_MAX_Z) { br.consume(1); st = syn_guess(sc); continue; }
-			const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
-			if (e >> 11) {
-				if ((e >> 11) == 1u) {  // end_of_block
-					br.consume(2);
-					st = syn_block_end(st);
+			if (!run) break;
+			// ---- macroblock_type (+ quantiser scale), mpeg1.js:348-361
+			if (ph == PH_TYPE) {
+				if (br.bitpos() >= limit) { run = false; break; }
+				const uint32_t w = br.peek32();
+				const uint32_t e = sc.picture_type == 1 ? lds_u16(sbase + OFF_TYPE_I + (w >> 30) * 2u)
+				                                        : lds_u16(sbase + OFF_TYPE_P + (w >> 26) * 2u);
+				if ((e & 31u) == 0) {
+					SYN_RESYNC();
 				} else {
-					br.consume((w & 0x0007f000u) ? 20 : 28);  // escape (mpeg1.js:767-780)
+					const uint32_t type = e >> 5;
+					br.consume((int)(e & 31u) + ((type & 0x10u) ? 5 : 0));
+					ty = type & 3u;
+					rem = 0;
+					if (!(type & 1u) && (type & 8u)) ph = PH_MV_H;
+					else if (type & 2u) ph = PH_CBP;
+					else if (type & 1u) { ph = PH_DC; rem = 0x3fu; }
+					else ph = PH_MBA;
 				}
-				continue;
 			}
-			if (e == 0) { br.consume(1); st = syn_guess(sc); continue; }
-			br.consume((int)(e & 31u));
-			continue;
-		}
-		switch (ph) {
-		case PH_MBA:  // mpeg1.js:276 (nextBytesAreStartCode after every macroblock), then :295-310
-			if (((pos + 7u) >> 3) >= sc.end_byte) { st = PH_END; return; }
-			// fall through
-		case PH_MBA_STUFF:
-		case PH_MBA_ESC: {
-			const uint32_t e = clz_lut(sbase + OFF_MBA, w, VLC_MBA_MAX_Z);
-			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
-			br.consume((int)(e & 31u));
-			const uint32_t v = e >> 5;
-			if (v == 35u) st = PH_MBA_ESC;
-			else if (v == 34u && ph != PH_MBA_ESC) st = PH_MBA_STUFF;  // after an escape, 34 is an increment (mpeg1.js:297-306)
-			else st = PH_TYPE;
-			break;
-		}
-		case PH_TYPE: {
-			const uint32_t e = sc.picture_type == 1 ? lds_u16(sbase + OFF_TYPE_I + (w >> 30) * 2u)
-			                                        : lds_u16(sbase + OFF_TYPE_P + (w >> 26) * 2u);
-			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
-			const uint32_t type = e >> 5;
-			br.consume((int)(e & 31u) + ((type & 0x10u) ? 5 : 0));
-			if (!(type & 1u) && (type & 8u)) st = syn_make(PH_MV_H, 0, type & 3u);
-			else st = syn_after_mv(type);
-			break;
-		}
-		case PH_MV_H:
-		case PH_MV_V: {
-			const uint32_t e = clz_lut(sbase + OFF_MOTION, w, VLC_MOTION_MAX_Z);
-			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
-			const int code = (int)(e >> 5) - 16;
-			br.consume((int)(e & 31u) + ((code != 0 && sc.f != 1) ? sc.r_size : 0));
-			st = ph == PH_MV_H ? syn_make(PH_MV_V, 0, st >> 10) : syn_after_mv(st >> 10);
-			break;
-		}
-		case PH_CBP: {
-			const uint32_t e = clz_lut(sbase + OFF_CBP, w, VLC_CBP_MAX_Z);
-			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
-			br.consume((int)(e & 31u));
-			st = syn_blocks(e >> 5, st >> 10);
-			break;
-		}
-		case PH_DC: {
-			const uint32_t rem = (st >> 4) & 63u;  // blocks 0..3 are the mask bits 0x20..0x04
-			const uint32_t e = rem >= 4u ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
-			                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
-			if ((e & 31u) == 0) { br.consume(1); st = syn_guess(sc); continue; }
-			br.consume((int)(e & 31u) + (int)(e >> 5));
-			st = (st & ~15u) | PH_AC;
-			break;
-		}
-		default:  // PH_AC_FIRST: a leading '1' is (0, +-1), never end_of_block (mpeg1.js:757-760)
-			if (w >> 31) br.consume(2);
-			st = (st & ~15u) | PH_AC;
-			break;
+			// ---- motion vectors (mpeg1.js:395-457): code + residual, values not needed
+			while (ph == PH_MV_H || ph == PH_MV_V) {
+				if (br.bitpos() >= limit) { run = false; break; }
+				const uint32_t e = clz_lut(sbase + OFF_MOTION, br.peek32(), VLC_MOTION_MAX_Z);
+				if ((e & 31u) == 0) { SYN_RESYNC(); break; }
+				const int code = (int)(e >> 5) - 16;
+				br.consume((int)(e & 31u) + ((code != 0 && sc.f != 1) ? sc.r_size : 0));
+				if (ph == PH_MV_H) ph = PH_MV_V;
+				else if (ty & 2u) ph = PH_CBP;
+				else ph = PH_MBA;  // motion only: no blocks (intra macroblocks carry no vectors)
+			}
+			if (!run) break;
+			// ---- coded_block_pattern (mpeg1.js:376-384)
+			if (ph == PH_CBP) {
+				if (br.bitpos() >= limit) { run = false; break; }
+				const uint32_t e = clz_lut(sbase + OFF_CBP, br.peek32(), VLC_CBP_MAX_Z);
+				if ((e & 31u) == 0) {
+					SYN_RESYNC();
+				} else {
+					br.consume((int)(e & 31u));
+					rem = e >> 5;
+					ty &= 1u;
+					ph = rem == 0 ? PH_MBA : ((ty & 1u) ? PH_DC : PH_AC_FIRST);
+				}
+			}
+		} while (0);
+		// ---- blocks (mpeg1.js:698-790), current block = highest bit of rem; at most six per macroblock
+#pragma unroll 1
+		for (int b = 0; b < 6; b++) {
+			bool in = run && ph >= PH_DC && ph <= PH_AC;
+			if (in && ph == PH_DC) {
+				if (br.bitpos() >= limit) { run = false; in = false; }
+				else {
+					const uint32_t w = br.peek32();  // blocks 0..3 are the mask bits 0x20..0x04
+					const uint32_t e = rem >= 4u ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
+					                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
+					if ((e & 31u) == 0) SYN_RESYNC();
+					else br.consume((int)(e & 31u) + (int)(e >> 5));
+					ph = PH_AC;
+				}
+			} else if (in && ph == PH_AC_FIRST) {  // a leading '1' is (0, +-1), never end_of_block (mpeg1.js:757-760)
+				if (br.bitpos() >= limit) { run = false; in = false; }
+				else {
+					if (br.peek32() >> 31) br.consume(2);
+					ph = PH_AC;
+				}
+			}
+			while (__any_sync(FULL_MASK, in)) {  // coefficient codes up to end_of_block, one look-up per trip
+				if (in) {
+					const uint32_t pos = br.bitpos();
+					if (pos >= limit) { run = false; in = false; }
+					else {
+						int n_unused = 0;
+						const int r = ac_step(br, sbase, n_unused, pos + MS_BITS <= limit);
+						if (r == 2) SYN_RESYNC();
+						else if (r == 1) {
+							rem &= ~(0x80000000u >> __clz((int)rem));
+							ph = rem == 0 ? PH_MBA : ((ty & 1u) ? PH_DC : PH_AC_FIRST);
+							in = false;
+						}
+					}
+				}
+			}
 		}
 	}
+#undef SYN_RESYNC
+	if (ph <= PH_TYPE || ph >= PH_END) { rem = 0; ty = 0; }
+	st = syn_make(ph, rem, ty);
 }
 
 // What the macroblocks a lane owns do to the slice state, relative to the state they start from.
@@ -599,18 +671,58 @@ __device__ uint32_t find_slice_end(const BitReader &br, uint32_t from, int lane)
 	return len;
 }
 
-// The macroblocks that START in [reader position, limit), walked in MODE.  Returns 0 when the lane
-// reached `limit`, 1 when the slice ended cleanly at the start code, 2 on anything else.
+// The macroblocks that START in [reader position, limit), walked in MODE (WALK_REL / WALK_ABS).
+// Returns 0 when the lane reached `limit` (or owns nothing), 1 when the slice ended cleanly at the
+// start code, 2 on anything else.  WARP-SYNCHRONOUS like syntax_run: a vote closes the macroblock
+// loop, a __syncwarp every block and a vote every look-up of the coefficient loop.
 template <int MODE>
-__device__ __forceinline__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const ParseTask &t, int mb_size,
-                                          uint32_t limit, uint32_t end_byte, int lane) {
-	for (;;) {
-		if (!walk_macroblock<MODE>(br, sbase, ls, t, mb_size, lane)) return 2;
-		const uint32_t pos = br.bitpos();
-		const uint32_t i = (pos + 7u) >> 3;
-		if (i >= end_byte) return i == end_byte ? 1 : 2;
-		if (pos >= limit) return 0;
+__device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const ParseTask &t, int mb_size, bool owns,
+                          uint32_t limit, uint32_t end_byte, int lane) {
+	int how = 0;
+	bool work = owns;
+	while (__any_sync(FULL_MASK, work)) {
+		MbHead h;
+		h.mb = 0; h.cbp = 0; h.mv_h = h.mv_v = h.qscale = 0; h.intra = false; h.bit_pos = 0;
+		bool in_mb = false;
+		if (work) {
+			if (walk_mb_header<MODE>(br, sbase, ls, t, mb_size, lane, h) != 0) { how = 2; work = false; }
+			else in_mb = true;
+		}
+		uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)(MODE == WALK_ABS ? h.mb : 0) * (MB_COEF_INT16 / 2);
+		int done = 0, dc_mask = 0;
+#pragma unroll 1
+		for (int block = 0; block < 6; block++) {
+			int n = 0;
+			bool in = in_mb && (h.cbp & (0x20 >> block));
+			if (in && !walk_block_head(br, sbase, ls, h.intra, block, coef_mb + block * 32, MODE == WALK_ABS, n)) {
+				how = 2; work = false; in_mb = false; in = false;
+			}
+			while (__any_sync(FULL_MASK, in)) {
+				if (in) {
+					const int r = ac_step(br, sbase, n, true);
+					if (r == 2) { how = 2; work = false; in_mb = false; in = false; }
+					else if (r == 1) {
+						bool dc_only;
+						walk_block_tail(ls, n, dc_only);
+						done |= 0x20 >> block;
+						if (dc_only) dc_mask |= 0x20 >> block;
+						in = false;
+					}
+				}
+			}
+		}
+		if (in_mb) {
+			if (MODE == WALK_ABS)
+				reinterpret_cast<uint4 *>(t.hdr)[h.mb] =
+				    pack_record(h.mv_h, h.mv_v, MBF_PRESENT | (h.intra ? MBF_INTRA : 0), done, dc_mask, h.qscale, h.bit_pos);
+			ls.n_present++;
+			const uint32_t pos = br.bitpos();
+			const uint32_t i = (pos + 7u) >> 3;
+			if (i >= end_byte) { how = i == end_byte ? 1 : 2; work = false; }
+			else if (pos >= limit) work = false;
+		}
 	}
+	return how;
 }
 
 // One slice: the reader is at its first macroblock (bit p_start), `ps` holds the picture constants and
@@ -636,9 +748,9 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 	if (active) {
 		br.seek_bit(s_lo);
 		my_st = lane == 0 ? (uint32_t)PH_MBA : syn_guess(sc);
-		syntax_run(br, sbase, sc, s_hi, my_st, false);
-		my_pos = br.bitpos();
 	}
+	syntax_run(br, sbase, sc, active, s_hi, my_st, false);
+	if (active) my_pos = br.bitpos();
 	uint32_t e_pos = my_pos, e_st = my_st;  // exit state of sub-sequence `lane`, as known so far
 
 	// ---- B: run on into the following sub-sequences until the chains have merged
@@ -649,12 +761,9 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 		const int idx = lane + 1 + round;  // the sub-sequence this lane walks in this round
 		if (idx >= K) merged = true;
 		const bool arrive = !merged;
-		if (arrive) {
-			const uint32_t lim = idx < K - 1 ? p_start + (uint32_t)(idx + 1) * L : end_bit;
-			syntax_run(br, sbase, sc, lim, my_st, false);
-			my_pos = br.bitpos();
-		}
-		__syncwarp();
+		const uint32_t lim = (arrive && idx < K - 1) ? p_start + (uint32_t)(idx + 1) * L : end_bit;
+		syntax_run(br, sbase, sc, arrive, lim, my_st, false);
+		if (arrive) my_pos = br.bitpos();
 		const int src = lane - 1 - round;  // the lane that arrives at the end of sub-sequence `lane` in this round
 		const uint32_t v_pos = __shfl_sync(FULL_MASK, my_pos, src & 31), v_st = __shfl_sync(FULL_MASK, my_st, src & 31);
 		const int v_arrive = __shfl_sync(FULL_MASK, (int)arrive, src & 31);
@@ -673,15 +782,14 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 	if (lane == 0) { in_pos = p_start; in_st = PH_MBA; }
 	bool bad = false, owns = false;
 	uint32_t q = 0;
-	if (active) {
-		if ((in_st & 15u) == PH_ERR) bad = true;
-		else if ((in_st & 15u) != PH_END) {
-			br.seek_bit(in_pos);
-			uint32_t st = in_st;
-			syntax_run(br, sbase, sc, s_hi, st, true);
+	{
+		const bool seek = active && (in_st & 15u) < PH_END;
+		uint32_t st = in_st;
+		if (seek) br.seek_bit(in_pos);
+		syntax_run(br, sbase, sc, seek, s_hi, st, true);
+		if (seek) {
 			q = br.bitpos();
-			if ((st & 15u) == PH_ERR) bad = true;
-			else if ((st & 15u) == PH_MBA && q < s_hi && ((q + 7u) >> 3) < end_byte) owns = true;
+			if ((st & 15u) == PH_MBA && q < s_hi && ((q + 7u) >> 3) < end_byte) owns = true;
 		}
 	}
 	PictureState ls = ps;  // picture constants; the rest is set per pass
@@ -694,14 +802,15 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 		ls.dc_y = ls.dc_b4 = ls.dc_b5 = 0;
 		ls.qs_set = ls.dc_abs = ls.mv_abs = ls.anomaly = false;
 		ls.n_present = ls.n_coded = ls.error = 0;
-		how = walk_owned<WALK_REL>(br, sbase, ls, t, mb_size, s_hi, end_byte, lane);
+	}
+	how = walk_owned<WALK_REL>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane);
+	if (owns) {
 		if (how == 2) bad = true;
 		sum.d_addr = ls.mb_addr; sum.qs = ls.qscale;
 		sum.dcy = ls.dc_y; sum.dc4 = ls.dc_b4; sum.dc5 = ls.dc_b5;
 		sum.mvh = ls.mv_h_prev; sum.mvv = ls.mv_v_prev;
 		sum.flags = (ls.qs_set ? 1u : 0u) | (ls.dc_abs ? 2u : 0u) | (ls.mv_abs ? 4u : 0u);
 	}
-	__syncwarp();
 	if (__any_sync(FULL_MASK, bad)) return false;
 	const unsigned enders = __ballot_sync(FULL_MASK, how == 1);
 	if (__popc(enders) != 1) return false;  // exactly one lane sees the slice end at its start code
@@ -726,10 +835,9 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 		ls.mv_h_prev = x.mvh; ls.mv_v_prev = x.mvv;
 		ls.mv_h = ps.full_pel ? x.mvh * 2 : x.mvh;
 		ls.mv_v = ps.full_pel ? x.mvv * 2 : x.mvv;
-		const int how_abs = walk_owned<WALK_ABS>(br, sbase, ls, t, mb_size, s_hi, end_byte, lane);
-		if (how_abs != how) bad = true;
 	}
-	__syncwarp();
+	const int how_abs = walk_owned<WALK_ABS>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane);
+	if (how_abs != how || ls.anomaly) bad = true;
 	if (__any_sync(FULL_MASK, bad)) return false;
 	int n_present = ls.n_present, n_coded = ls.n_coded, error = ls.error;
 	for (int d = 16; d > 0; d >>= 1) {
@@ -823,7 +931,7 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
 					}
 				} else {
 					do {
-						if (!walk_macroblock<WALK_SERIAL>(br, sbase, ps, t, mb_size, lane)) {
+						if (!walk_macroblock(br, sbase, ps, t, mb_size, lane)) {
 							if (!ps.error) ps.error = PARSE_ERR_INVALID_VLC;
 							break;
 						}

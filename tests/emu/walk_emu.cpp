@@ -1,17 +1,17 @@
 // walk_emu.cpp -- TEST INFRASTRUCTURE, not part of the product library.
 //
 // Compiles jsmpeg_b200/csrc/walk.cuh (the stage-1a walk, device code) for the HOST and runs one "warp"
-// as 32 host threads: the warp collectives become barrier + exchange, shared memory becomes a static
+// as 32 coroutines of one thread: the warp collectives become barrier + exchange, shared memory becomes a static
 // array.  tests/test_walk_emu.py uses it to check, on machines without a GPU, that the lane-parallel
 // walk produces exactly the records of the serial walk (the GPU parity tests then check both against
 // the oracle).  Build: g++ -O2 -std=c++17 -shared -fPIC -pthread -I/usr/local/cuda/include.
 #define JSMPEG_WALK_EMU 1
 #include <string.h>
 
+#include <ucontext.h>
+
 #include <algorithm>
-#include <condition_variable>
 #include <mutex>
-#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>  // vector types only
@@ -19,27 +19,35 @@
 using std::max;
 using std::min;
 
-// ---- a reusable barrier for the 32 "lanes"
+// ---- the 32 "lanes" are coroutines of one thread: a collective yields round-robin until all arrived
 namespace emu {
+static ucontext_t main_ctx, ctx[32];
+static bool finished[32];
+static int lane;  // the lane that is running
+static int arrived = 0, generation = 0;
+static uint64_t slots[32];
+
+static void yield_to_next() {
+	const int from = lane;
+	int to = from;
+	do { to = (to + 1) & 31; } while (finished[to] && to != from);
+	if (to == from) return;
+	lane = to;
+	swapcontext(&ctx[from], &ctx[to]);
+	lane = from;
+}
 struct Barrier {
-	std::mutex m;
-	std::condition_variable cv;
-	int waiting = 0, generation = 0;
 	void wait() {
-		std::unique_lock<std::mutex> lk(m);
 		const int gen = generation;
-		if (++waiting == 32) {
-			waiting = 0;
+		if (++arrived == 32) {  // the last lane to arrive releases the others
+			arrived = 0;
 			generation++;
-			cv.notify_all();
-		} else {
-			cv.wait(lk, [&] { return gen != generation; });
+			return;
 		}
+		while (generation == gen) yield_to_next();
 	}
 };
 static Barrier bar;
-static uint64_t slots[32];
-static thread_local int lane;
 
 template <class T>
 static T exchange(T v, int src) {
@@ -55,7 +63,7 @@ static T exchange(T v, int src) {
 }  // namespace emu
 
 // ---- the CUDA intrinsics walk.cuh uses
-static inline void __syncwarp() { emu::bar.wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::bar.wait(); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu::exchange(v, src); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu::exchange(v, emu::lane - d >= 0 ? emu::lane - d : emu::lane); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::exchange(v, emu::lane ^ m); }
@@ -95,13 +103,37 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 	seq.mb_size = mb_width * mb_height;
 	ParseTask t;
 	t.es = es; t.es_len = es_len; t.start_byte = start_byte; t.seq = &seq; t.hdr = hdr; t.coef = coef; t.info = info;
-	std::vector<std::thread> warp;
-	for (int l = 0; l < 32; l++)
-		warp.emplace_back([&, l] {
-			emu::lane = l;
-			if (lanes) walk_picture<true>(t, 0, l);
-			else walk_picture<false>(t, 0, l);
-		});
-	for (auto &th : warp) th.join();
+	// every collective is executed by all 32 lanes (walk.cuh's rule), so no lane finishes while another
+	// still waits in one: a finished lane is simply skipped by the round-robin
+	static ParseTask task;
+	static int use_lanes;
+	task = t;
+	use_lanes = lanes;
+	static std::vector<std::vector<char>> stacks(32, std::vector<char>(1 << 20));
+	struct Entry {
+		static void run() {
+			const int l = emu::lane;
+			if (use_lanes) walk_picture<true>(task, 0, l);
+			else walk_picture<false>(task, 0, l);
+			emu::finished[l] = true;
+			for (int k = 0; k < 32; k++)
+				if (!emu::finished[k]) {
+					emu::lane = k;
+					setcontext(&emu::ctx[k]);
+				}
+			setcontext(&emu::main_ctx);
+		}
+	};
+	emu::arrived = 0;
+	for (int l = 0; l < 32; l++) {
+		emu::finished[l] = false;
+		getcontext(&emu::ctx[l]);
+		emu::ctx[l].uc_stack.ss_sp = stacks[l].data();
+		emu::ctx[l].uc_stack.ss_size = stacks[l].size();
+		emu::ctx[l].uc_link = nullptr;
+		makecontext(&emu::ctx[l], Entry::run, 0);
+	}
+	emu::lane = 0;
+	swapcontext(&emu::main_ctx, &emu::ctx[0]);
 	return 0;
 }

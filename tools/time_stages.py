@@ -31,4 +31,4 @@ for rep in range(reps):
     st = bd.stats()
     print(f"streams={streams} pictures={n} step={dt * 1e3:8.2f} ms scan={st['scan_ms']:6.2f} parse={st['parse_ms']:8.2f} ms (walk {st['walk_ms']:.2f}) "
           f"recon={st['recon_ms']:7.2f} ms fps={n / dt:9.0f} coded_blocks/pic={st['coded_blocks'] / max(1, st['pictures_decoded']):.0f} "
-          f"errors={st['parse_errors']}", flush=True)
+          f"errors={st['parse_errors']} lane_walk={st['lane_walk_pictures']}", flush=True)
