@@ -361,3 +361,31 @@ def test_corrupted_streams_terminate_and_stay_in_bounds(seed):
     assert bd.get_index(0) <= len(es) * 8
     bd.close()
     golden.check_against_golden(capi.product_library(), "rows_ip")
+
+
+# ---- the lane-parallel walk (JSMPEG_B200_WALK=lanes) against the same checkers ---------------------
+
+def test_lane_parallel_walk_in_a_child_process():
+    """The walk variant is chosen once per process (first launch), so the stage-1 record parity, the
+    golden streams and a whole-clip decode are repeated in a child process with
+    JSMPEG_B200_WALK=lanes; the child also checks that the lane-parallel walk, not its serial
+    fall-back, produced the pictures of a clean clip."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("JSMPEG_B200_WALK") == "lanes":
+        pytest.skip("already running with the lane-parallel walk")
+    env = dict(os.environ, JSMPEG_B200_WALK="lanes")
+    here = os.path.dirname(os.path.abspath(__file__))
+    check = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import helpers\n"
+        "from jsmpeg_b200.batch import BatchDecoder, OUT_DEVICE\n"
+        "es = b''.join(p for _, p in helpers.clip_packets(640, 480, 13))\n"
+        "bd = BatchDecoder(1); bd.write(0, es); n = bd.decode(13, OUT_DEVICE); st = bd.stats(); bd.close()\n"
+        "assert n == 13 and st['lane_walk_pictures'] == 13, (n, st['lane_walk_pictures'])\n" % here)
+    subprocess.run([sys.executable, "-c", check], env=env, check=True, timeout=300)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
+                        "-k", "stage1_parse or golden or whole_clip or corrupted"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
