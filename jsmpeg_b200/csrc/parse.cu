@@ -45,7 +45,7 @@ template <bool LANES>
 __global__ void __launch_bounds__(WALK_THREADS)
 walk_pictures_kernel(const ParseTask *__restrict__ tasks, int n_tasks, const uint4 *__restrict__ ms_table) {
 	extern __shared__ __align__(128) uint8_t smem[];
-	walk_tables_init(smem, threadIdx.x, WALK_THREADS, ms_table);
+	walk_tables_init(smem, threadIdx.x, WALK_THREADS, ms_table, LANES);
 	__syncthreads();
 
 	const int lane = threadIdx.x & 31;
@@ -167,12 +167,12 @@ static const uint16_t *ms_table_for_current_device() {
 	CUDA_CHECK(cudaGetDevice(&dev));
 	if (tables[dev]) return tables[dev];
 	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                                (int)(OFF_MS + (2u << MS_BITS))));  // per device, once
+	                                (int)WALK_SMEM_SERIAL));  // per device, once
 	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                                (int)(OFF_MS + (2u << MS_BITS))));
+	                                (int)WALK_SMEM_LANES));
 	std::vector<uint16_t> dct((VLC_DCT_MAX_Z + 1) * 32);
 	CUDA_CHECK(cudaMemcpyFromSymbol(dct.data(), VLC_DCT_COEFF, dct.size() * sizeof(uint16_t)));
-	std::vector<uint16_t> ms(1u << MS_BITS);
+	std::vector<uint16_t> ms(MS_TABLE_ENTRIES);
 	build_ms_table(dct.data(), ms.data());
 	uint16_t *d = nullptr;
 	CUDA_CHECK(cudaMalloc(&d, ms.size() * sizeof(uint16_t)));
@@ -186,7 +186,6 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 	if (n_tasks <= 0) return;
 	const uint16_t *ms = ms_table_for_current_device();
 	const int per_cta = WALK_THREADS / 32;
-	const size_t walk_smem = OFF_MS + (2u << MS_BITS);
 	// The wave arrives sorted by picture size, largest first.  Group 0 (largest pictures) stays on
 	// `stream`; the other groups go to side streams, each walk followed by its own expand.
 	// JSMPEG_B200_PARSE_GROUPS=1 keeps stage 1 on one stream (used for the ncu launch list: ncu
@@ -201,6 +200,7 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 		const char *e = getenv("JSMPEG_B200_WALK");
 		return e && !strcmp(e, "lanes");
 	}();
+	const size_t walk_smem = lane_walk ? WALK_SMEM_LANES : WALK_SMEM_SERIAL;
 	const int groups = (fork && n_tasks >= 64 * max_groups) ? max_groups : 1;
 	if (groups > 1) CUDA_CHECK(cudaEventRecord(fork->fork, stream));
 	for (int g = 0; g < groups; g++) {

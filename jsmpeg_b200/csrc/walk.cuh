@@ -24,6 +24,9 @@ namespace {
 constexpr int WALK_THREADS = JSMPEG_WALK_THREADS;  // walk kernel: the pictures of a CTA share one multi-symbol table
 constexpr int MS_BITS = JSMPEG_MS_BITS;            // multi-symbol table is indexed by the next MS_BITS bits (2 << MS_BITS bytes)
 constexpr uint32_t OFF_MS = 4096;      // uint16[1 << MS_BITS], after the per-symbol tables
+constexpr uint32_t OFF_MS_FIRST = OFF_MS + (2u << MS_BITS);  // uint16[1 << (MS_BITS - 1)]: dct_coeff_first variant, prefixes with a leading 1 (lane-parallel walk only)
+constexpr uint32_t MS_TABLE_ENTRIES = (1u << MS_BITS) + (1u << (MS_BITS - 1));
+constexpr uint32_t WALK_SMEM_SERIAL = OFF_MS + (2u << MS_BITS), WALK_SMEM_LANES = OFF_MS + 2u * MS_TABLE_ENTRIES;
 
 // shared-memory layout (byte offsets from the dynamic shared base)
 constexpr uint32_t OFF_DCT = 0;                                        // uint16[384]
@@ -53,7 +56,7 @@ __device__ __forceinline__ void sts_s16(uint32_t addr, int v) {
 }
 #else
 // host emulation (tests only): `emu_smem` stands in for the CTA's shared memory, addresses are offsets into it
-static uint8_t emu_smem[OFF_MS + (2u << MS_BITS)];
+static uint8_t emu_smem[WALK_SMEM_LANES];
 static inline uint32_t lds_u16(uint32_t addr) { uint16_t v; memcpy(&v, emu_smem + addr, 2); return v; }
 static inline uint32_t lds_u8(uint32_t addr) { return emu_smem[addr]; }
 #endif
@@ -181,8 +184,9 @@ __device__ __forceinline__ uint16_t walk_entry(uint16_t e) {
 // One coded block (bitstream side of src/mpeg1.js:698-811): intra DC with its predictor, then only
 // code lengths.  Leaves {bit offset of the first coefficient code, dc * 8} in the block's slot.
 // head: DC size VLC + differential + predictor (mpeg1.js:705-751), the parked pair, dct_coeff_first
+template <bool DEFER>
 __device__ __forceinline__ bool walk_block_head(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
-                                                uint32_t *__restrict__ slot, bool store, int &n) {
+                                                uint32_t *__restrict__ slot, bool store, int &n, bool &defer_first) {
 	n = 0;
 	int dc8 = 0;
 	if (intra) {
@@ -191,19 +195,29 @@ __device__ __forceinline__ bool walk_block_head(BitReader &br, uint32_t sbase, P
 		                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
 		const int len = e & 31, size = e >> 5;
 		if (len == 0) return false;
-		br.consume(len);
 		int *pred = block < 4 ? &ps.dc_y : (block == 4 ? &ps.dc_b4 : &ps.dc_b5);
 		int dc = *pred;
-		if (size > 0) {
-			const int diff = (int)br.read(size);
-			dc += (diff & (1 << (size - 1))) ? diff : (int)((0xffffffffu << size) | (uint32_t)(diff + 1));
+		if (DEFER) {  // code and differential (at most 8 + 8 bits) sit in the same 32-bit peek: the window moves once
+			if (size > 0) {
+				const int diff = (int)((w << len) >> (32 - size));
+				dc += (diff & (1 << (size - 1))) ? diff : (int)((0xffffffffu << size) | (uint32_t)(diff + 1));
+			}
+			br.consume(len + size);
+		} else {
+			br.consume(len);
+			if (size > 0) {
+				const int diff = (int)br.read(size);
+				dc += (diff & (1 << (size - 1))) ? diff : (int)((0xffffffffu << size) | (uint32_t)(diff + 1));
+			}
 		}
 		*pred = dc;
 		dc8 = max(-32768, min(32767, dc * 8));  // x PREMULTIPLIER[0] = dc << 8 in stage 2 (mpeg1.js:747)
 		n = 1;
 	}
 	if (store) *reinterpret_cast<uint2 *>(slot) = make_uint2(br.bitpos(), (uint32_t)dc8 & 0xffffu);
-	if (!intra && (br.peek32() >> 31)) {  // dct_coeff_first: a leading '1' is (0, +-1), never end_of_block
+	if (DEFER) {
+		defer_first = !intra;  // the caller's first look-up resolves dct_coeff_first (ac_step)
+	} else if (!intra && (br.peek32() >> 31)) {  // dct_coeff_first: a leading '1' is (0, +-1), never end_of_block
 		br.consume(2);
 		n = 1;
 	}
@@ -217,7 +231,8 @@ __device__ __forceinline__ void walk_block_tail(PictureState &ps, int n, bool &d
 __device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
                                            uint32_t *__restrict__ slot, bool store, bool &dc_only) {
 	int n;
-	if (!walk_block_head(br, sbase, ps, intra, block, slot, store, n)) return false;
+	bool unused;
+	if (!walk_block_head<false>(br, sbase, ps, intra, block, slot, store, n, unused)) return false;
 	for (;;) {
 		const uint32_t w = br.peek32();
 		// (Resolving '10' / '11s' arithmetically before the look-up was measured 8 % SLOWER: it defeats the
@@ -250,33 +265,36 @@ __device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, Pictur
 }
 // The same loop, one look-up per call (the lane-parallel walk votes between look-ups so that the lanes
 // stay in step): 0 = go on, 1 = end_of_block consumed, 2 = invalid code.  `combine` = several codes
-// may be taken at once.
-__device__ __forceinline__ int ac_step(BitReader &br, uint32_t sbase, int &n, bool combine) {
+// may be taken at once; `first` = the block's first coefficient of a non-intra block, where a leading
+// '1' is (0, +-1) and never end_of_block (mpeg1.js:757-760): a second table covers that case so that
+// a block start costs no extra trip.  The escape is resolved before the clz table: with 32 chains in
+// lock-step every path some lane needs is issued for all, so the rare path must stay rare.
+__device__ __forceinline__ int ac_step(BitReader &br, uint32_t sbase, int &n, bool combine, bool first) {
+	// every path only decides (bits, run sum, end_of_block); the window moves ONCE, after they rejoin
 	const uint32_t w = br.peek32();
-	if (combine) {
-		const uint32_t m = lds_u16(sbase + OFF_MS + (w >> (32 - MS_BITS)) * 2u);
-		if (m & 15u) {
-			n += (int)((m >> 4) & 63u);
-			br.consume((int)(m & 15u));
-			return (m & 0x400u) ? 1 : 0;
+	const bool lead = first && (w >> 31);
+	uint32_t m = lead ? (2u | (1u << 4)) : 0u;  // not combining: the leading '1s' alone, or the clz table
+	if (combine)
+		m = lds_u16(sbase + (lead ? OFF_MS_FIRST + ((w >> (32 - MS_BITS)) & ((1u << (MS_BITS - 1)) - 1u)) * 2u
+		                          : OFF_MS + (w >> (32 - MS_BITS)) * 2u));
+	int len = (int)(m & 15u), dn = (int)((m >> 4) & 63u), ret = (int)((m >> 10) & 1u);
+	if (len == 0) {
+		if ((w >> 26) == 1u) {  // escape (mpeg1.js:767-780): 6-bit run, 8 (+8) bit level
+			dn = (int)((w >> 20) & 63u) + 1;
+			len = (w & 0x0007f000u) ? 20 : 28;
+		} else {  // a code longer than the window, or end_of_block when not combining
+			const int z = __clz((int)w);
+			if (z > VLC_DCT_MAX_Z) return 2;
+			const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+			if (e == 0 || (e >> 11) == 2u) return 2;  // (the escape was taken above)
+			ret = (int)(e >> 11);            // 1 = end_of_block (two bits)
+			len = (int)(e & 31u);
+			dn = ret ? 0 : (int)(e >> 5);
 		}
 	}
-	const int z = __clz((int)w);
-	if (z > VLC_DCT_MAX_Z) return 2;
-	const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
-	if (e == 0) return 2;
-	if ((e >> 11) == 1u) {  // end_of_block
-		br.consume(2);
-		return 1;
-	}
-	if (e >> 11) {  // escape
-		n += (int)((w >> 20) & 63u) + 1;
-		br.consume((w & 0x0007f000u) ? 20 : 28);
-		return 0;
-	}
-	n += (int)(e >> 5);
-	br.consume((int)(e & 31u));
-	return 0;
+	n += dn;
+	br.consume(len);
+	return ret;
 }
 
 // mpeg1.js:395-457, one component
@@ -475,6 +493,13 @@ __device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps,
 enum { PH_MBA = 0, PH_MBA_STUFF, PH_MBA_ESC, PH_TYPE, PH_MV_H, PH_MV_V, PH_CBP, PH_DC, PH_AC_FIRST, PH_AC, PH_END };
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
+// the votes that close the lock-step loops; the host emulation counts trips and participating lanes per site
+#ifdef JSMPEG_WALK_EMU
+#define WK_VOTE(site, pred) emu_vote(site, pred)
+#else
+#define WK_VOTE(site, pred) __any_sync(FULL_MASK, pred)
+#endif
+enum { VOTE_SYN_MB = 0, VOTE_SYN_AC, VOTE_OWN_MB, VOTE_OWN_AC, VOTE_SITES };
 constexpr uint32_t MIN_SUBSEQ_BITS = 2048;  // below this a sub-sequence is too short for chains to merge in it
 
 struct SliceConst {
@@ -510,7 +535,7 @@ __device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, 
 	const uint32_t guess_ty = sc.picture_type == 1 ? 1u : 0u;
 	bool run = live && ph < PH_END;
 #define SYN_RESYNC() do { br.consume(1); ph = PH_AC; rem = 1u; ty = guess_ty; } while (0)
-	while (__any_sync(FULL_MASK, run)) {
+	while (WK_VOTE(VOTE_SYN_MB, run)) {
 		if (run) do {  // the stages before the blocks; `break` leaves them
 			// ---- macroblock_address_increment (mpeg1.js:295-310), after the slice-end test of mpeg1.js:276
 			while (run && ph <= PH_MBA_ESC) {
@@ -572,39 +597,34 @@ __device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, 
 				}
 			}
 		} while (0);
-		// ---- blocks (mpeg1.js:698-790), current block = highest bit of rem; at most six per macroblock
-#pragma unroll 1
-		for (int b = 0; b < 6; b++) {
-			bool in = run && ph >= PH_DC && ph <= PH_AC;
-			if (in && ph == PH_DC) {
-				if (br.bitpos() >= limit) { run = false; in = false; }
-				else {
-					const uint32_t w = br.peek32();  // blocks 0..3 are the mask bits 0x20..0x04
-					const uint32_t e = rem >= 4u ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
-					                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
-					if ((e & 31u) == 0) SYN_RESYNC();
-					else br.consume((int)(e & 31u) + (int)(e >> 5));
-					ph = PH_AC;
+		// ---- blocks (mpeg1.js:698-790), current block = highest bit of rem.  One look-up per trip for
+		// whatever block the lane is in: lanes wait for the longest MACROBLOCK of the 32, not the longest block
+		bool in = run && ph >= PH_DC && ph <= PH_AC;
+		while (WK_VOTE(VOTE_SYN_AC, in)) {
+			if (in) {
+				if (ph == PH_DC) {
+					if (br.bitpos() >= limit) { run = false; in = false; }
+					else {
+						const uint32_t w = br.peek32();  // blocks 0..3 are the mask bits 0x20..0x04
+						const uint32_t e = rem >= 4u ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
+						                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
+						if ((e & 31u) == 0) SYN_RESYNC();
+						else br.consume((int)(e & 31u) + (int)(e >> 5));
+						ph = PH_AC;
+					}
 				}
-			} else if (in && ph == PH_AC_FIRST) {  // a leading '1' is (0, +-1), never end_of_block (mpeg1.js:757-760)
-				if (br.bitpos() >= limit) { run = false; in = false; }
-				else {
-					if (br.peek32() >> 31) br.consume(2);
-					ph = PH_AC;
-				}
-			}
-			while (__any_sync(FULL_MASK, in)) {  // coefficient codes up to end_of_block, one look-up per trip
 				if (in) {
 					const uint32_t pos = br.bitpos();
 					if (pos >= limit) { run = false; in = false; }
 					else {
 						int n_unused = 0;
-						const int r = ac_step(br, sbase, n_unused, pos + MS_BITS <= limit);
+						const int r = ac_step(br, sbase, n_unused, pos + MS_BITS <= limit, ph == PH_AC_FIRST);
+						ph = PH_AC;
 						if (r == 2) SYN_RESYNC();
 						else if (r == 1) {
 							rem &= ~(0x80000000u >> __clz((int)rem));
 							ph = rem == 0 ? PH_MBA : ((ty & 1u) ? PH_DC : PH_AC_FIRST);
-							in = false;
+							if (rem == 0) in = false;
 						}
 					}
 				}
@@ -680,7 +700,7 @@ __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const
                           uint32_t limit, uint32_t end_byte, int lane) {
 	int how = 0;
 	bool work = owns;
-	while (__any_sync(FULL_MASK, work)) {
+	while (WK_VOTE(VOTE_OWN_MB, work)) {
 		MbHead h;
 		h.mb = 0; h.cbp = 0; h.mv_h = h.mv_v = h.qscale = 0; h.intra = false; h.bit_pos = 0;
 		bool in_mb = false;
@@ -690,24 +710,31 @@ __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const
 		}
 		uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)(MODE == WALK_ABS ? h.mb : 0) * (MB_COEF_INT16 / 2);
 		int done = 0, dc_mask = 0;
-#pragma unroll 1
-		for (int block = 0; block < 6; block++) {
-			int n = 0;
-			bool in = in_mb && (h.cbp & (0x20 >> block));
-			if (in && !walk_block_head(br, sbase, ls, h.intra, block, coef_mb + block * 32, MODE == WALK_ABS, n)) {
-				how = 2; work = false; in_mb = false; in = false;
-			}
-			while (__any_sync(FULL_MASK, in)) {
-				if (in) {
-					const int r = ac_step(br, sbase, n, true);
-					if (r == 2) { how = 2; work = false; in_mb = false; in = false; }
-					else if (r == 1) {
-						bool dc_only;
-						walk_block_tail(ls, n, dc_only);
-						done |= 0x20 >> block;
-						if (dc_only) dc_mask |= 0x20 >> block;
-						in = false;
-					}
+		// the coded blocks of the macroblock, one look-up per trip; a block's head (intra DC, the parked
+		// pair) rides on the trip of its first look-up
+		uint32_t rem = in_mb ? (uint32_t)h.cbp : 0u;  // blocks still to walk, current = highest bit
+		bool at_head = true, first = false;
+		int n = 0;
+		bool in = rem != 0;
+		while (WK_VOTE(VOTE_OWN_AC, in)) {
+			if (in) {
+				const int block = __clz((int)rem) - 26;  // mask bit 0x20 >> block
+				bool ok = true;
+				if (at_head) {
+					ok = walk_block_head<true>(br, sbase, ls, h.intra, block, coef_mb + block * 32, MODE == WALK_ABS, n, first);
+					at_head = false;
+				}
+				const int r = ok ? ac_step(br, sbase, n, true, first) : 2;
+				first = false;
+				if (r == 2) { how = 2; work = false; in_mb = false; in = false; }
+				else if (r == 1) {
+					bool dc_only;
+					walk_block_tail(ls, n, dc_only);
+					done |= 0x20 >> block;
+					if (dc_only) dc_mask |= 0x20 >> block;
+					rem &= ~(0x20u >> block);
+					at_head = true;
+					if (rem == 0) in = false;
 				}
 			}
 		}
@@ -856,7 +883,7 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 // one picture = one warp
 
 // the shared-memory tables of the walk; `ms_table` is the device's multi-symbol table (build_ms_table)
-__device__ __forceinline__ void walk_tables_init(uint8_t *smem, int tid, int nthreads, const uint4 *__restrict__ ms_table) {
+__device__ __forceinline__ void walk_tables_init(uint8_t *smem, int tid, int nthreads, const uint4 *__restrict__ ms_table, bool with_first) {
 	uint16_t *s16 = reinterpret_cast<uint16_t *>(smem);
 	for (int i = tid; i < (VLC_DCT_MAX_Z + 1) * 32; i += nthreads) s16[OFF_DCT / 2 + i] = walk_entry(VLC_DCT_COEFF[i]);
 	for (int i = tid; i < (VLC_MBA_MAX_Z + 1) * 32; i += nthreads) s16[OFF_MBA / 2 + i] = VLC_MBA[i];
@@ -867,7 +894,8 @@ __device__ __forceinline__ void walk_tables_init(uint8_t *smem, int tid, int nth
 	for (int i = tid; i < 4; i += nthreads) s16[OFF_TYPE_I / 2 + i] = VLC_MBTYPE_I[i];
 	for (int i = tid; i < 64; i += nthreads) s16[OFF_TYPE_P / 2 + i] = VLC_MBTYPE_P[i];
 	uint4 *ms = reinterpret_cast<uint4 *>(smem + OFF_MS);
-	for (int i = tid; i < (2 << MS_BITS) / 16; i += nthreads) ms[i] = __ldg(ms_table + i);
+	const int n16 = (int)(with_first ? 2u * MS_TABLE_ENTRIES : (2u << MS_BITS)) / 16;
+	for (int i = tid; i < n16; i += nthreads) ms[i] = __ldg(ms_table + i);
 }
 
 // decodePicture (mpeg1.js:174-247), bitstream side.  LANES: every slice is first tried with the
@@ -971,10 +999,11 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
 // sign bits) that fit, greedily.  Entry: bits 0..3 = bits to consume (0 = first code does not fit
 // or is an escape: take the single-symbol path), bits 4..9 = sum of (run + 1), bit 10 = the last
 // code consumed was end_of_block.  `dct` is the generated clz-indexed DCT table (VLC_DCT_COEFF).
+// It is followed by the dct_coeff_first variant for the prefixes with a leading 1: that '1s' is the
+// code (0, +-1), then the same greedy continuation.  `ms` holds MS_TABLE_ENTRIES entries.
 static inline void build_ms_table(const uint16_t *dct, uint16_t *ms) {
-	for (uint32_t prefix = 0; prefix < (1u << MS_BITS); prefix++) {
-		const uint32_t w = prefix << (32 - MS_BITS);
-		int pos = 0, n = 0, eob = 0;
+	auto greedy = [&](uint32_t w, int pos, int n) {
+		int eob = 0;
 		for (;;) {
 			const uint32_t v = w << pos;  // bits beyond the prefix read as 0 and are never trusted: lengths are checked
 			int z = 0;
@@ -991,8 +1020,11 @@ static inline void build_ms_table(const uint16_t *dct, uint16_t *ms) {
 			pos += len + 1;
 			n += run + 1;
 		}
-		ms[prefix] = (uint16_t)(pos | (n << 4) | (eob << 10));
-	}
+		return (uint16_t)(pos | (n << 4) | (eob << 10));
+	};
+	for (uint32_t prefix = 0; prefix < (1u << MS_BITS); prefix++) ms[prefix] = greedy(prefix << (32 - MS_BITS), 0, 0);
+	for (uint32_t low = 0; low < (1u << (MS_BITS - 1)); low++)
+		ms[(1u << MS_BITS) + low] = greedy((1u << 31) | (low << (32 - MS_BITS)), 2, 1);
 }
 
 }  // namespace

@@ -85,16 +85,34 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t, uint32_t sel) {
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 
+// trips and participating lanes of the lock-step loops, per vote site (walk.cuh: WK_VOTE)
+static uint64_t vote_trips[8], vote_lanes[8];
+static inline int emu_vote(int site, int pred) {
+	const unsigned m = __ballot_sync(0xffffffffu, pred);
+	if (emu::lane == 0 && m) {
+		vote_trips[site]++;
+		vote_lanes[site] += __builtin_popcount(m);
+	}
+	return m != 0;
+}
+extern "C" void emu_vote_counters(uint64_t *trips, uint64_t *lanes, int reset) {
+	for (int i = 0; i < 8; i++) {
+		trips[i] = vote_trips[i];
+		lanes[i] = vote_lanes[i];
+		if (reset) vote_trips[i] = vote_lanes[i] = 0;
+	}
+}
+
 #define VLC_TABLE_QUALIFIER static const
 #include "../../jsmpeg_b200/csrc/walk.cuh"
 
 extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t start_byte, int mb_width, int mb_height,
                                 mb_record_t *hdr, int16_t *coef, picture_info_t *info, int lanes) {
 	static std::once_flag once;
-	static std::vector<uint16_t> ms(1u << MS_BITS);
+	static std::vector<uint16_t> ms(MS_TABLE_ENTRIES);
 	std::call_once(once, [] {
 		build_ms_table(VLC_DCT_COEFF, ms.data());
-		walk_tables_init(emu_smem, 0, 1, reinterpret_cast<const uint4 *>(ms.data()));
+		walk_tables_init(emu_smem, 0, 1, reinterpret_cast<const uint4 *>(ms.data()), true);
 	});
 	SeqParams seq;
 	memset(&seq, 0, sizeof(seq));
