@@ -39,21 +39,28 @@ constexpr int CTA_THREADS = 128;       // expand kernel
 constexpr uint32_t TILE_PITCH = 144;   // bytes between the per-thread 64 x int16 tiles of the expand kernel (128 + 16: bank spread)
 
 // ==================================================================================================
-// 1a: one warp per picture (walk.cuh); LANES selects the lane-parallel walk with serial fall-back
+// 1a: one warp per picture (walk.cuh), serial or lane-parallel with serial fall-back
 
-template <bool LANES>
-__global__ void __launch_bounds__(WALK_THREADS)
-walk_pictures_kernel(const ParseTask *__restrict__ tasks, int n_tasks, const uint4 *__restrict__ ms_table) {
-	extern __shared__ __align__(128) uint8_t smem[];
-	walk_tables_init(smem, threadIdx.x, WALK_THREADS, ms_table, LANES);
-	__syncthreads();
-
-	const int lane = threadIdx.x & 31;
-	const int task_id = blockIdx.x * (WALK_THREADS / 32) + (threadIdx.x >> 5);
-	if (task_id >= n_tasks) return;
-	const ParseTask t = tasks[task_id];
-	walk_picture<LANES>(t, smem_base(smem), lane);
-}
+// the serial walk keeps the allocation it was tuned with (63 registers, no occupancy hint); the
+// lane-parallel walk is held to 64 registers = 4 resident CTAs per SM (measured: 46.4 ms per step
+// against 47.9 ms with the 80 registers it takes unbounded)
+#ifndef JSMPEG_LANES_MIN_CTAS
+#define JSMPEG_LANES_MIN_CTAS 4
+#endif
+#define LANES_BOUNDS __launch_bounds__(WALK_THREADS, JSMPEG_LANES_MIN_CTAS)
+#define WALK_KERNEL(NAME, LANES, BOUNDS)                                                                          \
+	__global__ void BOUNDS NAME(const ParseTask *__restrict__ tasks, int n_tasks, const uint4 *__restrict__ ms_table) { \
+		extern __shared__ __align__(128) uint8_t smem[];                                                          \
+		walk_tables_init(smem, threadIdx.x, WALK_THREADS, ms_table, LANES);                                       \
+		__syncthreads();                                                                                          \
+		const int lane = threadIdx.x & 31;                                                                        \
+		const int task_id = blockIdx.x * (WALK_THREADS / 32) + (threadIdx.x >> 5);                                \
+		if (task_id >= n_tasks) return;                                                                           \
+		const ParseTask t = tasks[task_id];                                                                       \
+		walk_picture<LANES>(t, smem_base(smem), lane);                                                            \
+	}
+WALK_KERNEL(walk_pictures_kernel, false, __launch_bounds__(WALK_THREADS))
+WALK_KERNEL(walk_pictures_lanes_kernel, true, LANES_BOUNDS)
 
 // ==================================================================================================
 // 1b: expand every coded block (one thread per block slot)
@@ -166,9 +173,9 @@ static const uint16_t *ms_table_for_current_device() {
 	int dev = 0;
 	CUDA_CHECK(cudaGetDevice(&dev));
 	if (tables[dev]) return tables[dev];
-	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                (int)WALK_SMEM_SERIAL));  // per device, once
-	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                (int)WALK_SMEM_LANES));
 	std::vector<uint16_t> dct((VLC_DCT_MAX_Z + 1) * 32);
 	CUDA_CHECK(cudaMemcpyFromSymbol(dct.data(), VLC_DCT_COEFF, dct.size() * sizeof(uint16_t)));
@@ -195,10 +202,10 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 		const int g = e ? atoi(e) : PARSE_GROUPS;
 		return g < 1 ? 1 : (g > PARSE_GROUPS ? PARSE_GROUPS : g);
 	}();
-	// JSMPEG_B200_WALK=lanes selects the lane-parallel walk (walk.cuh); default: the serial walk
+	// the lane-parallel walk (walk.cuh) is the default; JSMPEG_B200_WALK=serial selects the one-chain-per-warp walk
 	static const bool lane_walk = [] {
 		const char *e = getenv("JSMPEG_B200_WALK");
-		return e && !strcmp(e, "lanes");
+		return !(e && !strcmp(e, "serial"));
 	}();
 	const size_t walk_smem = lane_walk ? WALK_SMEM_LANES : WALK_SMEM_SERIAL;
 	const int groups = (fork && n_tasks >= 64 * max_groups) ? max_groups : 1;
@@ -212,10 +219,10 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 		cudaStream_t st = g == 0 ? stream : fork->side[g];
 		if (g > 0) CUDA_CHECK(cudaStreamWaitEvent(st, fork->fork, 0));
 		if (lane_walk)
-			walk_pictures_kernel<true><<<(n + per_cta - 1) / per_cta, WALK_THREADS, walk_smem, st>>>(
+			walk_pictures_lanes_kernel<<<(n + per_cta - 1) / per_cta, WALK_THREADS, walk_smem, st>>>(
 			    tasks + lo, n, reinterpret_cast<const uint4 *>(ms));
 		else
-			walk_pictures_kernel<false><<<(n + per_cta - 1) / per_cta, WALK_THREADS, walk_smem, st>>>(
+			walk_pictures_kernel<<<(n + per_cta - 1) / per_cta, WALK_THREADS, walk_smem, st>>>(
 			    tasks + lo, n, reinterpret_cast<const uint4 *>(ms));
 		if (g == 0 && walk_done) CUDA_CHECK(cudaEventRecord(walk_done, st));
 		dim3 grid((max_mb_size * 6 + CTA_THREADS - 1) / CTA_THREADS, n);

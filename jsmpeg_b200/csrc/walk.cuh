@@ -148,7 +148,6 @@ struct PictureState {
 	// lane-parallel walk only: which parts of a RELATIVE state no longer depend on the state the lane
 	// started from, and whether a case outside the lane-parallel walk's domain was met
 	bool qs_set, dc_abs, mv_abs, anomaly;
-	int sync_rounds;  // rounds of pass B over all slices (diagnostic, info.reserved[1])
 };
 
 #ifndef JSMPEG_WALK_EMU
@@ -469,26 +468,26 @@ __device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps,
 // syntax state falls into step with the true one after a while; Klein & Wiseman 2003, and
 // Weissenberger & Schmidt 2018/2021 for Huffman/JPEG on GPUs):
 //
-//   A  every lane > 0 starts at the first bit of its sub-sequence in a GUESSED syntax state and runs a
-//      syntax-only automaton (code lengths and the state machine of mpeg1.js:294-392/698-790, no
-//      values) to the first code boundary at or beyond the end of its sub-sequence; lane 0 starts in
-//      the true state.  The (bit position, syntax state) reached is the sub-sequence's exit state.
-//   B  every lane keeps going through the NEXT sub-sequence and compares the exit state it reaches
-//      with the one the owner of that sub-sequence found.  Equal: the two chains have merged, the lane
-//      stops.  Different: it replaces the stored exit state and goes on to the following sub-sequence.
-//      Lane 0 carries the truth, so when all lanes have stopped every stored exit state is the true
-//      chain's (normally after ONE round: sub-sequences are thousands of bits long, chains merge
-//      within a few macroblocks).
-//   C  every lane starts from the true entry state of its sub-sequence, finds the first macroblock
-//      that STARTS in it and walks the macroblocks starting in it with full semantics but RELATIVE
-//      predictors (WALK_REL) -- a summary: address advance, last quantiser scale, DC and motion
-//      predictors as "absolute after a reset" or "delta".  A warp scan of the summaries (an
+//   W  warm-up: every lane > 0 starts WARMUP_BITS before its sub-sequence in a GUESSED syntax state and
+//      runs a syntax-only automaton (code lengths and the state machine of mpeg1.js:294-392/698-790,
+//      no values) to the first macroblock start at or beyond the start of its sub-sequence.  By then
+//      it has, almost always, merged with the true chain (chains merge within a few macroblocks).
+//      Lane 0, and lanes whose warm-up would begin before the slice, start in the true state.
+//   C  every lane walks the macroblocks that START in its sub-sequence with full semantics but
+//      RELATIVE predictors (WALK_REL) -- a summary: address advance, last quantiser scale, DC and
+//      motion predictors as "absolute after a reset" or "delta".  Where lane i stops must be exactly
+//      where lane i+1 started: if that holds for every lane, every lane walked the true chain (lane 0
+//      did, and each lane hands the true position to the next).  A warp scan of the summaries (an
 //      associative composition) gives every lane the absolute state at its first macroblock.
 //   D  every lane walks its macroblocks again with the absolute state and stores (WALK_ABS).
 //
-// Anything outside the clean domain -- an invalid code on the true chain, an address outside the
-// picture, a slice that does not end exactly at the next start code -- makes the warp discard the
-// attempt and walk the whole picture with the serial code, which defines the behaviour there.
+// Anything outside the clean domain -- a warm-up that did not merge, an invalid code on the true chain,
+// an address outside the picture, a slice that does not end exactly at the next start code -- makes
+// the warp discard the attempt and walk the whole picture with the serial code, which defines the
+// behaviour there.
+// (The first version followed Weissenberger & Schmidt more literally: full-length speculative pass,
+// then rounds of "run on through the next sub-sequence and compare exit states" -- 4.3 passes over the
+// bits instead of 2.2; see DESIGN.md.)
 
 enum { PH_MBA = 0, PH_MBA_STUFF, PH_MBA_ESC, PH_TYPE, PH_MV_H, PH_MV_V, PH_CBP, PH_DC, PH_AC_FIRST, PH_AC, PH_END };
 
@@ -500,7 +499,11 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 #define WK_VOTE(site, pred) __any_sync(FULL_MASK, pred)
 #endif
 enum { VOTE_SYN_MB = 0, VOTE_SYN_AC, VOTE_OWN_MB, VOTE_OWN_AC, VOTE_SITES };
-constexpr uint32_t MIN_SUBSEQ_BITS = 2048;  // below this a sub-sequence is too short for chains to merge in it
+constexpr uint32_t MIN_SUBSEQ_BITS = 2048;  // shorter sub-sequences are not worth a lane
+#ifndef JSMPEG_WARMUP_BITS
+#define JSMPEG_WARMUP_BITS 8192
+#endif
+constexpr uint32_t WARMUP_BITS = JSMPEG_WARMUP_BITS;  // how far before its sub-sequence a lane starts guessing
 
 struct SliceConst {
 	int picture_type, r_size, f;
@@ -514,14 +517,11 @@ __device__ __forceinline__ uint32_t syn_make(int phase, uint32_t rem, uint32_t t
 // true macroblock start often enough.
 __device__ __forceinline__ uint32_t syn_guess(const SliceConst &sc) { return syn_make(PH_AC, 1u, sc.picture_type == 1 ? 1u : 0u); }
 
-// Runs the syntax-only automaton from the reader's position in state `st` until the first code
-// boundary at or beyond bit `limit` (or END; or, if asked, the first macroblock start).
+// Runs the syntax-only automaton from the reader's position in state `st` until the first MACROBLOCK
+// START at or beyond bit `limit` (state PH_MBA) or the end of the slice (PH_END).
 // An invalid code does not stop a chain: it drops one bit and guesses again (a chain that dies can
-// never merge, and every sub-sequence behind a dead lane costs the lanes before it a round).  If it
-// is the TRUE chain that meets an invalid code, pass C/D meet it too, with full semantics, and the
-// picture goes to the serial walk.
-// Several coefficient codes are taken per look-up only while that cannot jump over `limit`, so that
-// the boundary reached depends on the chain alone, not on where a lane joined it.
+// never merge).  If it is the TRUE chain that meets an invalid code, pass C/D meet it too, with full
+// semantics, and the picture goes to the serial walk.
 //
 // WARP-SYNCHRONOUS: all 32 lanes call it together (`live` = this lane has something to run).  The
 // automaton is written in the order of the syntax, one macroblock per trip of the outer loop and one
@@ -529,19 +529,19 @@ __device__ __forceinline__ uint32_t syn_guess(const SliceConst &sc) { return syn
 // the same stage at the same time.  (Left to themselves, lanes that leave a loop early never wait for
 // the others: measured on B200, the first version ran with 4 of 32 lanes active on average and its
 // per-lane macroblock loops with ONE.)
-__device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, bool live, uint32_t limit, uint32_t &st, bool stop_at_mb_start) {
+__device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, bool live, uint32_t limit, uint32_t &st) {
 	int ph = (int)(st & 15u);
 	uint32_t rem = (st >> 4) & 63u, ty = st >> 10;
 	const uint32_t guess_ty = sc.picture_type == 1 ? 1u : 0u;
+	const uint32_t end_bit = sc.end_byte * 8u;
 	bool run = live && ph < PH_END;
 #define SYN_RESYNC() do { br.consume(1); ph = PH_AC; rem = 1u; ty = guess_ty; } while (0)
 	while (WK_VOTE(VOTE_SYN_MB, run)) {
 		if (run) do {  // the stages before the blocks; `break` leaves them
 			// ---- macroblock_address_increment (mpeg1.js:295-310), after the slice-end test of mpeg1.js:276
 			while (run && ph <= PH_MBA_ESC) {
-				if (stop_at_mb_start && ph == PH_MBA) { run = false; break; }
 				const uint32_t pos = br.bitpos();
-				if (pos >= limit) { run = false; break; }
+				if (ph == PH_MBA && pos >= limit) { run = false; break; }
 				if (ph == PH_MBA && ((pos + 7u) >> 3) >= sc.end_byte) { ph = PH_END; run = false; break; }
 				const uint32_t e = clz_lut(sbase + OFF_MBA, br.peek32(), VLC_MBA_MAX_Z);
 				if ((e & 31u) == 0) { SYN_RESYNC(); break; }
@@ -554,7 +554,6 @@ __device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, 
 			if (!run) break;
 			// ---- macroblock_type (+ quantiser scale), mpeg1.js:348-361
 			if (ph == PH_TYPE) {
-				if (br.bitpos() >= limit) { run = false; break; }
 				const uint32_t w = br.peek32();
 				const uint32_t e = sc.picture_type == 1 ? lds_u16(sbase + OFF_TYPE_I + (w >> 30) * 2u)
 				                                        : lds_u16(sbase + OFF_TYPE_P + (w >> 26) * 2u);
@@ -573,7 +572,6 @@ __device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, 
 			}
 			// ---- motion vectors (mpeg1.js:395-457): code + residual, values not needed
 			while (ph == PH_MV_H || ph == PH_MV_V) {
-				if (br.bitpos() >= limit) { run = false; break; }
 				const uint32_t e = clz_lut(sbase + OFF_MOTION, br.peek32(), VLC_MOTION_MAX_Z);
 				if ((e & 31u) == 0) { SYN_RESYNC(); break; }
 				const int code = (int)(e >> 5) - 16;
@@ -582,10 +580,8 @@ __device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, 
 				else if (ty & 2u) ph = PH_CBP;
 				else ph = PH_MBA;  // motion only: no blocks (intra macroblocks carry no vectors)
 			}
-			if (!run) break;
 			// ---- coded_block_pattern (mpeg1.js:376-384)
 			if (ph == PH_CBP) {
-				if (br.bitpos() >= limit) { run = false; break; }
 				const uint32_t e = clz_lut(sbase + OFF_CBP, br.peek32(), VLC_CBP_MAX_Z);
 				if ((e & 31u) == 0) {
 					SYN_RESYNC();
@@ -602,9 +598,10 @@ __device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, 
 		bool in = run && ph >= PH_DC && ph <= PH_AC;
 		while (WK_VOTE(VOTE_SYN_AC, in)) {
 			if (in) {
-				if (ph == PH_DC) {
-					if (br.bitpos() >= limit) { run = false; in = false; }
-					else {
+				if (br.bitpos() >= end_bit) {  // a chain of garbage must end with the slice
+					ph = PH_END; run = false; in = false;
+				} else {
+					if (ph == PH_DC) {
 						const uint32_t w = br.peek32();  // blocks 0..3 are the mask bits 0x20..0x04
 						const uint32_t e = rem >= 4u ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
 						                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
@@ -612,20 +609,14 @@ __device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, 
 						else br.consume((int)(e & 31u) + (int)(e >> 5));
 						ph = PH_AC;
 					}
-				}
-				if (in) {
-					const uint32_t pos = br.bitpos();
-					if (pos >= limit) { run = false; in = false; }
-					else {
-						int n_unused = 0;
-						const int r = ac_step(br, sbase, n_unused, pos + MS_BITS <= limit, ph == PH_AC_FIRST);
-						ph = PH_AC;
-						if (r == 2) SYN_RESYNC();
-						else if (r == 1) {
-							rem &= ~(0x80000000u >> __clz((int)rem));
-							ph = rem == 0 ? PH_MBA : ((ty & 1u) ? PH_DC : PH_AC_FIRST);
-							if (rem == 0) in = false;
-						}
+					int n_unused = 0;
+					const int r = ac_step(br, sbase, n_unused, true, ph == PH_AC_FIRST);
+					ph = PH_AC;
+					if (r == 2) SYN_RESYNC();
+					else if (r == 1) {
+						rem &= ~(0x80000000u >> __clz((int)rem));
+						ph = rem == 0 ? PH_MBA : ((ty & 1u) ? PH_DC : PH_AC_FIRST);
+						if (rem == 0) in = false;
 					}
 				}
 			}
@@ -693,13 +684,14 @@ __device__ uint32_t find_slice_end(const BitReader &br, uint32_t from, int lane)
 
 // The macroblocks that START in [reader position, limit), walked in MODE (WALK_REL / WALK_ABS).
 // Returns 0 when the lane reached `limit` (or owns nothing), 1 when the slice ended cleanly at the
-// start code, 2 on anything else.  WARP-SYNCHRONOUS like syntax_run: a vote closes the macroblock
+// start code, 2 on anything else; stop_pos = the bit position after the lane's last macroblock.  WARP-SYNCHRONOUS like syntax_run: a vote closes the macroblock
 // loop, a __syncwarp every block and a vote every look-up of the coefficient loop.
 template <int MODE>
 __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const ParseTask &t, int mb_size, bool owns,
-                          uint32_t limit, uint32_t end_byte, int lane) {
+                          uint32_t limit, uint32_t end_byte, int lane, uint32_t &stop_pos) {
 	int how = 0;
 	bool work = owns;
+	if (owns) stop_pos = br.bitpos();
 	while (WK_VOTE(VOTE_OWN_MB, work)) {
 		MbHead h;
 		h.mb = 0; h.cbp = 0; h.mv_h = h.mv_v = h.qscale = 0; h.intra = false; h.bit_pos = 0;
@@ -745,6 +737,7 @@ __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const
 			ls.n_present++;
 			const uint32_t pos = br.bitpos();
 			const uint32_t i = (pos + 7u) >> 3;
+			stop_pos = pos;
 			if (i >= end_byte) { how = i == end_byte ? 1 : 2; work = false; }
 			else if (pos >= limit) work = false;
 		}
@@ -770,55 +763,24 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 	SliceConst sc;
 	sc.picture_type = ps.picture_type; sc.r_size = ps.r_size; sc.f = ps.f; sc.end_byte = end_byte;
 
-	// ---- A: own sub-sequence, from a guessed state (lane 0: the true one)
-	uint32_t my_pos = end_bit, my_st = PH_END;
+	// ---- W: warm-up to the first macroblock that starts in the sub-sequence.  Chains merge within a few
+	// macroblocks, so the warm-up is WARMUP_BITS or 48 average macroblocks, whichever is longer
+	const uint32_t warm = max(WARMUP_BITS, total / (uint32_t)mb_size * 48u);
+	uint32_t st = PH_MBA;
 	if (active) {
-		br.seek_bit(s_lo);
-		my_st = lane == 0 ? (uint32_t)PH_MBA : syn_guess(sc);
-	}
-	syntax_run(br, sbase, sc, active, s_hi, my_st, false);
-	if (active) my_pos = br.bitpos();
-	uint32_t e_pos = my_pos, e_st = my_st;  // exit state of sub-sequence `lane`, as known so far
-
-	// ---- B: run on into the following sub-sequences until the chains have merged
-	bool merged = !active || lane >= K - 1 || (my_st & 15u) >= PH_END;
-	for (int round = 0; round < K - 1; round++) {
-		if (!__any_sync(FULL_MASK, !merged)) break;
-		ps.sync_rounds++;
-		const int idx = lane + 1 + round;  // the sub-sequence this lane walks in this round
-		if (idx >= K) merged = true;
-		const bool arrive = !merged;
-		const uint32_t lim = (arrive && idx < K - 1) ? p_start + (uint32_t)(idx + 1) * L : end_bit;
-		syntax_run(br, sbase, sc, arrive, lim, my_st, false);
-		if (arrive) my_pos = br.bitpos();
-		const int src = lane - 1 - round;  // the lane that arrives at the end of sub-sequence `lane` in this round
-		const uint32_t v_pos = __shfl_sync(FULL_MASK, my_pos, src & 31), v_st = __shfl_sync(FULL_MASK, my_st, src & 31);
-		const int v_arrive = __shfl_sync(FULL_MASK, (int)arrive, src & 31);
-		int same = 0;
-		if (src >= 0 && v_arrive) {
-			same = v_pos == e_pos && v_st == e_st;
-			e_pos = v_pos;
-			e_st = v_st;
-		}
-		const int got = __shfl_sync(FULL_MASK, same, idx & 31);
-		if (arrive && (got || (my_st & 15u) >= PH_END)) merged = true;  // a dead chain stops: it must not overwrite further exit states
-	}
-
-	// ---- C: first macroblock starting in the sub-sequence, then the relative summary of the owned macroblocks
-	uint32_t in_pos = __shfl_up_sync(FULL_MASK, e_pos, 1), in_st = __shfl_up_sync(FULL_MASK, e_st, 1);
-	if (lane == 0) { in_pos = p_start; in_st = PH_MBA; }
-	bool bad = false, owns = false;
-	uint32_t q = 0;
-	{
-		const bool seek = active && (in_st & 15u) < PH_END;
-		uint32_t st = in_st;
-		if (seek) br.seek_bit(in_pos);
-		syntax_run(br, sbase, sc, seek, s_hi, st, true);
-		if (seek) {
-			q = br.bitpos();
-			if ((st & 15u) == PH_MBA && q < s_hi && ((q + 7u) >> 3) < end_byte) owns = true;
+		if (lane == 0 || s_lo - p_start <= warm) {
+			br.seek_bit(p_start);  // the true chain from the slice's first macroblock
+		} else {
+			br.seek_bit(s_lo - warm);
+			st = syn_guess(sc);
 		}
 	}
+	syntax_run(br, sbase, sc, active && lane > 0, s_lo, st);
+	const uint32_t q = active ? br.bitpos() : end_bit;
+	const bool owns = active && (st & 15u) == PH_MBA && q < s_hi && ((q + 7u) >> 3) < end_byte;
+	bool bad = false;
+
+	// ---- C: the relative summary of the owned macroblocks; every lane must stop where the next one started
 	PictureState ls = ps;  // picture constants; the rest is set per pass
 	LaneSum sum;
 	sum.d_addr = 0; sum.qs = 0; sum.dcy = sum.dc4 = sum.dc5 = 0; sum.mvh = sum.mvv = 0; sum.flags = 0;
@@ -830,7 +792,10 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 		ls.qs_set = ls.dc_abs = ls.mv_abs = ls.anomaly = false;
 		ls.n_present = ls.n_coded = ls.error = 0;
 	}
-	how = walk_owned<WALK_REL>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane);
+	uint32_t stop_pos = q;
+	how = walk_owned<WALK_REL>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos);
+	const uint32_t next_q = __shfl_down_sync(FULL_MASK, q, 1);
+	if (active && lane < K - 1 && stop_pos != next_q) bad = true;  // the warm-up of lane + 1 had not merged
 	if (owns) {
 		if (how == 2) bad = true;
 		sum.d_addr = ls.mb_addr; sum.qs = ls.qscale;
@@ -863,7 +828,7 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 		ls.mv_h = ps.full_pel ? x.mvh * 2 : x.mvh;
 		ls.mv_v = ps.full_pel ? x.mvv * 2 : x.mvv;
 	}
-	const int how_abs = walk_owned<WALK_ABS>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane);
+	const int how_abs = walk_owned<WALK_ABS>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos);
 	if (how_abs != how || ls.anomaly) bad = true;
 	if (__any_sync(FULL_MASK, bad)) return false;
 	int n_present = ls.n_present, n_coded = ls.n_coded, error = ls.error;
@@ -921,7 +886,6 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
 		ps.n_present = ps.n_coded = ps.error = 0;
 		ps.full_pel = 0; ps.r_size = 0; ps.f = 1;
 		ps.qs_set = ps.dc_abs = ps.mv_abs = ps.anomaly = false;
-		ps.sync_rounds = 0;
 		int f_code = 0;
 		int status = PIC_IGNORED;
 
@@ -987,8 +951,7 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
 			info.n_coded_blocks = ps.n_coded;
 			info.error = ps.error;
 			info.reserved[0] = (LANES && lanes && go) ? 1 : 0;
-			info.reserved[1] = (LANES && lanes) ? ps.sync_rounds : 0;
-			info.reserved[2] = 0;
+			info.reserved[1] = info.reserved[2] = 0;
 			*t.info = info;
 		}
 		return;

@@ -67,6 +67,7 @@ static inline void __syncwarp(unsigned = 0xffffffffu) { emu::bar.wait(); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu::exchange(v, src); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu::exchange(v, emu::lane - d >= 0 ? emu::lane - d : emu::lane); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::exchange(v, emu::lane ^ m); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu::exchange(v, emu::lane + d < 32 ? emu::lane + d : emu::lane); }
 static inline unsigned __ballot_sync(unsigned, int pred) {
 	emu::slots[emu::lane] = pred ? 1 : 0;
 	emu::bar.wait();

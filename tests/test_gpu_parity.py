@@ -363,28 +363,34 @@ def test_corrupted_streams_terminate_and_stay_in_bounds(seed):
     golden.check_against_golden(capi.product_library(), "rows_ip")
 
 
-# ---- the lane-parallel walk (JSMPEG_B200_WALK=lanes) against the same checkers ---------------------
+# ---- both walks of stage 1a against the same checkers ---------------------------------------------
 
-def test_lane_parallel_walk_in_a_child_process():
+def test_clean_clip_is_walked_by_the_lane_parallel_walk():
+    """Default configuration: the lane-parallel walk, not its serial fall-back, produces every picture
+    of a clean clip (a silent fall-back would still be bit-exact, only slow)."""
+    import os
+    if os.environ.get("JSMPEG_B200_WALK") == "serial":
+        pytest.skip("serial walk selected")
+    es = b"".join(p for _, p in clip_packets(640, 480, 13))
+    bd = BatchDecoder(1)
+    bd.write(0, es)
+    n = bd.decode(13, OUT_DEVICE)
+    st = bd.stats()
+    bd.close()
+    assert n == 13 and st["lane_walk_pictures"] == 13, (n, st["lane_walk_pictures"])
+
+
+def test_serial_walk_in_a_child_process():
     """The walk variant is chosen once per process (first launch), so the stage-1 record parity, the
-    golden streams and a whole-clip decode are repeated in a child process with
-    JSMPEG_B200_WALK=lanes; the child also checks that the lane-parallel walk, not its serial
-    fall-back, produced the pictures of a clean clip."""
+    golden streams, a whole-clip decode and the corrupted-stream contract are repeated in a child
+    process with JSMPEG_B200_WALK=serial (the one-chain-per-warp walk the lane-parallel one falls back
+    to inside the same kernel)."""
     import os
     import subprocess
     import sys
-    if os.environ.get("JSMPEG_B200_WALK") == "lanes":
-        pytest.skip("already running with the lane-parallel walk")
-    env = dict(os.environ, JSMPEG_B200_WALK="lanes")
-    here = os.path.dirname(os.path.abspath(__file__))
-    check = (
-        "import sys; sys.path.insert(0, %r)\n"
-        "import helpers\n"
-        "from jsmpeg_b200.batch import BatchDecoder, OUT_DEVICE\n"
-        "es = b''.join(p for _, p in helpers.clip_packets(640, 480, 13))\n"
-        "bd = BatchDecoder(1); bd.write(0, es); n = bd.decode(13, OUT_DEVICE); st = bd.stats(); bd.close()\n"
-        "assert n == 13 and st['lane_walk_pictures'] == 13, (n, st['lane_walk_pictures'])\n" % here)
-    subprocess.run([sys.executable, "-c", check], env=env, check=True, timeout=300)
+    if os.environ.get("JSMPEG_B200_WALK") == "serial":
+        pytest.skip("already running with the serial walk")
+    env = dict(os.environ, JSMPEG_B200_WALK="serial")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
                         "-k", "stage1_parse or golden or whole_clip or corrupted"],
                        env=env, capture_output=True, text=True, timeout=900)
