@@ -112,3 +112,21 @@ def test_truncated_and_corrupt_streams_fall_back_identically():
         for pos in rng.integers(200, len(es), size=4):
             bad[pos] ^= 1 << int(rng.integers(0, 8))
         check_stream(lib, bytes(bad), f"corrupt {trial}")
+
+
+def test_walks_are_memory_safe_under_address_sanitizer():
+    """Both walks on exact-size heap buffers (clean, bit-flipped and truncated streams) with the
+    emulation library built with -fsanitize=address: no read or write outside the ES, the record
+    arrays or the picture info.  (compute-sanitizer covers the same on the GPU when there is budget.)"""
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not asan or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    lib = os.path.join(HERE, "emu", "libwalk_emu_asan.so")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-fsanitize=address", "-fno-omit-frame-pointer",
+                           "-Wno-attributes", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include", "-o", lib, EMU_SRC])
+    # three pictures of every stream here; ASAN_CHECK_PICTURES=0 python tests/emu/asan_check.py <lib> runs all (minutes)
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0",
+               ASAN_CHECK_PICTURES=os.environ.get("ASAN_CHECK_PICTURES", "60"))
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "asan_check.py"), lib], env=env, capture_output=True, text=True,
+                       timeout=1200)
+    assert r.returncode == 0 and "asan clean over" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
