@@ -425,7 +425,9 @@ def main():
                               "reconstruct": st["recon_ms"] / args.steps},
         "stage1": {"es_mbit_per_s": st["es_bytes"] * 8 / (st["parse_ms"] / 1e3) / 1e6 if st["parse_ms"] else None,
                    "pictures_per_s": st["pictures"] / (st["parse_ms"] / 1e3) if st["parse_ms"] else None,
-                   "parse_errors": st["parse_errors"]},
+                   "parse_errors": st["parse_errors"],
+                   "walk": os.environ.get("JSMPEG_B200_WALK") or "lanes",
+                   "lane_walk_pictures_per_step": st.get("lane_walk_pictures", 0) / args.steps},
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
