@@ -8,18 +8,21 @@
 // has been decoded.  Everything ELSE the reference does per symbol (run/level bookkeeping,
 // zig-zag, dequantisation, oddification, clipping, the store) does not feed that chain.  So:
 //
-//   1a  walk_pictures_kernel    one warp per PICTURE (every picture starts at a byte-aligned start
-//       code and resets all predictor state in its slice headers, and nothing in the parse depends
-//       on decoded pixels, so all buffered pictures of all streams are walked concurrently).
+//   1a  walk_pictures_{lanes_,}kernel   one warp per PICTURE (every picture starts at a byte-aligned
+//       start code and resets all predictor state in its slice headers, and nothing in the parse
+//       depends on decoded pixels, so all buffered pictures of all streams are walked concurrently).
 //       The walk does the minimum that is serial: macroblock headers (address increment, type,
 //       quantiser, motion vectors with their predictors, coded block pattern), intra DC
 //       differentials with their predictors, and for the AC coefficients only LUT -> code length
 //       -> shift.  It emits the 16-byte macroblock record and, per coded block, the bit offset of
 //       its first coefficient code (parked in the block's own 128-byte coefficient slot).
+//       Default: the LANE-PARALLEL walk -- the 32 lanes take 32 sub-sequences of the picture's bits
+//       and find the chain by VLC self-synchronisation (walk.cuh); the serial walk (all lanes on one
+//       chain) is its in-kernel fall-back and, with JSMPEG_B200_WALK=serial, a kernel of its own.
 //   1b  expand_blocks_kernel    one thread per coded BLOCK, all blocks of all pictures at once:
 //       re-reads the block's codes from its bit offset, does run/level -> zig-zag -> dequantise ->
-//       oddify -> clip (src/mpeg1.js:757-811) into a shared-memory tile and writes the 64 x int16
-//       block record with 16-byte stores.
+//       oddify -> clip (src/mpeg1.js:757-811) into a shared-memory tile; the 64 x int16 block record
+//       leaves as one 128-byte TMA bulk store.
 //
 // VLCs are decoded with clz-indexed look-up tables in shared memory (tools/gen_tables.py; pinned
 // to the reference's trees by tests/test_vlc_tables.py) instead of the reference's one-bit-per-step
