@@ -333,6 +333,12 @@ __device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int 
 	return r;
 }
 
+#ifdef JSMPEG_WALK_EMU
+#define WK_EMU_SYNC() __syncwarp()
+#else
+#define WK_EMU_SYNC() ((void)0)
+#endif
+
 // How a macroblock is walked:
 //   WALK_SERIAL  the whole warp walks the same macroblock redundantly, lane 0 stores (one warp = one chain)
 //   WALK_REL     one lane walks it, nothing is stored and no address is checked: the state is RELATIVE to the
@@ -374,8 +380,16 @@ __device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, Pic
 			// skipped macroblocks: predicted copy with the current vector (mpeg1.js:336-346)
 			const int n_skip = increment - 1;
 			const uint4 rec = pack_record(ps.mv_h, ps.mv_v, MBF_PRESENT | MBF_SKIPPED, 0, 0, ps.qscale, br.bitpos());
-			if (MODE == WALK_SERIAL)
+			if (MODE == WALK_SERIAL) {
+				// In a broken stream these addresses may have been stored before, or be stored again later,
+				// by lane 0 (a macroblock record).  The converged warp issues the stores in program order;
+				// the host emulation, whose lanes run independently between collectives, needs the order
+				// spelled out.  (Making these unconditional __syncwarp()s is on the round-2 list: two
+				// instructions, wants a GPU run.)
+				WK_EMU_SYNC();
 				for (int k = lane; k < n_skip; k += 32) reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
+				WK_EMU_SYNC();
+			}
 			if (MODE == WALK_ABS)
 				for (int k = 0; k < n_skip; k++) reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
 			ps.n_present += n_skip;
@@ -496,6 +510,7 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 #ifdef JSMPEG_WALK_EMU
 #define WK_VOTE(site, pred) emu_vote(site, pred)
 #else
+
 #define WK_VOTE(site, pred) __any_sync(FULL_MASK, pred)
 #endif
 enum { VOTE_SYN_MB = 0, VOTE_SYN_AC, VOTE_OWN_MB, VOTE_OWN_AC, VOTE_SITES };
@@ -684,8 +699,9 @@ __device__ uint32_t find_slice_end(const BitReader &br, uint32_t from, int lane)
 
 // The macroblocks that START in [reader position, limit), walked in MODE (WALK_REL / WALK_ABS).
 // Returns 0 when the lane reached `limit` (or owns nothing), 1 when the slice ended cleanly at the
-// start code, 2 on anything else; stop_pos = the bit position after the lane's last macroblock.  WARP-SYNCHRONOUS like syntax_run: a vote closes the macroblock
-// loop, a __syncwarp every block and a vote every look-up of the coefficient loop.
+// start code, 2 on anything else; stop_pos = the bit position after the lane's last macroblock.
+// WARP-SYNCHRONOUS like syntax_run: one vote closes the macroblock loop, one every look-up of the
+// coefficient loop.
 template <int MODE>
 __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const ParseTask &t, int mb_size, bool owns,
                           uint32_t limit, uint32_t end_byte, int lane, uint32_t &stop_pos) {

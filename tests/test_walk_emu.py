@@ -130,3 +130,30 @@ def test_walks_are_memory_safe_under_address_sanitizer():
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "asan_check.py"), lib], env=env, capture_output=True, text=True,
                        timeout=1200)
     assert r.returncode == 0 and "asan clean over" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_device_walk_code_matches_the_oracle_records(name):
+    """The device code of both walks, emulated on the host, against the ORACLE (the CPU restatement
+    pinned to the reference): macroblock records, end_bit and the picture counts of every picture the
+    oracle decodes.  The same comparison runs on the GPU (tests/test_gpu_parity.py); this one needs none."""
+    from jsmpeg_b200 import decoder
+    es = open(os.path.join(HERE, "golden", name + ".es"), "rb").read()
+    olib = helpers.oracle_lib()
+    d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
+    d.write(0, [es])
+    mb = olib.oracle_seq_params(d.decoder).contents.mb_size
+    lib = emu_lib()
+    mbw, mbh = stream_geometry(es)
+    buf = np.frombuffer(es + b"\0" * 16, dtype=np.uint8).copy()
+    checked = 0
+    while d.decode():
+        info = olib.oracle_last_picture_info(d.decoder).contents
+        want = np.ctypeslib.as_array(ctypes.cast(olib.oracle_last_mb_records(d.decoder), ctypes.POINTER(ctypes.c_uint32)),
+                                     shape=(mb, 4)).copy()
+        for lanes in (1, 0):
+            got, _, gi = walk(lib, buf, len(es), info.start_byte, mbw, mbh, lanes)
+            assert np.array_equal(got, want), f"{name}: picture at byte {info.start_byte}, lanes={lanes}: records differ"
+            assert (gi[1], gi[6], gi[7]) == (info.end_bit, info.n_present, info.n_coded_blocks), (name, info.start_byte, lanes)
+        checked += 1
+    assert checked > 0
