@@ -183,11 +183,11 @@ __device__ __forceinline__ uint16_t walk_entry(uint16_t e) {
 // One coded block (bitstream side of src/mpeg1.js:698-811): intra DC with its predictor, then only
 // code lengths.  Leaves {bit offset of the first coefficient code, dc * 8} in the block's slot.
 // head: DC size VLC + differential + predictor (mpeg1.js:705-751), the parked pair, dct_coeff_first
-template <bool DEFER>
+template <bool DEFER, bool RAW_DC = false>
 __device__ __forceinline__ bool walk_block_head(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
                                                 uint32_t *__restrict__ slot, bool store, int &n, bool &defer_first) {
 	n = 0;
-	int dc8 = 0;
+	int dc8 = 0, dc_raw = 0;
 	if (intra) {
 		const uint32_t w = br.peek32();
 		const uint32_t e = block < 4 ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
@@ -210,10 +210,12 @@ __device__ __forceinline__ bool walk_block_head(BitReader &br, uint32_t sbase, P
 			}
 		}
 		*pred = dc;
+		dc_raw = dc;
 		dc8 = max(-32768, min(32767, dc * 8));  // x PREMULTIPLIER[0] = dc << 8 in stage 2 (mpeg1.js:747)
 		n = 1;
 	}
-	if (store) *reinterpret_cast<uint2 *>(slot) = make_uint2(br.bitpos(), (uint32_t)dc8 & 0xffffu);
+	if (RAW_DC) *reinterpret_cast<uint2 *>(slot) = make_uint2(br.bitpos(), (uint32_t)dc_raw);  // staged: predictor value, possibly relative
+	else if (store) *reinterpret_cast<uint2 *>(slot) = make_uint2(br.bitpos(), (uint32_t)dc8 & 0xffffu);
 	if (DEFER) {
 		defer_first = !intra;  // the caller's first look-up resolves dct_coeff_first (ac_step)
 	} else if (!intra && (br.peek32() >> 31)) {  // dct_coeff_first: a leading '1' is (0, +-1), never end_of_block
@@ -345,12 +347,18 @@ __device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int 
 //                unknown state at the lane's first macroblock (summary pass of the lane-parallel walk)
 //   WALK_ABS     one lane walks it with the true state and stores; cases the lane-parallel walk leaves to
 //                the serial walk set ps.anomaly
-enum { WALK_SERIAL = 0, WALK_REL = 1, WALK_ABS = 2 };
+//   WALK_STAGE   (JSMPEG_LANES_FIXUP builds) WALK_REL that also leaves every macroblock as a relative
+//                record in a staging area; a fix-up then replaces the WALK_ABS pass
+enum { WALK_SERIAL = 0, WALK_REL = 1, WALK_ABS = 2, WALK_STAGE = 3 };
 
 struct MbHead {
 	int mb, cbp, mv_h, mv_v, qscale;
 	bool intra;
 	uint32_t bit_pos;
+	// WALK_STAGE only: the run of skipped macroblocks in front of this one
+	int n_skip, skip_first, skip_qs;
+	bool skip_qs_set;
+	uint32_t skip_bit;
 };
 
 // mpeg1.js:294-384, decodeMacroblock up to the blocks.  0: the blocks of h.cbp follow; 1: nothing more
@@ -372,10 +380,10 @@ __device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, Pic
 		if (MODE == WALK_ABS && ps.mb_addr + increment >= mb_size) { ps.anomaly = true; return 2; }
 		if (increment > 1) {  // mpeg1.js:323-334
 			ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;
-			if (MODE == WALK_REL) ps.dc_abs = true;
+			if (MODE == WALK_REL || MODE == WALK_STAGE) ps.dc_abs = true;
 			if (ps.picture_type == 2) {
 				ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;
-				if (MODE == WALK_REL) ps.mv_abs = true;
+				if (MODE == WALK_REL || MODE == WALK_STAGE) ps.mv_abs = true;
 			}
 			// skipped macroblocks: predicted copy with the current vector (mpeg1.js:336-346)
 			const int n_skip = increment - 1;
@@ -392,6 +400,10 @@ __device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, Pic
 			}
 			if (MODE == WALK_ABS)
 				for (int k = 0; k < n_skip; k++) reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
+			if (MODE == WALK_STAGE) {
+				h.n_skip = n_skip; h.skip_first = ps.mb_addr + 1; h.skip_qs = ps.qscale; h.skip_qs_set = ps.qs_set;
+				h.skip_bit = br.bitpos();
+			}
 			ps.n_present += n_skip;
 			ps.mb_addr += n_skip;
 		}
@@ -399,7 +411,7 @@ __device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, Pic
 	}
 	const int mb = ps.mb_addr;
 	h.mb = mb;
-	if (MODE != WALK_REL && (mb < 0 || mb >= mb_size)) {  // outside the picture: never write there
+	if (MODE != WALK_REL && MODE != WALK_STAGE && (mb < 0 || mb >= mb_size)) {  // outside the picture: never write there
 		if (MODE == WALK_ABS) ps.anomaly = true;
 		return 2;
 	}
@@ -414,22 +426,22 @@ __device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, Pic
 	h.intra = intra;
 	if (type & 0x10) {
 		ps.qscale = (int)br.read(5);
-		if (MODE == WALK_REL) ps.qs_set = true;
+		if (MODE == WALK_REL || MODE == WALK_STAGE) ps.qs_set = true;
 	}
 	h.bit_pos = br.bitpos();
 
 	if (intra) {
 		ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:363-367
-		if (MODE == WALK_REL) ps.mv_abs = true;
+		if (MODE == WALK_REL || MODE == WALK_STAGE) ps.mv_abs = true;
 	} else {
 		ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;                  // mpeg1.js:370-372
-		if (MODE == WALK_REL) ps.dc_abs = true;
+		if (MODE == WALK_REL || MODE == WALK_STAGE) ps.dc_abs = true;
 		if (type & 0x08) {
 			if (!parse_motion(br, sbase, ps, ps.mv_h_prev, ps.mv_h)) return 2;
 			if (!parse_motion(br, sbase, ps, ps.mv_v_prev, ps.mv_v)) return 2;
 		} else if (ps.picture_type == 2) {
 			ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:452-456
-			if (MODE == WALK_REL) ps.mv_abs = true;
+			if (MODE == WALK_REL || MODE == WALK_STAGE) ps.mv_abs = true;
 		}
 	}
 
@@ -702,21 +714,48 @@ __device__ uint32_t find_slice_end(const BitReader &br, uint32_t from, int lane)
 // start code, 2 on anything else; stop_pos = the bit position after the lane's last macroblock.
 // WARP-SYNCHRONOUS like syntax_run: one vote closes the macroblock loop, one every look-up of the
 // coefficient loop.
+// WALK_STAGE: where a lane leaves its macroblocks as relative records.  Entry j is the upper half
+// (bytes 64..127) of the picture's j-th 128-byte coefficient slot -- free until stage 1b fills the
+// slots, and never the 8 bytes at a slot's start where the final parked pairs go.  16 words:
+//   0      motion predictors after the macroblock's header (int16 h | int16 v << 16), or n_skip of a skip entry
+//   1      flags (1 intra, 2 skip entry, 4 motion absolute, 8 DC absolute, 16 quantiser scale set)
+//          | cbp << 8 | dc_only mask << 16 | quantiser scale << 24
+//   2      bit_pos            3   macroblock address relative to the lane's start (skip entry: the first skipped one)
+//   4..15  per block {bit offset of the first coefficient code, DC predictor value (relative unless flag 8)}
+struct StageArea {
+	uint32_t *base;  // entry j at base + j * 32 (words); the lane's entries are [first, first + cap)
+	int first, cap, count;
+};
+__device__ __forceinline__ uint32_t *stage_entry(const StageArea &sa, int k) { return sa.base + (size_t)(sa.first + k) * 32u + 16u; }
+
 template <int MODE>
 __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const ParseTask &t, int mb_size, bool owns,
-                          uint32_t limit, uint32_t end_byte, int lane, uint32_t &stop_pos) {
+                          uint32_t limit, uint32_t end_byte, int lane, uint32_t &stop_pos, StageArea *sa = nullptr) {
 	int how = 0;
 	bool work = owns;
 	if (owns) stop_pos = br.bitpos();
 	while (WK_VOTE(VOTE_OWN_MB, work)) {
 		MbHead h;
 		h.mb = 0; h.cbp = 0; h.mv_h = h.mv_v = h.qscale = 0; h.intra = false; h.bit_pos = 0;
+		h.n_skip = 0; h.skip_first = 0; h.skip_qs = 0; h.skip_qs_set = false; h.skip_bit = 0;
 		bool in_mb = false;
 		if (work) {
 			if (walk_mb_header<MODE>(br, sbase, ls, t, mb_size, lane, h) != 0) { how = 2; work = false; }
 			else in_mb = true;
 		}
 		uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)(MODE == WALK_ABS ? h.mb : 0) * (MB_COEF_INT16 / 2);
+		if (MODE == WALK_STAGE && in_mb) {
+			if (sa->count + (h.n_skip > 0 ? 2 : 1) > sa->cap) {  // more macroblocks than the lane has room to stage
+				how = 2; work = false; in_mb = false;
+			} else {
+				if (h.n_skip > 0) {
+					uint32_t *e = stage_entry(*sa, sa->count++);
+					*reinterpret_cast<uint4 *>(e) = make_uint4((uint32_t)h.n_skip, 2u | (h.skip_qs_set ? 16u : 0u) | ((uint32_t)h.skip_qs << 24),
+					                                          h.skip_bit, (uint32_t)h.skip_first);
+				}
+				coef_mb = stage_entry(*sa, sa->count) + 4;  // the blocks' pairs go straight into the entry
+			}
+		}
 		int done = 0, dc_mask = 0;
 		// the coded blocks of the macroblock, one look-up per trip; a block's head (intra DC, the parked
 		// pair) rides on the trip of its first look-up
@@ -729,7 +768,9 @@ __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const
 				const int block = __clz((int)rem) - 26;  // mask bit 0x20 >> block
 				bool ok = true;
 				if (at_head) {
-					ok = walk_block_head<true>(br, sbase, ls, h.intra, block, coef_mb + block * 32, MODE == WALK_ABS, n, first);
+					ok = MODE == WALK_STAGE
+					         ? walk_block_head<true, true>(br, sbase, ls, h.intra, block, coef_mb + block * 2, false, n, first)
+					         : walk_block_head<true>(br, sbase, ls, h.intra, block, coef_mb + block * 32, MODE == WALK_ABS, n, first);
 					at_head = false;
 				}
 				const int r = ok ? ac_step(br, sbase, n, true, first) : 2;
@@ -750,6 +791,13 @@ __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const
 			if (MODE == WALK_ABS)
 				reinterpret_cast<uint4 *>(t.hdr)[h.mb] =
 				    pack_record(h.mv_h, h.mv_v, MBF_PRESENT | (h.intra ? MBF_INTRA : 0), done, dc_mask, h.qscale, h.bit_pos);
+			if (MODE == WALK_STAGE) {
+				uint32_t *e = stage_entry(*sa, sa->count++);
+				const uint32_t flags = (h.intra ? 1u : 0u) | (ls.mv_abs ? 4u : 0u) | (ls.dc_abs ? 8u : 0u) | (ls.qs_set ? 16u : 0u);
+				*reinterpret_cast<uint4 *>(e) =
+				    make_uint4(((uint32_t)ls.mv_h_prev & 0xffffu) | ((uint32_t)ls.mv_v_prev << 16),
+				               flags | ((uint32_t)done << 8) | ((uint32_t)dc_mask << 16) | ((uint32_t)h.qscale << 24), h.bit_pos, (uint32_t)h.mb);
+			}
 			ls.n_present++;
 			const uint32_t pos = br.bitpos();
 			const uint32_t i = (pos + 7u) >> 3;
@@ -809,7 +857,17 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 		ls.n_present = ls.n_coded = ls.error = 0;
 	}
 	uint32_t stop_pos = q;
+#ifdef JSMPEG_LANES_FIXUP
+	if (!owns) ls.n_present = ls.n_coded = ls.error = 0;  // this pass's counts are the final ones
+	StageArea sa;
+	sa.base = reinterpret_cast<uint32_t *>(t.coef);
+	sa.cap = mb_size * 6 / K;  // the picture's block slots, shared out among the lanes in use
+	sa.first = active ? lane * sa.cap : 0;
+	sa.count = 0;
+	how = walk_owned<WALK_STAGE>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos, &sa);
+#else
 	how = walk_owned<WALK_REL>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos);
+#endif
 	const uint32_t next_q = __shfl_down_sync(FULL_MASK, q, 1);
 	if (active && lane < K - 1 && stop_pos != next_q) bad = true;  // the warm-up of lane + 1 had not merged
 	if (owns) {
@@ -833,6 +891,53 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 	const LaneSum before = shfl_up_sum(sum, 1);
 	const LaneSum x = lane == 0 ? x0 : compose(x0, before, ps.f);
 
+#ifdef JSMPEG_LANES_FIXUP
+	// ---- F: no second walk -- the staged relative records become the final ones.  Every staged value is
+	// cumulative since the lane's start, so each entry only needs the lane's absolute start state `x`.
+	{
+		int k = 0;
+		while (WK_VOTE(VOTE_OWN_MB, k < sa.count)) {
+			if (k < sa.count) {
+				const uint32_t *e = stage_entry(sa, k);
+				const uint4 w = *reinterpret_cast<const uint4 *>(e);
+				const uint32_t flags = w.y & 0xffu;
+				const int qs = (flags & 16u) ? (int)(w.y >> 24) : x.qs;
+				const int mb = x.d_addr + (int)w.w;
+				if (flags & 2u) {  // a run of skipped macroblocks (mpeg1.js:323-346): zero vector, the scale in force
+					const int n_skip = (int)w.x;
+					if (mb < 0 || mb + n_skip > mb_size) bad = true;
+					else {
+						const uint4 rec = pack_record(0, 0, MBF_PRESENT | MBF_SKIPPED, 0, 0, qs, w.z);
+						for (int i = 0; i < n_skip; i++) reinterpret_cast<uint4 *>(t.hdr)[mb + i] = rec;
+					}
+				} else if (mb < 0 || mb >= mb_size) {
+					bad = true;
+				} else {
+					int ph = (int)(int16_t)(w.x & 0xffffu), pv = (int)(int16_t)(w.x >> 16);
+					if (!(flags & 4u)) { ph = wrap_mv(x.mvh + ph, ps.f); pv = wrap_mv(x.mvv + pv, ps.f); }
+					const int cbp = (int)((w.y >> 8) & 0xffu);
+					uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)mb * (MB_COEF_INT16 / 2);
+					for (int block = 0; block < 6; block++) {
+						if (!(cbp & (0x20 >> block))) continue;
+						const uint2 pr = *reinterpret_cast<const uint2 *>(e + 4 + block * 2);
+						int dc8 = 0;
+						if (flags & 1u) {
+							int dc = (int)pr.y;
+							if (!(flags & 8u)) dc += block < 4 ? x.dcy : (block == 4 ? x.dc4 : x.dc5);
+							dc8 = max(-32768, min(32767, dc * 8));
+						}
+						*reinterpret_cast<uint2 *>(coef_mb + block * 32) = make_uint2(pr.x, (uint32_t)dc8 & 0xffffu);
+					}
+					reinterpret_cast<uint4 *>(t.hdr)[mb] =
+					    pack_record(ps.full_pel ? ph * 2 : ph, ps.full_pel ? pv * 2 : pv, MBF_PRESENT | ((flags & 1u) ? MBF_INTRA : 0),
+					                cbp, (int)((w.y >> 16) & 0xffu), qs, w.z);
+				}
+				k++;
+			}
+		}
+	}
+	if (__any_sync(FULL_MASK, bad)) return false;
+#else
 	// ---- D: the owned macroblocks again, absolute, storing
 	ls.n_present = ls.n_coded = ls.error = 0;
 	ls.anomaly = false;
@@ -847,6 +952,7 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 	const int how_abs = walk_owned<WALK_ABS>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos);
 	if (how_abs != how || ls.anomaly) bad = true;
 	if (__any_sync(FULL_MASK, bad)) return false;
+#endif
 	int n_present = ls.n_present, n_coded = ls.n_coded, error = ls.error;
 	for (int d = 16; d > 0; d >>= 1) {
 		n_present += __shfl_xor_sync(FULL_MASK, n_present, d);
