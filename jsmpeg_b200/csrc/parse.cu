@@ -85,6 +85,9 @@ expand_blocks_kernel(const ParseTask *__restrict__ tasks) {
 	const int slot_id = blockIdx.x * CTA_THREADS + threadIdx.x;  // mb * 6 + block
 	if (slot_id >= mb_size * 6) return;
 	if (t.info->status != PIC_DECODED) return;
+#ifdef JSMPEG_WALK_EMITS_BLOCKS
+	if (t.info->reserved[1]) return;  // the lane-parallel walk has written this picture's block records itself
+#endif
 	const int mb = slot_id / 6, block = slot_id - mb * 6;
 	const uint32_t rec = reinterpret_cast<const uint32_t *>(t.hdr + mb)[1];
 	if (!(rec & MBF_PRESENT) || !((rec >> 8) & (0x20u >> block))) return;

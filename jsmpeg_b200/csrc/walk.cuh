@@ -26,7 +26,20 @@ constexpr int MS_BITS = JSMPEG_MS_BITS;            // multi-symbol table is inde
 constexpr uint32_t OFF_MS = 4096;      // uint16[1 << MS_BITS], after the per-symbol tables
 constexpr uint32_t OFF_MS_FIRST = OFF_MS + (2u << MS_BITS);  // uint16[1 << (MS_BITS - 1)]: dct_coeff_first variant, prefixes with a leading 1 (lane-parallel walk only)
 constexpr uint32_t MS_TABLE_ENTRIES = (1u << MS_BITS) + (1u << (MS_BITS - 1));
-constexpr uint32_t WALK_SMEM_SERIAL = OFF_MS + (2u << MS_BITS), WALK_SMEM_LANES = OFF_MS + 2u * MS_TABLE_ENTRIES;
+constexpr uint32_t WALK_SMEM_SERIAL = OFF_MS + (2u << MS_BITS), WALK_SMEM_LANES_TABLES = OFF_MS + 2u * MS_TABLE_ENTRIES;
+#ifdef JSMPEG_WALK_EMITS_BLOCKS
+// Round-2 candidate, compiled out of the product by default: the storing pass of the lane-parallel walk
+// decodes the coefficient VALUES too and writes the finished 64 x int16 block records itself (what
+// stage 1b does today, from the parked offsets): the generated DCT table as it is, the zig-zag order,
+// and one 64 x int16 tile per lane.
+constexpr uint32_t OFF_DCT_RAW = 3328;  // uint16[384]: the 768 bytes up to OFF_MS
+constexpr uint32_t OFF_TILES = WALK_SMEM_LANES_TABLES;
+constexpr uint32_t EMIT_TILE_PITCH = 144;  // 128 + 16: equal indices of different lanes on different banks
+constexpr uint32_t WALK_SMEM_LANES = OFF_TILES + (uint32_t)JSMPEG_WALK_THREADS * EMIT_TILE_PITCH;
+static_assert(OFF_DCT_RAW + (VLC_DCT_MAX_Z + 1) * 64 <= OFF_MS, "raw DCT table must fit below the multi-symbol table");
+#else
+constexpr uint32_t WALK_SMEM_LANES = WALK_SMEM_LANES_TABLES;
+#endif
 
 // shared-memory layout (byte offsets from the dynamic shared base)
 constexpr uint32_t OFF_DCT = 0;                                        // uint16[384]
@@ -59,6 +72,7 @@ __device__ __forceinline__ void sts_s16(uint32_t addr, int v) {
 static uint8_t emu_smem[WALK_SMEM_LANES];
 static inline uint32_t lds_u16(uint32_t addr) { uint16_t v; memcpy(&v, emu_smem + addr, 2); return v; }
 static inline uint32_t lds_u8(uint32_t addr) { return emu_smem[addr]; }
+static inline void sts_s16(uint32_t addr, int v) { const int16_t x = (int16_t)v; memcpy(emu_smem + addr, &x, 2); }
 #endif
 // MSB-first bit window over a byte span (src/buffer.js:152-187); one copy per thread.
 struct BitReader {
@@ -298,6 +312,65 @@ __device__ __forceinline__ int ac_step(BitReader &br, uint32_t sbase, int &n, bo
 	return ret;
 }
 
+#ifdef JSMPEG_WALK_EMITS_BLOCKS
+// One coefficient code WITH its value (mpeg1.js:757-790): 0 = a coefficient (run, signed level),
+// 1 = end_of_block consumed, 2 = invalid code.
+__device__ __forceinline__ int ac_step_value(BitReader &br, uint32_t sbase, bool first, int &run, int &level) {
+	const uint32_t w = br.peek32();
+	int len;
+	if (first && (w >> 31)) {  // dct_coeff_first '1s'
+		run = 0;
+		level = (w & 0x40000000u) ? -1 : 1;
+		len = 2;
+	} else if ((w >> 26) == 1u) {  // escape: 6-bit run, 8 (+8) bit level (mpeg1.js:767-780)
+		run = (int)((w >> 20) & 63u);
+		const int l8 = (int)((w >> 12) & 255u);
+		if ((l8 & 127) == 0) { level = (int)((w >> 4) & 255u) - (l8 << 1); len = 28; }  // l8 == 128: second byte - 256
+		else { level = l8 > 128 ? l8 - 256 : l8; len = 20; }
+	} else {
+		const int z = __clz((int)w);
+		if (z > VLC_DCT_MAX_Z) return 2;
+		const uint32_t e = lds_u16(sbase + OFF_DCT_RAW + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+		const int l = (int)(e & 31u);
+		if (l == 0) return 2;
+		run = (int)((e >> 5) & 31u);
+		level = (int)(e >> 10);
+		if (level == 0) {  // end_of_block (the escape was taken above)
+			br.consume(l);
+			return 1;
+		}
+		if ((w >> (31 - l)) & 1u) level = -level;
+		len = l + 1;
+	}
+	br.consume(len);
+	return 0;
+}
+// dequantise, oddify toward zero, clip (mpeg1.js:794-807) and put the value into the lane's tile
+__device__ __forceinline__ void emit_coefficient(uint32_t sbase, uint32_t tile, int n, int level, bool intra, int qs, const uint8_t *__restrict__ quant) {
+	const uint32_t idx = lds_u8(sbase + OFF_ZIGZAG + (uint32_t)n);
+	level <<= 1;
+	if (!intra) level += level < 0 ? -1 : 1;
+	level = (level * qs * (int)__ldg(quant + idx)) >> 4;
+	if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
+	level = max(-2048, min(2047, level));
+	sts_s16(tile + idx * 2u, level);
+}
+// the finished tile -> the block's 128-byte record (one TMA bulk store, as in stage 1b), then clear it
+__device__ __forceinline__ void emit_block(uint32_t tile, void *slot) {
+#ifndef JSMPEG_WALK_EMU
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(slot), "r"(tile) : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 8; i++) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(tile + i * 16), "r"(0u) : "memory");
+#else
+	memcpy(slot, emu_smem + tile, 128);
+	memset(emu_smem + tile, 0, 128);
+#endif
+}
+#endif
+
 // mpeg1.js:395-457, one component
 __device__ __forceinline__ bool parse_motion(BitReader &br, uint32_t sbase, const PictureState &ps, int &prev, int &mv) {
 	const uint32_t e = clz_lut(sbase + OFF_MOTION, br.peek32(), VLC_MOTION_MAX_Z);
@@ -337,8 +410,10 @@ __device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int 
 
 #ifdef JSMPEG_WALK_EMU
 #define WK_EMU_SYNC() __syncwarp()
+#define WK_THREAD_IN_CTA() (emu::lane)
 #else
 #define WK_EMU_SYNC() ((void)0)
+#define WK_THREAD_IN_CTA() (threadIdx.x)
 #endif
 
 // How a macroblock is walked:
@@ -763,6 +838,43 @@ __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const
 		bool at_head = true, first = false;
 		int n = 0;
 		bool in = rem != 0;
+#ifdef JSMPEG_WALK_EMITS_BLOCKS
+		if (MODE == WALK_ABS) {  // the storing pass decodes the values and writes the finished block records itself
+			const uint32_t tile = sbase + OFF_TILES + (uint32_t)(WK_THREAD_IN_CTA()) * EMIT_TILE_PITCH;
+			const uint8_t *__restrict__ quant = h.intra ? t.seq->intra_q : t.seq->non_intra_q;
+			while (WK_VOTE(VOTE_OWN_AC, in)) {
+				if (in) {
+					const int block = __clz((int)rem) - 26;
+					bool ok = true;
+					if (at_head) {
+						uint2 pair = make_uint2(0u, 0u);
+						ok = walk_block_head<true>(br, sbase, ls, h.intra, block, reinterpret_cast<uint32_t *>(&pair), true, n, first);
+						if (ok && h.intra) sts_s16(tile, (int)(int16_t)(pair.y & 0xffffu));  // coefficient 0 = dc * 8
+						at_head = false;
+					}
+					int run = 0, level = 0;
+					const int r = ok ? ac_step_value(br, sbase, first, run, level) : 2;
+					first = false;
+					if (r == 2) { how = 2; work = false; in_mb = false; in = false; }
+					else if (r == 0) {
+						n += run;
+						if (n <= 63) emit_coefficient(sbase, tile, n, level, h.intra, h.qscale, quant);  // beyond 63: dropped, like JS
+						n++;
+						if (n > 4096) { how = 2; work = false; in_mb = false; in = false; }  // (cannot happen after a clean pass C)
+					} else {
+						emit_block(tile, coef_mb + block * 32);
+						bool dc_only;
+						walk_block_tail(ls, n, dc_only);
+						done |= 0x20 >> block;
+						if (dc_only) dc_mask |= 0x20 >> block;
+						rem &= ~(0x20u >> block);
+						at_head = true;
+						if (rem == 0) in = false;
+					}
+				}
+			}
+		} else
+#endif
 		while (WK_VOTE(VOTE_OWN_AC, in)) {
 			if (in) {
 				const int block = __clz((int)rem) - 26;  // mask bit 0x20 >> block
@@ -982,6 +1094,14 @@ __device__ __forceinline__ void walk_tables_init(uint8_t *smem, int tid, int nth
 	for (int i = tid; i < 64; i += nthreads) s16[OFF_TYPE_P / 2 + i] = VLC_MBTYPE_P[i];
 	uint4 *ms = reinterpret_cast<uint4 *>(smem + OFF_MS);
 	const int n16 = (int)(with_first ? 2u * MS_TABLE_ENTRIES : (2u << MS_BITS)) / 16;
+#ifdef JSMPEG_WALK_EMITS_BLOCKS
+	if (with_first) {
+		for (int i = tid; i < (VLC_DCT_MAX_Z + 1) * 32; i += nthreads) s16[OFF_DCT_RAW / 2 + i] = VLC_DCT_COEFF[i];
+		for (int i = tid; i < 64; i += nthreads) smem[OFF_ZIGZAG + i] = TBL_ZIG_ZAG[i];
+		uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + OFF_TILES);
+		for (int i = tid; i < nthreads * (int)(EMIT_TILE_PITCH / 4); i += nthreads) tiles[i] = 0u;
+	}
+#endif
 	for (int i = tid; i < n16; i += nthreads) ms[i] = __ldg(ms_table + i);
 }
 
@@ -1073,7 +1193,12 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
 			info.n_coded_blocks = ps.n_coded;
 			info.error = ps.error;
 			info.reserved[0] = (LANES && lanes && go) ? 1 : 0;
-			info.reserved[1] = info.reserved[2] = 0;
+#ifdef JSMPEG_WALK_EMITS_BLOCKS
+			info.reserved[1] = (LANES && lanes && go) ? 1 : 0;  // the block records are already written: stage 1b skips the picture
+#else
+			info.reserved[1] = 0;
+#endif
+			info.reserved[2] = 0;
 			*t.info = info;
 		}
 		return;

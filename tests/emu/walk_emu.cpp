@@ -107,6 +107,13 @@ extern "C" void emu_vote_counters(uint64_t *trips, uint64_t *lanes, int reset) {
 #define VLC_TABLE_QUALIFIER static const
 #include "../../jsmpeg_b200/csrc/walk.cuh"
 
+// the stream's quantiser matrices (de-zigzagged, as in SeqParams); only the block-emitting variant reads them
+static uint8_t emu_intra_q[64], emu_non_intra_q[64];
+extern "C" void emu_set_quant(const uint8_t *intra_q, const uint8_t *non_intra_q) {
+	memcpy(emu_intra_q, intra_q, 64);
+	memcpy(emu_non_intra_q, non_intra_q, 64);
+}
+
 extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t start_byte, int mb_width, int mb_height,
                                 mb_record_t *hdr, int16_t *coef, picture_info_t *info, int lanes) {
 	static std::once_flag once;
@@ -120,6 +127,8 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 	seq.mb_width = mb_width;
 	seq.mb_height = mb_height;
 	seq.mb_size = mb_width * mb_height;
+	memcpy(seq.intra_q, emu_intra_q, 64);
+	memcpy(seq.non_intra_q, emu_non_intra_q, 64);
 	ParseTask t;
 	t.es = es; t.es_len = es_len; t.start_byte = start_byte; t.seq = &seq; t.hdr = hdr; t.coef = coef; t.info = info;
 	// every collective is executed by all 32 lanes (walk.cuh's rule), so no lane finishes while another

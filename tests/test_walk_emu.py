@@ -177,3 +177,45 @@ def test_fixup_variant_reproduces_the_serial_walk():
     es = b"".join(p for _, p in helpers.clip_packets(640, 480, 7))
     used, n = check_stream(lib, es, "fixup clip")
     assert used == n
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_block_emitting_variant_matches_the_oracle_coefficients(name):
+    """-DJSMPEG_WALK_EMITS_BLOCKS (walk.cuh): the storing pass of the lane-parallel walk decodes the
+    coefficient values and writes the dequantised 64 x int16 block records itself (stage 1b's job).
+    Emulated, against the ORACLE's coefficient blocks and records.  Not in the product build yet."""
+    from jsmpeg_b200 import decoder
+    es = open(os.path.join(HERE, "golden", name + ".es"), "rb").read()
+    olib = helpers.oracle_lib()
+    d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
+    d.write(0, [es])
+    seq = olib.oracle_seq_params(d.decoder).contents
+    mb = seq.mb_size
+    lib = emu_lib("JSMPEG_WALK_EMITS_BLOCKS")
+    lib.emu_set_quant(bytes(seq.intra_q), bytes(seq.non_intra_q))
+    mbw, mbh = stream_geometry(es)
+    buf = np.frombuffer(es + b"\0" * 16, dtype=np.uint8).copy()
+    emitted = 0
+    while d.decode():
+        info = olib.oracle_last_picture_info(d.decoder).contents
+        want_hdr = np.ctypeslib.as_array(ctypes.cast(olib.oracle_last_mb_records(d.decoder), ctypes.POINTER(ctypes.c_uint32)),
+                                         shape=(mb, 4)).copy()
+        want = np.ctypeslib.as_array(ctypes.cast(olib.oracle_last_coefficients(d.decoder), ctypes.POINTER(ctypes.c_int16)),
+                                     shape=(mb * 6, 64)).copy()
+        hdr = np.zeros(mb * 4, dtype=np.uint32)
+        coef = np.zeros(mb * 6 * 32, dtype=np.uint32)
+        pinfo = np.zeros(12, dtype=np.int32)
+        lib.emu_walk_picture(buf.ctypes.data, len(es), info.start_byte, mbw, mbh, hdr.ctypes.data, coef.ctypes.data,
+                             pinfo.ctypes.data, 1)
+        assert np.array_equal(hdr.reshape(mb, 4), want_hdr), f"{name}: records differ, picture at byte {info.start_byte}"
+        if not pinfo[10]:
+            continue  # serial fall-back: the blocks are stage 1b's, not emitted here
+        emitted += 1
+        got = coef.view(np.int16).reshape(mb * 6, 64)
+        h = want_hdr.view(np.uint8).reshape(mb, 16)
+        present = (h[:, 4] & 1).astype(bool)
+        for blk in range(6):
+            coded = present & ((h[:, 5] & (0x20 >> blk)) != 0)
+            rows = np.nonzero(coded)[0] * 6 + blk
+            assert np.array_equal(got[rows], want[rows]), f"{name}: coefficient blocks differ, picture at byte {info.start_byte}, block {blk}"
+    assert emitted > 0
