@@ -83,18 +83,38 @@ struct BitReader {
 	uint32_t nextw;  // prefetched
 	uint64_t win;    // left-aligned window
 	int nbits;       // valid bits in win, >= 32 between calls
+#ifdef JSMPEG_WIDE_REFILL
+	// Round-2 candidate, compiled out by default: refills come from a 16-byte register cache, one
+	// 128-bit load per four words (the lane-parallel walk's top stall is the per-lane 4-byte load).
+	// Needs the ES base 16-byte aligned and 12 readable bytes past the last word (cudaMalloc + ES_PAD).
+	mutable uint4 cache;
+	mutable uint32_t cache_quad;  // index of the cached 16 bytes, 0xffffffff = none
+#endif
 
 	// (Measured and rejected on the 3840-picture wave: a branch-free variant relying on the zero pad
 	// after the data, 17 % slower; a software prefetch 256 B ahead at every refill, 7 % slower.)
 	__device__ __forceinline__ uint32_t load_word(uint32_t w) const {
 		const uint32_t byte = w * 4u;
 		if (byte >= len) return 0u;
+#ifdef JSMPEG_WIDE_REFILL
+		const uint32_t quad = w >> 2;
+		if (quad != cache_quad) {
+			cache = __ldg(reinterpret_cast<const uint4 *>(words) + quad);
+			cache_quad = quad;
+		}
+		const uint32_t k = w & 3u;
+		uint32_t v = __byte_perm(k == 0 ? cache.x : (k == 1 ? cache.y : (k == 2 ? cache.z : cache.w)), 0, 0x0123);
+#else
 		uint32_t v = __byte_perm(__ldg(words + w), 0, 0x0123);  // first byte -> MSB
+#endif
 		const uint32_t left = len - byte;
 		if (left < 4u) v &= 0xffffffffu << (8u * (4u - left));
 		return v;
 	}
 	__device__ __forceinline__ void seek_byte(uint32_t byte_pos) {
+#ifdef JSMPEG_WIDE_REFILL
+		cache_quad = 0xffffffffu;
+#endif
 		const uint32_t w = byte_pos >> 2;
 		win = ((uint64_t)load_word(w) << 32) | load_word(w + 1);
 		wpos = w + 2;

@@ -219,3 +219,20 @@ def test_block_emitting_variant_matches_the_oracle_coefficients(name):
             rows = np.nonzero(coded)[0] * 6 + blk
             assert np.array_equal(got[rows], want[rows]), f"{name}: coefficient blocks differ, picture at byte {info.start_byte}, block {blk}"
     assert emitted > 0
+
+
+def test_wide_refill_variant_reproduces_the_serial_walk():
+    """-DJSMPEG_WIDE_REFILL (walk.cuh): the bit window refills from a 16-byte register cache (one 128-bit
+    load per four words).  Both walks of that build against the default build's serial walk."""
+    import synth_es
+    wide, ref = emu_lib("JSMPEG_WIDE_REFILL"), emu_lib()
+    streams = [open(os.path.join(HERE, "golden", n + ".es"), "rb").read() for n in GOLDEN]
+    streams += [synth_es.make_case(n) for n in synth_es.CASES]
+    for es in streams:
+        mbw, mbh = stream_geometry(es)
+        buf = np.frombuffer(es + b"\0" * 32, dtype=np.uint8).copy()
+        for s in picture_starts(es):
+            h0, c0, i0 = walk(ref, buf, len(es), s, mbw, mbh, 0)
+            for lanes in (0, 1):
+                h1, c1, i1 = walk(wide, buf, len(es), s, mbw, mbh, lanes)
+                assert np.array_equal(h0, h1) and np.array_equal(c0, c1) and np.array_equal(i0[:9], i1[:9])
