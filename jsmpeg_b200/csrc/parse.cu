@@ -88,85 +88,10 @@ expand_blocks_kernel(const ParseTask *__restrict__ tasks) {
 #ifdef JSMPEG_WALK_EMITS_BLOCKS
 	if (t.info->reserved[1]) return;  // the lane-parallel walk has written this picture's block records itself
 #endif
-	const int mb = slot_id / 6, block = slot_id - mb * 6;
-	const uint32_t rec = reinterpret_cast<const uint32_t *>(t.hdr + mb)[1];
-	if (!(rec & MBF_PRESENT) || !((rec >> 8) & (0x20u >> block))) return;
-	const bool intra = rec & MBF_INTRA;
-	const int qs = (int)(rec >> 24);
-	const uint8_t *__restrict__ quant = intra ? t.seq->intra_q : t.seq->non_intra_q;
-
-	uint4 *slot = reinterpret_cast<uint4 *>(t.coef) + (size_t)slot_id * 8;
-	const uint2 parked = *reinterpret_cast<const uint2 *>(slot);  // left by the walk
 	const uint32_t sbase = smem_base(smem);
 	// this thread's 64 x int16 tile, linear (it leaves as one bulk copy); tiles are 144 bytes apart so
 	// that lanes writing the same coefficient index spread over the banks
-	const uint32_t sblock = sbase + OFF_BLOCKS + threadIdx.x * TILE_PITCH;
-
-	BitReader br;
-	br.words = reinterpret_cast<const uint32_t *>(t.es);
-	br.bytes = t.es;
-	br.len = t.es_len;
-	br.seek_byte(parked.x >> 3);
-	if (parked.x & 7u) br.consume((int)(parked.x & 7u));
-
-	int n = 0;
-	if (intra) {
-		sts_s16(sblock, (int)(int16_t)(parked.y & 0xffffu));  // coefficient 0
-		n = 1;
-	}
-	bool first = !intra;
-	for (;;) {  // mpeg1.js:757-811; the walk has already validated every code of this block
-		const uint32_t w = br.peek32();
-		const int z = min(__clz((int)w), VLC_DCT_MAX_Z);
-		const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
-		int len = e & 31;
-		int run = (e >> 5) & 31;
-		int level = e >> 10;
-		if (first && z == 0) {  // '1s'
-			len = 1;
-			run = 0;
-			level = 1;
-		}
-		first = false;
-		if (level == 0) {
-			if (run != 0 || len == 0) break;  // end_of_block (or, defensively, an invalid code)
-			// escape (mpeg1.js:767-780)
-			run = (w >> 20) & 63;
-			const int l8 = (w >> 12) & 255;
-			if ((l8 & 127) == 0) {
-				level = (int)((w >> 4) & 255) - (l8 << 1);  // l8 == 128: second byte - 256
-				br.consume(28);
-			} else {
-				level = l8 > 128 ? l8 - 256 : l8;
-				br.consume(20);
-			}
-		} else {
-			if ((w >> (31 - len)) & 1u) level = -level;
-			br.consume(len + 1);
-		}
-		n += run;
-		if (n > 63) {  // JS: ZIG_ZAG[n] undefined -> the store is a no-op (the walk flagged the picture)
-			if (n > 4096) break;
-			n++;
-			continue;
-		}
-		const uint32_t idx = lds_u8(sbase + OFF_ZIGZAG + (uint32_t)n);
-		n++;
-		// dequantise, oddify toward zero, clip (mpeg1.js:794-807)
-		level <<= 1;
-		if (!intra) level += level < 0 ? -1 : 1;
-		level = (level * qs * (int)__ldg(quant + idx)) >> 4;
-		if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
-		level = max(-2048, min(2047, level));
-		sts_s16(sblock + idx * 2u, level);
-	}
-	// The finished block leaves as ONE 128-byte TMA bulk store (shared -> global, SASS UBLKCP): whole
-	// lines reach L2, whereas eight 16-byte stores per thread half-fill 32-byte sectors and made L2
-	// read every sector back before merging (ncu: 23.5 GB read for 22 GB written per step).
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
-	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(slot), "r"(sblock) : "memory");
-	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must outlive the read
+	expand_block(t, slot_id, sbase, sbase + OFF_BLOCKS + threadIdx.x * TILE_PITCH);
 }
 
 }  // namespace

@@ -1,10 +1,15 @@
-// walk.cuh -- stage 1a, the walk of one picture's bitstream (sm_100a device code).
+// walk.cuh -- stage 1 device code: the walk of one picture's bitstream (1a) and the per-block expansion
+// (1b) (sm_100a).
 //
 // Included by parse.cu (the kernels, the tables' upload and the launcher live there).  The same text
 // compiles for the host when JSMPEG_WALK_EMU is defined and the including file supplies the few CUDA
-// intrinsics it uses (tests/emu/walk_emu.cpp runs a "warp" as 32 host threads): that is how the
-// lane-parallel walk is checked against the serial one on machines without a GPU.  Nothing in the
-// product library is built that way.
+// intrinsics it uses (tests/emu/walk_emu.cpp runs a "warp" as 32 coroutines): that is how the
+// lane-parallel walk is checked against the serial one, and both plus stage 1b against the oracle, on
+// machines without a GPU.  Nothing in the product library is built that way.
+//
+// Compile-time candidates that the emulation has verified and no GPU run has measured yet (DESIGN.md
+// section 10, tools/ab_variants.py) are compiled OUT by default: JSMPEG_LANES_FIXUP,
+// JSMPEG_WALK_EMITS_BLOCKS, JSMPEG_WIDE_REFILL.
 #pragma once
 #include "common.cuh"
 
@@ -69,7 +74,8 @@ __device__ __forceinline__ void sts_s16(uint32_t addr, int v) {
 }
 #else
 // host emulation (tests only): `emu_smem` stands in for the CTA's shared memory, addresses are offsets into it
-static uint8_t emu_smem[WALK_SMEM_LANES];
+constexpr uint32_t EMU_EXPAND_BASE = (WALK_SMEM_LANES + 127u) & ~127u;  // a second "CTA": stage 1b's own tables and tile
+static uint8_t emu_smem[EMU_EXPAND_BASE + 8192];
 static inline uint32_t lds_u16(uint32_t addr) { uint16_t v; memcpy(&v, emu_smem + addr, 2); return v; }
 static inline uint32_t lds_u8(uint32_t addr) { return emu_smem[addr]; }
 static inline void sts_s16(uint32_t addr, int v) { const int16_t x = (int16_t)v; memcpy(emu_smem + addr, &x, 2); }
@@ -1223,6 +1229,90 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
 		}
 		return;
 	}
+}
+
+// ==================================================================================================
+// 1b: one coded block, from the offset the walk parked to the finished 64 x int16 record.
+// sblock = the shared-memory address of this thread's (zeroed) 128-byte tile.
+__device__ __forceinline__ void expand_block(const ParseTask &t, int slot_id, uint32_t sbase, uint32_t sblock) {
+	const int mb = slot_id / 6, block = slot_id - mb * 6;
+	const uint32_t rec = reinterpret_cast<const uint32_t *>(t.hdr + mb)[1];
+	if (!(rec & MBF_PRESENT) || !((rec >> 8) & (0x20u >> block))) return;
+	const bool intra = rec & MBF_INTRA;
+	const int qs = (int)(rec >> 24);
+	const uint8_t *__restrict__ quant = intra ? t.seq->intra_q : t.seq->non_intra_q;
+
+	uint4 *slot = reinterpret_cast<uint4 *>(t.coef) + (size_t)slot_id * 8;
+	const uint2 parked = *reinterpret_cast<const uint2 *>(slot);  // left by the walk
+	BitReader br;
+	br.words = reinterpret_cast<const uint32_t *>(t.es);
+	br.bytes = t.es;
+	br.len = t.es_len;
+	br.seek_byte(parked.x >> 3);
+	if (parked.x & 7u) br.consume((int)(parked.x & 7u));
+
+	int n = 0;
+	if (intra) {
+		sts_s16(sblock, (int)(int16_t)(parked.y & 0xffffu));  // coefficient 0
+		n = 1;
+	}
+	bool first = !intra;
+	for (;;) {  // mpeg1.js:757-811; the walk has already validated every code of this block
+		const uint32_t w = br.peek32();
+		const int z = min(__clz((int)w), VLC_DCT_MAX_Z);
+		const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+		int len = e & 31;
+		int run = (e >> 5) & 31;
+		int level = e >> 10;
+		if (first && z == 0) {  // '1s'
+			len = 1;
+			run = 0;
+			level = 1;
+		}
+		first = false;
+		if (level == 0) {
+			if (run != 0 || len == 0) break;  // end_of_block (or, defensively, an invalid code)
+			// escape (mpeg1.js:767-780)
+			run = (w >> 20) & 63;
+			const int l8 = (w >> 12) & 255;
+			if ((l8 & 127) == 0) {
+				level = (int)((w >> 4) & 255) - (l8 << 1);  // l8 == 128: second byte - 256
+				br.consume(28);
+			} else {
+				level = l8 > 128 ? l8 - 256 : l8;
+				br.consume(20);
+			}
+		} else {
+			if ((w >> (31 - len)) & 1u) level = -level;
+			br.consume(len + 1);
+		}
+		n += run;
+		if (n > 63) {  // JS: ZIG_ZAG[n] undefined -> the store is a no-op (the walk flagged the picture)
+			if (n > 4096) break;
+			n++;
+			continue;
+		}
+		const uint32_t idx = lds_u8(sbase + OFF_ZIGZAG + (uint32_t)n);
+		n++;
+		// dequantise, oddify toward zero, clip (mpeg1.js:794-807)
+		level <<= 1;
+		if (!intra) level += level < 0 ? -1 : 1;
+		level = (level * qs * (int)__ldg(quant + idx)) >> 4;
+		if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
+		level = max(-2048, min(2047, level));
+		sts_s16(sblock + idx * 2u, level);
+	}
+	// The finished block leaves as ONE 128-byte TMA bulk store (shared -> global, SASS UBLKCP): whole
+	// lines reach L2, whereas eight 16-byte stores per thread half-fill 32-byte sectors and made L2
+	// read every sector back before merging (ncu: 23.5 GB read for 22 GB written per step).
+#ifndef JSMPEG_WALK_EMU
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(slot), "r"(sblock) : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must outlive the read
+#else
+	memcpy(slot, emu_smem + sblock, 128);
+#endif
 }
 
 // Multi-symbol walk table: for every MS_BITS-bit prefix, the complete dct_coeff_next codes (with their

@@ -165,3 +165,27 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 	swapcontext(&emu::main_ctx, &emu::ctx[0]);
 	return 0;
 }
+
+// Stage 1b on the records the walk left: every block slot of the picture through expand_block
+// (jsmpeg_b200/csrc/walk.cuh), one "thread" after the other with its own zeroed tile.
+extern "C" int emu_expand_picture(const uint8_t *es, uint32_t es_len, int mb_width, int mb_height,
+                                  mb_record_t *hdr, int16_t *coef, picture_info_t *info) {
+	if (info->status != PIC_DECODED) return 0;
+	uint16_t *s16 = reinterpret_cast<uint16_t *>(emu_smem + EMU_EXPAND_BASE);
+	for (int i = 0; i < (VLC_DCT_MAX_Z + 1) * 32; i++) s16[OFF_DCT / 2 + i] = VLC_DCT_COEFF[i];
+	for (int i = 0; i < 64; i++) emu_smem[EMU_EXPAND_BASE + OFF_ZIGZAG + i] = TBL_ZIG_ZAG[i];
+	SeqParams seq;
+	memset(&seq, 0, sizeof(seq));
+	seq.mb_width = mb_width;
+	seq.mb_height = mb_height;
+	seq.mb_size = mb_width * mb_height;
+	memcpy(seq.intra_q, emu_intra_q, 64);
+	memcpy(seq.non_intra_q, emu_non_intra_q, 64);
+	ParseTask t;
+	t.es = es; t.es_len = es_len; t.start_byte = 0; t.seq = &seq; t.hdr = hdr; t.coef = coef; t.info = info;
+	for (int slot_id = 0; slot_id < seq.mb_size * 6; slot_id++) {
+		memset(emu_smem + EMU_EXPAND_BASE + OFF_BLOCKS, 0, 128);
+		expand_block(t, slot_id, EMU_EXPAND_BASE, EMU_EXPAND_BASE + OFF_BLOCKS);
+	}
+	return 0;
+}

@@ -236,3 +236,44 @@ def test_wide_refill_variant_reproduces_the_serial_walk():
             for lanes in (0, 1):
                 h1, c1, i1 = walk(wide, buf, len(es), s, mbw, mbh, lanes)
                 assert np.array_equal(h0, h1) and np.array_equal(c0, c1) and np.array_equal(i0[:9], i1[:9])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_stage1_device_code_matches_the_oracle_coefficients(name):
+    """Stage 1 end to end on the CPU: the emulated walk (lane-parallel and serial) followed by stage
+    1b's per-block device code (expand_block) against the ORACLE's dequantised coefficient blocks."""
+    from jsmpeg_b200 import decoder
+    es = open(os.path.join(HERE, "golden", name + ".es"), "rb").read()
+    olib = helpers.oracle_lib()
+    d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
+    d.write(0, [es])
+    seq = olib.oracle_seq_params(d.decoder).contents
+    mb = seq.mb_size
+    lib = emu_lib()
+    lib.emu_set_quant(bytes(seq.intra_q), bytes(seq.non_intra_q))
+    lib.emu_expand_picture.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p]
+    mbw, mbh = stream_geometry(es)
+    buf = np.frombuffer(es + b"\0" * 16, dtype=np.uint8).copy()
+    checked = 0
+    while d.decode():
+        info = olib.oracle_last_picture_info(d.decoder).contents
+        want_hdr = np.ctypeslib.as_array(ctypes.cast(olib.oracle_last_mb_records(d.decoder), ctypes.POINTER(ctypes.c_uint32)),
+                                         shape=(mb, 4)).copy()
+        want = np.ctypeslib.as_array(ctypes.cast(olib.oracle_last_coefficients(d.decoder), ctypes.POINTER(ctypes.c_int16)),
+                                     shape=(mb * 6, 64)).copy()
+        h = want_hdr.view(np.uint8).reshape(mb, 16)
+        present = (h[:, 4] & 1).astype(bool)
+        for lanes in (1, 0):
+            hdr = np.zeros(mb * 4, dtype=np.uint32)
+            coef = np.zeros(mb * 6 * 32, dtype=np.uint32)
+            pinfo = np.zeros(12, dtype=np.int32)
+            lib.emu_walk_picture(buf.ctypes.data, len(es), info.start_byte, mbw, mbh, hdr.ctypes.data, coef.ctypes.data,
+                                 pinfo.ctypes.data, lanes)
+            lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, coef.ctypes.data, pinfo.ctypes.data)
+            got = coef.view(np.int16).reshape(mb * 6, 64)
+            for blk in range(6):
+                rows = np.nonzero(present & ((h[:, 5] & (0x20 >> blk)) != 0))[0] * 6 + blk
+                assert np.array_equal(got[rows], want[rows]), f"{name}: picture at byte {info.start_byte}, lanes={lanes}, block {blk}"
+        checked += 1
+    assert checked > 0
