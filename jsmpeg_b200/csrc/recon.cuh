@@ -1,0 +1,352 @@
+// recon.cuh -- stage 2 device code: one 8x8 block = one thread (sm_100a).
+//
+// Included by recon.cu (kernel shell + launcher).  Like walk.cuh the same text compiles for the host
+// when JSMPEG_WALK_EMU is defined (tests/emu/walk_emu.cpp): the TMA copy and the packed-saturate /
+// dot-product instructions get plain C stand-ins, so that the CPU test-suite can run the whole hot
+// path -- walk, expand, reconstruct -- against the oracle's planes.
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+
+constexpr int THREADS = 128;
+constexpr int ROW_PITCH = 144;                       // bytes per staged block: 128 + 16 (bank spread)
+constexpr int WARP_STAGE = 32 * ROW_PITCH + 16;      // + the warp's mbarrier
+constexpr int MAX_TASKS = 80;  // per launch; (80 * 48 B) + 16 < 4 KB of kernel parameters
+
+struct CompactTask {
+	const mb_record_t *hdr;
+	const int16_t *coef;
+	uint8_t *cur;        // Y at 0, Cr at coded_size, Cb at coded_size * 5 / 4
+	const uint8_t *fwd;
+	int32_t mb_width, mb_height;
+	int32_t pad[2];
+};
+
+struct ReconParams {
+	CompactTask t[MAX_TASKS];
+};
+
+// PREMULTIPLIER_MATRIX (src/mpeg1.js:1026-1035) = outer product of these AAN scales, rounded as the
+// reference's table is; kept as a constexpr so that every use folds into an immediate.
+__device__ constexpr int PM[64] = {
+    32, 44, 42, 38, 32, 25, 17, 9,  44, 62, 58, 52, 44, 35, 24, 12, 42, 58, 55, 49, 42, 33, 23, 12,
+    38, 52, 49, 44, 38, 30, 20, 10, 32, 44, 42, 38, 32, 25, 17, 9,  25, 35, 33, 30, 25, 20, 14, 7,
+    17, 24, 23, 20, 17, 14, 9,  5,  9,  12, 12, 10, 9,  7,  5,  2};
+
+// One 8-point pass of the reference IDCT on v[o], v[o+s], ... v[o+7s].
+// Column pass: no scaling; row pass: (v + 128) >> 8.
+template <bool ROW, int O, int S>
+__device__ __forceinline__ void idct8(int (&v)[64]) {
+	const int b1 = v[O + 4 * S];
+	const int b3 = v[O + 2 * S] + v[O + 6 * S];
+	const int b4 = v[O + 5 * S] - v[O + 3 * S];
+	const int t1 = v[O + 1 * S] + v[O + 7 * S];
+	const int t2 = v[O + 3 * S] + v[O + 5 * S];
+	const int b6 = v[O + 1 * S] - v[O + 7 * S];
+	const int b7 = t1 + t2;
+	const int m0 = v[O];
+	const int x4 = ((b6 * 473 - b4 * 196 + 128) >> 8) - b7;
+	const int x0 = x4 - (((t1 - t2) * 362 + 128) >> 8);
+	const int x1 = m0 - b1;
+	const int x2 = (((v[O + 2 * S] - v[O + 6 * S]) * 362 + 128) >> 8) - b3;
+	const int x3 = m0 + b1;
+	const int y3 = x1 + x2, y4 = x3 + b3, y5 = x1 - x2, y6 = x3 - b3;
+	const int y7 = -x0 - ((b4 * 473 + b6 * 196 + 128) >> 8);
+	if (ROW) {
+		v[O] = (b7 + y4 + 128) >> 8;         v[O + 1 * S] = (x4 + y3 + 128) >> 8;
+		v[O + 2 * S] = (y5 - x0 + 128) >> 8; v[O + 3 * S] = (y6 - y7 + 128) >> 8;
+		v[O + 4 * S] = (y6 + y7 + 128) >> 8; v[O + 5 * S] = (x0 + y5 + 128) >> 8;
+		v[O + 6 * S] = (y3 - x4 + 128) >> 8; v[O + 7 * S] = (y4 - b7 + 128) >> 8;
+	} else {
+		v[O] = b7 + y4;         v[O + 1 * S] = x4 + y3; v[O + 2 * S] = y5 - x0; v[O + 3 * S] = y6 - y7;
+		v[O + 4 * S] = y6 + y7; v[O + 5 * S] = x0 + y5; v[O + 6 * S] = y3 - x4; v[O + 7 * S] = y4 - b7;
+	}
+}
+
+template <int I>
+__device__ __forceinline__ void idct_columns(int (&v)[64]) {
+	if constexpr (I < 8) {
+		idct8<false, I, 8>(v);
+		idct_columns<I + 1>(v);
+	}
+}
+template <int I>
+__device__ __forceinline__ void idct_rows(int (&v)[64]) {
+	if constexpr (I < 8) {
+		idct8<true, I * 8, 1>(v);
+		idct_rows<I + 1>(v);
+	}
+}
+
+__device__ __forceinline__ uint32_t pack_sat_u8x4(int a, int b, int c, int d) {
+	// PTX: d[7:0] = sat(b_op), d[15:8] = sat(a_op), d[31:16] = c_op[15:0]
+#ifndef JSMPEG_WALK_EMU
+	uint32_t hi, r;
+	const uint32_t zero = 0;
+	asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(zero));
+	asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+	return r;
+#else
+	auto sat = [](int x) { return (uint32_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); };
+	return sat(a) | sat(b) << 8 | sat(c) << 16 | sat(d) << 24;
+#endif
+}
+
+// packed predicted samples p (4 per word) + 4 residuals -> 4 saturated output samples
+__device__ __forceinline__ uint32_t add_sat4(uint32_t p, int r0, int r1, int r2, int r3) {
+	return pack_sat_u8x4((int)(p & 255u) + r0, (int)((p >> 8) & 255u) + r1, (int)((p >> 16) & 255u) + r2, (int)(p >> 24) + r3);
+}
+
+// 9 consecutive samples starting at flat index i of a plane whose base is 4-byte aligned:
+// a = samples 0..3, b = 4..7, c (low byte) = sample 8.
+__device__ __forceinline__ void row9(const uint8_t *__restrict__ plane, int i, uint32_t &a, uint32_t &b, uint32_t &c) {
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(plane) + (i >> 2);
+	const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+	const uint32_t sh = (uint32_t)(i & 3) * 8u;
+	a = __funnelshift_r(w0, w1, sh);
+	b = __funnelshift_r(w1, w2, sh);
+	c = w2 >> sh;
+}
+
+// dp4a with unsigned bytes in `a` and signed bytes in `b`: sum_i a.b[i] * b.b[i] + c (integer dot
+// product unit, off the ALU pipe that bounds this kernel)
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+#ifndef JSMPEG_WALK_EMU
+	int d;
+	asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+#else
+	for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 255u) * (int)(int8_t)((b >> (8 * i)) & 255u);
+	return c;
+#endif
+}
+
+// Prediction of the 8 rows of one block + residual.  The four half-pel cases of the reference
+// (copy, (a+b+1)>>1 horizontally or vertically, (a+b+c+d+2)>>2; src/mpeg1.js:481-556) are ONE
+// formula with per-thread tap weights:
+//     (wA*A + wB*B + wC*C + wD*D + 2) >> 2,   (wA,wB,wC,wD) = (4,0,0,0) | (2,2,0,0) | (2,0,2,0) | (1,1,1,1)
+// ((4A+2)>>2 = A, (2A+2B+2)>>2 = (A+B+1)>>1).  Per output sample: one PRMT gathers the four taps
+// into a word, one dp4a applies the weights (accumulator preloaded with the rounding 2).
+// The lanes of a warp hold blocks of different macroblocks, i.e. different parities: the weights
+// are data, the instruction stream is the same for every lane.
+// FULLPEL (warp-uniform: no lane has a half-pel component) is the plain copy: one dp4a per sample
+// selects the byte and adds the residual.
+template <bool FULLPEL>
+__device__ __forceinline__ void predict_rows(const uint8_t *__restrict__ splane, int src, int stride, uint32_t weights,
+                                             bool coded, const int (&v)[64], uint8_t *__restrict__ dst) {
+	uint32_t a0, a1, a2;
+	row9(splane, src, a0, a1, a2);
+#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		uint32_t c0 = 0, c1 = 0, c2 = 0;
+		int s[8];
+		if (FULLPEL) {
+			if (r < 7) row9(splane, src + (r + 1) * stride, c0, c1, c2);
+#pragma unroll
+			for (int x = 0; x < 4; x++) {
+				s[x] = dp4a_us(a0, 1u << (8 * x), coded ? v[r * 8 + x] : 0);
+				s[4 + x] = dp4a_us(a1, 1u << (8 * x), coded ? v[r * 8 + 4 + x] : 0);
+			}
+		} else {
+			row9(splane, src + (r + 1) * stride, c0, c1, c2);  // row 8 is inside the plane (checked by the caller)
+			const uint32_t sa0 = __funnelshift_r(a0, a1, 8), sa1 = __funnelshift_r(a1, a2, 8);  // samples 1..4, 5..8
+			const uint32_t sc0 = __funnelshift_r(c0, c1, 8), sc1 = __funnelshift_r(c1, c2, 8);
+			// taps (A, B, C, D) = (row[x], row[x+1], next[x], next[x+1]) as one word per sample
+			s[0] = dp4a_us(__byte_perm(a0, c0, 0x5410), weights, 2);
+			s[1] = dp4a_us(__byte_perm(a0, c0, 0x6521), weights, 2);
+			s[2] = dp4a_us(__byte_perm(a0, c0, 0x7632), weights, 2);
+			s[3] = dp4a_us(__byte_perm(sa0, sc0, 0x7632), weights, 2);
+			s[4] = dp4a_us(__byte_perm(a1, c1, 0x5410), weights, 2);
+			s[5] = dp4a_us(__byte_perm(a1, c1, 0x6521), weights, 2);
+			s[6] = dp4a_us(__byte_perm(a1, c1, 0x7632), weights, 2);
+			s[7] = dp4a_us(__byte_perm(sa1, sc1, 0x7632), weights, 2);
+#pragma unroll
+			for (int x = 0; x < 8; x++) s[x] = (s[x] >> 2) + (coded ? v[r * 8 + x] : 0);
+		}
+		uint2 out;
+		out.x = pack_sat_u8x4(s[0], s[1], s[2], s[3]);
+		out.y = pack_sat_u8x4(s[4], s[5], s[6], s[7]);
+		*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+		a0 = c0; a1 = c1; a2 = c2;
+	}
+}
+
+#ifndef JSMPEG_WALK_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#else
+static inline uint32_t smem_u32(const void *) { return 0; }
+#endif
+
+// One 8x8 block: `slot` is its number in the picture (see above), `wstage` the warp's staging area.
+// WARP-CONVERGENT: the 32 lanes of a warp call it together (two collectives inside).
+__device__ __forceinline__ void reconstruct_block(const CompactTask &t, int slot, int lane, uint8_t *wstage) {
+	const int W = t.mb_width;
+	const int slots_per_row = 6 * W;
+	const bool in_picture = slot < slots_per_row * t.mb_height;
+	const int mb_row = in_picture ? slot / slots_per_row : 0;
+	const int s = in_picture ? slot - mb_row * slots_per_row : 0;
+	// [luma top 2W | luma bottom 2W | Cb W | Cr W]
+	int b, mb_col;
+	if (s < 4 * W) {
+		const int by = s >= 2 * W;
+		const int bx = s - by * 2 * W;
+		mb_col = bx >> 1;
+		b = by * 2 + (bx & 1);
+	} else {
+		const int c = s - 4 * W;
+		const int second = c >= W;
+		mb_col = c - second * W;
+		b = 4 + second;  // block 4 -> Cb plane, block 5 -> Cr plane (mpeg1.js:829-834)
+	}
+	const int mb = mb_row * W + mb_col;
+
+	uint2 rec = make_uint2(0, 0);
+	if (in_picture) rec = __ldg(reinterpret_cast<const uint2 *>(t.hdr + mb));
+	const int flags = rec.y & 0xff;
+	const bool present = flags & MBF_PRESENT;  // an untouched macroblock keeps the two-pictures-old content
+	const bool intra = flags & MBF_INTRA;
+	const int bit = 0x20 >> b;
+	const bool coded = present && ((rec.y >> 8) & bit);
+	const bool dc_only = coded && ((rec.y >> 16) & bit);
+	const bool full = coded && !dc_only;
+
+	// ---- coefficient records of the warp's blocks: one TMA bulk copy per lane
+	const uint32_t mbar = smem_u32(wstage + 32 * ROW_PITCH);
+	const uint32_t my_row = smem_u32(wstage + lane * ROW_PITCH);
+	const int16_t *cblk = t.coef + ((size_t)mb * 6 + b) * 64;
+	const unsigned full_mask = __ballot_sync(0xffffffffu, full);
+	if (full_mask) {  // warp-uniform
+#ifndef JSMPEG_WALK_EMU
+		if (lane == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(128u * (uint32_t)__popc(full_mask)) : "memory");
+		}
+		__syncwarp();
+		if (full)
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];"
+			             ::"r"(my_row), "l"(cblk), "r"(mbar) : "memory");
+#else
+		(void)mbar;
+		if (full) memcpy(wstage + lane * ROW_PITCH, cblk, 128);  // the emulated "TMA": the lane's record into its staging row
+#endif
+	}
+
+	const int stride_y = W * 16;
+	const int ysize = stride_y * t.mb_height * 16;
+	int stride, plane_off, plane_size, origin;
+	if (b < 4) {
+		stride = stride_y; plane_off = 0; plane_size = ysize;
+		origin = (mb_row * 16 + (b >> 1) * 8) * stride + mb_col * 16 + (b & 1) * 8;
+	} else {
+		stride = stride_y >> 1; plane_size = ysize >> 2;
+		plane_off = b == 4 ? ysize + plane_size : ysize;  // Cb is the third plane, Cr the second
+		origin = mb_row * 8 * stride + mb_col * 8;
+	}
+
+	if (full_mask) {  // wait for the warp's copies (phase 0 of a barrier used once)
+#ifndef JSMPEG_WALK_EMU
+		uint32_t done = 0;
+		while (!done)
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+			             : "=r"(done) : "r"(mbar) : "memory");
+#endif
+	}
+	// motion vector of this block's plane, and whether ANY lane of the warp needs half-pel taps
+	int mh = (int)(int16_t)(rec.x & 0xffffu), mv = (int)(int16_t)(rec.x >> 16);
+	if (b >= 4) { mh /= 2; mv /= 2; }  // truncation toward zero (mpeg1.js:562-565)
+	const bool oh = mh & 1, ov = mv & 1;
+	const bool warp_halfpel = __any_sync(0xffffffffu, present && !intra && (oh || ov));
+	if (!present) return;
+
+	// ---- residual: 64 values in registers
+	int v[64];
+	if (full) {
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			uint4 q;
+#ifndef JSMPEG_WALK_EMU
+			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(my_row + i * 16));
+#else
+			(void)my_row;
+			memcpy(&q, wstage + lane * ROW_PITCH + i * 16, 16);
+#endif
+			// dp2a: (lo16 * b0 + hi16 * b1): one instruction per coefficient, no unpacking on the ALU pipe
+			v[i * 8 + 0] = __dp2a_lo((int)q.x, PM[i * 8 + 0], 0); v[i * 8 + 1] = __dp2a_lo((int)q.x, PM[i * 8 + 1] << 8, 0);
+			v[i * 8 + 2] = __dp2a_lo((int)q.y, PM[i * 8 + 2], 0); v[i * 8 + 3] = __dp2a_lo((int)q.y, PM[i * 8 + 3] << 8, 0);
+			v[i * 8 + 4] = __dp2a_lo((int)q.z, PM[i * 8 + 4], 0); v[i * 8 + 5] = __dp2a_lo((int)q.z, PM[i * 8 + 5] << 8, 0);
+			v[i * 8 + 6] = __dp2a_lo((int)q.w, PM[i * 8 + 6], 0); v[i * 8 + 7] = __dp2a_lo((int)q.w, PM[i * 8 + 7] << 8, 0);
+		}
+		idct_columns<0>(v);
+		idct_rows<0>(v);
+	} else {
+		int dc = 0;
+		if (coded) dc = ((int)__ldg(cblk) * PM[0] + 128) >> 8;  // mpeg1.js:838-841, 850-853
+#pragma unroll
+		for (int i = 0; i < 64; i++) v[i] = dc;
+	}
+
+	uint8_t *dst = t.cur + plane_off + origin;
+	if (intra) {
+#pragma unroll
+		for (int r = 0; r < 8; r++) {
+			uint2 out;
+			out.x = pack_sat_u8x4(v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
+			out.y = pack_sat_u8x4(v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+			*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+		}
+		return;
+	}
+
+	// ---- prediction from the forward picture + residual
+	const int src = origin + (mv >> 1) * stride + (mh >> 1);  // flat index (mpeg1.js:479, 567)
+	const uint8_t *splane = t.fwd + plane_off;
+	if (src >= 0 && src + 8 * stride + 8 < plane_size) {
+		// tap weights of this lane: bytes (wA, wB, wC, wD)
+		const uint32_t weights = oh ? (ov ? 0x01010101u : 0x00000202u) : (ov ? 0x00020002u : 0x00000004u);
+		if (warp_halfpel) predict_rows<false>(splane, src, stride, weights, coded, v, dst);
+		else predict_rows<true>(splane, src, stride, weights, coded, v, dst);
+		return;
+	}
+	// vector leaves the plane: per-tap bounds check, any outside tap zeroes the sample
+#pragma unroll 1
+	for (int r = 0; r < 8; r++) {
+		uint32_t p[2] = {0, 0};
+		for (int x = 0; x < 8; x++) {
+			const int i = src + r * stride + x;
+			const int taps[4] = {i, i + 1, i + stride, i + stride + 1};
+			const bool use[4] = {true, (bool)oh, (bool)ov, oh && ov};
+			int sum = 0, n = 0;
+			bool inside = true;
+			for (int k = 0; k < 4; k++) {
+				if (!use[k]) continue;
+				if (taps[k] < 0 || taps[k] >= plane_size) { inside = false; continue; }
+				sum += splane[taps[k]];
+				n++;
+			}
+			const int px = !inside ? 0 : (n == 4 ? (sum + 2) >> 2 : (n == 2 ? (sum + 1) >> 1 : sum));
+			p[x >> 2] |= (uint32_t)px << (8 * (x & 3));
+		}
+		// v[] is indexed dynamically only on this rare path (spills to local memory are fine here)
+		int rr[8];
+#pragma unroll
+		for (int x = 0; x < 8; x++) {
+			int acc = 0;
+#pragma unroll
+			for (int q = 0; q < 8; q++) acc = (q == r) ? v[q * 8 + x] : acc;
+			rr[x] = acc;
+		}
+		uint2 out;
+		if (coded) {
+			out.x = add_sat4(p[0], rr[0], rr[1], rr[2], rr[3]);
+			out.y = add_sat4(p[1], rr[4], rr[5], rr[6], rr[7]);
+		} else {
+			out.x = p[0]; out.y = p[1];
+		}
+		*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+	}
+}
+
+}  // namespace

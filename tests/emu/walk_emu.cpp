@@ -80,9 +80,19 @@ static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pre
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
-static inline uint32_t __byte_perm(uint32_t a, uint32_t, uint32_t sel) {
-	if (sel != 0x0123) abort();  // the only selector the walk uses: byte swap
-	return __builtin_bswap32(a);
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {  // PRMT, default mode (selectors 0..7)
+	const uint64_t ab = ((uint64_t)b << 32) | a;
+	uint32_t r = 0;
+	for (int i = 0; i < 4; i++) {
+		const uint32_t k = (sel >> (4 * i)) & 15u;
+		if (k > 7) abort();  // sign-replicating selectors are not used
+		r |= (uint32_t)((ab >> (8 * k)) & 255u) << (8 * i);
+	}
+	return r;
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
+static inline int __dp2a_lo(int a, int b, int c) {  // c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (all signed)
+	return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)(b & 0xff) + (int)(int16_t)((uint32_t)a >> 16) * (int)(int8_t)((b >> 8) & 0xff);
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 
@@ -106,6 +116,38 @@ extern "C" void emu_vote_counters(uint64_t *trips, uint64_t *lanes, int reset) {
 
 #define VLC_TABLE_QUALIFIER static const
 #include "../../jsmpeg_b200/csrc/walk.cuh"
+#include "../../jsmpeg_b200/csrc/recon.cuh"
+
+// Runs `body(lane)` as the 32 lanes of one warp.  Every collective is executed by all 32 lanes (the
+// device code's rule), so no lane finishes while another still waits in one: a finished lane is simply
+// skipped by the round-robin.
+static void (*warp_body)(int);
+static void warp_entry() {
+	const int l = emu::lane;
+	warp_body(l);
+	emu::finished[l] = true;
+	for (int k = 0; k < 32; k++)
+		if (!emu::finished[k]) {
+			emu::lane = k;
+			setcontext(&emu::ctx[k]);
+		}
+	setcontext(&emu::main_ctx);
+}
+static void run_warp(void (*body)(int)) {
+	static std::vector<std::vector<char>> stacks(32, std::vector<char>(1 << 20));
+	warp_body = body;
+	emu::arrived = 0;
+	for (int l = 0; l < 32; l++) {
+		emu::finished[l] = false;
+		getcontext(&emu::ctx[l]);
+		emu::ctx[l].uc_stack.ss_sp = stacks[l].data();
+		emu::ctx[l].uc_stack.ss_size = stacks[l].size();
+		emu::ctx[l].uc_link = nullptr;
+		makecontext(&emu::ctx[l], warp_entry, 0);
+	}
+	emu::lane = 0;
+	swapcontext(&emu::main_ctx, &emu::ctx[0]);
+}
 
 // the stream's quantiser matrices (de-zigzagged, as in SeqParams); only the block-emitting variant reads them
 static uint8_t emu_intra_q[64], emu_non_intra_q[64];
@@ -131,38 +173,14 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 	memcpy(seq.non_intra_q, emu_non_intra_q, 64);
 	ParseTask t;
 	t.es = es; t.es_len = es_len; t.start_byte = start_byte; t.seq = &seq; t.hdr = hdr; t.coef = coef; t.info = info;
-	// every collective is executed by all 32 lanes (walk.cuh's rule), so no lane finishes while another
-	// still waits in one: a finished lane is simply skipped by the round-robin
 	static ParseTask task;
 	static int use_lanes;
 	task = t;
 	use_lanes = lanes;
-	static std::vector<std::vector<char>> stacks(32, std::vector<char>(1 << 20));
-	struct Entry {
-		static void run() {
-			const int l = emu::lane;
-			if (use_lanes) walk_picture<true>(task, 0, l);
-			else walk_picture<false>(task, 0, l);
-			emu::finished[l] = true;
-			for (int k = 0; k < 32; k++)
-				if (!emu::finished[k]) {
-					emu::lane = k;
-					setcontext(&emu::ctx[k]);
-				}
-			setcontext(&emu::main_ctx);
-		}
-	};
-	emu::arrived = 0;
-	for (int l = 0; l < 32; l++) {
-		emu::finished[l] = false;
-		getcontext(&emu::ctx[l]);
-		emu::ctx[l].uc_stack.ss_sp = stacks[l].data();
-		emu::ctx[l].uc_stack.ss_size = stacks[l].size();
-		emu::ctx[l].uc_link = nullptr;
-		makecontext(&emu::ctx[l], Entry::run, 0);
-	}
-	emu::lane = 0;
-	swapcontext(&emu::main_ctx, &emu::ctx[0]);
+	run_warp([](int l) {
+		if (use_lanes) walk_picture<true>(task, 0, l);
+		else walk_picture<false>(task, 0, l);
+	});
 	return 0;
 }
 
@@ -187,5 +205,20 @@ extern "C" int emu_expand_picture(const uint8_t *es, uint32_t es_len, int mb_wid
 		memset(emu_smem + EMU_EXPAND_BASE + OFF_BLOCKS, 0, 128);
 		expand_block(t, slot_id, EMU_EXPAND_BASE, EMU_EXPAND_BASE + OFF_BLOCKS);
 	}
+	return 0;
+}
+
+
+// Stage 2: every block slot of the picture through reconstruct_block (jsmpeg_b200/csrc/recon.cuh), a
+// warp of 32 consecutive slots at a time.  cur / fwd: Y | Cr | Cb contiguous, like the product's plane sets.
+extern "C" int emu_reconstruct_picture(const mb_record_t *hdr, const int16_t *coef, uint8_t *cur, const uint8_t *fwd,
+                                       int mb_width, int mb_height) {
+	static CompactTask task;
+	static int first_slot;
+	static uint8_t wstage[WARP_STAGE];
+	task.hdr = hdr; task.coef = coef; task.cur = cur; task.fwd = fwd; task.mb_width = mb_width; task.mb_height = mb_height;
+	const int slots = mb_width * mb_height * 6;
+	for (first_slot = 0; first_slot < slots; first_slot += 32)
+		run_warp([](int l) { reconstruct_block(task, first_slot + l, l, wstage); });
 	return 0;
 }
