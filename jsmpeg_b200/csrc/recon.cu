@@ -40,7 +40,7 @@ namespace {
 __global__ void __launch_bounds__(THREADS, 5)
 reconstruct_kernel(const __grid_constant__ ReconParams params) {
 	__shared__ __align__(16) uint8_t stage[(THREADS / 32) * WARP_STAGE];
-	reconstruct_block(params.t[blockIdx.y], blockIdx.x * THREADS + threadIdx.x, threadIdx.x & 31, stage + (threadIdx.x >> 5) * WARP_STAGE);
+	reconstruct_block(params.t[blockIdx.y], blockIdx.x * THREADS, threadIdx.x, stage);
 }
 
 }  // namespace

@@ -179,11 +179,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 static inline uint32_t smem_u32(const void *) { return 0; }
 #endif
 
-// One 8x8 block: `slot` is its number in the picture (see above), `wstage` the warp's staging area.
+// One 8x8 block: slot first_slot + tid of the picture (see above); `stage` = the CTA's staging area
+// (one WARP_STAGE per warp), tid = the thread's index in the CTA.
 // WARP-CONVERGENT: the 32 lanes of a warp call it together (two collectives inside).
-__device__ __forceinline__ void reconstruct_block(const CompactTask &t, int slot, int lane, uint8_t *wstage) {
+__device__ __forceinline__ void reconstruct_block(const CompactTask &t, int first_slot, int tid, uint8_t *stage) {
 	const int W = t.mb_width;
 	const int slots_per_row = 6 * W;
+	const int slot = first_slot + tid;
+	const int lane = tid & 31;
 	const bool in_picture = slot < slots_per_row * t.mb_height;
 	const int mb_row = in_picture ? slot / slots_per_row : 0;
 	const int s = in_picture ? slot - mb_row * slots_per_row : 0;
@@ -213,6 +216,7 @@ __device__ __forceinline__ void reconstruct_block(const CompactTask &t, int slot
 	const bool full = coded && !dc_only;
 
 	// ---- coefficient records of the warp's blocks: one TMA bulk copy per lane
+	uint8_t *wstage = stage + (tid >> 5) * WARP_STAGE;
 	const uint32_t mbar = smem_u32(wstage + 32 * ROW_PITCH);
 	const uint32_t my_row = smem_u32(wstage + lane * ROW_PITCH);
 	const int16_t *cblk = t.coef + ((size_t)mb * 6 + b) * 64;

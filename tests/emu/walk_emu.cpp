@@ -219,6 +219,6 @@ extern "C" int emu_reconstruct_picture(const mb_record_t *hdr, const int16_t *co
 	task.hdr = hdr; task.coef = coef; task.cur = cur; task.fwd = fwd; task.mb_width = mb_width; task.mb_height = mb_height;
 	const int slots = mb_width * mb_height * 6;
 	for (first_slot = 0; first_slot < slots; first_slot += 32)
-		run_warp([](int l) { reconstruct_block(task, first_slot + l, l, wstage); });
+		run_warp([](int l) { reconstruct_block(task, first_slot, l, wstage); });
 	return 0;
 }
