@@ -279,14 +279,9 @@ def test_stage1_device_code_matches_the_oracle_coefficients(name):
     assert checked > 0
 
 
-@pytest.mark.parametrize("name", GOLDEN)
-def test_whole_hot_path_device_code_matches_the_oracle_planes(name):
-    """The whole hot path on the CPU: emulated walk (lane-parallel) -> stage 1b -> stage 2
-    (jsmpeg_b200/csrc/recon.cuh, a warp = 32 coroutines, the TMA copy and the packed instructions
-    replaced by plain C) with the product's ping-pong planes, against the ORACLE's planes of every
-    decoded picture.  Bit-exact, like the GPU parity tests -- which remain the check of the real thing."""
+def _pipeline_against_oracle_planes(es, what):
+    name = what
     from jsmpeg_b200 import decoder
-    es = open(os.path.join(HERE, "golden", name + ".es"), "rb").read()
     olib = helpers.oracle_lib()
     d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
     d.write(0, [es])
@@ -323,3 +318,21 @@ def test_whole_hot_path_device_code_matches_the_oracle_planes(name):
         cur ^= 1
         checked += 1
     assert checked > 0
+    return checked
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_whole_hot_path_device_code_matches_the_oracle_planes(name):
+
+    """The whole hot path on the CPU: emulated walk (lane-parallel) -> stage 1b -> stage 2
+    (jsmpeg_b200/csrc/recon.cuh, a warp = 32 coroutines, the TMA copy and the packed instructions
+    replaced by plain C) with the product's ping-pong planes, against the ORACLE's planes of every
+    decoded picture.  Bit-exact, like the GPU parity tests -- which remain the check of the real thing."""
+    _pipeline_against_oracle_planes(open(os.path.join(HERE, "golden", name + ".es"), "rb").read(), name)
+
+
+def test_whole_hot_path_device_code_on_an_encoder_clip():
+    """The same on an FFmpeg-made I+P clip (one slice per picture, half-pel vectors everywhere)."""
+    pytest.importorskip("cv2")
+    es = b"".join(p for _, p in helpers.clip_packets(320, 240, 14))
+    assert _pipeline_against_oracle_planes(es, "clip 320x240") == 14
