@@ -279,8 +279,7 @@ def test_stage1_device_code_matches_the_oracle_coefficients(name):
     assert checked > 0
 
 
-def _pipeline_against_oracle_planes(es, what):
-    name = what
+def _pipeline_against_oracle_planes(es, name):
     from jsmpeg_b200 import decoder
     olib = helpers.oracle_lib()
     d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
@@ -323,7 +322,6 @@ def _pipeline_against_oracle_planes(es, what):
 
 @pytest.mark.parametrize("name", GOLDEN)
 def test_whole_hot_path_device_code_matches_the_oracle_planes(name):
-
     """The whole hot path on the CPU: emulated walk (lane-parallel) -> stage 1b -> stage 2
     (jsmpeg_b200/csrc/recon.cuh, a warp = 32 coroutines, the TMA copy and the packed instructions
     replaced by plain C) with the product's ping-pong planes, against the ORACLE's planes of every
