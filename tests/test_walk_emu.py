@@ -279,14 +279,14 @@ def test_stage1_device_code_matches_the_oracle_coefficients(name):
     assert checked > 0
 
 
-def _pipeline_against_oracle_planes(es, name):
+def _pipeline_against_oracle_planes(es, name, define=None):
     from jsmpeg_b200 import decoder
     olib = helpers.oracle_lib()
     d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
     d.write(0, [es])
     seq = olib.oracle_seq_params(d.decoder).contents
     mb = seq.mb_size
-    lib = emu_lib()
+    lib = emu_lib(define)
     lib.emu_set_quant(bytes(seq.intra_q), bytes(seq.non_intra_q))
     lib.emu_expand_picture.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p]
@@ -307,7 +307,8 @@ def _pipeline_against_oracle_planes(es, name):
                              pinfo.ctypes.data, 1)
         if pinfo[2] != 1:
             continue  # B / D picture or P without f_code: consumed, nothing decoded, no swap (mpeg1.js:181-193)
-        lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, coef.ctypes.data, pinfo.ctypes.data)
+        if not (define == "JSMPEG_WALK_EMITS_BLOCKS" and pinfo[10]):  # that variant's walk has written the blocks already
+            lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, coef.ctypes.data, pinfo.ctypes.data)
         lib.emu_reconstruct_picture(hdr.ctypes.data, coef.ctypes.data, planes[cur].ctypes.data, planes[cur ^ 1].ctypes.data, mbw, mbh)
         y, cr, cb = d.planes()
         got = planes[cur]
@@ -334,3 +335,14 @@ def test_whole_hot_path_device_code_on_an_encoder_clip():
     pytest.importorskip("cv2")
     es = b"".join(p for _, p in helpers.clip_packets(320, 240, 14))
     assert _pipeline_against_oracle_planes(es, "clip 320x240") == 14
+
+
+@pytest.mark.parametrize("define", ["JSMPEG_LANES_FIXUP", "JSMPEG_WALK_EMITS_BLOCKS", "JSMPEG_WIDE_REFILL"])
+def test_round2_candidates_through_the_whole_pipeline(define):
+    """The compiled-out candidates of walk.cuh, each through walk -> (expand) -> reconstruct against the
+    oracle's planes on two golden streams and an encoder clip."""
+    for name in ("rows_ip", "skips_stuffing_escape_mba"):
+        _pipeline_against_oracle_planes(open(os.path.join(HERE, "golden", name + ".es"), "rb").read(), name, define)
+    pytest.importorskip("cv2")
+    es = b"".join(p for _, p in helpers.clip_packets(320, 240, 8))
+    assert _pipeline_against_oracle_planes(es, "clip 320x240", define) == 8
