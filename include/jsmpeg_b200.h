@@ -33,14 +33,19 @@ typedef enum {
 	BIT_BUFFER_MODE_EXPAND = 2
 } bit_buffer_mode_t;
 
-/* mpeg1.h:12 / mpeg1.c:777-782.  Never fails (aborts on a CUDA error).  Uses the CUDA device set
- * with jsmpeg_b200_set_default_device, else the one named by the environment variable
+/* mpeg1.h:12 / mpeg1.c:777-782.  Never fails and never takes the process down: without a usable
+ * CUDA device (or after any CUDA error later on) the decoder is DEAD -- decode() returns false like
+ * "no sequence header yet", writes are swallowed, jsmpeg_b200_decoder_last_error says why (the
+ * reason is also printed to stderr once).  Uses the CUDA device set with
+ * jsmpeg_b200_set_default_device, else the one named by the environment variable
  * JSMPEG_B200_DEVICE, else device 0. */
 mpeg1_decoder_t *mpeg1_decoder_create(unsigned int buffer_size, bit_buffer_mode_t buffer_mode);
 /* mpeg1.h:13 / mpeg1.c:784-798 */
 void mpeg1_decoder_destroy(mpeg1_decoder_t *self);
 /* mpeg1.h:14 / mpeg1.c:800-802, buffer.c:48-65: room for byte_size more bytes (EXPAND: grows;
- * EVICT: discards consumed bytes, buffer.c:167-190); the pointer is HOST memory (pinned). */
+ * EVICT: discards consumed bytes, buffer.c:167-190); the pointer is HOST memory (pinned) and ALWAYS
+ * covers byte_size bytes -- where the reference's own sizing (buffer.c:53-57) would not, the buffer
+ * grows to length + byte_size (csrc/bitbuffer.h). */
 void *mpeg1_decoder_get_write_ptr(mpeg1_decoder_t *self, unsigned int byte_size);
 /* mpeg1.h:15-16 / mpeg1.c:804-810: read position in BITS */
 int mpeg1_decoder_get_index(mpeg1_decoder_t *self);
@@ -90,9 +95,18 @@ typedef struct jsmpeg_b200_stats_t {
 } jsmpeg_b200_stats_t;
 
 /* n_streams decoders on CUDA device `device`.  max_slots bounds the pictures parsed ahead
- * (records resident in HBM); 0 = choose from free memory. */
+ * (records resident in HBM; cut to what the device can hold); 0 = choose from free memory.
+ * Never NULL; a batch without a usable device is dead (see jsmpeg_b200_batch_last_error). */
 jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigned int max_slots);
 void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b);
+/* NULL while the batch works; otherwise the first failure (a CUDA error text).  A dead batch returns
+ * 0 / -1 / false from every call and never touches the device again. */
+const char *jsmpeg_b200_batch_last_error(jsmpeg_b200_batch_t *b);
+/* Tuning knobs, 0 on success.  "chunk_pictures" G: a parse wave is queued in chunks of G pictures per
+ * stream and chunk k is reconstructed while chunk k+1 is being parsed (0 = one chunk, no overlap;
+ * default from the environment variable JSMPEG_B200_CHUNK, else 0).  "lookahead": pictures parsed
+ * ahead per stream beyond the ones a decode call asks for. */
+int jsmpeg_b200_batch_set_option(jsmpeg_b200_batch_t *b, const char *name, int value);
 
 /* per-stream twins of the reference ABI */
 void *jsmpeg_b200_batch_get_write_ptr(jsmpeg_b200_batch_t *b, int stream, unsigned int byte_size);
@@ -158,6 +172,9 @@ int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t
 int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, const void *coef,
                                   const uint8_t *fwd_y, const uint8_t *fwd_cr, const uint8_t *fwd_cb,
                                   uint8_t *cur_y, uint8_t *cur_cr, uint8_t *cur_cb);
+
+/* NULL while the decoder works, else why it is dead (see mpeg1_decoder_create). */
+const char *jsmpeg_b200_decoder_last_error(mpeg1_decoder_t *self);
 
 /* CUDA device for decoders created through the reference ABI from now on (the reference ABI has no
  * device argument; the JS/Python class passes its `device` option here). */

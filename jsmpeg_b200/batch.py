@@ -55,6 +55,9 @@ _BATCH_ABI = {
                                                        _VP, _VP, _VP, _VP, _VP]),
     "jsmpeg_b200_debug_reconstruct": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "jsmpeg_b200_set_default_device": (None, [ctypes.c_int]),
+    "jsmpeg_b200_batch_last_error": (ctypes.c_char_p, [_VP]),
+    "jsmpeg_b200_batch_set_option": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_int]),
+    "jsmpeg_b200_decoder_last_error": (ctypes.c_char_p, [_VP]),
     "jsmpeg_b200_version": (ctypes.c_char_p, []),
 }
 
@@ -70,11 +73,17 @@ def bind_batch_abi(lib):
 class BatchDecoder:
     """``n_streams`` independent MPEG-1 video decoders on one B200."""
 
-    def __init__(self, n_streams, device=0, max_slots=0, lib=None):
+    def __init__(self, n_streams, device=0, max_slots=0, lib=None, chunk_pictures=None):
         from . import capi
         self.lib = lib if lib is not None else capi.product_library()
         self.n_streams = n_streams
         self.handle = self.lib.jsmpeg_b200_batch_create(n_streams, device, max_slots)
+        err = self.lib.jsmpeg_b200_batch_last_error(self.handle)
+        if err:  # no usable CUDA device: the C ABI answers "false" for ever; the Python host says so loudly
+            self.close()
+            raise RuntimeError(err.decode(errors="replace"))
+        if chunk_pictures is not None:
+            self.set_option("chunk_pictures", chunk_pictures)
 
     def close(self):
         if self.handle:
@@ -82,6 +91,14 @@ class BatchDecoder:
             self.handle = None
 
     __del__ = close
+
+    def set_option(self, name, value):
+        if self.lib.jsmpeg_b200_batch_set_option(self.handle, name.encode(), int(value)) != 0:
+            raise ValueError(f"unknown option {name!r}")
+
+    def last_error(self):
+        err = self.lib.jsmpeg_b200_batch_last_error(self.handle)
+        return err.decode(errors="replace") if err else None
 
     def write(self, stream, data):
         """Two-phase write of the reference ABI (get_write_ptr / memcpy / did_write)."""

@@ -5,16 +5,27 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <stdexcept>
+#include <string>
+
 #include "records.h"
 
-#define CUDA_CHECK(expr)                                                                         \
-	do {                                                                                         \
-		cudaError_t _e = (expr);                                                                 \
-		if (_e != cudaSuccess) {                                                                 \
-			fprintf(stderr, "jsmpeg_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e),   \
-			        __FILE__, __LINE__, cudaGetErrorString(_e));                                 \
-			abort();                                                                             \
-		}                                                                                        \
+// A failed CUDA call never takes the host process down (the reference "never fails": a decoder that
+// cannot work answers decode() == false).  CUDA_CHECK throws; every C-ABI entry point catches, marks
+// its decoder dead (jsmpeg_b200_batch_last_error) and returns its failure value (engine.cu).
+struct CudaFailure : std::runtime_error {
+	cudaError_t code;
+	CudaFailure(cudaError_t c, const std::string &what) : std::runtime_error(what), code(c) {}
+};
+[[noreturn]] inline void throw_cuda_failure(cudaError_t e, const char *file, int line) {
+	char msg[512];
+	snprintf(msg, sizeof msg, "jsmpeg_b200: CUDA error %s at %s:%d: %s", cudaGetErrorName(e), file, line, cudaGetErrorString(e));
+	throw CudaFailure(e, msg);
+}
+#define CUDA_CHECK(expr)                                                  \
+	do {                                                                  \
+		cudaError_t _e = (expr);                                          \
+		if (_e != cudaSuccess) throw_cuda_failure(_e, __FILE__, __LINE__); \
 	} while (0)
 
 // Per-stream sequence parameters as the kernels need them (reference mpeg1.js:78-153).
@@ -23,17 +34,34 @@ struct SeqParams {
 	int32_t coded_width, coded_height;
 	uint8_t intra_q[64];     // de-zigzagged (mpeg1.js:100-116)
 	uint8_t non_intra_q[64];
+	// the same two matrices in COEFFICIENT (zig-zag) order, as stage 1b wants them: entry n of table k
+	// (0 intra, 1 non-intra) = (raster index of coefficient n) * 2 | Q[raster index] << 8 (seq_fill_xq)
+	uint16_t xq[2][64];
 };
+
+// host helper: derive SeqParams::xq from the de-zigzagged matrices (ZIG_ZAG, mpeg1.js:996-1005)
+inline void seq_fill_xq(SeqParams &sp) {
+	static const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48,
+	                               41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22,
+	                               15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+	for (int n = 0; n < 64; n++) {
+		sp.xq[0][n] = (uint16_t)(zz[n] * 2 | sp.intra_q[zz[n]] << 8);
+		sp.xq[1][n] = (uint16_t)(zz[n] * 2 | sp.non_intra_q[zz[n]] << 8);
+	}
+}
 
 // Stage 1: one warp parses one picture.
 struct ParseTask {
-	const uint8_t *es;     // 4-byte aligned base of the stream's ES mirror in HBM
+	const uint8_t *es;     // 16-byte aligned base of the stream's ES mirror in HBM, >= 64 readable bytes past es_len
 	uint32_t es_len;       // valid bytes (bytes past it read as zero, like a JS typed array)
 	uint32_t start_byte;   // first byte after the 00 00 01 00 picture start code
 	const SeqParams *seq;  // device pointer
-	mb_record_t *hdr;      // [mb_size], pre-zeroed (no MBF_PRESENT)
+	mb_record_t *hdr;      // [mb_size]
 	int16_t *coef;         // [mb_size][6][64]
 	picture_info_t *info;  // out
+	uint2 *park;           // [mb_size][6]: per coded block {bit offset of its first coefficient code, intra dc * 8},
+	                       // the walk's hand-over to stage 1b (a dense side array, written and read as a stream)
+	int32_t mb_width, mb_size;  // copies of the sequence parameters (no dependent load in front of the walk)
 };
 
 struct PlaneSet {
@@ -64,6 +92,8 @@ struct ParseFork {
 };
 void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream,
                            cudaEvent_t walk_done = nullptr, const ParseFork *fork = nullptr);
+// how many size groups (walk + expand launch pairs) launch_parse_pictures uses for n_tasks pictures
+int parse_group_count(int n_tasks, bool forked);
 // `tasks_host` is read on the host at launch time: the table travels in the kernel parameters
 void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream);
 void launch_rgba(const ReconTask *tasks, int n_tasks, int max_width, int max_height, cudaStream_t stream);

@@ -2,32 +2,45 @@
 // the two C ABIs declared in include/jsmpeg_b200.h.
 //
 // What stays on the host is exactly what is bookkeeping in the reference too: the bit-buffer write
-// protocol (src/wasm/buffer.c:48-71, 157-190), the sequence header (src/mpeg1.js:78-153, parsed
-// once per stream) and the decode() state machine (src/wasm/mpeg1.c:853-864, 947-995: which
+// protocol (src/wasm/buffer.c:48-71, 157-190; bitbuffer.h), the sequence header (src/mpeg1.js:78-153,
+// parsed once per stream) and the decode() state machine (src/wasm/mpeg1.c:853-864, 947-995: which
 // picture is next, where the bit index ends up, when planes swap).  All per-byte, per-bit and
-// per-pixel work runs in the three kernels (scan.cu, parse.cu, recon.cu).  There is no CPU
-// fallback: without a CUDA device every entry point aborts with the CUDA error.
+// per-pixel work runs in the kernels (scan.cu, parse.cu, recon.cu).  There is no CPU fallback:
+// without a usable CUDA device a decoder is created DEAD -- every entry point returns its failure
+// value (decode() == false, like "no sequence header yet"), the reason is printed once and kept for
+// jsmpeg_b200_batch_last_error.  Nothing here calls abort(): a plugin must not take its host process
+// (a Node player) down.
 //
 // Wave model.  decode() on a stream needs (a) the next picture start code, (b) that picture's
 // records, (c) its reconstruction from the previous picture.  (a) comes from the start-code index
 // built when bytes become resident; (b) for MANY pictures (all streams x pictures ahead) is one
-// parse launch, one warp per picture; (c) is one launch per picture STEP covering every stream
+// parse wave, one warp per picture; (c) is one launch per picture STEP covering every stream
 // that has a picture at that step.  The reference's serial semantics are re-established on the
 // host after the parse: picture j+1 of a stream is accepted only if its start code is the first
 // one at/after the bit index where picture j's parse ended (otherwise the look-ahead is discarded
 // and re-planned from there).
+//
+// Pipeline.  A round's parse wave can be cut into CHUNKS by picture ordinal (pictures [kG, (k+1)G)
+// of every stream; option "chunk_pictures"); all chunks are queued on the parse stream at once, each
+// followed by the read-back of its picture infos.  The host then takes chunk after chunk: waits for
+// that chunk's infos only, does the acceptance above, and queues the chunk's reconstruct launches on
+// a SECOND stream -- while the parse of the following chunks is running.  Stage 1 (latency-bound, few
+// resident warps) and stage 2 (bandwidth / issue-bound) are natural co-runners; round 1 serialised
+// them with a host synchronisation between the parse wave and the first reconstruct launch.
 #include <algorithm>
 #include <cstring>
 #include <deque>
+#include <string>
 #include <vector>
 
+#include "bitbuffer.h"
 #include "common.cuh"
 #include "../../include/jsmpeg_b200.h"
 
 namespace {
 
 constexpr int HOST_RING = 4;
-constexpr uint32_t ES_PAD = 512;  // readable slack after the ES mirror (chunk prefetch reads ahead)
+constexpr uint32_t ES_PAD = 512;  // readable, zeroed slack after the ES mirror (the walk's ring prefetches 64 bytes ahead)
 
 template <typename T>
 T *dev_alloc(size_t n) {
@@ -42,18 +55,21 @@ T *pinned_alloc(size_t n) {
 	return p;
 }
 
+// the bit buffer lives in pinned host memory (H2D copies of new bytes run at PCIe speed)
+void *bb_pinned_alloc(size_t n, void *) { return pinned_alloc<uint8_t>(n); }
+void bb_pinned_release(void *p, void *) { (void)cudaFreeHost(p); }
+const bitbuffer::Allocator kPinned = {bb_pinned_alloc, bb_pinned_release, nullptr};
+
 struct Parsed {
 	uint32_t pos;           // byte position of the 00 00 01 00 start code
 	uint32_t len_at_parse;  // buffer length the parse saw
 	int slot;
+	bool ready;             // `info` has arrived from the device
 	picture_info_t info;
 };
 
 struct Stream {
-	// host bit buffer (pinned) -- src/wasm/buffer.c
-	uint8_t *h_bytes = nullptr;
-	uint32_t capacity = 0, length = 0, index = 0;
-	int mode = BIT_BUFFER_MODE_EXPAND;
+	bitbuffer::Buffer bb;  // host bit buffer (pinned) -- src/wasm/buffer.c
 	// sequence header
 	bool has_seq = false;
 	float frame_rate = 0.f;
@@ -84,23 +100,32 @@ struct Stream {
 
 struct jsmpeg_b200_batch_t {
 	int device = 0;
+	bool dead = false;  // a CUDA call failed: every entry point returns its failure value from now on
+	std::string error;
+	std::vector<uint8_t> dead_scratch;  // where get_write_ptr points a caller's memcpy once dead
 	std::vector<Stream> streams;
-	cudaStream_t st_main = nullptr, st_copy = nullptr;
-	cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_mid = nullptr, ev_step = nullptr, ev_copied[2] = {nullptr, nullptr};
+	cudaStream_t st_main = nullptr, st_recon = nullptr, st_copy = nullptr;  // uploads + scan + parse | reconstruct | copy-out
+	cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_mid = nullptr, ev_step = nullptr, ev_round = nullptr, ev_copied[2] = {nullptr, nullptr};
+	std::vector<cudaEvent_t> ev_info;            // per chunk: its picture infos are on the host
+	std::vector<cudaEvent_t> ev_rec0, ev_rec1;   // per chunk: around its reconstruct launches (timing)
 	// record slots
 	unsigned max_slots_req = 0;
 	int slot_mb = 0, n_slots = 0;
 	mb_record_t *d_hdr = nullptr;
 	int16_t *d_coef = nullptr;
+	uint2 *d_park = nullptr;
 	picture_info_t *d_info = nullptr, *h_info = nullptr;
 	std::vector<int> free_slots;
 	int lookahead = 1;
+	int chunk_pictures = 0;      // G of the pipeline; 0 = the whole wave is one chunk
+	int chunk_min_wave = 256;    // waves with fewer new pictures stay whole
+	bool recon_pending = false;  // reconstruct launches of an earlier round may still read record slots
 	// task staging
 	ParseTask *h_ptasks = nullptr, *d_ptasks = nullptr;
 	int ptask_cap = 0;
 	ReconTask *h_rtasks = nullptr, *d_rtasks = nullptr;
 	int rtask_cap = 0;
-	bool copies_outstanding[2] = {false, false};
+	uint64_t copy_steps = 0;  // reconstruct launches with a copy-out so far (event parity)
 	ParseFork fork{};
 	std::vector<void *> copy_dst, copy_src;
 	std::vector<size_t> copy_size;
@@ -114,6 +139,30 @@ namespace {
 using Batch = jsmpeg_b200_batch_t;
 
 void use_device(Batch *b) { CUDA_CHECK(cudaSetDevice(b->device)); }
+
+void mark_dead(Batch *b, const char *what) {
+	if (!b->dead) fprintf(stderr, "%s\njsmpeg_b200: decoder disabled (decode() returns false from now on)\n", what);
+	b->dead = true;
+	if (b->error.empty()) b->error = what;
+}
+
+// Every C-ABI entry point that touches CUDA runs through here.
+template <typename R, typename F>
+R guarded(Batch *b, R fail, F &&f) {
+	if (!b || b->dead) return fail;
+	try {
+		return f();
+	} catch (const std::exception &e) {
+		mark_dead(b, e.what());
+	} catch (...) {
+		mark_dead(b, "jsmpeg_b200: unknown failure");
+	}
+	return fail;
+}
+template <typename F>
+void guarded_void(Batch *b, F &&f) {
+	guarded<int>(b, 0, [&] { f(); return 0; });
+}
 
 void release_slot(Batch *b, int slot) { b->free_slots.push_back(slot); }
 
@@ -131,40 +180,13 @@ void forget_index(Batch *b, Stream &s) {
 
 // ---- bit buffer (host) ------------------------------------------------------------------------
 
-void host_resize(Stream &s, uint32_t cap) {
-	uint8_t *n = pinned_alloc<uint8_t>(cap);
-	if (s.h_bytes) {
-		memcpy(n, s.h_bytes, std::min(s.length, cap));
-		CUDA_CHECK(cudaFreeHost(s.h_bytes));
-	}
-	s.h_bytes = n;
-	s.capacity = cap;
-	if (s.index > (s.length << 3)) s.index = s.length << 3;  // buffer.c:160-163
-}
-
-// src/wasm/buffer.c:48-65 get_write_ptr, :167-190 evict
+// src/wasm/buffer.c:48-65 get_write_ptr, :167-190 evict (bitbuffer.h)
 void *stream_get_write_ptr(Batch *b, Stream &s, uint32_t n) {
-	uint32_t avail = s.capacity - s.length;
-	if (n > avail) {
-		if (s.mode == BIT_BUFFER_MODE_EXPAND) {
-			uint32_t cap = s.capacity * 2;
-			if (cap + avail < n) cap = n - avail;
-			host_resize(s, cap);
-		} else {
-			uint32_t pos = s.index >> 3;
-			if (pos == s.length || n > avail + pos) {  // nothing unread, or emergency evacuation
-				s.length = 0;
-				s.index = 0;
-				forget_index(b, s);
-			} else if (pos != 0) {
-				memmove(s.h_bytes, s.h_bytes + pos, s.length - pos);
-				s.length -= pos;
-				s.index -= pos << 3;
-				forget_index(b, s);
-			}
-		}
-	}
-	return s.h_bytes + s.length;
+	bool moved = false;
+	uint8_t *p = bitbuffer::get_write_ptr(s.bb, n, kPinned, moved);
+	if (moved) forget_index(b, s);  // byte positions changed: the HBM mirror, the index and the look-ahead are void
+	if (!p) throw std::runtime_error("jsmpeg_b200: bit buffer cannot hold the write (more than 4 GiB - 1 bytes)");
+	return p;
 }
 
 // MSB-first reader for the (tiny, once-per-stream) sequence header on the host
@@ -192,7 +214,7 @@ const uint8_t kDefaultIntraQ[64] = {8, 16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 2
 
 // src/mpeg1.js:78-153 decodeSequenceHeader + initBuffers (first header only, mpeg1.c:812-819)
 void parse_sequence_header(Batch *b, Stream &s, uint32_t bit_index) {
-	HostBits hb{s.h_bytes, s.length, bit_index};
+	HostBits hb{s.bb.bytes, s.bb.length, bit_index};
 	s.width = (int)hb.read(12);
 	s.height = (int)hb.read(12);
 	hb.read(4);
@@ -202,7 +224,8 @@ void parse_sequence_header(Batch *b, Stream &s, uint32_t bit_index) {
 	else memcpy(s.seq.intra_q, kDefaultIntraQ, 64);
 	if (hb.read(1)) { for (int i = 0; i < 64; i++) s.seq.non_intra_q[kZigZag[i]] = (uint8_t)hb.read(8); }
 	else memset(s.seq.non_intra_q, 16, 64);
-	s.index = hb.idx;
+	seq_fill_xq(s.seq);
+	s.bb.index = hb.idx;
 	s.seq_end_index = hb.idx;
 	s.seq.mb_width = (s.width + 15) >> 4;
 	s.seq.mb_height = (s.height + 15) >> 4;
@@ -228,19 +251,20 @@ void parse_sequence_header(Batch *b, Stream &s, uint32_t bit_index) {
 
 // src/wasm/mpeg1.c:812-819 did_write
 void stream_did_write(Batch *b, Stream &s, uint32_t n) {
-	s.length += n;
+	if ((uint64_t)s.bb.length + n > s.bb.capacity) n = s.bb.capacity - s.bb.length;  // never beyond what get_write_ptr handed out
+	s.bb.length += n;
 	if (!s.has_seq) {
 		// findStartCode(SEQUENCE): serial host scan of the not-yet-consumed head of the stream
-		uint32_t i = (s.index + 7) >> 3;
+		uint32_t i = (s.bb.index + 7) >> 3;
 		bool found = false;
-		for (; i + 3 < s.length; i++) {
-			if (s.h_bytes[i] == 0 && s.h_bytes[i + 1] == 0 && s.h_bytes[i + 2] == 1) {
-				if (s.h_bytes[i + 3] == 0xB3) { found = true; break; }
+		for (; i + 3 < s.bb.length; i++) {
+			if (s.bb.bytes[i] == 0 && s.bb.bytes[i + 1] == 0 && s.bb.bytes[i + 2] == 1) {
+				if (s.bb.bytes[i + 3] == 0xB3) { found = true; break; }
 				i += 3;  // index jumps past the code (buffer.js:121-123)
 			}
 		}
 		if (found) parse_sequence_header(b, s, (i + 4) << 3);
-		else s.index = s.length << 3;
+		else s.bb.index = s.bb.length << 3;
 	}
 }
 
@@ -248,9 +272,9 @@ void stream_did_write(Batch *b, Stream &s, uint32_t n) {
 
 // Room for `need` ES bytes (+ pad) in the HBM mirror; what is already resident stays resident.
 void reserve_device_es(Batch *b, Stream &s, uint32_t need) {
-	if (need + ES_PAD <= s.d_capacity) return;
-	uint32_t cap = std::max<uint32_t>(need + ES_PAD, s.d_capacity * 2);
-	cap = (cap + 255u) & ~255u;
+	if ((uint64_t)need + ES_PAD <= s.d_capacity) return;
+	uint64_t cap = std::max<uint64_t>((uint64_t)need + ES_PAD, (uint64_t)s.d_capacity * 2);
+	cap = std::min<uint64_t>((cap + 255u) & ~255ull, 0xffffff00ull);
 	uint8_t *n = dev_alloc<uint8_t>(cap);
 	if (s.d_es) {
 		if (s.d_valid) CUDA_CHECK(cudaMemcpyAsync(n, s.d_es, s.d_valid, cudaMemcpyDeviceToDevice, b->st_main));
@@ -258,36 +282,46 @@ void reserve_device_es(Batch *b, Stream &s, uint32_t need) {
 		CUDA_CHECK(cudaFree(s.d_es));
 	}
 	s.d_es = n;
-	s.d_capacity = cap;
+	s.d_capacity = (uint32_t)cap;
+}
+
+void launch_scan(Batch *b, Stream &s) {
+	CUDA_CHECK(cudaMemsetAsync(s.d_scan, 0, sizeof(uint32_t), b->st_main));
+	launch_scan_start_codes(s.d_es, s.scan_from, s.bb.length, s.d_scan + 1, s.scan_cap - 1, s.d_scan, b->st_main);
+	b->stats.kernel_launches++;
+	CUDA_CHECK(cudaMemcpyAsync(s.h_scan, s.d_scan, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->st_main));
+}
+
+void reserve_scan(Stream &s, uint32_t entries) {
+	if (entries + 1 <= s.scan_cap) return;
+	if (s.d_scan) CUDA_CHECK(cudaFree(s.d_scan));
+	s.d_scan = nullptr;
+	if (s.h_scan) CUDA_CHECK(cudaFreeHost(s.h_scan));
+	s.h_scan = nullptr;
+	s.scan_cap = 0;
+	s.d_scan = dev_alloc<uint32_t>(entries + 1);
+	s.h_scan = pinned_alloc<uint32_t>(entries + 1);
+	s.scan_cap = entries + 1;
 }
 
 void begin_upload(Batch *b, Stream &s) {
 	s.scan_pending = false;
-	if (s.d_valid >= s.length && s.scanned >= s.length) return;
-	reserve_device_es(b, s, s.length);
-	if (s.d_valid < s.length) {
+	if (s.d_valid >= s.bb.length && s.scanned >= s.bb.length) return;
+	reserve_device_es(b, s, s.bb.length);
+	if (s.d_valid < s.bb.length) {
 		uint32_t from = s.d_valid & ~15u;
-		CUDA_CHECK(cudaMemcpyAsync(s.d_es + from, s.h_bytes + from, s.length - from, cudaMemcpyHostToDevice, b->st_main));
-		b->stats.h2d_bytes += s.length - from;
-		s.d_valid = s.length;
+		CUDA_CHECK(cudaMemcpyAsync(s.d_es + from, s.bb.bytes + from, s.bb.length - from, cudaMemcpyHostToDevice, b->st_main));
+		b->stats.h2d_bytes += s.bb.length - from;
+		s.d_valid = s.bb.length;
 		// the kernels rely on zeros right after the data (bytes past the end read as 0, like JS)
-		CUDA_CHECK(cudaMemsetAsync(s.d_es + s.length, 0, ES_PAD, b->st_main));
+		CUDA_CHECK(cudaMemsetAsync(s.d_es + s.bb.length, 0, ES_PAD, b->st_main));
 	}
-	if (s.scanned < s.length) {
-		uint32_t from = s.scanned >= 3 ? s.scanned - 3 : 0;
-		uint32_t want = (s.length - from) / 4 + 16;  // start codes cannot overlap
-		want = std::min<uint32_t>(want, 1u << 20);
-		if (want + 1 > s.scan_cap) {
-			if (s.d_scan) CUDA_CHECK(cudaFree(s.d_scan));
-			if (s.h_scan) CUDA_CHECK(cudaFreeHost(s.h_scan));
-			s.scan_cap = want + 1;
-			s.d_scan = dev_alloc<uint32_t>(s.scan_cap);
-			s.h_scan = pinned_alloc<uint32_t>(s.scan_cap);
-		}
-		CUDA_CHECK(cudaMemsetAsync(s.d_scan, 0, sizeof(uint32_t), b->st_main));
-		launch_scan_start_codes(s.d_es, from, s.length, s.d_scan + 1, s.scan_cap - 1, s.d_scan, b->st_main);
-		b->stats.kernel_launches++;
-		s.scan_from = from;
+	if (s.scanned < s.bb.length) {
+		s.scan_from = s.scanned >= 3 ? s.scanned - 3 : 0;
+		// room for one picture per 2 KiB (real streams: one per tens of KiB).  A stream that packs them
+		// denser overflows the list; the scan is then repeated with the count it reported (upload_all).
+		reserve_scan(s, std::max<uint32_t>(4096u, (s.bb.length - s.scan_from) / 2048u + 16u));
+		launch_scan(b, s);
 		s.scan_pending = true;
 	}
 }
@@ -297,10 +331,7 @@ long upload_all(Batch *b) {
 	bool any = false;
 	for (auto &s : b->streams) {
 		begin_upload(b, s);
-		if (s.scan_pending) {
-			any = true;
-			CUDA_CHECK(cudaMemcpyAsync(s.h_scan, s.d_scan, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->st_main));
-		}
+		any |= s.scan_pending;
 	}
 	if (any) {
 		CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
@@ -308,12 +339,19 @@ long upload_all(Batch *b) {
 		float ms = 0;
 		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_b));
 		b->stats.scan_ms += ms;
+		// a list that overflowed (hostile input: start codes cannot overlap, so at most length / 4 of them)
+		// is scanned again with room for the count the kernel reported
+		bool again = false;
+		for (auto &s : b->streams) {
+			if (!s.scan_pending || s.h_scan[0] <= s.scan_cap - 1) continue;
+			reserve_scan(s, s.h_scan[0] + 16u);
+			launch_scan(b, s);
+			again = true;
+		}
+		if (again) CUDA_CHECK(cudaStreamSynchronize(b->st_main));
 		for (auto &s : b->streams) {
 			if (!s.scan_pending) continue;
-			if (s.h_scan[0] > s.scan_cap - 1) {
-				fprintf(stderr, "jsmpeg_b200: start-code index overflow (%u > %u)\n", s.h_scan[0], s.scan_cap - 1);
-				abort();
-			}
+			if (s.h_scan[0] > s.scan_cap - 1) throw std::runtime_error("jsmpeg_b200: start-code index overflow after a rescan");
 			if (s.h_scan[0]) {
 				CUDA_CHECK(cudaMemcpyAsync(s.h_scan + 1, s.d_scan + 1, s.h_scan[0] * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->st_main));
 				b->stats.d2h_bytes += s.h_scan[0] * sizeof(uint32_t);
@@ -326,7 +364,7 @@ long upload_all(Batch *b) {
 			std::sort(s.h_scan + 1, s.h_scan + 1 + n);
 			// the rescanned window starts 3 bytes before the old frontier, so nothing is reported twice
 			for (uint32_t i = 1; i <= n; i++) s.pics.push_back(s.h_scan[i]);
-			s.scanned = s.length;
+			s.scanned = s.bb.length;
 			s.scan_pending = false;
 		}
 	}
@@ -338,42 +376,75 @@ long upload_all(Batch *b) {
 // ---- record slots ----------------------------------------------------------------------------------
 
 void ensure_pool(Batch *b) {
-	int need_mb = 0, active = 0;
-	for (auto &s : b->streams) if (s.has_seq) { need_mb = std::max(need_mb, s.seq.mb_size); active++; }
+	int need_mb = 0;
+	for (auto &s : b->streams) if (s.has_seq) need_mb = std::max(need_mb, s.seq.mb_size);
 	if (need_mb <= b->slot_mb || need_mb == 0) return;
 	for (auto &s : b->streams) flush_cache(b, s);
-	if (b->d_hdr) { CUDA_CHECK(cudaFree(b->d_hdr)); CUDA_CHECK(cudaFree(b->d_coef)); CUDA_CHECK(cudaFree(b->d_info)); CUDA_CHECK(cudaFreeHost(b->h_info)); }
-	const size_t slot_bytes = (size_t)need_mb * (sizeof(mb_record_t) + MB_COEF_INT16 * sizeof(int16_t));
+	CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+	CUDA_CHECK(cudaStreamSynchronize(b->st_recon));
+	b->recon_pending = false;
+	if (b->d_hdr) { CUDA_CHECK(cudaFree(b->d_hdr)); b->d_hdr = nullptr; }
+	if (b->d_coef) { CUDA_CHECK(cudaFree(b->d_coef)); b->d_coef = nullptr; }
+	if (b->d_park) { CUDA_CHECK(cudaFree(b->d_park)); b->d_park = nullptr; }
+	if (b->d_info) { CUDA_CHECK(cudaFree(b->d_info)); b->d_info = nullptr; }
+	if (b->h_info) { CUDA_CHECK(cudaFreeHost(b->h_info)); b->h_info = nullptr; }
+	b->slot_mb = 0;
+	b->n_slots = 0;
+	b->free_slots.clear();
+	// per macroblock: 16 B record + 6 x 128 B coefficient blocks + 6 x 8 B {bit offset, dc} side array
+	const size_t slot_bytes = (size_t)need_mb * (sizeof(mb_record_t) + MB_COEF_INT16 * sizeof(int16_t) + 6 * sizeof(uint2));
 	size_t n = b->max_slots_req;
-	if (n == 0) {
-		size_t free_b = 0, total_b = 0;
-		CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-		n = (size_t)(0.45 * (double)free_b) / slot_bytes;
-		n = std::min<size_t>(n, 4096);
-	}
-	n = std::max<size_t>(n, 2);
-	b->slot_mb = need_mb;
-	b->n_slots = (int)n;
+	size_t free_b = 0, total_b = 0;
+	CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+	const size_t fit = (size_t)(0.9 * (double)free_b) / slot_bytes;  // a request beyond the device is cut, not fatal
+	if (n == 0) n = std::min<size_t>((size_t)(0.45 * (double)free_b) / slot_bytes, 4096);
+	n = std::max<size_t>(std::min(n, fit), 2);
 	b->d_hdr = dev_alloc<mb_record_t>(n * need_mb);
 	b->d_coef = dev_alloc<int16_t>(n * need_mb * MB_COEF_INT16);
+	b->d_park = dev_alloc<uint2>(n * need_mb * 6);
 	b->d_info = dev_alloc<picture_info_t>(n);
 	b->h_info = pinned_alloc<picture_info_t>(n);
-	b->free_slots.clear();
+	b->slot_mb = need_mb;
+	b->n_slots = (int)n;
 	for (int i = (int)n - 1; i >= 0; i--) b->free_slots.push_back(i);
 }
 
 void ensure_task_caps(Batch *b, int n_parse, int n_recon) {
 	if (n_parse > b->ptask_cap) {
-		if (b->h_ptasks) { CUDA_CHECK(cudaFreeHost(b->h_ptasks)); CUDA_CHECK(cudaFree(b->d_ptasks)); }
-		b->ptask_cap = std::max(n_parse, b->ptask_cap * 2);
-		b->h_ptasks = pinned_alloc<ParseTask>(b->ptask_cap);
-		b->d_ptasks = dev_alloc<ParseTask>(b->ptask_cap);
+		if (b->h_ptasks) { CUDA_CHECK(cudaFreeHost(b->h_ptasks)); b->h_ptasks = nullptr; }
+		if (b->d_ptasks) { CUDA_CHECK(cudaFree(b->d_ptasks)); b->d_ptasks = nullptr; }
+		const int cap = std::max(n_parse, b->ptask_cap * 2);
+		b->ptask_cap = 0;
+		b->h_ptasks = pinned_alloc<ParseTask>(cap);
+		b->d_ptasks = dev_alloc<ParseTask>(cap);
+		b->ptask_cap = cap;
 	}
 	if (n_recon > b->rtask_cap) {
-		if (b->h_rtasks) { CUDA_CHECK(cudaFreeHost(b->h_rtasks)); CUDA_CHECK(cudaFree(b->d_rtasks)); }
-		b->rtask_cap = std::max(n_recon, b->rtask_cap * 2);
-		b->h_rtasks = pinned_alloc<ReconTask>(b->rtask_cap);
-		b->d_rtasks = dev_alloc<ReconTask>(b->rtask_cap);
+		if (b->h_rtasks) { CUDA_CHECK(cudaFreeHost(b->h_rtasks)); b->h_rtasks = nullptr; }
+		if (b->d_rtasks) { CUDA_CHECK(cudaFree(b->d_rtasks)); b->d_rtasks = nullptr; }
+		const int cap = std::max(n_recon, b->rtask_cap * 2);
+		b->rtask_cap = 0;
+		b->h_rtasks = pinned_alloc<ReconTask>(cap);
+		b->d_rtasks = dev_alloc<ReconTask>(cap);
+		b->rtask_cap = cap;
+	}
+}
+
+void ensure_chunk_events(Batch *b, size_t n) {
+	while (b->ev_info.size() < n) {
+		cudaEvent_t e = nullptr;
+		CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		b->ev_info.push_back(e);
+	}
+	while (b->ev_rec0.size() < n) {
+		cudaEvent_t e = nullptr;
+		CUDA_CHECK(cudaEventCreate(&e));
+		b->ev_rec0.push_back(e);
+	}
+	while (b->ev_rec1.size() < n) {
+		cudaEvent_t e = nullptr;
+		CUDA_CHECK(cudaEventCreate(&e));
+		b->ev_rec1.push_back(e);
 	}
 }
 
@@ -387,22 +458,57 @@ PlaneSet plane_set(const Stream &s, uint8_t *base) {
 
 bool entry_stale(const Stream &s, const Parsed &e) {
 	// a parse that ran into the end of the data it saw must be redone once more data is there
-	return e.len_at_parse != s.length && (uint64_t)e.info.end_bit + 64 >= (uint64_t)e.len_at_parse * 8;
+	return e.len_at_parse != s.bb.length && (uint64_t)e.info.end_bit + 64 >= (uint64_t)e.len_at_parse * 8;
 }
 
-// One chunk: parse ahead what is missing (one wave), then consume up to want[s] pictures per stream.
-// Returns pictures consumed; `progress[s]` gets the per-stream count, `more[s]` whether the stream
-// may have further pictures.
-long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &progress, std::vector<char> &more, int flags) {
+// The copy-out of one reconstruct launch's pictures (OUT_HOST), on the copy stream.
+void copy_out_step(Batch *b, const std::vector<ReconTask> &tasks, const std::vector<int> &stream_ids) {
+	CUDA_CHECK(cudaEventRecord(b->ev_step, b->st_recon));
+	CUDA_CHECK(cudaStreamWaitEvent(b->st_copy, b->ev_step, 0));
+	// all pictures of the step leave in ONE batched copy call (cudaMemcpyBatchAsync, CUDA 12.8+)
+	const size_t n_copy = tasks.size();
+	b->copy_dst.resize(n_copy);
+	b->copy_src.resize(n_copy);
+	b->copy_size.resize(n_copy);
+	for (size_t i = 0; i < n_copy; i++) {
+		Stream &s = b->streams[stream_ids[i]];
+		s.h_head = (s.h_head + 1) % HOST_RING;
+		b->copy_dst[i] = s.h_planes[s.h_head];
+		b->copy_src[i] = tasks[i].cur.y;
+		b->copy_size[i] = (size_t)s.coded_size * 3 / 2;
+		b->stats.d2h_bytes += b->copy_size[i];
+	}
+	bool batched = false;
+	if (b->batch_copy_ok && n_copy > 1) {
+		cudaMemcpyAttributes attr{};
+		attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+		size_t attr_idx = 0, fail_idx = 0;
+		cudaError_t e = cudaMemcpyBatchAsync(b->copy_dst.data(), b->copy_src.data(), b->copy_size.data(), n_copy,
+		                                     &attr, &attr_idx, 1, &fail_idx, b->st_copy);
+		if (e == cudaSuccess) batched = true;
+		else { (void)cudaGetLastError(); b->batch_copy_ok = false; }  // older driver: plain copies from now on
+	}
+	if (!batched)
+		for (size_t i = 0; i < n_copy; i++)
+			CUDA_CHECK(cudaMemcpyAsync(b->copy_dst[i], b->copy_src[i], b->copy_size[i], cudaMemcpyDeviceToHost, b->st_copy));
+	CUDA_CHECK(cudaEventRecord(b->ev_copied[b->copy_steps & 1], b->st_copy));
+	b->copy_steps++;
+}
+
+// One round: parse ahead what is missing (one wave, queued chunk by chunk), then -- chunk after chunk, as
+// the chunks' infos arrive -- consume up to want[s] pictures per stream in decode() order and queue their
+// reconstruction.  Returns pictures consumed; `progress[s]` gets the per-stream count, `more[s]` whether
+// the stream may have further pictures.
+long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &progress, std::vector<char> &more, int flags) {
 	const int S = (int)b->streams.size();
 	// ---- 1. plan the parse wave
-	struct NewParse { int stream; size_t cache_idx; uint32_t bytes; };
+	struct NewParse { int stream; size_t cache_idx; uint32_t bytes; int chunk; };
 	std::vector<NewParse> fresh;
 	for (int si = 0; si < S; si++) {
 		Stream &s = b->streams[si];
 		progress[si] = 0;
 		if (!s.has_seq || want[si] <= 0) { more[si] = 0; continue; }
-		const uint32_t from_byte = (s.index + 7) >> 3;
+		const uint32_t from_byte = (s.bb.index + 7) >> 3;
 		auto it = std::lower_bound(s.pics.begin(), s.pics.end(), from_byte);
 		if (!s.cache.empty() && (it == s.pics.end() || s.cache.front().pos != *it)) flush_cache(b, s);
 		for (size_t j = 0; j < s.cache.size(); j++) {
@@ -418,297 +524,220 @@ long decode_chunk(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 		while ((int)s.cache.size() < target && next < s.pics.end() && !b->free_slots.empty()) {
 			Parsed p{};
 			p.pos = *next;
-			p.len_at_parse = s.length;
+			p.len_at_parse = s.bb.length;
 			p.slot = b->free_slots.back();
+			p.ready = false;
 			b->free_slots.pop_back();
 			s.cache.push_back(p);
 			++next;
-			fresh.push_back({si, s.cache.size() - 1, (next < s.pics.end() ? *next : s.length) - p.pos});
+			fresh.push_back({si, s.cache.size() - 1, (next < s.pics.end() ? *next : s.bb.length) - p.pos, 0});
 		}
 	}
-	// ---- 2. parse wave.  Longest pictures first: a CTA's warps, and consecutive CTAs (which land on
-	// different SMs), then carry similar amounts of work and the wave ends without a long tail.
+	// ---- 2. chunks by picture ordinal (position in the stream's look-ahead); a small wave stays whole
+	const int G = (b->chunk_pictures > 0 && (int)fresh.size() >= b->chunk_min_wave) ? b->chunk_pictures : 0;
+	int n_chunks = 1;
+	if (G > 0) {
+		for (auto &f : fresh) { f.chunk = (int)(f.cache_idx / (size_t)G); n_chunks = std::max(n_chunks, f.chunk + 1); }
+		int max_ordinal = 0;
+		for (int si = 0; si < S; si++) max_ordinal = std::max(max_ordinal, std::max(want[si], 0));
+		n_chunks = std::max(n_chunks, (max_ordinal + G - 1) / G);
+	}
+	ensure_chunk_events(b, (size_t)n_chunks);
+	std::vector<int> chunk_off(n_chunks + 1, 0);
 	if (!fresh.empty()) {
-		std::stable_sort(fresh.begin(), fresh.end(), [](const NewParse &a, const NewParse &b) { return a.bytes > b.bytes; });
+		// Within a chunk, longest pictures first: a CTA's warps, and consecutive CTAs (which land on different
+		// SMs), then carry similar amounts of work and the chunk's walk ends without a long tail.
+		std::stable_sort(fresh.begin(), fresh.end(), [](const NewParse &x, const NewParse &y) {
+			return x.chunk != y.chunk ? x.chunk < y.chunk : x.bytes > y.bytes;
+		});
+		for (auto &f : fresh) chunk_off[f.chunk + 1]++;
+		for (int c = 0; c < n_chunks; c++) chunk_off[c + 1] += chunk_off[c];
 		ensure_task_caps(b, (int)fresh.size(), 0);
 		for (size_t i = 0; i < fresh.size(); i++) {
 			Stream &s = b->streams[fresh[i].stream];
 			Parsed &p = s.cache[fresh[i].cache_idx];
 			ParseTask &t = b->h_ptasks[i];
 			t.es = s.d_es;
-			t.es_len = s.length;
+			t.es_len = s.bb.length;
 			t.start_byte = p.pos + 4;
 			t.seq = s.d_seq;
 			t.hdr = b->d_hdr + (size_t)p.slot * b->slot_mb;
 			t.coef = b->d_coef + (size_t)p.slot * b->slot_mb * MB_COEF_INT16;
+			t.park = b->d_park + (size_t)p.slot * b->slot_mb * 6;
 			t.info = b->d_info + i;
+			t.mb_width = s.seq.mb_width;
+			t.mb_size = s.seq.mb_size;
+		}
+		if (b->recon_pending) {  // slots freed by the previous round are still being read by its reconstruct launches
+			CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_round, 0));
+			b->recon_pending = false;
 		}
 		CUDA_CHECK(cudaMemcpyAsync(b->d_ptasks, b->h_ptasks, fresh.size() * sizeof(ParseTask), cudaMemcpyHostToDevice, b->st_main));
 		CUDA_CHECK(cudaEventRecord(b->ev_a, b->st_main));
-		launch_parse_pictures(b->d_ptasks, (int)fresh.size(), b->slot_mb, b->st_main, b->ev_mid, &b->fork);
-		CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
-		CUDA_CHECK(cudaMemcpyAsync(b->h_info, b->d_info, fresh.size() * sizeof(picture_info_t), cudaMemcpyDeviceToHost, b->st_main));
-		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
-		float ms = 0;
-		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_b));
-		b->stats.parse_ms += ms;
-		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_mid));
-		b->stats.walk_ms += ms;
-		b->stats.kernel_launches += 2 * (fresh.size() >= 64 * PARSE_GROUPS ? PARSE_GROUPS : 1);  // walk + expand per size group
+		bool mid_recorded = false;
+		for (int c = 0; c < n_chunks; c++) {
+			const int lo = chunk_off[c], n = chunk_off[c + 1] - lo;
+			if (n > 0) {
+				launch_parse_pictures(b->d_ptasks + lo, n, b->slot_mb, b->st_main, mid_recorded ? nullptr : b->ev_mid, &b->fork);
+				mid_recorded = true;
+				b->stats.kernel_launches += 2 * parse_group_count(n, true);  // walk + expand per size group
+				CUDA_CHECK(cudaMemcpyAsync(b->h_info + lo, b->d_info + lo, n * sizeof(picture_info_t), cudaMemcpyDeviceToHost, b->st_main));
+			}
+			if (c == n_chunks - 1) CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
+			CUDA_CHECK(cudaEventRecord(b->ev_info[c], b->st_main));
+		}
 		b->stats.h2d_bytes += fresh.size() * sizeof(ParseTask);
 		b->stats.d2h_bytes += fresh.size() * sizeof(picture_info_t);
-		for (size_t i = 0; i < fresh.size(); i++) {
-			Parsed &p = b->streams[fresh[i].stream].cache[fresh[i].cache_idx];
-			p.info = b->h_info[i];
-			if (p.info.error == PARSE_ERR_INVALID_VLC) b->stats.parse_errors++;
-			if (p.info.reserved[0]) b->stats.lane_walk_pictures++;
-		}
 	}
-	// ---- 3. consume in decode() order per stream; step j of a stream -> recon launch j
-	std::vector<std::vector<ReconTask>> steps;
-	std::vector<std::vector<int>> step_streams;
+	// ---- 3. chunk after chunk: absorb the infos, consume in decode() order, queue the reconstruction
 	long consumed = 0;
+	std::vector<char> open(S, 0);  // stream still consuming in this round
+	std::vector<int> taken(S, 0);  // pictures consumed (= ordinal of the stream's next picture)
 	for (int si = 0; si < S; si++) {
-		Stream &s = b->streams[si];
-		if (!s.has_seq || want[si] <= 0) continue;
-		more[si] = 1;
-		int step = 0;
-		for (int j = 0; j < want[si]; j++) {
-			const uint32_t from_byte = (s.index + 7) >> 3;
-			auto it = std::lower_bound(s.pics.begin(), s.pics.end(), from_byte);
-			if (it == s.pics.end()) {  // findStartCode(PICTURE) == -1: index parks at the end (buffer.js:126-127)
-				s.index = s.length << 3;
-				more[si] = 0;
-				break;
-			}
-			if (s.cache.empty() || s.cache.front().pos != *it || entry_stale(s, s.cache.front())) {
-				flush_cache(b, s);  // look-ahead does not match the serial order: re-plan next chunk
-				break;
-			}
-			const Parsed e = s.cache.front();
-			s.cache.pop_front();
-			s.index = e.info.end_bit;
-			progress[si]++;
-			consumed++;
-			b->stats.pictures++;
-			b->stats.es_bytes += (e.info.end_bit >> 3) - e.pos;
-			if (e.info.status == PIC_DECODED) {
-				ReconTask t{};
-				t.hdr = b->d_hdr + (size_t)e.slot * b->slot_mb;
-				t.coef = b->d_coef + (size_t)e.slot * b->slot_mb * MB_COEF_INT16;
-				t.cur = plane_set(s, s.d_planes[s.cur]);
-				t.fwd = plane_set(s, s.d_planes[1 - s.cur]);
-				t.mb_width = s.seq.mb_width;
-				t.mb_size = s.seq.mb_size;
-				t.coded_width = s.seq.coded_width;
-				t.coded_height = s.seq.coded_height;
-				t.width = s.width;
-				t.height = s.height;
-				t.rgba = nullptr;
-				if (flags & JSMPEG_B200_OUT_RGBA) {
-					if (!s.d_rgba) s.d_rgba = dev_alloc<uint8_t>((size_t)s.width * s.height * 4);
-					t.rgba = s.d_rgba;
-				}
-				if ((int)steps.size() <= step) { steps.emplace_back(); step_streams.emplace_back(); }
-				steps[step].push_back(t);
-				step_streams[step].push_back(si);
-				step++;
-				s.cur ^= 1;  // mpeg1.js:221-246: the picture just decoded becomes `forward`
-				b->stats.pictures_decoded++;
-				b->stats.coded_blocks += e.info.n_coded_blocks;
-				b->stats.macroblocks += e.info.n_present;
-				const uint64_t planes = (uint64_t)s.coded_size * 3 / 2;
-				b->stats.algorithmic_bytes += planes + (e.info.picture_type == 2 ? planes : 0) +
-				                              (uint64_t)s.seq.mb_size * sizeof(mb_record_t) + (uint64_t)e.info.n_coded_blocks * 128;
-			}
-			release_slot(b, e.slot);  // stream order: the next parse launch runs after this chunk's recon launches
-		}
+		const Stream &s = b->streams[si];
+		if (s.has_seq && want[si] > 0) { open[si] = 1; more[si] = 1; }
 	}
-	// ---- 4. reconstruction, one launch per step
-	if (!steps.empty()) {
+	int rec_chunks = 0;
+	for (int c = 0; c < n_chunks; c++) {
+		const int lo = chunk_off[c], n = chunk_off[c + 1] - lo;
+		if (n > 0) {
+			CUDA_CHECK(cudaEventSynchronize(b->ev_info[c]));
+			for (int i = lo; i < lo + n; i++) {
+				Stream &s = b->streams[fresh[i].stream];
+				// cache indices were taken at planning time; `taken` pictures have left the front since
+				const size_t tk = (size_t)taken[fresh[i].stream];
+				if (fresh[i].cache_idx < tk || fresh[i].cache_idx - tk >= s.cache.size()) continue;  // flushed meanwhile
+				Parsed &p = s.cache[fresh[i].cache_idx - tk];
+				p.info = b->h_info[i];
+				p.ready = true;
+				if (p.info.error == PARSE_ERR_INVALID_VLC) b->stats.parse_errors++;
+				if (p.info.reserved[0]) b->stats.lane_walk_pictures++;
+			}
+		}
+		// step j of a stream -> reconstruct launch j of the chunk
+		std::vector<std::vector<ReconTask>> steps;
+		std::vector<std::vector<int>> step_streams;
+		const int ordinal_end = G > 0 ? (c + 1) * G : 0x7fffffff;
+		for (int si = 0; si < S; si++) {
+			if (!open[si]) continue;
+			Stream &s = b->streams[si];
+			int step = 0;
+			while (taken[si] < want[si] && taken[si] < ordinal_end) {
+				const uint32_t from_byte = (s.bb.index + 7) >> 3;
+				auto it = std::lower_bound(s.pics.begin(), s.pics.end(), from_byte);
+				if (it == s.pics.end()) {  // findStartCode(PICTURE) == -1: index parks at the end (buffer.js:126-127)
+					s.bb.index = s.bb.length << 3;
+					more[si] = 0;
+					open[si] = 0;
+					break;
+				}
+				if (s.cache.empty() || !s.cache.front().ready || s.cache.front().pos != *it || entry_stale(s, s.cache.front())) {
+					// the look-ahead does not match the serial order: re-plan in the next round.  (Entries of later
+					// chunks may still be in flight; their slots are reused only by parses queued behind them.)
+					flush_cache(b, s);
+					open[si] = 0;
+					taken[si] = 0x40000000;  // nothing of this stream's planning-time indices is valid any more
+					break;
+				}
+				const Parsed e = s.cache.front();
+				s.cache.pop_front();
+				s.bb.index = e.info.end_bit;
+				taken[si]++;
+				progress[si]++;
+				consumed++;
+				b->stats.pictures++;
+				b->stats.es_bytes += (e.info.end_bit >> 3) - e.pos;
+				if (e.info.status == PIC_DECODED) {
+					ReconTask t{};
+					t.hdr = b->d_hdr + (size_t)e.slot * b->slot_mb;
+					t.coef = b->d_coef + (size_t)e.slot * b->slot_mb * MB_COEF_INT16;
+					t.cur = plane_set(s, s.d_planes[s.cur]);
+					t.fwd = plane_set(s, s.d_planes[1 - s.cur]);
+					t.mb_width = s.seq.mb_width;
+					t.mb_size = s.seq.mb_size;
+					t.coded_width = s.seq.coded_width;
+					t.coded_height = s.seq.coded_height;
+					t.width = s.width;
+					t.height = s.height;
+					t.rgba = nullptr;
+					if (flags & JSMPEG_B200_OUT_RGBA) {
+						if (!s.d_rgba) s.d_rgba = dev_alloc<uint8_t>((size_t)s.width * s.height * 4);
+						t.rgba = s.d_rgba;
+					}
+					if ((int)steps.size() <= step) { steps.emplace_back(); step_streams.emplace_back(); }
+					steps[step].push_back(t);
+					step_streams[step].push_back(si);
+					step++;
+					s.cur ^= 1;  // mpeg1.js:221-246: the picture just decoded becomes `forward`
+					b->stats.pictures_decoded++;
+					b->stats.coded_blocks += e.info.n_coded_blocks;
+					b->stats.macroblocks += e.info.n_present;
+					const uint64_t planes = (uint64_t)s.coded_size * 3 / 2;
+					b->stats.algorithmic_bytes += planes + (e.info.picture_type == 2 ? planes : 0) +
+					                              (uint64_t)s.seq.mb_size * sizeof(mb_record_t) + (uint64_t)e.info.n_coded_blocks * 128;
+				}
+				release_slot(b, e.slot);  // reused by the NEXT round's parse, which waits for this round's reconstruction (ev_round)
+			}
+			if (open[si] && taken[si] >= want[si]) open[si] = 0;
+		}
+		// ---- 4. reconstruction of the chunk, one launch per step, on the reconstruct stream
+		if (steps.empty()) continue;
 		size_t total = 0;
 		for (auto &v : steps) total += v.size();
 		ensure_task_caps(b, 0, (int)total);
 		size_t off = 0;
 		for (auto &v : steps) { memcpy(b->h_rtasks + off, v.data(), v.size() * sizeof(ReconTask)); off += v.size(); }
 		if (flags & JSMPEG_B200_OUT_RGBA) {  // only the RGBA epilogue reads the task table from HBM
-			CUDA_CHECK(cudaMemcpyAsync(b->d_rtasks, b->h_rtasks, total * sizeof(ReconTask), cudaMemcpyHostToDevice, b->st_main));
+			CUDA_CHECK(cudaStreamSynchronize(b->st_recon));  // the previous chunk's epilogue reads the same table
+			CUDA_CHECK(cudaMemcpyAsync(b->d_rtasks, b->h_rtasks, total * sizeof(ReconTask), cudaMemcpyHostToDevice, b->st_recon));
 			b->stats.h2d_bytes += total * sizeof(ReconTask);
 		}
-		for (int i = 0; i < 2; i++)  // planes of the previous chunk may still be on their way out
-			if (b->copies_outstanding[i]) CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_copied[i], 0));
-		CUDA_CHECK(cudaEventRecord(b->ev_c, b->st_main));
+		CUDA_CHECK(cudaEventRecord(b->ev_rec0[rec_chunks], b->st_recon));
 		off = 0;
 		for (size_t f = 0; f < steps.size(); f++) {
-			// step f overwrites the plane set that step f-2 produced: its copy-out must be done
-			if ((flags & JSMPEG_B200_OUT_HOST) && f >= 2) CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_copied[f & 1], 0));
-			launch_reconstruct(b->h_rtasks + off, (int)steps[f].size(), b->st_main);
+			// A launch overwrites, per stream, the plane set written two of that stream's pictures ago, i.e. by
+			// a launch at least two copy-out launches back: the copy-out recorded two launches ago must be done
+			// (the copy stream is in order, so that covers every earlier one).
+			if ((flags & JSMPEG_B200_OUT_HOST) && b->copy_steps >= 2)
+				CUDA_CHECK(cudaStreamWaitEvent(b->st_recon, b->ev_copied[b->copy_steps & 1], 0));
+			launch_reconstruct(b->h_rtasks + off, (int)steps[f].size(), b->st_recon);
 			b->stats.kernel_launches++;
 			b->stats.recon_launches++;
 			if (flags & JSMPEG_B200_OUT_RGBA) {
 				int mw = 0, mh = 0;
 				for (auto &t : steps[f]) { mw = std::max(mw, t.width); mh = std::max(mh, t.height); }
-				launch_rgba(b->d_rtasks + off, (int)steps[f].size(), mw, mh, b->st_main);
+				launch_rgba(b->d_rtasks + off, (int)steps[f].size(), mw, mh, b->st_recon);
 				b->stats.kernel_launches++;
 			}
-			if (flags & JSMPEG_B200_OUT_HOST) {
-				// copy this step's pictures out on the copy stream while the next step reconstructs
-				CUDA_CHECK(cudaEventRecord(b->ev_step, b->st_main));
-				CUDA_CHECK(cudaStreamWaitEvent(b->st_copy, b->ev_step, 0));
-				// all pictures of the step leave in ONE batched copy call (cudaMemcpyBatchAsync, CUDA 12.8+)
-				const size_t n_copy = steps[f].size();
-				b->copy_dst.resize(n_copy);
-				b->copy_src.resize(n_copy);
-				b->copy_size.resize(n_copy);
-				for (size_t i = 0; i < n_copy; i++) {
-					Stream &s = b->streams[step_streams[f][i]];
-					s.h_head = (s.h_head + 1) % HOST_RING;
-					b->copy_dst[i] = s.h_planes[s.h_head];
-					b->copy_src[i] = steps[f][i].cur.y;
-					b->copy_size[i] = (size_t)s.coded_size * 3 / 2;
-					b->stats.d2h_bytes += b->copy_size[i];
-				}
-				bool batched = false;
-				if (b->batch_copy_ok && n_copy > 1) {
-					cudaMemcpyAttributes attr{};
-					attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-					size_t attr_idx = 0, fail_idx = 0;
-					cudaError_t e = cudaMemcpyBatchAsync(b->copy_dst.data(), b->copy_src.data(), b->copy_size.data(), n_copy,
-					                                     &attr, &attr_idx, 1, &fail_idx, b->st_copy);
-					if (e == cudaSuccess) batched = true;
-					else { (void)cudaGetLastError(); b->batch_copy_ok = false; }  // older driver: plain copies from now on
-				}
-				if (!batched)
-					for (size_t i = 0; i < n_copy; i++)
-						CUDA_CHECK(cudaMemcpyAsync(b->copy_dst[i], b->copy_src[i], b->copy_size[i], cudaMemcpyDeviceToHost, b->st_copy));
-				CUDA_CHECK(cudaEventRecord(b->ev_copied[f & 1], b->st_copy));
-				b->copies_outstanding[f & 1] = true;
-			}
+			if (flags & JSMPEG_B200_OUT_HOST) copy_out_step(b, steps[f], step_streams[f]);  // while the next step reconstructs
 			off += steps[f].size();
 		}
-		CUDA_CHECK(cudaEventRecord(b->ev_d, b->st_main));
-		CUDA_CHECK(cudaEventSynchronize(b->ev_d));
+		CUDA_CHECK(cudaEventRecord(b->ev_rec1[rec_chunks], b->st_recon));
+		rec_chunks++;
+		// h_rtasks is read at launch time only (the table travels in the kernel parameters), so the next chunk may reuse it
+	}
+	if (rec_chunks) {
+		CUDA_CHECK(cudaEventRecord(b->ev_round, b->st_recon));
+		b->recon_pending = true;
+		CUDA_CHECK(cudaEventSynchronize(b->ev_rec1[rec_chunks - 1]));
+		for (int k = 0; k < rec_chunks; k++) {
+			float ms = 0;
+			CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_rec0[k], b->ev_rec1[k]));
+			b->stats.recon_ms += ms;
+		}
+	}
+	if (!fresh.empty()) {
+		CUDA_CHECK(cudaEventSynchronize(b->ev_b));
 		float ms = 0;
-		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_c, b->ev_d));
-		b->stats.recon_ms += ms;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_b));
+		b->stats.parse_ms += ms;
+		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_mid));
+		b->stats.walk_ms += ms;
 	}
 	return consumed;
 }
 
-}  // namespace
-
-// ================================================================================================
-// C ABI, part 2 (batch)
-
-extern "C" {
-
-const char *jsmpeg_b200_version(void) { return "jsmpeg_b200 0.1 (sm_100a)"; }
-
-
-jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigned int max_slots) {
-	Batch *b = new Batch();
-	b->device = device;
-	use_device(b);
-	b->streams.resize(std::max(n_streams, 1));
-	b->max_slots_req = max_slots;
-	CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
-	CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
-	cudaEvent_t *evs[] = {&b->ev_a, &b->ev_b, &b->ev_c, &b->ev_d, &b->ev_mid};
-	for (auto e : evs) CUDA_CHECK(cudaEventCreate(e));
-	CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_step, cudaEventDisableTiming));
-	for (auto &e : b->ev_copied) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-	CUDA_CHECK(cudaEventCreateWithFlags(&b->fork.fork, cudaEventDisableTiming));
-	for (int i = 0; i < PARSE_GROUPS; i++) {
-		CUDA_CHECK(cudaStreamCreateWithFlags(&b->fork.side[i], cudaStreamNonBlocking));
-		CUDA_CHECK(cudaEventCreateWithFlags(&b->fork.join[i], cudaEventDisableTiming));
-	}
-	return b;
-}
-
-void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
-	if (!b) return;
-	use_device(b);
-	CUDA_CHECK(cudaDeviceSynchronize());
-	for (auto &s : b->streams) {
-		if (s.h_bytes) cudaFreeHost(s.h_bytes);
-		if (s.d_seq) cudaFree(s.d_seq);
-		if (s.d_es) cudaFree(s.d_es);
-		if (s.d_scan) cudaFree(s.d_scan);
-		if (s.h_scan) cudaFreeHost(s.h_scan);
-		if (s.d_rgba) cudaFree(s.d_rgba);
-		for (auto p : s.d_planes) if (p) cudaFree(p);
-		for (auto p : s.h_planes) if (p) cudaFreeHost(p);
-	}
-	if (b->d_hdr) { cudaFree(b->d_hdr); cudaFree(b->d_coef); cudaFree(b->d_info); cudaFreeHost(b->h_info); }
-	if (b->h_ptasks) { cudaFreeHost(b->h_ptasks); cudaFree(b->d_ptasks); }
-	if (b->h_rtasks) { cudaFreeHost(b->h_rtasks); cudaFree(b->d_rtasks); }
-	ts_scratch_destroy(b->ts);
-	cudaEvent_t evs[] = {b->ev_a, b->ev_b, b->ev_c, b->ev_d, b->ev_mid, b->ev_step, b->ev_copied[0], b->ev_copied[1]};
-	for (auto e : evs) cudaEventDestroy(e);
-	cudaEventDestroy(b->fork.fork);
-	for (int i = 0; i < PARSE_GROUPS; i++) { cudaEventDestroy(b->fork.join[i]); cudaStreamDestroy(b->fork.side[i]); }
-	cudaStreamDestroy(b->st_main);
-	cudaStreamDestroy(b->st_copy);
-	delete b;
-}
-
-void *jsmpeg_b200_batch_get_write_ptr(jsmpeg_b200_batch_t *b, int stream, unsigned int byte_size) {
-	use_device(b);
-	return stream_get_write_ptr(b, b->streams[stream], byte_size);
-}
-
-void jsmpeg_b200_batch_did_write(jsmpeg_b200_batch_t *b, int stream, unsigned int byte_size) {
-	use_device(b);
-	stream_did_write(b, b->streams[stream], byte_size);
-}
-
-int jsmpeg_b200_batch_get_index(jsmpeg_b200_batch_t *b, int stream) { return (int)b->streams[stream].index; }
-
-void jsmpeg_b200_batch_set_index(jsmpeg_b200_batch_t *b, int stream, unsigned int index) {
-	Stream &s = b->streams[stream];
-	s.index = index;
-	flush_cache(b, s);
-}
-
-int jsmpeg_b200_batch_stream_info(jsmpeg_b200_batch_t *b, int stream, int *width, int *height, int *coded_size, float *frame_rate) {
-	const Stream &s = b->streams[stream];
-	if (width) *width = s.width;
-	if (height) *height = s.height;
-	if (coded_size) *coded_size = s.coded_size;
-	if (frame_rate) *frame_rate = s.frame_rate;
-	return s.has_seq ? 1 : 0;
-}
-
-long jsmpeg_b200_batch_upload(jsmpeg_b200_batch_t *b) {
-	use_device(b);
-	return upload_all(b);
-}
-
-void jsmpeg_b200_batch_rewind(jsmpeg_b200_batch_t *b) {
-	use_device(b);
-	for (auto &s : b->streams) {
-		flush_cache(b, s);
-		s.pics.clear();
-		s.scanned = 0;
-		s.index = s.has_seq ? s.seq_end_index : 0;  // where did_write left it (mpeg1.c:812-819)
-	}
-}
-
-void jsmpeg_b200_batch_reset(jsmpeg_b200_batch_t *b) {
-	use_device(b);
-	for (auto &s : b->streams) {
-		forget_index(b, s);
-		s.length = 0;
-		s.index = 0;
-		s.cur = 0;
-		s.h_head = -1;
-		if (s.has_seq)
-			for (auto p : s.d_planes) CUDA_CHECK(cudaMemsetAsync(p, 0, (size_t)s.coded_size * 3 / 2, b->st_main));
-	}
-	CUDA_CHECK(cudaStreamSynchronize(b->st_main));
-}
-
-long jsmpeg_b200_batch_decode(jsmpeg_b200_batch_t *b, int n_pictures, int flags) {
+long batch_decode(Batch *b, int n_pictures, int flags) {
 	use_device(b);
 	upload_all(b);
 	ensure_pool(b);
@@ -727,7 +756,7 @@ long jsmpeg_b200_batch_decode(jsmpeg_b200_batch_t *b, int n_pictures, int flags)
 		const int per_stream = std::max(1, (int)(b->free_slots.size() + cached) / active);
 		for (int i = 0; i < S; i++)
 			want[i] = (more[i] && b->streams[i].has_seq) ? std::min(remaining[i], per_stream) : 0;
-		const long got = decode_chunk(b, want, progress, more, flags);
+		const long got = decode_round(b, want, progress, more, flags);
 		total += got;
 		bool replanned = false;
 		for (int i = 0; i < S; i++) {
@@ -737,12 +766,171 @@ long jsmpeg_b200_batch_decode(jsmpeg_b200_batch_t *b, int n_pictures, int flags)
 		if (got == 0 && (!replanned || ++idle_rounds > 2)) break;
 		if (got) idle_rounds = 0;
 	}
-	for (int i = 0; i < 2; i++) {
-		if (b->copies_outstanding[i]) CUDA_CHECK(cudaEventSynchronize(b->ev_copied[i]));
-		b->copies_outstanding[i] = false;
-	}
+	CUDA_CHECK(cudaStreamSynchronize(b->st_recon));
+	CUDA_CHECK(cudaStreamSynchronize(b->st_copy));
 	CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+	b->recon_pending = false;
 	return total;
+}
+
+int env_int(const char *name, int fallback) {
+	const char *e = getenv(name);
+	return e && *e ? atoi(e) : fallback;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI, part 2 (batch)
+
+extern "C" {
+
+const char *jsmpeg_b200_version(void) { return "jsmpeg_b200 0.2 (sm_100a)"; }
+
+jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigned int max_slots) {
+	Batch *b = new Batch();
+	b->device = device;
+	b->streams.resize(std::max(n_streams, 1));
+	b->max_slots_req = max_slots;
+	b->chunk_pictures = std::max(0, env_int("JSMPEG_B200_CHUNK", 0));
+	b->chunk_min_wave = std::max(1, env_int("JSMPEG_B200_CHUNK_MIN_WAVE", 256));
+	try {
+		use_device(b);
+		CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
+		CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_recon, cudaStreamNonBlocking));
+		CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
+		cudaEvent_t *evs[] = {&b->ev_a, &b->ev_b, &b->ev_mid};
+		for (auto e : evs) CUDA_CHECK(cudaEventCreate(e));
+		CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_step, cudaEventDisableTiming));
+		CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_round, cudaEventDisableTiming));
+		for (auto &e : b->ev_copied) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		CUDA_CHECK(cudaEventCreateWithFlags(&b->fork.fork, cudaEventDisableTiming));
+		for (int i = 0; i < PARSE_GROUPS; i++) {
+			CUDA_CHECK(cudaStreamCreateWithFlags(&b->fork.side[i], cudaStreamNonBlocking));
+			CUDA_CHECK(cudaEventCreateWithFlags(&b->fork.join[i], cudaEventDisableTiming));
+		}
+	} catch (const std::exception &e) {
+		mark_dead(b, e.what());  // no usable device: a decoder that answers false, not a dead process
+	}
+	return b;
+}
+
+void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
+	if (!b) return;
+	// best effort, nothing here may throw: the context may be the very thing that failed
+	(void)cudaSetDevice(b->device);
+	(void)cudaDeviceSynchronize();
+	for (auto &s : b->streams) {
+		if (s.bb.bytes) cudaFreeHost(s.bb.bytes);
+		if (s.d_seq) cudaFree(s.d_seq);
+		if (s.d_es) cudaFree(s.d_es);
+		if (s.d_scan) cudaFree(s.d_scan);
+		if (s.h_scan) cudaFreeHost(s.h_scan);
+		if (s.d_rgba) cudaFree(s.d_rgba);
+		for (auto p : s.d_planes) if (p) cudaFree(p);
+		for (auto p : s.h_planes) if (p) cudaFreeHost(p);
+	}
+	if (b->d_hdr) cudaFree(b->d_hdr);
+	if (b->d_coef) cudaFree(b->d_coef);
+	if (b->d_park) cudaFree(b->d_park);
+	if (b->d_info) cudaFree(b->d_info);
+	if (b->h_info) cudaFreeHost(b->h_info);
+	if (b->h_ptasks) cudaFreeHost(b->h_ptasks);
+	if (b->d_ptasks) cudaFree(b->d_ptasks);
+	if (b->h_rtasks) cudaFreeHost(b->h_rtasks);
+	if (b->d_rtasks) cudaFree(b->d_rtasks);
+	ts_scratch_destroy(b->ts);
+	cudaEvent_t evs[] = {b->ev_a, b->ev_b, b->ev_mid, b->ev_step, b->ev_round, b->ev_copied[0], b->ev_copied[1], b->fork.fork};
+	for (auto e : evs) if (e) cudaEventDestroy(e);
+	for (auto v : {&b->ev_info, &b->ev_rec0, &b->ev_rec1}) for (auto e : *v) if (e) cudaEventDestroy(e);
+	for (int i = 0; i < PARSE_GROUPS; i++) {
+		if (b->fork.join[i]) cudaEventDestroy(b->fork.join[i]);
+		if (b->fork.side[i]) cudaStreamDestroy(b->fork.side[i]);
+	}
+	for (auto st : {b->st_main, b->st_recon, b->st_copy}) if (st) cudaStreamDestroy(st);
+	(void)cudaGetLastError();
+	delete b;
+}
+
+const char *jsmpeg_b200_batch_last_error(jsmpeg_b200_batch_t *b) { return (b && b->dead) ? b->error.c_str() : nullptr; }
+
+int jsmpeg_b200_batch_set_option(jsmpeg_b200_batch_t *b, const char *name, int value) {
+	if (!b || !name) return -1;
+	if (!strcmp(name, "chunk_pictures")) { b->chunk_pictures = std::max(0, value); return 0; }
+	if (!strcmp(name, "chunk_min_wave")) { b->chunk_min_wave = std::max(1, value); return 0; }
+	if (!strcmp(name, "lookahead")) { b->lookahead = std::max(1, value); return 0; }
+	return -1;
+}
+
+void *jsmpeg_b200_batch_get_write_ptr(jsmpeg_b200_batch_t *b, int stream, unsigned int byte_size) {
+	void *p = guarded<void *>(b, nullptr, [&]() -> void * {
+		use_device(b);
+		return stream_get_write_ptr(b, b->streams[stream], byte_size);
+	});
+	if (p) return p;
+	// dead decoder: the caller's memcpy still needs somewhere to go
+	b->dead_scratch.resize(std::max<size_t>(byte_size, 1));
+	return b->dead_scratch.data();
+}
+
+void jsmpeg_b200_batch_did_write(jsmpeg_b200_batch_t *b, int stream, unsigned int byte_size) {
+	guarded_void(b, [&] {
+		use_device(b);
+		stream_did_write(b, b->streams[stream], byte_size);
+	});
+}
+
+int jsmpeg_b200_batch_get_index(jsmpeg_b200_batch_t *b, int stream) { return (int)b->streams[stream].bb.index; }
+
+void jsmpeg_b200_batch_set_index(jsmpeg_b200_batch_t *b, int stream, unsigned int index) {
+	Stream &s = b->streams[stream];
+	s.bb.index = index;
+	flush_cache(b, s);
+}
+
+int jsmpeg_b200_batch_stream_info(jsmpeg_b200_batch_t *b, int stream, int *width, int *height, int *coded_size, float *frame_rate) {
+	const Stream &s = b->streams[stream];
+	if (width) *width = s.width;
+	if (height) *height = s.height;
+	if (coded_size) *coded_size = s.coded_size;
+	if (frame_rate) *frame_rate = s.frame_rate;
+	return s.has_seq ? 1 : 0;
+}
+
+long jsmpeg_b200_batch_upload(jsmpeg_b200_batch_t *b) {
+	return guarded<long>(b, 0, [&] {
+		use_device(b);
+		return upload_all(b);
+	});
+}
+
+void jsmpeg_b200_batch_rewind(jsmpeg_b200_batch_t *b) {
+	for (auto &s : b->streams) {
+		flush_cache(b, s);
+		s.pics.clear();
+		s.scanned = 0;
+		s.bb.index = s.has_seq ? s.seq_end_index : 0;  // where did_write left it (mpeg1.c:812-819)
+	}
+}
+
+void jsmpeg_b200_batch_reset(jsmpeg_b200_batch_t *b) {
+	guarded_void(b, [&] {
+		use_device(b);
+		for (auto &s : b->streams) {
+			forget_index(b, s);
+			s.bb.length = 0;
+			s.bb.index = 0;
+			s.cur = 0;
+			s.h_head = -1;
+			if (s.has_seq)
+				for (auto p : s.d_planes) CUDA_CHECK(cudaMemsetAsync(p, 0, (size_t)s.coded_size * 3 / 2, b->st_main));
+		}
+		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+	});
+}
+
+long jsmpeg_b200_batch_decode(jsmpeg_b200_batch_t *b, int n_pictures, int flags) {
+	return guarded<long>(b, 0, [&] { return batch_decode(b, n_pictures, flags); });
 }
 
 int jsmpeg_b200_batch_get_planes(jsmpeg_b200_batch_t *b, int stream, void **y, void **cr, void **cb) {
@@ -773,60 +961,66 @@ int jsmpeg_b200_batch_get_rgba(jsmpeg_b200_batch_t *b, int stream, void **rgba) 
 }
 
 int jsmpeg_b200_batch_read_planes(jsmpeg_b200_batch_t *b, int stream, void *y, void *cr, void *cb) {
-	use_device(b);
-	const Stream &s = b->streams[stream];
-	if (!s.has_seq) return -1;
-	PlaneSet p = plane_set(s, s.d_planes[1 - s.cur]);
-	if (y) CUDA_CHECK(cudaMemcpy(y, p.y, s.coded_size, cudaMemcpyDeviceToHost));
-	if (cr) CUDA_CHECK(cudaMemcpy(cr, p.cr, s.coded_size >> 2, cudaMemcpyDeviceToHost));
-	if (cb) CUDA_CHECK(cudaMemcpy(cb, p.cb, s.coded_size >> 2, cudaMemcpyDeviceToHost));
-	return 0;
+	return guarded<int>(b, -1, [&] {
+		use_device(b);
+		const Stream &s = b->streams[stream];
+		if (!s.has_seq) return -1;
+		PlaneSet p = plane_set(s, s.d_planes[1 - s.cur]);
+		if (y) CUDA_CHECK(cudaMemcpy(y, p.y, s.coded_size, cudaMemcpyDeviceToHost));
+		if (cr) CUDA_CHECK(cudaMemcpy(cr, p.cr, s.coded_size >> 2, cudaMemcpyDeviceToHost));
+		if (cb) CUDA_CHECK(cudaMemcpy(cb, p.cb, s.coded_size >> 2, cudaMemcpyDeviceToHost));
+		return 0;
+	});
 }
 
 long jsmpeg_b200_batch_write_ts(jsmpeg_b200_batch_t *b, int stream, const uint8_t *ts, size_t n_bytes, int stream_id,
                                 uint64_t *pts_out, uint32_t *offset_out, int n_max, int *n_pes) {
-	use_device(b);
-	Stream &s = b->streams[stream];
-	if (!b->ts) b->ts = ts_scratch_create();
 	if (n_pes) *n_pes = 0;
-	if (s.ts_bound.empty()) s.ts_bound.assign(8192, 0);
-	const long total = ts_demux_measure(b->ts, ts, n_bytes, stream_id, s.ts_bound.data(), b->st_main);
-	if (total <= 0) return total;
-	// room in the host bit buffer (the reference's write protocol, may expand or evict) and in HBM
-	uint8_t *hdst = static_cast<uint8_t *>(stream_get_write_ptr(b, s, (uint32_t)total));
-	reserve_device_es(b, s, s.length + (uint32_t)total);
-	if (s.d_valid < s.length) {  // bytes written the ordinary way that are not resident yet
-		CUDA_CHECK(cudaMemcpyAsync(s.d_es + s.d_valid, s.h_bytes + s.d_valid, s.length - s.d_valid, cudaMemcpyHostToDevice, b->st_main));
-		b->stats.h2d_bytes += s.length - s.d_valid;
-		s.d_valid = s.length;
-	}
-	const int count = ts_demux_gather(b->ts, n_bytes, s.d_es, s.length, pts_out, offset_out, n_max, b->st_main);
-	b->stats.kernel_launches += 4;
-	b->stats.h2d_bytes += n_bytes;
-	// the host keeps a mirror of the ES (sequence header parse, EVICT bookkeeping): copy the new bytes back
-	CUDA_CHECK(cudaMemcpyAsync(hdst, s.d_es + s.length, (size_t)total, cudaMemcpyDeviceToHost, b->st_main));
-	CUDA_CHECK(cudaMemsetAsync(s.d_es + s.length + total, 0, ES_PAD, b->st_main));
-	CUDA_CHECK(cudaStreamSynchronize(b->st_main));
-	b->stats.d2h_bytes += (uint64_t)total;
-	stream_did_write(b, s, (uint32_t)total);
-	s.d_valid = s.length;
-	if (n_pes) *n_pes = count;
-	if (pts_out && offset_out && count > 1) {  // the device appends PES starts unordered: sort by offset
-		const int m = std::min(count, n_max);
-		std::vector<std::pair<uint32_t, uint64_t>> v(m);
-		for (int i = 0; i < m; i++) v[i] = {offset_out[i], pts_out[i]};
-		std::sort(v.begin(), v.end());
-		for (int i = 0; i < m; i++) { offset_out[i] = v[i].first; pts_out[i] = v[i].second; }
-	}
-	return total;
+	return guarded<long>(b, -1, [&]() -> long {
+		use_device(b);
+		Stream &s = b->streams[stream];
+		if (!b->ts) b->ts = ts_scratch_create();
+		if (s.ts_bound.empty()) s.ts_bound.assign(8192, 0);
+		const long total = ts_demux_measure(b->ts, ts, n_bytes, stream_id, s.ts_bound.data(), b->st_main);
+		if (total <= 0) return total;
+		// room in the host bit buffer (the reference's write protocol, may expand or evict) and in HBM
+		uint8_t *hdst = static_cast<uint8_t *>(stream_get_write_ptr(b, s, (uint32_t)total));
+		reserve_device_es(b, s, s.bb.length + (uint32_t)total);
+		if (s.d_valid < s.bb.length) {  // bytes written the ordinary way that are not resident yet
+			CUDA_CHECK(cudaMemcpyAsync(s.d_es + s.d_valid, s.bb.bytes + s.d_valid, s.bb.length - s.d_valid, cudaMemcpyHostToDevice, b->st_main));
+			b->stats.h2d_bytes += s.bb.length - s.d_valid;
+			s.d_valid = s.bb.length;
+		}
+		const int count = ts_demux_gather(b->ts, n_bytes, s.d_es, s.bb.length, pts_out, offset_out, n_max, b->st_main);
+		b->stats.kernel_launches += 4;
+		b->stats.h2d_bytes += n_bytes;
+		// the host keeps a mirror of the ES (sequence header parse, EVICT bookkeeping): copy the new bytes back
+		CUDA_CHECK(cudaMemcpyAsync(hdst, s.d_es + s.bb.length, (size_t)total, cudaMemcpyDeviceToHost, b->st_main));
+		CUDA_CHECK(cudaMemsetAsync(s.d_es + s.bb.length + total, 0, ES_PAD, b->st_main));
+		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+		b->stats.d2h_bytes += (uint64_t)total;
+		stream_did_write(b, s, (uint32_t)total);
+		s.d_valid = s.bb.length;
+		if (n_pes) *n_pes = count;
+		if (pts_out && offset_out && count > 1) {  // the device appends PES starts unordered: sort by offset
+			const int m = std::min(count, n_max);
+			std::vector<std::pair<uint32_t, uint64_t>> v(m);
+			for (int i = 0; i < m; i++) v[i] = {offset_out[i], pts_out[i]};
+			std::sort(v.begin(), v.end());
+			for (int i = 0; i < m; i++) { offset_out[i] = v[i].first; pts_out[i] = v[i].second; }
+		}
+		return total;
+	});
 }
 
 int jsmpeg_b200_batch_read_rgba(jsmpeg_b200_batch_t *b, int stream, void *rgba) {
-	use_device(b);
-	const Stream &s = b->streams[stream];
-	if (!s.has_seq || !s.d_rgba) return -1;
-	CUDA_CHECK(cudaMemcpy(rgba, s.d_rgba, (size_t)s.width * s.height * 4, cudaMemcpyDeviceToHost));
-	return 0;
+	return guarded<int>(b, -1, [&] {
+		use_device(b);
+		const Stream &s = b->streams[stream];
+		if (!s.has_seq || !s.d_rgba) return -1;
+		CUDA_CHECK(cudaMemcpy(rgba, s.d_rgba, (size_t)s.width * s.height * 4, cudaMemcpyDeviceToHost));
+		return 0;
+	});
 }
 
 void jsmpeg_b200_batch_get_stats(jsmpeg_b200_batch_t *b, jsmpeg_b200_stats_t *out) { *out = b->stats; }
@@ -843,23 +1037,26 @@ static int g_default_device = -1;  // -1: JSMPEG_B200_DEVICE or 0
 void jsmpeg_b200_set_default_device(int device) { g_default_device = device; }
 
 mpeg1_decoder_t *mpeg1_decoder_create(unsigned int buffer_size, bit_buffer_mode_t buffer_mode) {
-	const char *dev = getenv("JSMPEG_B200_DEVICE");
-	const char *slots = getenv("JSMPEG_B200_LOOKAHEAD");
-	int lookahead = slots ? atoi(slots) : 16;
+	int lookahead = env_int("JSMPEG_B200_LOOKAHEAD", 16);
 	if (lookahead < 1) lookahead = 1;
 	mpeg1_decoder_t *d = new mpeg1_decoder_t();
-	d->b = jsmpeg_b200_batch_create(1, g_default_device >= 0 ? g_default_device : (dev ? atoi(dev) : 0), (unsigned)lookahead + 1);
+	d->b = jsmpeg_b200_batch_create(1, g_default_device >= 0 ? g_default_device : env_int("JSMPEG_B200_DEVICE", 0), (unsigned)lookahead + 1);
 	d->b->lookahead = lookahead;
 	Stream &s = d->b->streams[0];
-	s.mode = buffer_mode;
-	host_resize(s, buffer_size ? buffer_size : 1);
+	s.bb.mode = buffer_mode;
+	guarded_void(d->b, [&] {
+		if (!bitbuffer::resize(s.bb, buffer_size ? buffer_size : 1, kPinned)) throw std::runtime_error("jsmpeg_b200: bit buffer allocation failed");
+	});
 	return d;
 }
 
 void mpeg1_decoder_destroy(mpeg1_decoder_t *self) {
+	if (!self) return;
 	jsmpeg_b200_batch_destroy(self->b);
 	delete self;
 }
+
+const char *jsmpeg_b200_decoder_last_error(mpeg1_decoder_t *self) { return self ? jsmpeg_b200_batch_last_error(self->b) : nullptr; }
 
 void *mpeg1_decoder_get_write_ptr(mpeg1_decoder_t *self, unsigned int byte_size) {
 	return jsmpeg_b200_batch_get_write_ptr(self->b, 0, byte_size);
@@ -893,64 +1090,78 @@ bool mpeg1_decoder_decode(mpeg1_decoder_t *self) {
 int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t start_byte, int mb_width,
                                     int mb_height, const uint8_t *intra_q, const uint8_t *non_intra_q,
                                     void *info_out, void *hdr_out, void *coef_out) {
-	SeqParams sp{};
-	sp.mb_width = mb_width; sp.mb_height = mb_height; sp.mb_size = mb_width * mb_height;
-	sp.coded_width = mb_width * 16; sp.coded_height = mb_height * 16;
-	memcpy(sp.intra_q, intra_q, 64);
-	memcpy(sp.non_intra_q, non_intra_q, 64);
-	const size_t n_mb = sp.mb_size;
-	uint8_t *d_es = dev_alloc<uint8_t>(es_len + ES_PAD);
-	SeqParams *d_seq = dev_alloc<SeqParams>(1);
-	mb_record_t *d_hdr = dev_alloc<mb_record_t>(n_mb);
-	int16_t *d_coef = dev_alloc<int16_t>(n_mb * MB_COEF_INT16);
-	picture_info_t *d_info = dev_alloc<picture_info_t>(1);
-	ParseTask *d_task = dev_alloc<ParseTask>(1);
-	CUDA_CHECK(cudaMemcpy(d_es, es, es_len, cudaMemcpyHostToDevice));
-	CUDA_CHECK(cudaMemset(d_es + es_len, 0, ES_PAD));
-	CUDA_CHECK(cudaMemcpy(d_seq, &sp, sizeof(sp), cudaMemcpyHostToDevice));
-	CUDA_CHECK(cudaMemset(d_coef, 0, n_mb * MB_COEF_INT16 * sizeof(int16_t)));
-	ParseTask t{d_es, es_len, start_byte, d_seq, d_hdr, d_coef, d_info};
-	CUDA_CHECK(cudaMemcpy(d_task, &t, sizeof(t), cudaMemcpyHostToDevice));
-	launch_parse_pictures(d_task, 1, sp.mb_size, 0);
-	CUDA_CHECK(cudaGetLastError());
-	CUDA_CHECK(cudaDeviceSynchronize());
-	CUDA_CHECK(cudaMemcpy(info_out, d_info, sizeof(picture_info_t), cudaMemcpyDeviceToHost));
-	CUDA_CHECK(cudaMemcpy(hdr_out, d_hdr, n_mb * sizeof(mb_record_t), cudaMemcpyDeviceToHost));
-	CUDA_CHECK(cudaMemcpy(coef_out, d_coef, n_mb * MB_COEF_INT16 * sizeof(int16_t), cudaMemcpyDeviceToHost));
-	cudaFree(d_es); cudaFree(d_seq); cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_info); cudaFree(d_task);
-	return 0;
+	try {
+		SeqParams sp{};
+		sp.mb_width = mb_width; sp.mb_height = mb_height; sp.mb_size = mb_width * mb_height;
+		sp.coded_width = mb_width * 16; sp.coded_height = mb_height * 16;
+		memcpy(sp.intra_q, intra_q, 64);
+		memcpy(sp.non_intra_q, non_intra_q, 64);
+		seq_fill_xq(sp);
+		const size_t n_mb = sp.mb_size;
+		uint8_t *d_es = dev_alloc<uint8_t>(es_len + ES_PAD);
+		SeqParams *d_seq = dev_alloc<SeqParams>(1);
+		mb_record_t *d_hdr = dev_alloc<mb_record_t>(n_mb);
+		int16_t *d_coef = dev_alloc<int16_t>(n_mb * MB_COEF_INT16);
+		uint2 *d_park = dev_alloc<uint2>(n_mb * 6);
+		picture_info_t *d_info = dev_alloc<picture_info_t>(1);
+		ParseTask *d_task = dev_alloc<ParseTask>(1);
+		CUDA_CHECK(cudaMemcpy(d_es, es, es_len, cudaMemcpyHostToDevice));
+		CUDA_CHECK(cudaMemset(d_es + es_len, 0, ES_PAD));
+		CUDA_CHECK(cudaMemcpy(d_seq, &sp, sizeof(sp), cudaMemcpyHostToDevice));
+		CUDA_CHECK(cudaMemset(d_coef, 0, n_mb * MB_COEF_INT16 * sizeof(int16_t)));
+		ParseTask t{};
+		t.es = d_es; t.es_len = es_len; t.start_byte = start_byte; t.seq = d_seq; t.hdr = d_hdr; t.coef = d_coef; t.info = d_info;
+		t.park = d_park; t.mb_width = mb_width; t.mb_size = sp.mb_size;
+		CUDA_CHECK(cudaMemcpy(d_task, &t, sizeof(t), cudaMemcpyHostToDevice));
+		launch_parse_pictures(d_task, 1, sp.mb_size, 0);
+		CUDA_CHECK(cudaGetLastError());
+		CUDA_CHECK(cudaDeviceSynchronize());
+		CUDA_CHECK(cudaMemcpy(info_out, d_info, sizeof(picture_info_t), cudaMemcpyDeviceToHost));
+		CUDA_CHECK(cudaMemcpy(hdr_out, d_hdr, n_mb * sizeof(mb_record_t), cudaMemcpyDeviceToHost));
+		CUDA_CHECK(cudaMemcpy(coef_out, d_coef, n_mb * MB_COEF_INT16 * sizeof(int16_t), cudaMemcpyDeviceToHost));
+		cudaFree(d_es); cudaFree(d_seq); cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_park); cudaFree(d_info); cudaFree(d_task);
+		return 0;
+	} catch (const std::exception &e) {
+		fprintf(stderr, "%s\n", e.what());
+		return -1;
+	}
 }
 
 int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, const void *coef,
                                   const uint8_t *fwd_y, const uint8_t *fwd_cr, const uint8_t *fwd_cb,
                                   uint8_t *cur_y, uint8_t *cur_cr, uint8_t *cur_cb) {
-	const size_t n_mb = (size_t)mb_width * mb_height;
-	const size_t ysz = n_mb * 256, csz = ysz / 4, total = ysz + 2 * csz;
-	mb_record_t *d_hdr = dev_alloc<mb_record_t>(n_mb);
-	int16_t *d_coef = dev_alloc<int16_t>(n_mb * MB_COEF_INT16);
-	uint8_t *d_fwd = dev_alloc<uint8_t>(total + 64), *d_cur = dev_alloc<uint8_t>(total + 64);
-	CUDA_CHECK(cudaMemcpy(d_hdr, hdr, n_mb * sizeof(mb_record_t), cudaMemcpyHostToDevice));
-	CUDA_CHECK(cudaMemcpy(d_coef, coef, n_mb * MB_COEF_INT16 * sizeof(int16_t), cudaMemcpyHostToDevice));
-	CUDA_CHECK(cudaMemcpy(d_fwd, fwd_y, ysz, cudaMemcpyHostToDevice));
-	CUDA_CHECK(cudaMemcpy(d_fwd + ysz, fwd_cr, csz, cudaMemcpyHostToDevice));
-	CUDA_CHECK(cudaMemcpy(d_fwd + ysz + csz, fwd_cb, csz, cudaMemcpyHostToDevice));
-	CUDA_CHECK(cudaMemcpy(d_cur, cur_y, ysz, cudaMemcpyHostToDevice));
-	CUDA_CHECK(cudaMemcpy(d_cur + ysz, cur_cr, csz, cudaMemcpyHostToDevice));
-	CUDA_CHECK(cudaMemcpy(d_cur + ysz + csz, cur_cb, csz, cudaMemcpyHostToDevice));
-	ReconTask t{};
-	t.hdr = d_hdr; t.coef = d_coef;
-	t.cur = PlaneSet{d_cur, d_cur + ysz, d_cur + ysz + csz};
-	t.fwd = PlaneSet{d_fwd, d_fwd + ysz, d_fwd + ysz + csz};
-	t.mb_width = mb_width; t.mb_size = (int)n_mb;
-	t.coded_width = mb_width * 16; t.coded_height = mb_height * 16;
-	launch_reconstruct(&t, 1, 0);
-	CUDA_CHECK(cudaGetLastError());
-	CUDA_CHECK(cudaDeviceSynchronize());
-	CUDA_CHECK(cudaMemcpy(cur_y, d_cur, ysz, cudaMemcpyDeviceToHost));
-	CUDA_CHECK(cudaMemcpy(cur_cr, d_cur + ysz, csz, cudaMemcpyDeviceToHost));
-	CUDA_CHECK(cudaMemcpy(cur_cb, d_cur + ysz + csz, csz, cudaMemcpyDeviceToHost));
-	cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_fwd); cudaFree(d_cur);
-	return 0;
+	try {
+		const size_t n_mb = (size_t)mb_width * mb_height;
+		const size_t ysz = n_mb * 256, csz = ysz / 4, total = ysz + 2 * csz;
+		mb_record_t *d_hdr = dev_alloc<mb_record_t>(n_mb);
+		int16_t *d_coef = dev_alloc<int16_t>(n_mb * MB_COEF_INT16);
+		uint8_t *d_fwd = dev_alloc<uint8_t>(total + 64), *d_cur = dev_alloc<uint8_t>(total + 64);
+		CUDA_CHECK(cudaMemcpy(d_hdr, hdr, n_mb * sizeof(mb_record_t), cudaMemcpyHostToDevice));
+		CUDA_CHECK(cudaMemcpy(d_coef, coef, n_mb * MB_COEF_INT16 * sizeof(int16_t), cudaMemcpyHostToDevice));
+		CUDA_CHECK(cudaMemcpy(d_fwd, fwd_y, ysz, cudaMemcpyHostToDevice));
+		CUDA_CHECK(cudaMemcpy(d_fwd + ysz, fwd_cr, csz, cudaMemcpyHostToDevice));
+		CUDA_CHECK(cudaMemcpy(d_fwd + ysz + csz, fwd_cb, csz, cudaMemcpyHostToDevice));
+		CUDA_CHECK(cudaMemcpy(d_cur, cur_y, ysz, cudaMemcpyHostToDevice));
+		CUDA_CHECK(cudaMemcpy(d_cur + ysz, cur_cr, csz, cudaMemcpyHostToDevice));
+		CUDA_CHECK(cudaMemcpy(d_cur + ysz + csz, cur_cb, csz, cudaMemcpyHostToDevice));
+		ReconTask t{};
+		t.hdr = d_hdr; t.coef = d_coef;
+		t.cur = PlaneSet{d_cur, d_cur + ysz, d_cur + ysz + csz};
+		t.fwd = PlaneSet{d_fwd, d_fwd + ysz, d_fwd + ysz + csz};
+		t.mb_width = mb_width; t.mb_size = (int)n_mb;
+		t.coded_width = mb_width * 16; t.coded_height = mb_height * 16;
+		launch_reconstruct(&t, 1, 0);
+		CUDA_CHECK(cudaGetLastError());
+		CUDA_CHECK(cudaDeviceSynchronize());
+		CUDA_CHECK(cudaMemcpy(cur_y, d_cur, ysz, cudaMemcpyDeviceToHost));
+		CUDA_CHECK(cudaMemcpy(cur_cr, d_cur + ysz, csz, cudaMemcpyDeviceToHost));
+		CUDA_CHECK(cudaMemcpy(cur_cb, d_cur + ysz + csz, csz, cudaMemcpyDeviceToHost));
+		cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_fwd); cudaFree(d_cur);
+		return 0;
+	} catch (const std::exception &e) {
+		fprintf(stderr, "%s\n", e.what());
+		return -1;
+	}
 }
 
 }  // extern "C"

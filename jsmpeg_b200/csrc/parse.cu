@@ -40,6 +40,7 @@ namespace {
 
 constexpr int CTA_THREADS = 128;       // expand kernel
 constexpr uint32_t TILE_PITCH = 144;   // bytes between the per-thread 64 x int16 tiles of the expand kernel (128 + 16: bank spread)
+constexpr uint32_t EXPAND_SMEM = EXP_OFF_TILES + CTA_THREADS * TILE_PITCH;
 
 // ==================================================================================================
 // 1a: one warp per picture (walk.cuh), serial or lane-parallel with serial fall-back
@@ -60,38 +61,48 @@ constexpr uint32_t TILE_PITCH = 144;   // bytes between the per-thread 64 x int1
 		const int task_id = blockIdx.x * (WALK_THREADS / 32) + (threadIdx.x >> 5);                                \
 		if (task_id >= n_tasks) return;                                                                           \
 		const ParseTask t = tasks[task_id];                                                                       \
-		walk_picture<LANES>(t, smem_base(smem), lane);                                                            \
+		const uint32_t sbase = smem_base(smem);                                                                   \
+		walk_picture<LANES>(t, sbase, lane, LANES ? sbase + OFF_RING + threadIdx.x * RING_BYTES : 0u);            \
 	}
 WALK_KERNEL(walk_pictures_kernel, false, __launch_bounds__(WALK_THREADS))
 WALK_KERNEL(walk_pictures_lanes_kernel, true, LANES_BOUNDS)
 
 // ==================================================================================================
-// 1b: expand every coded block (one thread per block slot)
+// 1b: expand every coded block (one thread per block slot, grid.y = picture)
 
 __global__ void __launch_bounds__(CTA_THREADS)
 expand_blocks_kernel(const ParseTask *__restrict__ tasks) {
 	extern __shared__ __align__(128) uint8_t smem[];
+	const ParseTask &t = tasks[blockIdx.y];
+	const int slot_id = blockIdx.x * CTA_THREADS + threadIdx.x;  // mb * 6 + block
+	const bool in_picture = slot_id < t.mb_size * 6;
+	// this thread's inputs are requested before the tables are staged: one exposed latency, not two.
+	// (A picture that was not decoded has no present macroblock: the walk clears the records first.)
+	const int mb = in_picture ? slot_id / 6 : 0;
+	uint32_t rec = 0;
+	uint2 parked = make_uint2(0u, 0u);
+	if (in_picture) {
+		rec = __ldg(reinterpret_cast<const uint32_t *>(t.hdr + mb) + 1);
+		parked = __ldg(t.park + slot_id);
+	}
 	{
-		uint16_t *s16 = reinterpret_cast<uint16_t *>(smem);
-		for (int i = threadIdx.x; i < (VLC_DCT_MAX_Z + 1) * 32; i += CTA_THREADS) s16[OFF_DCT / 2 + i] = VLC_DCT_COEFF[i];
-		for (int i = threadIdx.x; i < 64; i += CTA_THREADS) smem[OFF_ZIGZAG + i] = TBL_ZIG_ZAG[i];
-		uint32_t *blocks = reinterpret_cast<uint32_t *>(smem + OFF_BLOCKS);
-		for (int i = threadIdx.x; i < CTA_THREADS * (int)(TILE_PITCH / 4); i += CTA_THREADS) blocks[i] = 0u;
+		// tables: the DCT code table with values (768 B, 16 bytes per thread), the picture's two quantiser
+		// tables in zig-zag order (256 B, one entry per thread), and this thread's zeroed tile
+		if (threadIdx.x < (VLC_DCT_MAX_Z + 1) * 4)
+			reinterpret_cast<uint4 *>(smem + EXP_OFF_DCT)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(VLC_DCT_COEFF) + threadIdx.x);
+		reinterpret_cast<uint16_t *>(smem + EXP_OFF_XQ)[threadIdx.x] = __ldg(&t.seq->xq[0][0] + threadIdx.x);
+		uint4 *tile = reinterpret_cast<uint4 *>(smem + EXP_OFF_TILES + threadIdx.x * TILE_PITCH);
+#pragma unroll
+		for (int i = 0; i < (int)(TILE_PITCH / 16); i++) tile[i] = make_uint4(0u, 0u, 0u, 0u);
 	}
 	__syncthreads();
-
-	const ParseTask &t = tasks[blockIdx.y];
-	const int mb_size = t.seq->mb_size;
-	const int slot_id = blockIdx.x * CTA_THREADS + threadIdx.x;  // mb * 6 + block
-	if (slot_id >= mb_size * 6) return;
-	if (t.info->status != PIC_DECODED) return;
-#ifdef JSMPEG_WALK_EMITS_BLOCKS
-	if (t.info->reserved[1]) return;  // the lane-parallel walk has written this picture's block records itself
-#endif
+	const int block = slot_id - mb * 6;
+	if (!in_picture || !(rec & MBF_PRESENT) || !((rec >> 8) & (0x20u >> block))) return;
 	const uint32_t sbase = smem_base(smem);
 	// this thread's 64 x int16 tile, linear (it leaves as one bulk copy); tiles are 144 bytes apart so
 	// that lanes writing the same coefficient index spread over the banks
-	expand_block(t, slot_id, sbase, sbase + OFF_BLOCKS + threadIdx.x * TILE_PITCH);
+	expand_block(t, rec, parked, reinterpret_cast<uint4 *>(t.coef) + (size_t)slot_id * 8, sbase,
+	             sbase + EXP_OFF_TILES + threadIdx.x * TILE_PITCH);
 }
 
 }  // namespace
@@ -119,6 +130,22 @@ static const uint16_t *ms_table_for_current_device() {
 	return d;
 }
 
+// JSMPEG_B200_PARSE_GROUPS=1 keeps stage 1 on one stream (used for the ncu launch list: ncu
+// serialises concurrent kernels, so only the unforked run has comparable shares)
+static int max_parse_groups() {
+	static const int max_groups = [] {
+		const char *e = getenv("JSMPEG_B200_PARSE_GROUPS");
+		const int g = e ? atoi(e) : PARSE_GROUPS;
+		return g < 1 ? 1 : (g > PARSE_GROUPS ? PARSE_GROUPS : g);
+	}();
+	return max_groups;
+}
+
+int parse_group_count(int n_tasks, bool forked) {
+	const int max_groups = max_parse_groups();
+	return (forked && n_tasks >= 64 * max_groups) ? max_groups : 1;
+}
+
 void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream,
                            cudaEvent_t walk_done, const ParseFork *fork) {
 	if (n_tasks <= 0) return;
@@ -126,20 +153,13 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 	const int per_cta = WALK_THREADS / 32;
 	// The wave arrives sorted by picture size, largest first.  Group 0 (largest pictures) stays on
 	// `stream`; the other groups go to side streams, each walk followed by its own expand.
-	// JSMPEG_B200_PARSE_GROUPS=1 keeps stage 1 on one stream (used for the ncu launch list: ncu
-	// serialises concurrent kernels, so only the unforked run has comparable shares)
-	static const int max_groups = [] {
-		const char *e = getenv("JSMPEG_B200_PARSE_GROUPS");
-		const int g = e ? atoi(e) : PARSE_GROUPS;
-		return g < 1 ? 1 : (g > PARSE_GROUPS ? PARSE_GROUPS : g);
-	}();
 	// the lane-parallel walk (walk.cuh) is the default; JSMPEG_B200_WALK=serial selects the one-chain-per-warp walk
 	static const bool lane_walk = [] {
 		const char *e = getenv("JSMPEG_B200_WALK");
 		return !(e && !strcmp(e, "serial"));
 	}();
 	const size_t walk_smem = lane_walk ? WALK_SMEM_LANES : WALK_SMEM_SERIAL;
-	const int groups = (fork && n_tasks >= 64 * max_groups) ? max_groups : 1;
+	const int groups = parse_group_count(n_tasks, fork != nullptr);
 	if (groups > 1) CUDA_CHECK(cudaEventRecord(fork->fork, stream));
 	for (int g = 0; g < groups; g++) {
 		// equal groups; measured on the 3840-picture wave: unforked 59.8 ms, 4 groups 52.4, 8 groups 50.5,
@@ -157,7 +177,7 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 			    tasks + lo, n, reinterpret_cast<const uint4 *>(ms));
 		if (g == 0 && walk_done) CUDA_CHECK(cudaEventRecord(walk_done, st));
 		dim3 grid((max_mb_size * 6 + CTA_THREADS - 1) / CTA_THREADS, n);
-		expand_blocks_kernel<<<grid, CTA_THREADS, OFF_BLOCKS + CTA_THREADS * TILE_PITCH, st>>>(tasks + lo);
+		expand_blocks_kernel<<<grid, CTA_THREADS, EXPAND_SMEM, st>>>(tasks + lo);
 		if (g > 0) {
 			CUDA_CHECK(cudaEventRecord(fork->join[g], st));
 			CUDA_CHECK(cudaStreamWaitEvent(stream, fork->join[g], 0));

@@ -7,14 +7,15 @@
 // lane-parallel walk is checked against the serial one, and both plus stage 1b against the oracle, on
 // machines without a GPU.  Nothing in the product library is built that way.
 //
-// Compile-time candidates that the emulation has verified and no GPU run has measured yet (DESIGN.md
-// section 10, tools/ab_variants.py) are compiled OUT by default: JSMPEG_LANES_FIXUP,
-// JSMPEG_WALK_EMITS_BLOCKS, JSMPEG_WIDE_REFILL.
+// (Three candidates written at the end of round 1 were measured on the B200 at the start of round 2 and
+// deleted: staged relative records + fix-up instead of the second semantic pass: walk 20.5 -> 18.6 ms
+// but stage 1 unchanged at 29.8 ms; the storing pass writing the block records itself, no stage 1b:
+// walk 29.6 ms, stage 1 45 ms; 16-byte register-cached refills: walk 22.9 ms.  profiles/r2_variants.md.)
 #pragma once
 #include "common.cuh"
 
 #ifndef VLC_TABLE_QUALIFIER
-#define VLC_TABLE_QUALIFIER static __device__ const
+#define VLC_TABLE_QUALIFIER alignas(16) static __device__ const
 #endif
 #include "vlc_tables.h"
 
@@ -32,19 +33,9 @@ constexpr uint32_t OFF_MS = 4096;      // uint16[1 << MS_BITS], after the per-sy
 constexpr uint32_t OFF_MS_FIRST = OFF_MS + (2u << MS_BITS);  // uint16[1 << (MS_BITS - 1)]: dct_coeff_first variant, prefixes with a leading 1 (lane-parallel walk only)
 constexpr uint32_t MS_TABLE_ENTRIES = (1u << MS_BITS) + (1u << (MS_BITS - 1));
 constexpr uint32_t WALK_SMEM_SERIAL = OFF_MS + (2u << MS_BITS), WALK_SMEM_LANES_TABLES = OFF_MS + 2u * MS_TABLE_ENTRIES;
-#ifdef JSMPEG_WALK_EMITS_BLOCKS
-// Round-2 candidate, compiled out of the product by default: the storing pass of the lane-parallel walk
-// decodes the coefficient VALUES too and writes the finished 64 x int16 block records itself (what
-// stage 1b does today, from the parked offsets): the generated DCT table as it is, the zig-zag order,
-// and one 64 x int16 tile per lane.
-constexpr uint32_t OFF_DCT_RAW = 3328;  // uint16[384]: the 768 bytes up to OFF_MS
-constexpr uint32_t OFF_TILES = WALK_SMEM_LANES_TABLES;
-constexpr uint32_t EMIT_TILE_PITCH = 144;  // 128 + 16: equal indices of different lanes on different banks
-constexpr uint32_t WALK_SMEM_LANES = OFF_TILES + (uint32_t)JSMPEG_WALK_THREADS * EMIT_TILE_PITCH;
-static_assert(OFF_DCT_RAW + (VLC_DCT_MAX_Z + 1) * 64 <= OFF_MS, "raw DCT table must fit below the multi-symbol table");
-#else
-constexpr uint32_t WALK_SMEM_LANES = WALK_SMEM_LANES_TABLES;
-#endif
+// lane-parallel walk: after the tables, one 64-byte bitstream ring per lane (BitReaderT<true>)
+constexpr uint32_t OFF_RING = (WALK_SMEM_LANES_TABLES + 15u) & ~15u, RING_BYTES = 64;
+constexpr uint32_t WALK_SMEM_LANES = OFF_RING + (uint32_t)JSMPEG_WALK_THREADS * RING_BYTES;
 
 // shared-memory layout (byte offsets from the dynamic shared base)
 constexpr uint32_t OFF_DCT = 0;                                        // uint16[384]
@@ -55,8 +46,12 @@ constexpr uint32_t OFF_DC_LUMA = OFF_MOTION + (VLC_MOTION_MAX_Z + 1) * 64;  // u
 constexpr uint32_t OFF_DC_CHROMA = OFF_DC_LUMA + 256;                  // uint16[256]
 constexpr uint32_t OFF_TYPE_I = OFF_DC_CHROMA + 512;                   // uint16[4]
 constexpr uint32_t OFF_TYPE_P = OFF_TYPE_I + 8;                        // uint16[64]
-constexpr uint32_t OFF_ZIGZAG = OFF_TYPE_P + 128;                      // uint8[64]
-constexpr uint32_t OFF_BLOCKS = (OFF_ZIGZAG + 64 + 127) & ~127u;       // int16[64] per group
+static_assert(OFF_TYPE_P + 128 <= OFF_MS, "the per-symbol tables end before the multi-symbol table");
+// stage 1b (its own kernel, its own shared memory): the DCT table with values, the two quantiser tables
+// in zig-zag order (SeqParams::xq), one 64 x int16 tile per thread
+constexpr uint32_t EXP_OFF_DCT = 0;                                    // uint16[384]
+constexpr uint32_t EXP_OFF_XQ = EXP_OFF_DCT + (VLC_DCT_MAX_Z + 1) * 64;  // uint16[2][64]
+constexpr uint32_t EXP_OFF_TILES = (EXP_OFF_XQ + 256 + 127) & ~127u;
 
 #ifndef JSMPEG_WALK_EMU
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
@@ -81,50 +76,96 @@ static inline uint32_t lds_u8(uint32_t addr) { return emu_smem[addr]; }
 static inline void sts_s16(uint32_t addr, int v) { const int16_t x = (int16_t)v; memcpy(emu_smem + addr, &x, 2); }
 #endif
 // MSB-first bit window over a byte span (src/buffer.js:152-187); one copy per thread.
-struct BitReader {
-	const uint32_t *words;
+//
+// RING (the lane-parallel walk): the bytes reach the lane through its own 64-byte ring in shared memory,
+// filled by asynchronous 16-byte global -> shared copies (cp.async, SASS LDGSTS) issued three chunks
+// (48 bytes, some forty look-ups) ahead of the read position.  Round 1 refilled with one 4-byte global
+// load per lane, a single word ahead: with 1024 lanes per SM each on its own stream L1 thrashed (hit rate
+// 46 %) and the load's latency was the walk's top stall -- 35 % of all warp-stall samples sat on that
+// one instruction (profiles/r2_walk.md).  A 16-byte register cache per lane (loads still on demand) had
+// been measured slower; what was missing was distance, not width.
+template <bool RING>
+struct BitReaderT {
+	const uint32_t *words;  // 16-byte aligned base of the ES mirror (cudaMalloc), ES_PAD readable bytes past len
 	const uint8_t *bytes;
 	uint32_t len;    // valid bytes; everything past it reads as zero (JS typed-array semantics)
 	uint32_t wpos;   // index of the word held in `nextw` (the next one to enter the window)
 	uint32_t nextw;  // prefetched
 	uint64_t win;    // left-aligned window
 	int nbits;       // valid bits in win, >= 32 between calls
-#ifdef JSMPEG_WIDE_REFILL
-	// Round-2 candidate, compiled out by default: refills come from a 16-byte register cache, one
-	// 128-bit load per four words (the lane-parallel walk's top stall is the per-lane 4-byte load).
-	// Needs the ES base 16-byte aligned and 12 readable bytes past the last word (cudaMalloc + ES_PAD).
-	mutable uint4 cache;
-	mutable uint32_t cache_quad;  // index of the cached 16 bytes, 0xffffffff = none
-#endif
+	uint32_t ring;   // RING: shared-window address of this lane's ring (4 chunks of 16 bytes, chunk q in slot q & 3)
+	uint32_t qhead;  // RING: chunks below qhead have been requested
 
-	// (Measured and rejected on the 3840-picture wave: a branch-free variant relying on the zero pad
-	// after the data, 17 % slower; a software prefetch 256 B ahead at every refill, 7 % slower.)
-	__device__ __forceinline__ uint32_t load_word(uint32_t w) const {
-		const uint32_t byte = w * 4u;
-		if (byte >= len) return 0u;
-#ifdef JSMPEG_WIDE_REFILL
-		const uint32_t quad = w >> 2;
-		if (quad != cache_quad) {
-			cache = __ldg(reinterpret_cast<const uint4 *>(words) + quad);
-			cache_quad = quad;
-		}
-		const uint32_t k = w & 3u;
-		uint32_t v = __byte_perm(k == 0 ? cache.x : (k == 1 ? cache.y : (k == 2 ? cache.z : cache.w)), 0, 0x0123);
-#else
-		uint32_t v = __byte_perm(__ldg(words + w), 0, 0x0123);  // first byte -> MSB
-#endif
+	__device__ __forceinline__ uint32_t finish_word(uint32_t raw, uint32_t byte) const {
+		uint32_t v = __byte_perm(raw, 0, 0x0123);  // first byte -> MSB
 		const uint32_t left = len - byte;
 		if (left < 4u) v &= 0xffffffffu << (8u * (4u - left));
 		return v;
 	}
-	__device__ __forceinline__ void seek_byte(uint32_t byte_pos) {
-#ifdef JSMPEG_WIDE_REFILL
-		cache_quad = 0xffffffffu;
+	// any word, straight from global memory (random access: the slice-end search)
+	__device__ __forceinline__ uint32_t load_word_direct(uint32_t w) const {
+		const uint32_t byte = w * 4u;
+		if (byte >= len) return 0u;
+		return finish_word(__ldg(words + w), byte);
+	}
+#if !defined(JSMPEG_WALK_EMU)
+	// one commit group per chunk.  No branch: a chunk past the data is fetched from the zeroed pad behind
+	// it (clamped to the pad's first chunk, which is all zero and inside the allocation)
+	__device__ __forceinline__ void ring_request(uint32_t q) {
+		const uint32_t off = min(q << 4, (len + 15u) & ~15u);
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + ((q & 3u) << 4)), "l"(bytes + off) : "memory");
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	}
+	__device__ __forceinline__ uint32_t ring_word(uint32_t w) const {
+		uint32_t v;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + ((w & 15u) << 2)) : "memory");
+		return v;
+	}
 #endif
+	// the next word of a sequential read (w only grows between seeks)
+	// (Measured and rejected in round 1 for the global-load refill: a branch-free variant relying on the zero
+	// pad after the data, 17 % slower; a software prefetch 256 B ahead at every refill, 7 % slower.)
+	__device__ __forceinline__ uint32_t load_word(uint32_t w) {
+#if !defined(JSMPEG_WALK_EMU)
+		if (RING) {
+			// No test against len and no tail mask here: the mirror is followed by zeroed bytes (ES_PAD), a chunk
+			// past them is fetched from the pad too (ring_request), and no walk runs more than a macroblock
+			// header past the end of the data before it stops.
+			if ((w & 3u) == 0u) {  // first word of chunk q: chunk q - 1 is consumed; exactly one request keeps qhead = q + 4
+				ring_request(qhead++);
+				asm volatile("cp.async.wait_group 3;" ::: "memory");  // everything but the three newest chunks has landed
+			}
+			return __byte_perm(ring_word(w), 0, 0x0123);  // first byte -> MSB
+		}
+#endif
+		const uint32_t byte = w * 4u;
+		if (byte >= len) return 0u;
+		return finish_word(__ldg(words + w), byte);
+	}
+	__device__ __forceinline__ void seek_byte(uint32_t byte_pos) {
 		const uint32_t w = byte_pos >> 2;
-		win = ((uint64_t)load_word(w) << 32) | load_word(w + 1);
-		wpos = w + 2;
-		nextw = load_word(wpos);
+#if !defined(JSMPEG_WALK_EMU)
+		if (RING) {
+			asm volatile("cp.async.wait_all;" ::: "memory");  // nothing requested for the old position may still be landing
+			const uint32_t q0 = w >> 2;
+			ring_request(q0); ring_request(q0 + 1u); ring_request(q0 + 2u); ring_request(q0 + 3u);
+			qhead = q0 + 4u;
+			asm volatile("cp.async.wait_all;" ::: "memory");
+			auto raw = [&](uint32_t x) { return __byte_perm(ring_word(x), 0, 0x0123); };
+			win = ((uint64_t)raw(w) << 32) | raw(w + 1);
+			wpos = w + 2;
+			nextw = raw(wpos);
+			// w .. w + 2 lie in chunks q0, q0 + 1.  If they reach into q0 + 1, chunk q0 is consumed and that
+			// chunk's turn to extend the ring (load_word, first word of a chunk) is taken here -- after the
+			// reads, the new chunk goes into q0's slot -- so that qhead = (chunk of the next word) + 4 holds
+			if (((w + 2u) >> 2) != q0) ring_request(qhead++);
+		} else
+#endif
+		{
+			win = ((uint64_t)load_word(w) << 32) | load_word(w + 1);
+			wpos = w + 2;
+			nextw = load_word(wpos);
+		}
 		nbits = 64;
 		const int drop = (int)(byte_pos & 3u) * 8;
 		if (drop) consume(drop);
@@ -176,6 +217,7 @@ struct BitReader {
 		return -1;
 	}
 };
+using BitReader = BitReaderT<false>;  // stage 1b and the serial-walk kernel: plain global loads
 
 
 struct PictureState {
@@ -223,11 +265,11 @@ __device__ __forceinline__ uint16_t walk_entry(uint16_t e) {
 // One coded block (bitstream side of src/mpeg1.js:698-811): intra DC with its predictor, then only
 // code lengths.  Leaves {bit offset of the first coefficient code, dc * 8} in the block's slot.
 // head: DC size VLC + differential + predictor (mpeg1.js:705-751), the parked pair, dct_coeff_first
-template <bool DEFER, bool RAW_DC = false>
-__device__ __forceinline__ bool walk_block_head(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
-                                                uint32_t *__restrict__ slot, bool store, int &n, bool &defer_first) {
+template <bool DEFER, class BR>
+__device__ __forceinline__ bool walk_block_head(BR &br, uint32_t sbase, PictureState &ps, bool intra, int block,
+                                                uint2 *__restrict__ park, bool store, int &n, bool &defer_first) {
 	n = 0;
-	int dc8 = 0, dc_raw = 0;
+	int dc8 = 0;
 	if (intra) {
 		const uint32_t w = br.peek32();
 		const uint32_t e = block < 4 ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
@@ -250,12 +292,10 @@ __device__ __forceinline__ bool walk_block_head(BitReader &br, uint32_t sbase, P
 			}
 		}
 		*pred = dc;
-		dc_raw = dc;
 		dc8 = max(-32768, min(32767, dc * 8));  // x PREMULTIPLIER[0] = dc << 8 in stage 2 (mpeg1.js:747)
 		n = 1;
 	}
-	if (RAW_DC) *reinterpret_cast<uint2 *>(slot) = make_uint2(br.bitpos(), (uint32_t)dc_raw);  // staged: predictor value, possibly relative
-	else if (store) *reinterpret_cast<uint2 *>(slot) = make_uint2(br.bitpos(), (uint32_t)dc8 & 0xffffu);
+	if (store) *park = make_uint2(br.bitpos(), (uint32_t)dc8 & 0xffffu);
 	if (DEFER) {
 		defer_first = !intra;  // the caller's first look-up resolves dct_coeff_first (ac_step)
 	} else if (!intra && (br.peek32() >> 31)) {  // dct_coeff_first: a leading '1' is (0, +-1), never end_of_block
@@ -269,11 +309,12 @@ __device__ __forceinline__ void walk_block_tail(PictureState &ps, int n, bool &d
 	dc_only = (n == 1);  // mpeg1.js:838, 850
 	ps.n_coded++;
 }
-__device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, PictureState &ps, bool intra, int block,
-                                           uint32_t *__restrict__ slot, bool store, bool &dc_only) {
+template <class BR>
+__device__ __forceinline__ bool walk_block(BR &br, uint32_t sbase, PictureState &ps, bool intra, int block,
+                                           uint2 *__restrict__ park, bool store, bool &dc_only) {
 	int n;
 	bool unused;
-	if (!walk_block_head<false>(br, sbase, ps, intra, block, slot, store, n, unused)) return false;
+	if (!walk_block_head<false>(br, sbase, ps, intra, block, park, store, n, unused)) return false;
 	for (;;) {
 		const uint32_t w = br.peek32();
 		// (Resolving '10' / '11s' arithmetically before the look-up was measured 8 % SLOWER: it defeats the
@@ -310,7 +351,8 @@ __device__ __forceinline__ bool walk_block(BitReader &br, uint32_t sbase, Pictur
 // '1' is (0, +-1) and never end_of_block (mpeg1.js:757-760): a second table covers that case so that
 // a block start costs no extra trip.  The escape is resolved before the clz table: with 32 chains in
 // lock-step every path some lane needs is issued for all, so the rare path must stay rare.
-__device__ __forceinline__ int ac_step(BitReader &br, uint32_t sbase, int &n, bool combine, bool first) {
+template <class BR>
+__device__ __forceinline__ int ac_step(BR &br, uint32_t sbase, int &n, bool combine, bool first) {
 	// every path only decides (bits, run sum, end_of_block); the window moves ONCE, after they rejoin
 	const uint32_t w = br.peek32();
 	const bool lead = first && (w >> 31);
@@ -338,67 +380,10 @@ __device__ __forceinline__ int ac_step(BitReader &br, uint32_t sbase, int &n, bo
 	return ret;
 }
 
-#ifdef JSMPEG_WALK_EMITS_BLOCKS
-// One coefficient code WITH its value (mpeg1.js:757-790): 0 = a coefficient (run, signed level),
-// 1 = end_of_block consumed, 2 = invalid code.
-__device__ __forceinline__ int ac_step_value(BitReader &br, uint32_t sbase, bool first, int &run, int &level) {
-	const uint32_t w = br.peek32();
-	int len;
-	if (first && (w >> 31)) {  // dct_coeff_first '1s'
-		run = 0;
-		level = (w & 0x40000000u) ? -1 : 1;
-		len = 2;
-	} else if ((w >> 26) == 1u) {  // escape: 6-bit run, 8 (+8) bit level (mpeg1.js:767-780)
-		run = (int)((w >> 20) & 63u);
-		const int l8 = (int)((w >> 12) & 255u);
-		if ((l8 & 127) == 0) { level = (int)((w >> 4) & 255u) - (l8 << 1); len = 28; }  // l8 == 128: second byte - 256
-		else { level = l8 > 128 ? l8 - 256 : l8; len = 20; }
-	} else {
-		const int z = __clz((int)w);
-		if (z > VLC_DCT_MAX_Z) return 2;
-		const uint32_t e = lds_u16(sbase + OFF_DCT_RAW + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
-		const int l = (int)(e & 31u);
-		if (l == 0) return 2;
-		run = (int)((e >> 5) & 31u);
-		level = (int)(e >> 10);
-		if (level == 0) {  // end_of_block (the escape was taken above)
-			br.consume(l);
-			return 1;
-		}
-		if ((w >> (31 - l)) & 1u) level = -level;
-		len = l + 1;
-	}
-	br.consume(len);
-	return 0;
-}
-// dequantise, oddify toward zero, clip (mpeg1.js:794-807) and put the value into the lane's tile
-__device__ __forceinline__ void emit_coefficient(uint32_t sbase, uint32_t tile, int n, int level, bool intra, int qs, const uint8_t *__restrict__ quant) {
-	const uint32_t idx = lds_u8(sbase + OFF_ZIGZAG + (uint32_t)n);
-	level <<= 1;
-	if (!intra) level += level < 0 ? -1 : 1;
-	level = (level * qs * (int)__ldg(quant + idx)) >> 4;
-	if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
-	level = max(-2048, min(2047, level));
-	sts_s16(tile + idx * 2u, level);
-}
-// the finished tile -> the block's 128-byte record (one TMA bulk store, as in stage 1b), then clear it
-__device__ __forceinline__ void emit_block(uint32_t tile, void *slot) {
-#ifndef JSMPEG_WALK_EMU
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(slot), "r"(tile) : "memory");
-	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-#pragma unroll
-	for (int i = 0; i < 8; i++) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(tile + i * 16), "r"(0u) : "memory");
-#else
-	memcpy(slot, emu_smem + tile, 128);
-	memset(emu_smem + tile, 0, 128);
-#endif
-}
-#endif
 
 // mpeg1.js:395-457, one component
-__device__ __forceinline__ bool parse_motion(BitReader &br, uint32_t sbase, const PictureState &ps, int &prev, int &mv) {
+template <class BR>
+__device__ __forceinline__ bool parse_motion(BR &br, uint32_t sbase, const PictureState &ps, int &prev, int &mv) {
 	const uint32_t e = clz_lut(sbase + OFF_MOTION, br.peek32(), VLC_MOTION_MAX_Z);
 	const int len = e & 31;
 	if (len == 0) return false;
@@ -417,7 +402,8 @@ __device__ __forceinline__ bool parse_motion(BitReader &br, uint32_t sbase, cons
 	return true;
 }
 
-__device__ __forceinline__ int read_mba(BitReader &br, uint32_t sbase) {
+template <class BR>
+__device__ __forceinline__ int read_mba(BR &br, uint32_t sbase) {
 	const uint32_t e = clz_lut(sbase + OFF_MBA, br.peek32(), VLC_MBA_MAX_Z);
 	const int len = e & 31;
 	if (len == 0) return -1;
@@ -434,38 +420,24 @@ __device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int 
 	return r;
 }
 
-#ifdef JSMPEG_WALK_EMU
-#define WK_EMU_SYNC() __syncwarp()
-#define WK_THREAD_IN_CTA() (emu::lane)
-#else
-#define WK_EMU_SYNC() ((void)0)
-#define WK_THREAD_IN_CTA() (threadIdx.x)
-#endif
-
 // How a macroblock is walked:
 //   WALK_SERIAL  the whole warp walks the same macroblock redundantly, lane 0 stores (one warp = one chain)
 //   WALK_REL     one lane walks it, nothing is stored and no address is checked: the state is RELATIVE to the
 //                unknown state at the lane's first macroblock (summary pass of the lane-parallel walk)
 //   WALK_ABS     one lane walks it with the true state and stores; cases the lane-parallel walk leaves to
 //                the serial walk set ps.anomaly
-//   WALK_STAGE   (JSMPEG_LANES_FIXUP builds) WALK_REL that also leaves every macroblock as a relative
-//                record in a staging area; a fix-up then replaces the WALK_ABS pass
-enum { WALK_SERIAL = 0, WALK_REL = 1, WALK_ABS = 2, WALK_STAGE = 3 };
+enum { WALK_SERIAL = 0, WALK_REL = 1, WALK_ABS = 2 };
 
 struct MbHead {
 	int mb, cbp, mv_h, mv_v, qscale;
 	bool intra;
 	uint32_t bit_pos;
-	// WALK_STAGE only: the run of skipped macroblocks in front of this one
-	int n_skip, skip_first, skip_qs;
-	bool skip_qs_set;
-	uint32_t skip_bit;
 };
 
 // mpeg1.js:294-384, decodeMacroblock up to the blocks.  0: the blocks of h.cbp follow; 1: nothing more
 // to do for this macroblock, the slice goes on; 2: stop walking this slice.
-template <int MODE>
-__device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane, MbHead &h) {
+template <int MODE, class BR>
+__device__ __forceinline__ int walk_mb_header(BR &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane, MbHead &h) {
 	int increment = 0;
 	int v = read_mba(br, sbase);
 	while (v == 34) v = read_mba(br, sbase);                       // macroblock_stuffing
@@ -481,30 +453,24 @@ __device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, Pic
 		if (MODE == WALK_ABS && ps.mb_addr + increment >= mb_size) { ps.anomaly = true; return 2; }
 		if (increment > 1) {  // mpeg1.js:323-334
 			ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;
-			if (MODE == WALK_REL || MODE == WALK_STAGE) ps.dc_abs = true;
+			if (MODE == WALK_REL) ps.dc_abs = true;
 			if (ps.picture_type == 2) {
 				ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;
-				if (MODE == WALK_REL || MODE == WALK_STAGE) ps.mv_abs = true;
+				if (MODE == WALK_REL) ps.mv_abs = true;
 			}
 			// skipped macroblocks: predicted copy with the current vector (mpeg1.js:336-346)
 			const int n_skip = increment - 1;
 			const uint4 rec = pack_record(ps.mv_h, ps.mv_v, MBF_PRESENT | MBF_SKIPPED, 0, 0, ps.qscale, br.bitpos());
 			if (MODE == WALK_SERIAL) {
-				// In a broken stream these addresses may have been stored before, or be stored again later,
-				// by lane 0 (a macroblock record).  The converged warp issues the stores in program order;
-				// the host emulation, whose lanes run independently between collectives, needs the order
-				// spelled out.  (Making these unconditional __syncwarp()s is on the round-2 list: two
-				// instructions, wants a GPU run.)
-				WK_EMU_SYNC();
+				// In a broken stream these addresses may have been stored before, or be stored again later, by
+				// lane 0 (a macroblock record): the order of the lanes' stores is part of the result, and
+				// independent thread scheduling promises no program order between lanes without this.
+				__syncwarp();
 				for (int k = lane; k < n_skip; k += 32) reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
-				WK_EMU_SYNC();
+				__syncwarp();
 			}
 			if (MODE == WALK_ABS)
 				for (int k = 0; k < n_skip; k++) reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
-			if (MODE == WALK_STAGE) {
-				h.n_skip = n_skip; h.skip_first = ps.mb_addr + 1; h.skip_qs = ps.qscale; h.skip_qs_set = ps.qs_set;
-				h.skip_bit = br.bitpos();
-			}
 			ps.n_present += n_skip;
 			ps.mb_addr += n_skip;
 		}
@@ -512,7 +478,7 @@ __device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, Pic
 	}
 	const int mb = ps.mb_addr;
 	h.mb = mb;
-	if (MODE != WALK_REL && MODE != WALK_STAGE && (mb < 0 || mb >= mb_size)) {  // outside the picture: never write there
+	if (MODE != WALK_REL && (mb < 0 || mb >= mb_size)) {  // outside the picture: never write there
 		if (MODE == WALK_ABS) ps.anomaly = true;
 		return 2;
 	}
@@ -527,22 +493,22 @@ __device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, Pic
 	h.intra = intra;
 	if (type & 0x10) {
 		ps.qscale = (int)br.read(5);
-		if (MODE == WALK_REL || MODE == WALK_STAGE) ps.qs_set = true;
+		if (MODE == WALK_REL) ps.qs_set = true;
 	}
 	h.bit_pos = br.bitpos();
 
 	if (intra) {
 		ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:363-367
-		if (MODE == WALK_REL || MODE == WALK_STAGE) ps.mv_abs = true;
+		if (MODE == WALK_REL) ps.mv_abs = true;
 	} else {
 		ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;                  // mpeg1.js:370-372
-		if (MODE == WALK_REL || MODE == WALK_STAGE) ps.dc_abs = true;
+		if (MODE == WALK_REL) ps.dc_abs = true;
 		if (type & 0x08) {
 			if (!parse_motion(br, sbase, ps, ps.mv_h_prev, ps.mv_h)) return 2;
 			if (!parse_motion(br, sbase, ps, ps.mv_v_prev, ps.mv_v)) return 2;
 		} else if (ps.picture_type == 2) {
 			ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:452-456
-			if (MODE == WALK_REL || MODE == WALK_STAGE) ps.mv_abs = true;
+			if (MODE == WALK_REL) ps.mv_abs = true;
 		}
 	}
 
@@ -560,20 +526,21 @@ __device__ __forceinline__ int walk_mb_header(BitReader &br, uint32_t sbase, Pic
 }
 
 // mpeg1.js:294-392 decodeMacroblock, serial.  false = stop walking this slice.
-__device__ bool walk_macroblock(BitReader &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
+template <class BR>
+__device__ bool walk_macroblock(BR &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
 	MbHead h;
 	const int r = walk_mb_header<WALK_SERIAL>(br, sbase, ps, t, mb_size, lane, h);
 	if (r) return r == 1;
 	const int mb = h.mb, cbp = h.cbp;
 	const bool intra = h.intra;
-	uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)mb * (MB_COEF_INT16 / 2);
+	uint2 *park_mb = t.park + (size_t)mb * 6;
 	int done = 0, dc_mask = 0;
 	bool ok = true;
 #pragma unroll 1
 	for (int block = 0; block < 6; block++) {
 		if (cbp & (0x20 >> block)) {
 			bool dc_only;
-			ok = walk_block(br, sbase, ps, intra, block, coef_mb + block * 32, lane == 0, dc_only);
+			ok = walk_block(br, sbase, ps, intra, block, park_mb + block, lane == 0, dc_only);
 			if (!ok) break;
 			done |= 0x20 >> block;
 			if (dc_only) dc_mask |= 0x20 >> block;
@@ -657,7 +624,8 @@ __device__ __forceinline__ uint32_t syn_guess(const SliceConst &sc) { return syn
 // the same stage at the same time.  (Left to themselves, lanes that leave a loop early never wait for
 // the others: measured on B200, the first version ran with 4 of 32 lanes active on average and its
 // per-lane macroblock loops with ONE.)
-__device__ void syntax_run(BitReader &br, uint32_t sbase, const SliceConst &sc, bool live, uint32_t limit, uint32_t &st) {
+template <class BR>
+__device__ void syntax_run(BR &br, uint32_t sbase, const SliceConst &sc, bool live, uint32_t limit, uint32_t &st) {
 	int ph = (int)(st & 15u);
 	uint32_t rem = (st >> 4) & 63u, ty = st >> 10;
 	const uint32_t guess_ty = sc.picture_type == 1 ? 1u : 0u;
@@ -793,11 +761,12 @@ __device__ __forceinline__ LaneSum shfl_up_sum(const LaneSum &s, int d) {
 
 // The byte index of the first start code prefix (00 00 01) at or after `from`, or len: where
 // nextBytesAreStartCode (buffer.js:141-150) first becomes true.  The warp scans 128 bytes per step.
-__device__ uint32_t find_slice_end(const BitReader &br, uint32_t from, int lane) {
+template <class BR>
+__device__ uint32_t find_slice_end(const BR &br, uint32_t from, int lane) {
 	const uint32_t len = br.len;
 	for (uint32_t base = from >> 2; base * 4u < len; base += 32u) {
 		const uint32_t wi = base + (uint32_t)lane;
-		const uint64_t x = ((uint64_t)br.load_word(wi) << 32) | br.load_word(wi + 1u);  // bytes 4 wi .. 4 wi + 7
+		const uint64_t x = ((uint64_t)br.load_word_direct(wi) << 32) | br.load_word_direct(wi + 1u);  // bytes 4 wi .. 4 wi + 7
 		uint32_t hit = 0xffffffffu;
 #pragma unroll
 		for (int k = 3; k >= 0; k--) {
@@ -815,48 +784,21 @@ __device__ uint32_t find_slice_end(const BitReader &br, uint32_t from, int lane)
 // start code, 2 on anything else; stop_pos = the bit position after the lane's last macroblock.
 // WARP-SYNCHRONOUS like syntax_run: one vote closes the macroblock loop, one every look-up of the
 // coefficient loop.
-// WALK_STAGE: where a lane leaves its macroblocks as relative records.  Entry j is the upper half
-// (bytes 64..127) of the picture's j-th 128-byte coefficient slot -- free until stage 1b fills the
-// slots, and never the 8 bytes at a slot's start where the final parked pairs go.  16 words:
-//   0      motion predictors after the macroblock's header (int16 h | int16 v << 16), or n_skip of a skip entry
-//   1      flags (1 intra, 2 skip entry, 4 motion absolute, 8 DC absolute, 16 quantiser scale set)
-//          | cbp << 8 | dc_only mask << 16 | quantiser scale << 24
-//   2      bit_pos            3   macroblock address relative to the lane's start (skip entry: the first skipped one)
-//   4..15  per block {bit offset of the first coefficient code, DC predictor value (relative unless flag 8)}
-struct StageArea {
-	uint32_t *base;  // entry j at base + j * 32 (words); the lane's entries are [first, first + cap)
-	int first, cap, count;
-};
-__device__ __forceinline__ uint32_t *stage_entry(const StageArea &sa, int k) { return sa.base + (size_t)(sa.first + k) * 32u + 16u; }
-
-template <int MODE>
-__device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const ParseTask &t, int mb_size, bool owns,
-                          uint32_t limit, uint32_t end_byte, int lane, uint32_t &stop_pos, StageArea *sa = nullptr) {
+template <int MODE, class BR>
+__device__ int walk_owned(BR &br, uint32_t sbase, PictureState &ls, const ParseTask &t, int mb_size, bool owns,
+                          uint32_t limit, uint32_t end_byte, int lane, uint32_t &stop_pos) {
 	int how = 0;
 	bool work = owns;
 	if (owns) stop_pos = br.bitpos();
 	while (WK_VOTE(VOTE_OWN_MB, work)) {
 		MbHead h;
 		h.mb = 0; h.cbp = 0; h.mv_h = h.mv_v = h.qscale = 0; h.intra = false; h.bit_pos = 0;
-		h.n_skip = 0; h.skip_first = 0; h.skip_qs = 0; h.skip_qs_set = false; h.skip_bit = 0;
 		bool in_mb = false;
 		if (work) {
 			if (walk_mb_header<MODE>(br, sbase, ls, t, mb_size, lane, h) != 0) { how = 2; work = false; }
 			else in_mb = true;
 		}
-		uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)(MODE == WALK_ABS ? h.mb : 0) * (MB_COEF_INT16 / 2);
-		if (MODE == WALK_STAGE && in_mb) {
-			if (sa->count + (h.n_skip > 0 ? 2 : 1) > sa->cap) {  // more macroblocks than the lane has room to stage
-				how = 2; work = false; in_mb = false;
-			} else {
-				if (h.n_skip > 0) {
-					uint32_t *e = stage_entry(*sa, sa->count++);
-					*reinterpret_cast<uint4 *>(e) = make_uint4((uint32_t)h.n_skip, 2u | (h.skip_qs_set ? 16u : 0u) | ((uint32_t)h.skip_qs << 24),
-					                                          h.skip_bit, (uint32_t)h.skip_first);
-				}
-				coef_mb = stage_entry(*sa, sa->count) + 4;  // the blocks' pairs go straight into the entry
-			}
-		}
+		uint2 *park_mb = t.park + (size_t)(MODE == WALK_ABS ? h.mb : 0) * 6;
 		int done = 0, dc_mask = 0;
 		// the coded blocks of the macroblock, one look-up per trip; a block's head (intra DC, the parked
 		// pair) rides on the trip of its first look-up
@@ -864,51 +806,12 @@ __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const
 		bool at_head = true, first = false;
 		int n = 0;
 		bool in = rem != 0;
-#ifdef JSMPEG_WALK_EMITS_BLOCKS
-		if (MODE == WALK_ABS) {  // the storing pass decodes the values and writes the finished block records itself
-			const uint32_t tile = sbase + OFF_TILES + (uint32_t)(WK_THREAD_IN_CTA()) * EMIT_TILE_PITCH;
-			const uint8_t *__restrict__ quant = h.intra ? t.seq->intra_q : t.seq->non_intra_q;
-			while (WK_VOTE(VOTE_OWN_AC, in)) {
-				if (in) {
-					const int block = __clz((int)rem) - 26;
-					bool ok = true;
-					if (at_head) {
-						uint2 pair = make_uint2(0u, 0u);
-						ok = walk_block_head<true>(br, sbase, ls, h.intra, block, reinterpret_cast<uint32_t *>(&pair), true, n, first);
-						if (ok && h.intra) sts_s16(tile, (int)(int16_t)(pair.y & 0xffffu));  // coefficient 0 = dc * 8
-						at_head = false;
-					}
-					int run = 0, level = 0;
-					const int r = ok ? ac_step_value(br, sbase, first, run, level) : 2;
-					first = false;
-					if (r == 2) { how = 2; work = false; in_mb = false; in = false; }
-					else if (r == 0) {
-						n += run;
-						if (n <= 63) emit_coefficient(sbase, tile, n, level, h.intra, h.qscale, quant);  // beyond 63: dropped, like JS
-						n++;
-						if (n > 4096) { how = 2; work = false; in_mb = false; in = false; }  // (cannot happen after a clean pass C)
-					} else {
-						emit_block(tile, coef_mb + block * 32);
-						bool dc_only;
-						walk_block_tail(ls, n, dc_only);
-						done |= 0x20 >> block;
-						if (dc_only) dc_mask |= 0x20 >> block;
-						rem &= ~(0x20u >> block);
-						at_head = true;
-						if (rem == 0) in = false;
-					}
-				}
-			}
-		} else
-#endif
 		while (WK_VOTE(VOTE_OWN_AC, in)) {
 			if (in) {
 				const int block = __clz((int)rem) - 26;  // mask bit 0x20 >> block
 				bool ok = true;
 				if (at_head) {
-					ok = MODE == WALK_STAGE
-					         ? walk_block_head<true, true>(br, sbase, ls, h.intra, block, coef_mb + block * 2, false, n, first)
-					         : walk_block_head<true>(br, sbase, ls, h.intra, block, coef_mb + block * 32, MODE == WALK_ABS, n, first);
+					ok = walk_block_head<true>(br, sbase, ls, h.intra, block, park_mb + block, MODE == WALK_ABS, n, first);
 					at_head = false;
 				}
 				const int r = ok ? ac_step(br, sbase, n, true, first) : 2;
@@ -929,13 +832,6 @@ __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const
 			if (MODE == WALK_ABS)
 				reinterpret_cast<uint4 *>(t.hdr)[h.mb] =
 				    pack_record(h.mv_h, h.mv_v, MBF_PRESENT | (h.intra ? MBF_INTRA : 0), done, dc_mask, h.qscale, h.bit_pos);
-			if (MODE == WALK_STAGE) {
-				uint32_t *e = stage_entry(*sa, sa->count++);
-				const uint32_t flags = (h.intra ? 1u : 0u) | (ls.mv_abs ? 4u : 0u) | (ls.dc_abs ? 8u : 0u) | (ls.qs_set ? 16u : 0u);
-				*reinterpret_cast<uint4 *>(e) =
-				    make_uint4(((uint32_t)ls.mv_h_prev & 0xffffu) | ((uint32_t)ls.mv_v_prev << 16),
-				               flags | ((uint32_t)done << 8) | ((uint32_t)dc_mask << 16) | ((uint32_t)h.qscale << 24), h.bit_pos, (uint32_t)h.mb);
-			}
 			ls.n_present++;
 			const uint32_t pos = br.bitpos();
 			const uint32_t i = (pos + 7u) >> 3;
@@ -950,7 +846,8 @@ __device__ int walk_owned(BitReader &br, uint32_t sbase, PictureState &ls, const
 // One slice: the reader is at its first macroblock (bit p_start), `ps` holds the picture constants and
 // the slice's initial state (mb_addr, qscale).  true: records stored, ps totals updated, reader at the
 // start code prefix that ended the slice.  false: outside the clean domain, nothing is to be trusted.
-__device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
+template <class BR>
+__device__ bool walk_slice_lanes(BR &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
 	const uint32_t p_start = br.bitpos();
 	const uint32_t end_byte = find_slice_end(br, (p_start + 7u) >> 3, lane);
 	if (((p_start + 7u) >> 3) >= end_byte) return false;
@@ -995,17 +892,7 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 		ls.n_present = ls.n_coded = ls.error = 0;
 	}
 	uint32_t stop_pos = q;
-#ifdef JSMPEG_LANES_FIXUP
-	if (!owns) ls.n_present = ls.n_coded = ls.error = 0;  // this pass's counts are the final ones
-	StageArea sa;
-	sa.base = reinterpret_cast<uint32_t *>(t.coef);
-	sa.cap = mb_size * 6 / K;  // the picture's block slots, shared out among the lanes in use
-	sa.first = active ? lane * sa.cap : 0;
-	sa.count = 0;
-	how = walk_owned<WALK_STAGE>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos, &sa);
-#else
 	how = walk_owned<WALK_REL>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos);
-#endif
 	const uint32_t next_q = __shfl_down_sync(FULL_MASK, q, 1);
 	if (active && lane < K - 1 && stop_pos != next_q) bad = true;  // the warm-up of lane + 1 had not merged
 	if (owns) {
@@ -1029,53 +916,6 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 	const LaneSum before = shfl_up_sum(sum, 1);
 	const LaneSum x = lane == 0 ? x0 : compose(x0, before, ps.f);
 
-#ifdef JSMPEG_LANES_FIXUP
-	// ---- F: no second walk -- the staged relative records become the final ones.  Every staged value is
-	// cumulative since the lane's start, so each entry only needs the lane's absolute start state `x`.
-	{
-		int k = 0;
-		while (WK_VOTE(VOTE_OWN_MB, k < sa.count)) {
-			if (k < sa.count) {
-				const uint32_t *e = stage_entry(sa, k);
-				const uint4 w = *reinterpret_cast<const uint4 *>(e);
-				const uint32_t flags = w.y & 0xffu;
-				const int qs = (flags & 16u) ? (int)(w.y >> 24) : x.qs;
-				const int mb = x.d_addr + (int)w.w;
-				if (flags & 2u) {  // a run of skipped macroblocks (mpeg1.js:323-346): zero vector, the scale in force
-					const int n_skip = (int)w.x;
-					if (mb < 0 || mb + n_skip > mb_size) bad = true;
-					else {
-						const uint4 rec = pack_record(0, 0, MBF_PRESENT | MBF_SKIPPED, 0, 0, qs, w.z);
-						for (int i = 0; i < n_skip; i++) reinterpret_cast<uint4 *>(t.hdr)[mb + i] = rec;
-					}
-				} else if (mb < 0 || mb >= mb_size) {
-					bad = true;
-				} else {
-					int ph = (int)(int16_t)(w.x & 0xffffu), pv = (int)(int16_t)(w.x >> 16);
-					if (!(flags & 4u)) { ph = wrap_mv(x.mvh + ph, ps.f); pv = wrap_mv(x.mvv + pv, ps.f); }
-					const int cbp = (int)((w.y >> 8) & 0xffu);
-					uint32_t *coef_mb = reinterpret_cast<uint32_t *>(t.coef) + (size_t)mb * (MB_COEF_INT16 / 2);
-					for (int block = 0; block < 6; block++) {
-						if (!(cbp & (0x20 >> block))) continue;
-						const uint2 pr = *reinterpret_cast<const uint2 *>(e + 4 + block * 2);
-						int dc8 = 0;
-						if (flags & 1u) {
-							int dc = (int)pr.y;
-							if (!(flags & 8u)) dc += block < 4 ? x.dcy : (block == 4 ? x.dc4 : x.dc5);
-							dc8 = max(-32768, min(32767, dc * 8));
-						}
-						*reinterpret_cast<uint2 *>(coef_mb + block * 32) = make_uint2(pr.x, (uint32_t)dc8 & 0xffffu);
-					}
-					reinterpret_cast<uint4 *>(t.hdr)[mb] =
-					    pack_record(ps.full_pel ? ph * 2 : ph, ps.full_pel ? pv * 2 : pv, MBF_PRESENT | ((flags & 1u) ? MBF_INTRA : 0),
-					                cbp, (int)((w.y >> 16) & 0xffu), qs, w.z);
-				}
-				k++;
-			}
-		}
-	}
-	if (__any_sync(FULL_MASK, bad)) return false;
-#else
 	// ---- D: the owned macroblocks again, absolute, storing
 	ls.n_present = ls.n_coded = ls.error = 0;
 	ls.anomaly = false;
@@ -1090,7 +930,6 @@ __device__ bool walk_slice_lanes(BitReader &br, uint32_t sbase, PictureState &ps
 	const int how_abs = walk_owned<WALK_ABS>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos);
 	if (how_abs != how || ls.anomaly) bad = true;
 	if (__any_sync(FULL_MASK, bad)) return false;
-#endif
 	int n_present = ls.n_present, n_coded = ls.n_coded, error = ls.error;
 	for (int d = 16; d > 0; d >>= 1) {
 		n_present += __shfl_xor_sync(FULL_MASK, n_present, d);
@@ -1120,14 +959,6 @@ __device__ __forceinline__ void walk_tables_init(uint8_t *smem, int tid, int nth
 	for (int i = tid; i < 64; i += nthreads) s16[OFF_TYPE_P / 2 + i] = VLC_MBTYPE_P[i];
 	uint4 *ms = reinterpret_cast<uint4 *>(smem + OFF_MS);
 	const int n16 = (int)(with_first ? 2u * MS_TABLE_ENTRIES : (2u << MS_BITS)) / 16;
-#ifdef JSMPEG_WALK_EMITS_BLOCKS
-	if (with_first) {
-		for (int i = tid; i < (VLC_DCT_MAX_Z + 1) * 32; i += nthreads) s16[OFF_DCT_RAW / 2 + i] = VLC_DCT_COEFF[i];
-		for (int i = tid; i < 64; i += nthreads) smem[OFF_ZIGZAG + i] = TBL_ZIG_ZAG[i];
-		uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + OFF_TILES);
-		for (int i = tid; i < nthreads * (int)(EMIT_TILE_PITCH / 4); i += nthreads) tiles[i] = 0u;
-	}
-#endif
 	for (int i = tid; i < n16; i += nthreads) ms[i] = __ldg(ms_table + i);
 }
 
@@ -1135,8 +966,8 @@ __device__ __forceinline__ void walk_tables_init(uint8_t *smem, int tid, int nth
 // lane-parallel walk; the first slice outside its domain makes the warp start the picture over with
 // the serial walk (info.reserved[0] tells which one produced the records).
 template <bool LANES>
-__device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
-	const int mb_width = t.seq->mb_width, mb_size = t.seq->mb_size;
+__device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane, uint32_t ring) {
+	const int mb_width = t.mb_width, mb_size = t.mb_size;
 	bool lanes = LANES;
 	for (;;) {
 		// no macroblock is present until the walk reaches it (an address no slice covers keeps the
@@ -1144,10 +975,12 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
 		for (int i = lane; i < mb_size; i += 32) reinterpret_cast<uint4 *>(t.hdr)[i] = make_uint4(0, 0, 0, 0);
 		__syncwarp();
 
-		BitReader br;
+		BitReaderT<LANES> br;
 		br.words = reinterpret_cast<const uint32_t *>(t.es);
 		br.bytes = t.es;
 		br.len = t.es_len;
+		br.ring = ring;
+		br.qhead = 0;
 		br.seek_byte(t.start_byte);
 
 		PictureState ps;
@@ -1219,11 +1052,7 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
 			info.n_coded_blocks = ps.n_coded;
 			info.error = ps.error;
 			info.reserved[0] = (LANES && lanes && go) ? 1 : 0;
-#ifdef JSMPEG_WALK_EMITS_BLOCKS
-			info.reserved[1] = (LANES && lanes && go) ? 1 : 0;  // the block records are already written: stage 1b skips the picture
-#else
 			info.reserved[1] = 0;
-#endif
 			info.reserved[2] = 0;
 			*t.info = info;
 		}
@@ -1233,34 +1062,33 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane) {
 
 // ==================================================================================================
 // 1b: one coded block, from the offset the walk parked to the finished 64 x int16 record.
-// sblock = the shared-memory address of this thread's (zeroed) 128-byte tile.
-__device__ __forceinline__ void expand_block(const ParseTask &t, int slot_id, uint32_t sbase, uint32_t sblock) {
-	const int mb = slot_id / 6, block = slot_id - mb * 6;
-	const uint32_t rec = reinterpret_cast<const uint32_t *>(t.hdr + mb)[1];
-	if (!(rec & MBF_PRESENT) || !((rec >> 8) & (0x20u >> block))) return;
+// rec = the macroblock record's second word (flags | cbp << 8 | dc_only << 16 | quantiser scale << 24),
+// parked = {bit offset of the block's first coefficient code, intra dc * 8} from the walk's dense side
+// array, stile = the shared-memory address of this thread's (zeroed) 128-byte tile.
+__device__ __forceinline__ void expand_block(const ParseTask &t, uint32_t rec, uint2 parked, uint4 *__restrict__ slot,
+                                             uint32_t sbase, uint32_t stile) {
 	const bool intra = rec & MBF_INTRA;
 	const int qs = (int)(rec >> 24);
-	const uint8_t *__restrict__ quant = intra ? t.seq->intra_q : t.seq->non_intra_q;
-
-	uint4 *slot = reinterpret_cast<uint4 *>(t.coef) + (size_t)slot_id * 8;
-	const uint2 parked = *reinterpret_cast<const uint2 *>(slot);  // left by the walk
+	// quantiser table in coefficient (zig-zag) order: entry n = raster index * 2 | Q[raster index] << 8
+	const uint32_t xq = sbase + EXP_OFF_XQ + (intra ? 0u : 128u);
 	BitReader br;
 	br.words = reinterpret_cast<const uint32_t *>(t.es);
 	br.bytes = t.es;
 	br.len = t.es_len;
-	br.seek_byte(parked.x >> 3);
-	if (parked.x & 7u) br.consume((int)(parked.x & 7u));
+	br.ring = 0;
+	br.qhead = 0;
+	br.seek_bit(parked.x);
 
 	int n = 0;
 	if (intra) {
-		sts_s16(sblock, (int)(int16_t)(parked.y & 0xffffu));  // coefficient 0
+		sts_s16(stile, (int)(int16_t)(parked.y & 0xffffu));  // coefficient 0
 		n = 1;
 	}
 	bool first = !intra;
 	for (;;) {  // mpeg1.js:757-811; the walk has already validated every code of this block
 		const uint32_t w = br.peek32();
 		const int z = min(__clz((int)w), VLC_DCT_MAX_Z);
-		const uint32_t e = lds_u16(sbase + OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
+		const uint32_t e = lds_u16(sbase + EXP_OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
 		int len = e & 31;
 		int run = (e >> 5) & 31;
 		int level = e >> 10;
@@ -1292,26 +1120,26 @@ __device__ __forceinline__ void expand_block(const ParseTask &t, int slot_id, ui
 			n++;
 			continue;
 		}
-		const uint32_t idx = lds_u8(sbase + OFF_ZIGZAG + (uint32_t)n);
+		const uint32_t q = lds_u16(xq + (uint32_t)n * 2u);
 		n++;
 		// dequantise, oddify toward zero, clip (mpeg1.js:794-807)
 		level <<= 1;
 		if (!intra) level += level < 0 ? -1 : 1;
-		level = (level * qs * (int)__ldg(quant + idx)) >> 4;
+		level = (level * qs * (int)(q >> 8)) >> 4;
 		if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
 		level = max(-2048, min(2047, level));
-		sts_s16(sblock + idx * 2u, level);
+		sts_s16(stile + (q & 0xffu), level);
 	}
 	// The finished block leaves as ONE 128-byte TMA bulk store (shared -> global, SASS UBLKCP): whole
 	// lines reach L2, whereas eight 16-byte stores per thread half-fill 32-byte sectors and made L2
 	// read every sector back before merging (ncu: 23.5 GB read for 22 GB written per step).
 #ifndef JSMPEG_WALK_EMU
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
-	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(slot), "r"(sblock) : "memory");
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(slot), "r"(stile) : "memory");
 	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must outlive the read
 #else
-	memcpy(slot, emu_smem + sblock, 128);
+	memcpy(slot, emu_smem + stile, 128);
 #endif
 }
 

@@ -56,6 +56,13 @@ class MPEG1Video:
         if options.get("device") is not None and hasattr(self.functions, "jsmpeg_b200_set_default_device"):
             self.functions.jsmpeg_b200_set_default_device(int(options["device"]))
         self.decoder = self.functions.mpeg1_decoder_create(self.bufferSize, self.bufferMode)
+        # the product library never fails in create (reference behaviour); a decoder without a usable CUDA
+        # device is dead and answers decode() == False for ever.  The Python host says so loudly instead.
+        if hasattr(self.functions, "jsmpeg_b200_decoder_last_error"):
+            err = self.functions.jsmpeg_b200_decoder_last_error(self.decoder)
+            if err:
+                self.destroy()
+                raise RuntimeError(err.decode(errors="replace"))
 
     # ---- src/decoder.js:19-35 / src/mpeg1-wasm.js:32-50
     def destroy(self):

@@ -24,9 +24,9 @@ def walk_exact(es, start, mbw, mbh, lanes):
     buf = np.zeros((n + 3) // 4 * 4, dtype=np.uint8)  # the walk reads whole words, like the device mirror
     buf[:n] = np.frombuffer(es, dtype=np.uint8)
     hdr = np.zeros(mb * 4, dtype=np.uint32)
-    coef = np.zeros(mb * 6 * 32, dtype=np.uint32)
+    park = np.zeros(mb * 6 * 2, dtype=np.uint32)  # exact size: the dense {bit offset, dc} side array
     info = np.zeros(12, dtype=np.int32)
-    lib.emu_walk_picture(buf.ctypes.data, n, start, mbw, mbh, hdr.ctypes.data, coef.ctypes.data, info.ctypes.data, lanes)
+    lib.emu_walk_picture(buf.ctypes.data, n, start, mbw, mbh, hdr.ctypes.data, park.ctypes.data, info.ctypes.data, lanes)
 
 
 rng = np.random.default_rng(3)

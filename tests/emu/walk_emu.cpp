@@ -149,15 +149,16 @@ static void run_warp(void (*body)(int)) {
 	swapcontext(&emu::main_ctx, &emu::ctx[0]);
 }
 
-// the stream's quantiser matrices (de-zigzagged, as in SeqParams); only the block-emitting variant reads them
+// the stream's quantiser matrices (de-zigzagged, as in SeqParams); stage 1b reads them
 static uint8_t emu_intra_q[64], emu_non_intra_q[64];
 extern "C" void emu_set_quant(const uint8_t *intra_q, const uint8_t *non_intra_q) {
 	memcpy(emu_intra_q, intra_q, 64);
 	memcpy(emu_non_intra_q, non_intra_q, 64);
 }
 
+// park: [mb_size][6] x {bit offset, dc * 8}, the walk's dense hand-over to stage 1b
 extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t start_byte, int mb_width, int mb_height,
-                                mb_record_t *hdr, int16_t *coef, picture_info_t *info, int lanes) {
+                                mb_record_t *hdr, uint2 *park, picture_info_t *info, int lanes) {
 	static std::once_flag once;
 	static std::vector<uint16_t> ms(MS_TABLE_ENTRIES);
 	std::call_once(once, [] {
@@ -172,14 +173,15 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 	memcpy(seq.intra_q, emu_intra_q, 64);
 	memcpy(seq.non_intra_q, emu_non_intra_q, 64);
 	ParseTask t;
-	t.es = es; t.es_len = es_len; t.start_byte = start_byte; t.seq = &seq; t.hdr = hdr; t.coef = coef; t.info = info;
+	t.es = es; t.es_len = es_len; t.start_byte = start_byte; t.seq = &seq; t.hdr = hdr; t.coef = nullptr; t.info = info;
+	t.park = park; t.mb_width = mb_width; t.mb_size = seq.mb_size;
 	static ParseTask task;
 	static int use_lanes;
 	task = t;
 	use_lanes = lanes;
 	run_warp([](int l) {
-		if (use_lanes) walk_picture<true>(task, 0, l);
-		else walk_picture<false>(task, 0, l);
+		if (use_lanes) walk_picture<true>(task, 0, l, 0);
+		else walk_picture<false>(task, 0, l, 0);
 	});
 	return 0;
 }
@@ -187,11 +189,10 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 // Stage 1b on the records the walk left: every block slot of the picture through expand_block
 // (jsmpeg_b200/csrc/walk.cuh), one "thread" after the other with its own zeroed tile.
 extern "C" int emu_expand_picture(const uint8_t *es, uint32_t es_len, int mb_width, int mb_height,
-                                  mb_record_t *hdr, int16_t *coef, picture_info_t *info) {
+                                  mb_record_t *hdr, const uint2 *park, int16_t *coef, picture_info_t *info) {
 	if (info->status != PIC_DECODED) return 0;
 	uint16_t *s16 = reinterpret_cast<uint16_t *>(emu_smem + EMU_EXPAND_BASE);
-	for (int i = 0; i < (VLC_DCT_MAX_Z + 1) * 32; i++) s16[OFF_DCT / 2 + i] = VLC_DCT_COEFF[i];
-	for (int i = 0; i < 64; i++) emu_smem[EMU_EXPAND_BASE + OFF_ZIGZAG + i] = TBL_ZIG_ZAG[i];
+	for (int i = 0; i < (VLC_DCT_MAX_Z + 1) * 32; i++) s16[EXP_OFF_DCT / 2 + i] = VLC_DCT_COEFF[i];
 	SeqParams seq;
 	memset(&seq, 0, sizeof(seq));
 	seq.mb_width = mb_width;
@@ -199,11 +200,18 @@ extern "C" int emu_expand_picture(const uint8_t *es, uint32_t es_len, int mb_wid
 	seq.mb_size = mb_width * mb_height;
 	memcpy(seq.intra_q, emu_intra_q, 64);
 	memcpy(seq.non_intra_q, emu_non_intra_q, 64);
+	seq_fill_xq(seq);  // the host helper the product uses (common.cuh)
+	memcpy(emu_smem + EMU_EXPAND_BASE + EXP_OFF_XQ, seq.xq, sizeof(seq.xq));
 	ParseTask t;
 	t.es = es; t.es_len = es_len; t.start_byte = 0; t.seq = &seq; t.hdr = hdr; t.coef = coef; t.info = info;
-	for (int slot_id = 0; slot_id < seq.mb_size * 6; slot_id++) {
-		memset(emu_smem + EMU_EXPAND_BASE + OFF_BLOCKS, 0, 128);
-		expand_block(t, slot_id, EMU_EXPAND_BASE, EMU_EXPAND_BASE + OFF_BLOCKS);
+	t.park = const_cast<uint2 *>(park); t.mb_width = mb_width; t.mb_size = seq.mb_size;
+	for (int slot_id = 0; slot_id < seq.mb_size * 6; slot_id++) {  // the kernel shell of parse.cu, one thread after the other
+		const int mb = slot_id / 6, block = slot_id - mb * 6;
+		const uint32_t rec = reinterpret_cast<const uint32_t *>(hdr + mb)[1];
+		if (!(rec & MBF_PRESENT) || !((rec >> 8) & (0x20u >> block))) continue;
+		memset(emu_smem + EMU_EXPAND_BASE + EXP_OFF_TILES, 0, 128);
+		expand_block(t, rec, park[slot_id], reinterpret_cast<uint4 *>(coef) + (size_t)slot_id * 8, EMU_EXPAND_BASE,
+		             EMU_EXPAND_BASE + EXP_OFF_TILES);
 	}
 	return 0;
 }

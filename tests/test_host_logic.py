@@ -136,3 +136,44 @@ def test_stream_sharding_is_a_partition():
         owned = [assign_streams(512, r, world) for r in range(world)]
         assert sorted(sum(owned, [])) == list(range(512))
         assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+
+
+def test_without_a_cuda_device_the_c_abi_answers_false_and_the_python_host_raises():
+    """Boundary behaviour of the reference ("create never fails, decode returns false", src/wasm/mpeg1.c:777-782,
+    853-864) when there is no usable GPU: no abort(), a dead decoder that swallows writes and answers false, the
+    reason available through jsmpeg_b200_decoder_last_error; the Python host classes raise instead.  (Round 1
+    called abort() on any CUDA error.)  Skipped where a GPU is present: the same calls then simply work."""
+    if not os.path.exists(capi.PRODUCT_LIB):
+        pytest.skip("libjsmpeg_b200.so not built")
+    lib = capi.product_library()
+    d = lib.mpeg1_decoder_create(1000, capi.BIT_BUFFER_MODE_EXPAND)
+    err = lib.jsmpeg_b200_decoder_last_error(d)
+    if not err:
+        lib.mpeg1_decoder_destroy(d)
+        pytest.skip("a CUDA device is present")
+    assert b"CUDA error" in err
+    p = lib.mpeg1_decoder_get_write_ptr(d, 5000)  # more than the buffer: the caller's memcpy must still be safe
+    assert p
+    ctypes.memset(p, 0xB3, 5000)
+    lib.mpeg1_decoder_did_write(d, 5000)
+    assert lib.mpeg1_decoder_decode(d) is False
+    assert lib.mpeg1_decoder_has_sequence_header(d) == 0
+    assert lib.mpeg1_decoder_get_y_ptr(d) is None
+    assert lib.mpeg1_decoder_get_index(d) == 0
+    lib.mpeg1_decoder_destroy(d)
+    with pytest.raises(RuntimeError):
+        batch.BatchDecoder(2)
+    with pytest.raises(RuntimeError):
+        decoder.MPEG1Video({})
+
+
+def test_napi_addon_source_parses():
+    """addon/jsmpeg_b200_napi.c has never met a Node toolchain (none in this image): at least prove that it
+    is C that parses and type-checks against the N-API calls it uses (tests/stubs/node_api.h declares
+    exactly those, with the signatures of Node's js_native_api.h)."""
+    import subprocess
+    src = os.path.join(helpers.ROOT, "addon", "jsmpeg_b200_napi.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
+                        "-I", os.path.join(helpers.ROOT, "tests", "stubs"), "-I", os.path.join(helpers.ROOT, "include"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]

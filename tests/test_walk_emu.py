@@ -3,8 +3,9 @@
 tests/emu/walk_emu.cpp compiles the device code of jsmpeg_b200/csrc/walk.cuh for the host and runs a
 warp as 32 threads.  The serial walk is the one the GPU parity tests pin to the oracle; here every
 picture of the golden streams, of the syntax-level generator's cases and of encoder-made clips is
-walked both ways and the outputs must be identical: macroblock records, the parked
-{bit offset, dc} of every coded block, and the picture info (end_bit, counts, error).
+walked both ways and the outputs must be identical: macroblock records, the {bit offset, dc} pair of
+every coded block in the dense side array (the walk's hand-over to stage 1b), and the picture info
+(end_bit, counts, error).
 """
 import ctypes
 import os
@@ -23,10 +24,9 @@ CSRC = os.path.join(HERE, "..", "jsmpeg_b200", "csrc")
 
 
 def emu_lib(define=None):
-    """The emulation library; `define` builds a variant (e.g. "JSMPEG_LANES_FIXUP", a round-2 candidate
-    that is compiled out of the product by default)."""
+    """The emulation library; `define` builds a variant with -D<define>."""
     out = EMU_LIB if define is None else EMU_LIB.replace(".so", "_" + define.lower() + ".so")
-    deps = [EMU_SRC] + [os.path.join(CSRC, f) for f in ("walk.cuh", "common.cuh", "records.h", "vlc_tables.h")]
+    deps = [EMU_SRC] + [os.path.join(CSRC, f) for f in ("walk.cuh", "recon.cuh", "common.cuh", "records.h", "vlc_tables.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         tmp = out + ".%d.tmp" % os.getpid()
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-attributes", "-Wno-unknown-pragmas",
@@ -59,10 +59,10 @@ def picture_starts(es):
 def walk(lib, buf, n, start, mbw, mbh, lanes):
     mb = mbw * mbh
     hdr = np.zeros(mb * 4, dtype=np.uint32)
-    coef = np.full(mb * 6 * 32, 0xDEADBEEF, dtype=np.uint32)  # the walk parks 8 bytes per coded block
+    park = np.full(mb * 6 * 2, 0xDEADBEEF, dtype=np.uint32)  # 8 bytes per coded block: {bit offset, dc * 8}
     info = np.zeros(12, dtype=np.int32)
-    lib.emu_walk_picture(buf.ctypes.data, n, start, mbw, mbh, hdr.ctypes.data, coef.ctypes.data, info.ctypes.data, lanes)
-    return hdr.reshape(mb, 4), coef.reshape(mb * 6, 32)[:, :2].copy(), info
+    lib.emu_walk_picture(buf.ctypes.data, n, start, mbw, mbh, hdr.ctypes.data, park.ctypes.data, info.ctypes.data, lanes)
+    return hdr.reshape(mb, 4), park.reshape(mb * 6, 2), info
 
 
 def check_stream(lib, es, what, expect_lanes=None):
@@ -164,80 +164,6 @@ def test_device_walk_code_matches_the_oracle_records(name):
     assert checked > 0
 
 
-def test_fixup_variant_reproduces_the_serial_walk():
-    """-DJSMPEG_LANES_FIXUP (walk.cuh): pass C stages relative records and a fix-up replaces the second
-    semantic pass.  Not in the product build yet (it wants a GPU measurement first); kept honest here."""
-    import synth_es
-    lib = emu_lib("JSMPEG_LANES_FIXUP")
-    for name in GOLDEN:
-        check_stream(lib, open(os.path.join(HERE, "golden", name + ".es"), "rb").read(), "fixup " + name)
-    for name in synth_es.CASES:
-        check_stream(lib, synth_es.make_case(name), "fixup " + name)
-    pytest.importorskip("cv2")
-    es = b"".join(p for _, p in helpers.clip_packets(640, 480, 7))
-    used, n = check_stream(lib, es, "fixup clip")
-    assert used == n
-
-
-@pytest.mark.parametrize("name", GOLDEN)
-def test_block_emitting_variant_matches_the_oracle_coefficients(name):
-    """-DJSMPEG_WALK_EMITS_BLOCKS (walk.cuh): the storing pass of the lane-parallel walk decodes the
-    coefficient values and writes the dequantised 64 x int16 block records itself (stage 1b's job).
-    Emulated, against the ORACLE's coefficient blocks and records.  Not in the product build yet."""
-    from jsmpeg_b200 import decoder
-    es = open(os.path.join(HERE, "golden", name + ".es"), "rb").read()
-    olib = helpers.oracle_lib()
-    d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
-    d.write(0, [es])
-    seq = olib.oracle_seq_params(d.decoder).contents
-    mb = seq.mb_size
-    lib = emu_lib("JSMPEG_WALK_EMITS_BLOCKS")
-    lib.emu_set_quant(bytes(seq.intra_q), bytes(seq.non_intra_q))
-    mbw, mbh = stream_geometry(es)
-    buf = np.frombuffer(es + b"\0" * 16, dtype=np.uint8).copy()
-    emitted = 0
-    while d.decode():
-        info = olib.oracle_last_picture_info(d.decoder).contents
-        want_hdr = np.ctypeslib.as_array(ctypes.cast(olib.oracle_last_mb_records(d.decoder), ctypes.POINTER(ctypes.c_uint32)),
-                                         shape=(mb, 4)).copy()
-        want = np.ctypeslib.as_array(ctypes.cast(olib.oracle_last_coefficients(d.decoder), ctypes.POINTER(ctypes.c_int16)),
-                                     shape=(mb * 6, 64)).copy()
-        hdr = np.zeros(mb * 4, dtype=np.uint32)
-        coef = np.zeros(mb * 6 * 32, dtype=np.uint32)
-        pinfo = np.zeros(12, dtype=np.int32)
-        lib.emu_walk_picture(buf.ctypes.data, len(es), info.start_byte, mbw, mbh, hdr.ctypes.data, coef.ctypes.data,
-                             pinfo.ctypes.data, 1)
-        assert np.array_equal(hdr.reshape(mb, 4), want_hdr), f"{name}: records differ, picture at byte {info.start_byte}"
-        if not pinfo[10]:
-            continue  # serial fall-back: the blocks are stage 1b's, not emitted here
-        emitted += 1
-        got = coef.view(np.int16).reshape(mb * 6, 64)
-        h = want_hdr.view(np.uint8).reshape(mb, 16)
-        present = (h[:, 4] & 1).astype(bool)
-        for blk in range(6):
-            coded = present & ((h[:, 5] & (0x20 >> blk)) != 0)
-            rows = np.nonzero(coded)[0] * 6 + blk
-            assert np.array_equal(got[rows], want[rows]), f"{name}: coefficient blocks differ, picture at byte {info.start_byte}, block {blk}"
-    assert emitted > 0
-
-
-def test_wide_refill_variant_reproduces_the_serial_walk():
-    """-DJSMPEG_WIDE_REFILL (walk.cuh): the bit window refills from a 16-byte register cache (one 128-bit
-    load per four words).  Both walks of that build against the default build's serial walk."""
-    import synth_es
-    wide, ref = emu_lib("JSMPEG_WIDE_REFILL"), emu_lib()
-    streams = [open(os.path.join(HERE, "golden", n + ".es"), "rb").read() for n in GOLDEN]
-    streams += [synth_es.make_case(n) for n in synth_es.CASES]
-    for es in streams:
-        mbw, mbh = stream_geometry(es)
-        buf = np.frombuffer(es + b"\0" * 32, dtype=np.uint8).copy()
-        for s in picture_starts(es):
-            h0, c0, i0 = walk(ref, buf, len(es), s, mbw, mbh, 0)
-            for lanes in (0, 1):
-                h1, c1, i1 = walk(wide, buf, len(es), s, mbw, mbh, lanes)
-                assert np.array_equal(h0, h1) and np.array_equal(c0, c1) and np.array_equal(i0[:9], i1[:9])
-
-
 @pytest.mark.parametrize("name", GOLDEN)
 def test_stage1_device_code_matches_the_oracle_coefficients(name):
     """Stage 1 end to end on the CPU: the emulated walk (lane-parallel and serial) followed by stage
@@ -252,7 +178,7 @@ def test_stage1_device_code_matches_the_oracle_coefficients(name):
     lib = emu_lib()
     lib.emu_set_quant(bytes(seq.intra_q), bytes(seq.non_intra_q))
     lib.emu_expand_picture.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                       ctypes.c_void_p, ctypes.c_void_p]
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     mbw, mbh = stream_geometry(es)
     buf = np.frombuffer(es + b"\0" * 16, dtype=np.uint8).copy()
     checked = 0
@@ -266,11 +192,13 @@ def test_stage1_device_code_matches_the_oracle_coefficients(name):
         present = (h[:, 4] & 1).astype(bool)
         for lanes in (1, 0):
             hdr = np.zeros(mb * 4, dtype=np.uint32)
+            park = np.zeros(mb * 6 * 2, dtype=np.uint32)
             coef = np.zeros(mb * 6 * 32, dtype=np.uint32)
             pinfo = np.zeros(12, dtype=np.int32)
-            lib.emu_walk_picture(buf.ctypes.data, len(es), info.start_byte, mbw, mbh, hdr.ctypes.data, coef.ctypes.data,
+            lib.emu_walk_picture(buf.ctypes.data, len(es), info.start_byte, mbw, mbh, hdr.ctypes.data, park.ctypes.data,
                                  pinfo.ctypes.data, lanes)
-            lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, coef.ctypes.data, pinfo.ctypes.data)
+            lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, park.ctypes.data, coef.ctypes.data,
+                                   pinfo.ctypes.data)
             got = coef.view(np.int16).reshape(mb * 6, 64)
             for blk in range(6):
                 rows = np.nonzero(present & ((h[:, 5] & (0x20 >> blk)) != 0))[0] * 6 + blk
@@ -289,7 +217,7 @@ def _pipeline_against_oracle_planes(es, name, define=None):
     lib = emu_lib(define)
     lib.emu_set_quant(bytes(seq.intra_q), bytes(seq.non_intra_q))
     lib.emu_expand_picture.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                       ctypes.c_void_p, ctypes.c_void_p]
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.emu_reconstruct_picture.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_int, ctypes.c_int]
     mbw, mbh = stream_geometry(es)
@@ -301,14 +229,15 @@ def _pipeline_against_oracle_planes(es, name, define=None):
     while d.decode():
         info = olib.oracle_last_picture_info(d.decoder).contents
         hdr = np.zeros(mb * 4, dtype=np.uint32)
+        park = np.zeros(mb * 6 * 2, dtype=np.uint32)
         coef = np.zeros(mb * 6 * 32, dtype=np.uint32)
         pinfo = np.zeros(12, dtype=np.int32)
-        lib.emu_walk_picture(buf.ctypes.data, len(es), info.start_byte, mbw, mbh, hdr.ctypes.data, coef.ctypes.data,
+        lib.emu_walk_picture(buf.ctypes.data, len(es), info.start_byte, mbw, mbh, hdr.ctypes.data, park.ctypes.data,
                              pinfo.ctypes.data, 1)
         if pinfo[2] != 1:
             continue  # B / D picture or P without f_code: consumed, nothing decoded, no swap (mpeg1.js:181-193)
-        if not (define == "JSMPEG_WALK_EMITS_BLOCKS" and pinfo[10]):  # that variant's walk has written the blocks already
-            lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, coef.ctypes.data, pinfo.ctypes.data)
+        lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, park.ctypes.data, coef.ctypes.data,
+                               pinfo.ctypes.data)
         lib.emu_reconstruct_picture(hdr.ctypes.data, coef.ctypes.data, planes[cur].ctypes.data, planes[cur ^ 1].ctypes.data, mbw, mbh)
         y, cr, cb = d.planes()
         got = planes[cur]
@@ -335,14 +264,3 @@ def test_whole_hot_path_device_code_on_an_encoder_clip():
     pytest.importorskip("cv2")
     es = b"".join(p for _, p in helpers.clip_packets(320, 240, 14))
     assert _pipeline_against_oracle_planes(es, "clip 320x240") == 14
-
-
-@pytest.mark.parametrize("define", ["JSMPEG_LANES_FIXUP", "JSMPEG_WALK_EMITS_BLOCKS", "JSMPEG_WIDE_REFILL"])
-def test_round2_candidates_through_the_whole_pipeline(define):
-    """The compiled-out candidates of walk.cuh, each through walk -> (expand) -> reconstruct against the
-    oracle's planes on two golden streams and an encoder clip."""
-    for name in ("rows_ip", "skips_stuffing_escape_mba"):
-        _pipeline_against_oracle_planes(open(os.path.join(HERE, "golden", name + ".es"), "rb").read(), name, define)
-    pytest.importorskip("cv2")
-    es = b"".join(p for _, p in helpers.clip_packets(320, 240, 8))
-    assert _pipeline_against_oracle_planes(es, "clip 320x240", define) == 8
