@@ -5,11 +5,11 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own C on the host cores
 
 Workload (BASELINE.json configs[3], weak-scaled to configs[4]): STREAMS_PER_GPU = 64 independent
-1920x1080 MPEG-1 I+P elementary streams of PICTURES = 60 pictures each per GPU (demuxed from
-synthetic MPEG-TS clips made by tools/gen_streams.py: seeded content encoded by cv2's FFmpeg;
-DISTINCT clips are encoded and replicated into separate buffers to reach 64 streams).
-One STEP = every picture of every stream once: start-code scan + VLC parse (stage 1) +
-IDCT/MC reconstruction (stage 2).
+1920x1080 MPEG-1 I+P elementary streams of PICTURES = 60 pictures each per GPU, every stream its OWN
+clip (seed 1234 + rank * 64 + i), demuxed from synthetic MPEG-TS made by
+tools/gen_streams.py (seeded content encoded by cv2's FFmpeg, GOP 12, one slice per picture).
+One STEP = every picture of every stream once: start-code scan + VLC parse (stage 1) + IDCT/MC
+reconstruction (stage 2).
 
   value  frames/s with the elementary streams already resident in HBM (jsmpeg_b200_batch_rewind
          forgets the start-code index and all parsed records, so scan + parse + reconstruct are
@@ -17,10 +17,21 @@ IDCT/MC reconstruction (stage 2).
   e2e    the same through the reference-facing call sequence with HOST buffers: per step every
          stream is written again from host memory (get_write_ptr/memcpy/did_write -> H2D) and
          every decoded picture's Y/Cr/Cb planes are copied back to pinned host memory (D2H).
-         The 64 streams are driven as E2E_GROUPS independent BatchDecoders from host threads, so
-         that one group's PCIe copy-out overlaps another group's write + parse.
-  roofline  stage-2 kernel: algorithmic bytes / CUDA-event time of its launches.
-  cpu_baseline  oracle/_ref (the unmodified reference C, compiled in place) on all host threads.
+         The streams are driven as several independent BatchDecoders from host threads, so
+         that one group's PCIe copy-out overlaps another group's write + parse.  The rank is bound
+         to the CPUs of its GPU's NUMA node first (pinned rings are then node-local).
+  verified  after the timed region the LAST picture of every stream of the rank (60 pictures deep into
+         the P chains) is read back and its FNV-1a hash compared with the unmodified reference C
+         (oracle/_ref) decoding the same stream on the host; the run FAILS (exit 1) on any difference
+         or if any picture fell back from the lane-parallel walk.
+  roofline  stage-2 kernel: algorithmic bytes / CUDA-event time of its launches on the
+         stream they run on; in the value leg nothing else runs beside them.
+  cpu_baseline  oracle/_ref (the unmodified reference C, compiled in place) on the host cores this
+         process may really use: min(affinity, cgroup cpu.max quota) -- os.cpu_count() alone overstates
+         a container's share.
+  config_720p, single_stream_1080p  (N = 1 only) BASELINE configs[1] / [2]: the same legs at 64 x
+         1280x720, and ONE 1080p stream through the 15-function reference ABI (ms per
+         mpeg1_decoder_decode, look-ahead 16 and 1) beside one host core of the reference.
 
 Timing: wall clock between torch.cuda.synchronize() + barrier on both sides of exactly K steps
 (every step ends host-synchronised), max over ranks; per-kernel times are CUDA events recorded on
@@ -32,6 +43,7 @@ from __future__ import annotations
 import argparse
 import ctypes
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -48,39 +60,73 @@ WIDTH = int(os.environ.get("BENCH_WIDTH", 1920))    # the env overrides exist fo
 HEIGHT = int(os.environ.get("BENCH_HEIGHT", 1080))
 STREAMS_PER_GPU = int(os.environ.get("BENCH_STREAMS", 64))
 PICTURES = int(os.environ.get("BENCH_PICTURES", 60))
-DISTINCT = int(os.environ.get("BENCH_DISTINCT", 8))
+DISTINCT = int(os.environ.get("BENCH_DISTINCT", 0)) or STREAMS_PER_GPU  # distinct clips per rank
 NOISE = 9
 E2E_GROUPS = int(os.environ.get("BENCH_E2E_GROUPS", 16))
 VALUE_GROUPS = int(os.environ.get("BENCH_VALUE_GROUPS", 1))
+EXTRAS = os.environ.get("BENCH_EXTRAS", "1") != "0"   # config_720p + single_stream_1080p (N = 1 only)
 
 
 def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def _encode_one(seed):
+# ------------------------------------------------------------------------------------------------
+# host: how many cores this process really has
+
+def host_cores():
+    """os.cpu_count() says what the machine has; a container gets its scheduler affinity and, on top,
+    a cgroup CPU quota (cpu.max = '<quota> <period>').  usable = min(affinity, quota)."""
+    out = {"cpu_count": os.cpu_count(), "affinity": len(os.sched_getaffinity(0)), "cgroup_quota_cpus": None}
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    out["cgroup_quota_cpus"] = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    out["cgroup_quota_cpus"] = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    usable = out["affinity"]
+    if out["cgroup_quota_cpus"]:
+        usable = min(usable, max(1, int(math.floor(out["cgroup_quota_cpus"] + 1e-6))))
+    out["usable"] = max(1, usable)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic streams
+
+def _encode_one(args):
     import gen_streams
-    gen_streams.make_clip_ts(WIDTH, HEIGHT, PICTURES, seed=seed, noise=NOISE)
+    w, h, n, seed = args
+    gen_streams.make_clip_ts(w, h, n, seed=seed, noise=NOISE)
     return seed
 
 
-def load_streams(rank, world):
-    """DISTINCT elementary streams (bytes).  Rank 0 encodes (in parallel processes), the others
-    read the cache."""
+def load_streams(seeds, width=None, height=None, workers=None):
+    """One elementary stream (bytes) per seed; the clips are encoded in parallel processes first
+    (cached under /tmp, so the reference arm and this arm of one box encode once)."""
     import gen_streams
-    seeds = [1234 + i for i in range(DISTINCT)]
-    if rank == 0:
-        from concurrent.futures import ProcessPoolExecutor
-        with ProcessPoolExecutor(max_workers=min(len(seeds), os.cpu_count() or 1)) as ex:
-            list(ex.map(_encode_one, seeds))
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
+    width, height = width or WIDTH, height or HEIGHT
+    from concurrent.futures import ProcessPoolExecutor
+    workers = workers or host_cores()["usable"]
+    with ProcessPoolExecutor(max_workers=max(1, min(len(seeds), workers))) as ex:
+        list(ex.map(_encode_one, [(width, height, PICTURES, s) for s in seeds]))
     out = []
     for s in seeds:
-        packets = gen_streams.make_clip_es(WIDTH, HEIGHT, PICTURES, seed=s, noise=NOISE)
+        packets = gen_streams.make_clip_es(width, height, PICTURES, seed=s, noise=NOISE)
         out.append(b"".join(p for _, p in packets))
     return out
+
+
+def rank_seeds(rank, n=None):
+    n = n or STREAMS_PER_GPU
+    return [1234 + rank * STREAMS_PER_GPU + (i % DISTINCT) for i in range(n)]
 
 
 class ClockSampler:
@@ -98,7 +144,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -159,19 +205,36 @@ def recorded_traffic():
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline
+# the reference on the host: reference arm / cpu baseline / checker
 
-def run_reference_cpu(clips, threads, loops):
-    """The reference's own C decoder (oracle/_ref, built from /root/reference/src/wasm/*.c in the
-    build container) on `threads` host threads; falls back to our CPU port of it (oracle/) when the
-    reference build is absent.  Returns (frames, seconds, kind)."""
-    ref = os.path.join(ROOT, "oracle", "_ref", "libjsmpeg_ref.so")
-    n = len(clips)
-    if os.path.exists(ref):
-        lib = ctypes.CDLL(ref)
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libjsmpeg_ref.so")
+_ref = None
+
+
+def ref_library():
+    """oracle/_ref/libjsmpeg_ref.so: the unmodified reference C (built from /root/reference/src/wasm/*.c
+    in the build container; travels with the tree) + our pthread harness oracle/ref_bench.c."""
+    global _ref
+    if _ref is None and os.path.exists(REF_LIB):
+        lib = ctypes.CDLL(REF_LIB, mode=os.RTLD_LOCAL | os.RTLD_NOW)
         lib.ref_bench_run.restype = ctypes.c_long
         lib.ref_bench_run.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_uint), ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        lib.ref_picture_hashes.restype = ctypes.c_long
+        lib.ref_picture_hashes.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64), ctypes.c_long]
+        lib.ref_hash_bytes.restype = ctypes.c_uint64
+        lib.ref_hash_bytes.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t]
+        _ref = lib
+    return _ref
+
+
+def run_reference_cpu(clips, threads, loops):
+    """The reference's own C decoder on `threads` host threads, clip c on thread c % threads; only the
+    decode() loops are inside the timed region (decoders are created and written before it).  Falls
+    back to our CPU port of it (oracle/) when the reference build is absent.  Returns (frames, seconds, kind)."""
+    n = len(clips)
+    lib = ref_library()
+    if lib is not None:
         arr = (ctypes.c_char_p * n)(*clips)
         lens = (ctypes.c_uint * n)(*[len(c) for c in clips])
         sec = ctypes.c_double()
@@ -182,6 +245,7 @@ def run_reference_cpu(clips, threads, loops):
     from jsmpeg_b200 import capi
     lib = capi.load_library(os.path.join(ROOT, "oracle", "liboracle.so"))
     counts = [0] * threads
+    spent = [0.0] * threads
 
     def work(t):
         for _ in range(loops):
@@ -189,17 +253,49 @@ def run_reference_cpu(clips, threads, loops):
                 d = lib.mpeg1_decoder_create(len(clips[c]) + 16, 2)
                 ctypes.memmove(lib.mpeg1_decoder_get_write_ptr(d, len(clips[c])), clips[c], len(clips[c]))
                 lib.mpeg1_decoder_did_write(d, len(clips[c]))
+                t0 = time.perf_counter()
                 while lib.mpeg1_decoder_decode(d):
                     counts[t] += 1
+                spent[t] += time.perf_counter() - t0
                 lib.mpeg1_decoder_destroy(d)
 
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-    t0 = time.perf_counter()
     for th in ths:
         th.start()
     for th in ths:
         th.join()
-    return sum(counts), time.perf_counter() - t0, "port"
+    return sum(counts), max(spent), "port"
+
+
+def reference_last_hashes(clips, workers):
+    """hash of the LAST picture of each clip, decoded by the reference on `workers` host threads."""
+    lib = ref_library()
+    if lib is None:
+        return None
+    out = [None] * len(clips)
+
+    def work(k):
+        for c in range(k, len(clips), workers):
+            buf = (ctypes.c_uint64 * (PICTURES + 4))()
+            n = lib.ref_picture_hashes(clips[c], len(clips[c]), buf, PICTURES + 4)
+            out[c] = (int(n), int(buf[min(n, PICTURES + 4) - 1]) if n > 0 else None)
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(workers)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    return out
+
+
+def fnv1a64_planes(y, cr, cb):
+    """FNV-1a 64 of Y | Cr | Cb exactly as oracle/ref_bench.c computes it (the hash is inherently serial;
+    Python ints would take seconds per picture, so the byte loop runs in the same C: ref_hash_bytes)."""
+    lib = ref_library()
+    h = 1469598103934665603
+    for a in (y, cr, cb):
+        h = lib.ref_hash_bytes(h, a.ctypes.data, a.size)
+    return int(h)
 
 
 def truncate_pictures(es, n_pictures):
@@ -215,12 +311,194 @@ def truncate_pictures(es, n_pictures):
         pos += 4
 
 
-def cpu_sample(clips, threads, pictures=None):
-    """Bounded sample for the reference timing: one clip per host thread (replicated round-robin
-    from the distinct clips), optionally only its first `pictures` pictures."""
-    if pictures is not None:
-        clips = [truncate_pictures(c, pictures) for c in clips]
-    return [clips[i % len(clips)] for i in range(threads)]
+# ------------------------------------------------------------------------------------------------
+# the GPU legs
+
+class Legs:
+    """The timed legs over one set of streams (one resolution) on this rank's GPU."""
+
+    def __init__(self, streams, width, height, local_rank, world, e2e_groups):
+        import torch
+        import torch.distributed as dist
+        from jsmpeg_b200.batch import OUT_DEVICE, OUT_HOST, BatchDecoder
+        self.torch, self.dist = torch, dist
+        self.OUT_DEVICE, self.OUT_HOST = OUT_DEVICE, OUT_HOST
+        self.streams, self.width, self.height = streams, width, height
+        self.local_rank, self.world = local_rank, world
+        n = len(streams)
+        # value: VALUE_GROUPS decoders share the streams; with more than one, each is driven by its own host thread
+        self.vgroups = [list(range(g, n, VALUE_GROUPS)) for g in range(VALUE_GROUPS)]
+        self.value_decoders = [BatchDecoder(len(g), device=local_rank, max_slots=len(g) * PICTURES + 8) for g in self.vgroups]
+        for dec, g in zip(self.value_decoders, self.vgroups):
+            for j, i in enumerate(g):
+                dec.write(j, streams[i])
+            dec.upload()  # elementary streams resident in HBM before the timed region
+        # e2e: smaller decoders, one host thread each (ctypes releases the GIL in the C calls)
+        e2e_groups = max(1, min(e2e_groups, n))
+        self.groups = [list(range(g, n, e2e_groups)) for g in range(e2e_groups)]
+        self.e2e_decoders = [BatchDecoder(len(g), device=local_rank, max_slots=len(g) * PICTURES + 8) for g in self.groups]
+        for dec, g in zip(self.e2e_decoders, self.groups):  # sequence headers parsed once, like a decoder that has seen its stream start
+            for j, i in enumerate(g):
+                dec.write(j, streams[i])
+
+    def close(self):
+        for d in self.value_decoders + self.e2e_decoders:
+            d.close()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def run_device(self, n_steps):
+        if VALUE_GROUPS == 1:
+            total = 0
+            for _ in range(n_steps):
+                self.value_decoders[0].rewind()
+                total += self.value_decoders[0].decode(PICTURES, self.OUT_DEVICE)
+            return total
+        counts = [0] * VALUE_GROUPS
+
+        def work(k):
+            dec = self.value_decoders[k]
+            for _ in range(n_steps):
+                dec.rewind()
+                counts[k] += dec.decode(PICTURES, self.OUT_DEVICE)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(VALUE_GROUPS)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        return sum(counts)
+
+    def run_e2e(self, n_steps):
+        """n_steps whole-workload steps: every group's thread runs its n_steps back to back (no
+        per-step join), so one group's PCIe copy-out overlaps the others' write + parse."""
+        counts = [0] * len(self.groups)
+
+        def work(k):
+            dec = self.e2e_decoders[k]
+            for _ in range(n_steps):
+                dec.reset()
+                for j, i in enumerate(self.groups[k]):
+                    dec.write(j, self.streams[i])
+                counts[k] += dec.decode(PICTURES, self.OUT_HOST)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self.groups))]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        return sum(counts)
+
+    def timed(self, run, steps, warmup, decoders):
+        """run(n) performs n steps and returns the pictures decoded."""
+        torch, dist = self.torch, self.dist
+        sampler = ClockSampler(self.local_rank)
+        sampler.start()  # started before the warm-up so that it is already streaming samples
+        run(warmup)
+        self.barrier()
+        for d in decoders:
+            d.reset_stats()
+        sampler.mark()
+        t0 = time.perf_counter()
+        frames = run(steps)
+        self.barrier()
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        st = {}
+        for d in decoders:
+            for k, v in d.stats().items():
+                st[k] = st.get(k, 0) + v
+        if self.world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fr = torch.tensor([frames], dtype=torch.float64, device="cuda")
+            dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+            dt, frames = float(t.item()), int(fr.item())
+        return frames, dt, st, clocks
+
+    def verify(self, seeds, workers):
+        """The last picture of every stream, as the value leg left it in HBM, against the reference's
+        decode of the same stream (FNV-1a 64 over Y | Cr | Cb).  Returns a dict for the JSON line."""
+        if ref_library() is None:
+            return {"verified": None, "why": "oracle/_ref not built on this box"}
+        # distinct clips only once on the host
+        uniq = {}
+        for i, s in enumerate(seeds):
+            uniq.setdefault(s, i)
+        order = list(uniq.values())
+        want = reference_last_hashes([self.streams[i] for i in order], workers)
+        want_by_seed = {seeds[i]: w for i, w in zip(order, want)}
+        bad, checked = [], 0
+        for dec, g in zip(self.value_decoders, self.vgroups):
+            for j, i in enumerate(g):
+                y, cr, cb = dec.read_planes(j)
+                n_ref, h_ref = want_by_seed[seeds[i]]
+                checked += 1
+                if n_ref != PICTURES or fnv1a64_planes(y, cr, cb) != h_ref:
+                    bad.append(i)
+        return {"verified": not bad, "streams_checked": checked, "pictures_deep": PICTURES, "mismatching_streams": bad[:16],
+                "checker": "oracle/_ref (unmodified reference C) on the host, FNV-1a 64 of Y|Cr|Cb of each stream's last picture"}
+
+
+def roofline_block(st, peak, peak_src, traffic):
+    recon_s = st["recon_ms"] / 1e3
+    achieved = st["algorithmic_bytes"] / recon_s / 1e9 if recon_s > 0 else 0.0
+    return {
+        "kernel": "reconstruct_kernel (stage 2: IDCT + motion compensation + add/clamp)",
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak if peak else None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": st["algorithmic_bytes"] / max(1, st["recon_launches"]),
+        "avg_launch_ms": st["recon_ms"] / max(1, st["recon_launches"]),
+        "launches": st["recon_launches"],
+        "timed": "CUDA events on the reconstruct stream around each chunk's launches; nothing runs beside them in this leg",
+        "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        "traffic_source": traffic["source"] if traffic else None,
+    }
+
+
+def single_stream_leg(es, width, height, device):
+    """ONE stream through the 15-function reference ABI (the drop-in use, src/player.js:226-228):
+    whole clip written once, then mpeg1_decoder_decode() until false, each call timed on the host."""
+    from jsmpeg_b200 import capi
+    lib = capi.product_library()
+    lib.jsmpeg_b200_set_default_device(device)
+    out = {}
+    for look in (16, 1):
+        os.environ["JSMPEG_B200_LOOKAHEAD"] = str(look)
+        per_call = []
+        for rep in range(3):  # first repetition = warm-up (allocations, table upload)
+            d = lib.mpeg1_decoder_create(len(es) + 16, capi.BIT_BUFFER_MODE_EXPAND)
+            ctypes.memmove(lib.mpeg1_decoder_get_write_ptr(d, len(es)), es, len(es))
+            lib.mpeg1_decoder_did_write(d, len(es))
+            calls = []
+            while True:
+                t0 = time.perf_counter()
+                ok = lib.mpeg1_decoder_decode(d)
+                dt = time.perf_counter() - t0
+                if not ok:
+                    break
+                calls.append(dt * 1e3)
+            lib.mpeg1_decoder_destroy(d)
+            if rep > 0:
+                per_call += calls
+        per_call.sort()
+        n = len(per_call)
+        out[f"lookahead_{look}"] = {
+            "fps": 1e3 * n / sum(per_call) if per_call else None, "calls": n,
+            "ms_per_decode_mean": sum(per_call) / n if n else None,
+            "ms_per_decode_p50": per_call[n // 2] if n else None,
+            "ms_per_decode_p99": per_call[min(n - 1, int(0.99 * n))] if n else None,
+        }
+    os.environ.pop("JSMPEG_B200_LOOKAHEAD", None)
+    f, s, kind = run_reference_cpu([es], 1, 2)
+    out["reference_one_core"] = {"fps": f / s if s > 0 else None, "kind": kind}
+    out["what"] = (f"one {width}x{height} stream, {PICTURES} pictures, mpeg1_decoder_create/get_write_ptr/did_write once, then "
+                   "mpeg1_decoder_decode() until false; every call ends with the picture's planes in pinned host memory")
+    return out
 
 
 def main():
@@ -231,16 +509,20 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="value leg only (used for the ncu launch list)")
+    ap.add_argument("--no-extras", action="store_true", help="skip config_720p / single_stream_1080p")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
 
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
     world = env_int("WORLD_SIZE", 1)
+    local_world = env_int("LOCAL_WORLD_SIZE", world)
     pix = WIDTH * HEIGHT
+    cores = host_cores()
     base_config = {
         "workload": f"{STREAMS_PER_GPU} independent {WIDTH}x{HEIGHT} MPEG-1 I+P elementary streams x {PICTURES} pictures per GPU "
                     f"(BASELINE configs[3]; weak-scaled x N GPUs = configs[4]), GOP 12, one slice per picture",
-        "streams_per_gpu": STREAMS_PER_GPU, "pictures_per_stream": PICTURES, "distinct_clips": DISTINCT,
+        "streams_per_gpu": STREAMS_PER_GPU, "pictures_per_stream": PICTURES, "distinct_clips_per_gpu": DISTINCT,
         "parallelism": f"streams sharded {STREAMS_PER_GPU} per GPU, no collective",
         "l2": "inputs larger than L2 (ES + records per step >> 126 MB); no explicit flush",
     }
@@ -248,28 +530,26 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        clips = load_streams(0, 1)
-        threads = os.cpu_count() or 1
-        ref_pictures = min(PICTURES, env_int("BENCH_REF_PICTURES", 30))  # bounded sample: keeps a step at ~5 s
-        sample = cpu_sample(clips, threads, ref_pictures)
+        threads = cores["usable"]
+        clips = load_streams(rank_seeds(0, min(threads, STREAMS_PER_GPU)))
+        sample = [clips[i % len(clips)] for i in range(threads)]  # one whole clip (all PICTURES pictures) per thread
         for _ in range(min(args.warmup, 1)):
-            run_reference_cpu(sample[:threads], threads, 1)
-        frames = 0
-        seconds = 0.0
-        kind = "reference"
+            run_reference_cpu(sample, threads, 1)
+        frames, seconds, kind = 0, 0.0, "reference"
         for _ in range(args.steps):
             f, s, kind = run_reference_cpu(sample, threads, 1)
             frames += f
             seconds += s
         fps = frames / seconds
-        desc = (f"{threads} threads x 1 clip x first {ref_pictures} of {PICTURES} pictures per step "
-                f"({len(clips)} distinct {WIDTH}x{HEIGHT} clips, same streams as the GPU arm)")
+        desc = (f"{threads} threads (usable cores: affinity {cores['affinity']}, cgroup quota {cores['cgroup_quota_cpus']}, "
+                f"cpu_count {cores['cpu_count']}) x 1 clip x all {PICTURES} pictures per step ({len(clips)} distinct {WIDTH}x{HEIGHT} "
+                f"clips, same streams as the GPU arm); only the decode() loops are timed")
         print(json.dumps({
             "impl": "reference", "metric": "MPEG-1 video decode frames/s", "value": fps, "unit": "frames/s",
             "gpix_per_s": fps * pix / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * seconds / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": base_config,
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": desc},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": desc, "host": cores},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }))
@@ -278,113 +558,41 @@ def main():
     # NCCL is used for the barrier / counter reduction only; keep its banner off stdout (one JSON line)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
+    # this rank's host side lives on its GPU's NUMA node: threads, pinned bit buffers and plane rings
+    from jsmpeg_b200 import capi
+    numa = capi.bind_host_to_device(local_rank)
+    cores_rank = host_cores()
+    per_rank_cores = max(1, cores_rank["usable"] // max(1, local_world) if cores_rank["cgroup_quota_cpus"] else cores_rank["usable"])
     import torch
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
-    from jsmpeg_b200.batch import OUT_DEVICE, OUT_HOST, BatchDecoder
+    seeds = rank_seeds(rank)
+    streams = load_streams(sorted(set(seeds)), workers=per_rank_cores)
+    by_seed = dict(zip(sorted(set(seeds)), streams))
+    streams = [by_seed[s] for s in seeds]
+    if world > 1:
+        dist.barrier()
+    e2e_groups = max(1, min(E2E_GROUPS, per_rank_cores))
+    legs = Legs(streams, WIDTH, HEIGHT, local_rank, world, e2e_groups)
 
-    clips = load_streams(rank, world)
-    streams = [clips[(i + rank) % len(clips)] for i in range(STREAMS_PER_GPU)]
-    # value: VALUE_GROUPS decoders share the 64 streams; with more than one, each is driven by its own
-    # host thread and the groups run free (one group's reconstruct/expand overlaps another's walk)
-    vgroups = [list(range(g, STREAMS_PER_GPU, VALUE_GROUPS)) for g in range(VALUE_GROUPS)]
-    value_decoders = [BatchDecoder(len(g), device=local_rank, max_slots=len(g) * PICTURES + 8) for g in vgroups]
-    for dec, g in zip(value_decoders, vgroups):
-        for j, i in enumerate(g):
-            dec.write(j, streams[i])
-        dec.upload()  # elementary streams resident in HBM before the timed region
-    bd = value_decoders[0]
-
-    def barrier():
-        torch.cuda.synchronize()
+    frames, dt, st, clocks = legs.timed(legs.run_device, args.steps, args.warmup, legs.value_decoders)
+    verdict = {"verified": None, "why": "--no-verify"}
+    if not args.no_verify:
+        verdict = legs.verify(seeds, per_rank_cores)
+        verdict["lane_walk_pictures_equal_pictures"] = st.get("lane_walk_pictures", 0) == st.get("pictures", -1)
         if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def step_device():
-        bd.rewind()
-        return bd.decode(PICTURES, OUT_DEVICE)
-
-    # e2e: E2E_GROUPS smaller decoders, one host thread each (ctypes releases the GIL in the C calls)
-    groups = [list(range(g, STREAMS_PER_GPU, E2E_GROUPS)) for g in range(E2E_GROUPS)]
-    e2e_decoders = [BatchDecoder(len(g), device=local_rank, max_slots=len(g) * PICTURES + 8) for g in groups]
-    for dec, g in zip(e2e_decoders, groups):   # sequence headers parsed once, like a decoder that has seen its stream start
-        for j, i in enumerate(g):
-            dec.write(j, streams[i])
-
-    def run_e2e(n_steps):
-        """n_steps whole-workload steps: every group's thread runs its n_steps back to back (no
-        per-step join), so one group's PCIe copy-out overlaps the others' write + parse."""
-        counts = [0] * E2E_GROUPS
-
-        def work(k):
-            dec = e2e_decoders[k]
-            for _ in range(n_steps):
-                dec.reset()
-                for j, i in enumerate(groups[k]):
-                    dec.write(j, streams[i])
-                counts[k] += dec.decode(PICTURES, OUT_HOST)
-
-        threads = [threading.Thread(target=work, args=(k,)) for k in range(E2E_GROUPS)]
-        for th in threads:
-            th.start()
-        for th in threads:
-            th.join()
-        return sum(counts)
-
-    def timed(run, steps, warmup, decoders):
-        """run(n) performs n steps and returns the pictures decoded."""
-        sampler = ClockSampler(local_rank)
-        sampler.start()  # started before the warm-up so that it is already streaming samples
-        run(warmup)
-        barrier()
-        for d in decoders:
-            d.reset_stats()
-        sampler.mark()
-        t0 = time.perf_counter()
-        frames = run(steps)
-        barrier()
-        dt = time.perf_counter() - t0
-        clocks = sampler.stop()
-        st = {}
-        for d in decoders:
-            for k, v in d.stats().items():
-                st[k] = st.get(k, 0) + v
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            fr = torch.tensor([frames], dtype=torch.float64, device="cuda")
-            dist.all_reduce(fr, op=dist.ReduceOp.SUM)
-            dt, frames = float(t.item()), int(fr.item())
-        return frames, dt, st, clocks
-
-    def run_device(n_steps):
-        if VALUE_GROUPS == 1:
-            return sum(step_device() for _ in range(n_steps))
-        counts = [0] * VALUE_GROUPS
-
-        def work(k):
-            dec = value_decoders[k]
-            for _ in range(n_steps):
-                dec.rewind()
-                counts[k] += dec.decode(PICTURES, OUT_DEVICE)
-
-        threads = [threading.Thread(target=work, args=(k,)) for k in range(VALUE_GROUPS)]
-        for th in threads:
-            th.start()
-        for th in threads:
-            th.join()
-        return sum(counts)
-
-    frames, dt, st, clocks = timed(run_device, args.steps, args.warmup, value_decoders)
+            ok = torch.tensor([1.0 if verdict["verified"] and verdict["lane_walk_pictures_equal_pictures"] else 0.0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            verdict["all_ranks"] = bool(ok.item() > 0.5)
     e_steps = args.steps
     if args.no_e2e:
         e_frames, e_dt, e_st, e_clocks = 0, 1.0, {"h2d_bytes": 0, "d2h_bytes": 0}, None
     else:
-        e_frames, e_dt, e_st, e_clocks = timed(run_e2e, e_steps, 3, e2e_decoders)
+        e_frames, e_dt, e_st, e_clocks = legs.timed(legs.run_e2e, e_steps, 3, legs.e2e_decoders)
+    legs.close()
 
     if rank != 0:
         if world > 1:
@@ -394,8 +602,6 @@ def main():
     fps = frames / dt
     e_fps = e_frames / e_dt
     peak, peak_src = measured_peak()
-    recon_s = st["recon_ms"] / 1e3
-    achieved = st["algorithmic_bytes"] / recon_s / 1e9 if recon_s > 0 else 0.0
     traffic = recorded_traffic()
     out = {
         "metric": "MPEG-1 video decode frames/s", "value": fps, "unit": "frames/s",
@@ -405,22 +611,14 @@ def main():
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": base_config,
         "clocks": clocks,
+        "verified": verdict.get("verified"), "verification": verdict,
         "e2e": {"value": e_fps, "unit": "frames/s", "gpix_per_s": e_fps * pix / 1e9,
                 "h2d_bytes_per_step": e_st["h2d_bytes"] // e_steps,
                 "d2h_bytes_per_step": e_st["d2h_bytes"] // e_steps,
                 "ms_per_step": 1e3 * e_dt / e_steps, "steps": e_steps, "warmup": 3,
-                "host_threads": E2E_GROUPS, "clocks": e_clocks},
+                "host_threads": e2e_groups, "numa": numa, "clocks": e_clocks},
         "gpu_launches": st["kernel_launches"], "value_host_threads": VALUE_GROUPS,
-        "roofline": {
-            "kernel": "reconstruct_kernel (stage 2: IDCT + motion compensation + add/clamp)",
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if peak else None, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": st["algorithmic_bytes"] / max(1, st["recon_launches"]),
-            "avg_launch_ms": st["recon_ms"] / max(1, st["recon_launches"]),
-            "launches": st["recon_launches"],
-            "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-            "traffic_source": traffic["source"] if traffic else None,
-        },
+        "roofline": roofline_block(st, peak, peak_src, traffic),
         "stage_ms_per_step": {"scan": st["scan_ms"] / args.steps, "parse": st["parse_ms"] / args.steps,
                               "reconstruct": st["recon_ms"] / args.steps},
         "stage1": {"es_mbit_per_s": st["es_bytes"] * 8 / (st["parse_ms"] / 1e3) / 1e6 if st["parse_ms"] else None,
@@ -428,19 +626,44 @@ def main():
                    "parse_errors": st["parse_errors"],
                    "walk": os.environ.get("JSMPEG_B200_WALK") or "lanes",
                    "lane_walk_pictures_per_step": st.get("lane_walk_pictures", 0) / args.steps},
+        "host": cores_rank,
     }
+    if world == 1 and EXTRAS and not args.no_extras:
+        # BASELINE configs[1]: 1280x720, the same legs
+        w2, h2 = 1280, 720
+        streams2 = load_streams(sorted(set(seeds)), w2, h2, workers=per_rank_cores)
+        by2 = dict(zip(sorted(set(seeds)), streams2))
+        legs2 = Legs([by2[s] for s in seeds], w2, h2, local_rank, 1, e2e_groups)
+        f2, dt2, st2, _ = legs2.timed(legs2.run_device, args.steps, args.warmup, legs2.value_decoders)
+        v2 = legs2.verify(seeds, per_rank_cores) if not args.no_verify else {"verified": None}
+        if args.no_e2e:
+            ef2, edt2 = 0, 1.0
+        else:
+            ef2, edt2, _, _ = legs2.timed(legs2.run_e2e, e_steps, 3, legs2.e2e_decoders)
+        legs2.close()
+        out["config_720p"] = {
+            "workload": f"{STREAMS_PER_GPU} x {w2}x{h2} x {PICTURES} pictures (BASELINE configs[1] shape, batched like configs[3])",
+            "value": f2 / dt2, "unit": "frames/s", "gpix_per_s": f2 / dt2 * w2 * h2 / 1e9, "ms_per_step": 1e3 * dt2 / args.steps,
+            "e2e": {"value": ef2 / edt2, "unit": "frames/s", "gpix_per_s": ef2 / edt2 * w2 * h2 / 1e9},
+            "roofline": roofline_block(st2, peak, peak_src, None), "verified": v2.get("verified"),
+            "stage_ms_per_step": {"scan": st2["scan_ms"] / args.steps, "parse": st2["parse_ms"] / args.steps,
+                                  "reconstruct": st2["recon_ms"] / args.steps},
+        }
+        # BASELINE configs[2]: one 1080p stream through the reference ABI
+        out["single_stream_1080p"] = single_stream_leg(streams[0], WIDTH, HEIGHT, local_rank)
     if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
-        sample = cpu_sample(clips, threads)
-        loops = 1
-        f, s, kind = run_reference_cpu(sample, threads, loops)
+        threads = cores_rank["usable"]
+        sample = [streams[i % len(streams)] for i in range(threads)]
+        f, s, kind = run_reference_cpu(sample, threads, 1)
         out["cpu_baseline"] = {"value": f / s, "unit": "frames/s", "gpix_per_s": f / s * pix / 1e9, "cores": threads,
-                               "kind": kind,
-                               "sample": f"{threads} threads x 1 clip x {PICTURES} pictures x {loops} loops of the same {WIDTH}x{HEIGHT} clips"}
+                               "kind": kind, "host": cores_rank,
+                               "sample": f"{threads} threads (usable cores = min(affinity, cgroup quota)) x 1 clip x all {PICTURES} "
+                                         f"pictures of the same {WIDTH}x{HEIGHT} clips; only the decode() loops are timed"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    bad = verdict.get("verified") is False or verdict.get("lane_walk_pictures_equal_pictures") is False
+    return 1 if bad else 0
 
 
 if __name__ == "__main__":

@@ -180,6 +180,12 @@ const char *jsmpeg_b200_decoder_last_error(mpeg1_decoder_t *self);
  * device argument; the JS/Python class passes its `device` option here). */
 void jsmpeg_b200_set_default_device(int device);
 
+/* Bind the calling thread (and the threads it creates, and the pages it first touches, from now on) to
+ * the CPUs of the NUMA node CUDA device `device` hangs off, intersected with its current affinity: a
+ * decoder's pinned bit buffer and plane ring should live next to its GPU.  Returns the number of CPUs
+ * bound to, 0 when the node is unknown (nothing changed), -1 on error; *node_out (may be NULL) = the node. */
+int jsmpeg_b200_bind_host_to_device(int device, int *node_out);
+
 const char *jsmpeg_b200_version(void);
 
 #ifdef __cplusplus

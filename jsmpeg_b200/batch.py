@@ -58,6 +58,7 @@ _BATCH_ABI = {
     "jsmpeg_b200_batch_last_error": (ctypes.c_char_p, [_VP]),
     "jsmpeg_b200_batch_set_option": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_int]),
     "jsmpeg_b200_decoder_last_error": (ctypes.c_char_p, [_VP]),
+    "jsmpeg_b200_bind_host_to_device": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "jsmpeg_b200_version": (ctypes.c_char_p, []),
 }
 

@@ -63,3 +63,11 @@ def product_library():
         from . import batch as _batch  # binds the batch-extension symbols on the same handle
         _batch.bind_batch_abi(_product)
     return _product
+
+
+def bind_host_to_device(device):
+    """Bind this thread (and the threads / pinned pages it creates from now on) to the CPUs of the NUMA
+    node of CUDA device `device` (jsmpeg_b200_bind_host_to_device).  Returns {"node", "cpus"}."""
+    node = ctypes.c_int(-1)
+    n = product_library().jsmpeg_b200_bind_host_to_device(int(device), ctypes.byref(node))
+    return {"node": node.value if n > 0 else None, "cpus": n if n > 0 else None, "bound": n > 0}

@@ -27,6 +27,8 @@
 // a SECOND stream -- while the parse of the following chunks is running.  Stage 1 (latency-bound, few
 // resident warps) and stage 2 (bandwidth / issue-bound) are natural co-runners; round 1 serialised
 // them with a host synchronisation between the parse wave and the first reconstruct launch.
+#include <sched.h>
+
 #include <algorithm>
 #include <cstring>
 #include <deque>
@@ -239,8 +241,9 @@ void parse_sequence_header(Batch *b, Stream &s, uint32_t bit_index) {
 	s.d_seq = dev_alloc<SeqParams>(1);
 	CUDA_CHECK(cudaMemcpyAsync(s.d_seq, &s.seq, sizeof(SeqParams), cudaMemcpyHostToDevice, b->st_main));
 	for (int i = 0; i < 2; i++) {
-		s.d_planes[i] = dev_alloc<uint8_t>(plane_bytes + 64);
-		CUDA_CHECK(cudaMemsetAsync(s.d_planes[i], 0, plane_bytes + 64, b->st_main));  // JS typed arrays start zeroed
+		// + coded_width + 64: stage 2's row loads may touch (never use) up to one row past a plane set's end
+		s.d_planes[i] = dev_alloc<uint8_t>(plane_bytes + s.seq.coded_width + 64);
+		CUDA_CHECK(cudaMemsetAsync(s.d_planes[i], 0, plane_bytes + s.seq.coded_width + 64, b->st_main));  // JS typed arrays start zeroed
 	}
 	for (int i = 0; i < HOST_RING; i++) {
 		s.h_planes[i] = pinned_alloc<uint8_t>(plane_bytes);
@@ -659,6 +662,7 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 					t.coded_height = s.seq.coded_height;
 					t.width = s.width;
 					t.height = s.height;
+					t.n_coded_blocks = e.info.n_coded_blocks;
 					t.rgba = nullptr;
 					if (flags & JSMPEG_B200_OUT_RGBA) {
 						if (!s.d_rgba) s.d_rgba = dev_alloc<uint8_t>((size_t)s.width * s.height * 4);
@@ -1033,6 +1037,48 @@ struct mpeg1_decoder_t {
 	jsmpeg_b200_batch_t *b;
 };
 
+// Host placement.  The pinned bit buffers and plane rings of a decoder are touched by the host threads
+// that drive it and by the GPU's copy engines; on a two-socket host a GPU hangs off ONE socket, and a
+// ring on the other socket costs every D2H byte a trip over the socket interconnect (round 1: the
+// 8-GPU e2e curve went flat at 4 GPUs).  This binds the CALLING THREAD -- and with it the threads it
+// creates and the pages it first touches from now on -- to the CPUs of the NUMA node of `device`
+// (sysfs: /sys/bus/pci/devices/<id>/numa_node, /sys/devices/system/node/node<k>/cpulist), intersected
+// with the affinity it already has.  Returns the number of CPUs bound to, 0 if the node is unknown
+// (nothing changed), -1 on error.  node_out (may be NULL) receives the node.
+int jsmpeg_b200_bind_host_to_device(int device, int *node_out) {
+	if (node_out) *node_out = -1;
+	char id[32] = {0};
+	if (cudaDeviceGetPCIBusId(id, sizeof id, device) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+	for (char *c = id; *c; c++) if (*c >= 'A' && *c <= 'F') *c += 'a' - 'A';
+	char path[128];
+	snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", id);
+	FILE *f = fopen(path, "r");
+	int node = -1;
+	if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+	if (node < 0) return 0;
+	snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+	f = fopen(path, "r");
+	if (!f) return 0;
+	cpu_set_t want, have, both;
+	CPU_ZERO(&want);
+	int lo, hi;
+	while (fscanf(f, "%d", &lo) == 1) {  // "0-31,64-95"
+		hi = lo;
+		int ch = fgetc(f);
+		if (ch == '-') { if (fscanf(f, "%d", &hi) != 1) hi = lo; ch = fgetc(f); }
+		for (int c = lo; c <= hi && c < CPU_SETSIZE; c++) CPU_SET(c, &want);
+		if (ch != ',') break;
+	}
+	fclose(f);
+	if (sched_getaffinity(0, sizeof have, &have) != 0) return -1;
+	CPU_AND(&both, &want, &have);
+	const int n = CPU_COUNT(&both);
+	if (n == 0) return 0;
+	if (sched_setaffinity(0, sizeof both, &both) != 0) return -1;
+	if (node_out) *node_out = node;
+	return n;
+}
+
 static int g_default_device = -1;  // -1: JSMPEG_B200_DEVICE or 0
 void jsmpeg_b200_set_default_device(int device) { g_default_device = device; }
 
@@ -1135,7 +1181,9 @@ int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, 
 		const size_t ysz = n_mb * 256, csz = ysz / 4, total = ysz + 2 * csz;
 		mb_record_t *d_hdr = dev_alloc<mb_record_t>(n_mb);
 		int16_t *d_coef = dev_alloc<int16_t>(n_mb * MB_COEF_INT16);
-		uint8_t *d_fwd = dev_alloc<uint8_t>(total + 64), *d_cur = dev_alloc<uint8_t>(total + 64);
+		const size_t pad = (size_t)mb_width * 16 + 64;
+		uint8_t *d_fwd = dev_alloc<uint8_t>(total + pad), *d_cur = dev_alloc<uint8_t>(total + pad);
+		CUDA_CHECK(cudaMemset(d_fwd + total, 0, pad));
 		CUDA_CHECK(cudaMemcpy(d_hdr, hdr, n_mb * sizeof(mb_record_t), cudaMemcpyHostToDevice));
 		CUDA_CHECK(cudaMemcpy(d_coef, coef, n_mb * MB_COEF_INT16 * sizeof(int16_t), cudaMemcpyHostToDevice));
 		CUDA_CHECK(cudaMemcpy(d_fwd, fwd_y, ysz, cudaMemcpyHostToDevice));
@@ -1150,6 +1198,12 @@ int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, 
 		t.fwd = PlaneSet{d_fwd, d_fwd + ysz, d_fwd + ysz + csz};
 		t.mb_width = mb_width; t.mb_size = (int)n_mb;
 		t.coded_width = mb_width * 16; t.coded_height = mb_height * 16;
+		{  // the count the walk would have reported
+			const mb_record_t *h = static_cast<const mb_record_t *>(hdr);
+			int n = 0;
+			for (size_t i = 0; i < n_mb; i++) if (h[i].flags & MBF_PRESENT) n += __builtin_popcount(h[i].cbp & 0x3f);
+			t.n_coded_blocks = n;
+		}
 		launch_reconstruct(&t, 1, 0);
 		CUDA_CHECK(cudaGetLastError());
 		CUDA_CHECK(cudaDeviceSynchronize());

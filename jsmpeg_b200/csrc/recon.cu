@@ -40,7 +40,7 @@ namespace {
 __global__ void __launch_bounds__(THREADS, 5)
 reconstruct_kernel(const __grid_constant__ ReconParams params) {
 	__shared__ __align__(16) uint8_t stage[(THREADS / 32) * WARP_STAGE];
-	reconstruct_block(params.t[blockIdx.y], blockIdx.x * THREADS, threadIdx.x, stage);
+	reconstruct_block(params, blockIdx.y, blockIdx.x * THREADS, threadIdx.x, stage);
 }
 
 }  // namespace
@@ -58,9 +58,16 @@ void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t s
 			p.t[i].fwd = t.fwd.y;
 			p.t[i].mb_width = t.mb_width;
 			p.t[i].mb_height = t.mb_size / t.mb_width;
-			p.t[i].pad[0] = p.t[i].pad[1] = 0;
+			p.t[i].row_magic = (uint32_t)(0x100000000ull / (uint64_t)(6 * t.mb_width)) + 1u;
+			// dense: at least 3 of 4 block slots carry a coded block -- fetching every slot's record before the
+			// header is known costs at most a third more record bytes and takes one memory latency off the chain
+			// (JSMPEG_B200_RECON_DENSE=0 / 1 forces one path: tests, A/B)
+			static const int force_dense = [] { const char *e = getenv("JSMPEG_B200_RECON_DENSE"); return e && *e ? atoi(e) : -1; }();
+			const bool dense = force_dense >= 0 ? force_dense != 0 : (int64_t)t.n_coded_blocks * 4 >= (int64_t)t.mb_size * 6 * 3;
+			p.t[i].flags = dense ? RT_DENSE : 0;
 			max_slots = max_slots > t.mb_size * 6 ? max_slots : t.mb_size * 6;
 		}
+		p.n_tasks = n;
 		dim3 grid((max_slots + THREADS - 1) / THREADS, n);
 		reconstruct_kernel<<<grid, THREADS, 0, stream>>>(p);
 	}

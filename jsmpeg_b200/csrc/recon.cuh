@@ -15,18 +15,30 @@ constexpr int ROW_PITCH = 144;                       // bytes per staged block: 
 constexpr int WARP_STAGE = 32 * ROW_PITCH + 16;      // + the warp's mbarrier
 constexpr int MAX_TASKS = 80;  // per launch; (80 * 48 B) + 16 < 4 KB of kernel parameters
 
+enum { RT_DENSE = 1 };  // CompactTask::flags
+
 struct CompactTask {
 	const mb_record_t *hdr;
 	const int16_t *coef;
-	uint8_t *cur;        // Y at 0, Cr at coded_size, Cb at coded_size * 5 / 4
+	uint8_t *cur;        // Y at 0, Cr at coded_size, Cb at coded_size * 5 / 4; readable for coded_width + 64 bytes past the end
 	const uint8_t *fwd;
 	int32_t mb_width, mb_height;
-	int32_t pad[2];
+	uint32_t row_magic;  // floor(2^32 / (6 mb_width)) + 1: slot / (6 mb_width) == umulhi(slot, row_magic) for every slot of a picture
+	uint32_t flags;      // RT_DENSE: almost every block is coded -- all coefficient records are requested before the header is known
 };
 
 struct ReconParams {
 	CompactTask t[MAX_TASKS];
+	int32_t n_tasks;
 };
+
+#ifndef JSMPEG_WALK_EMU
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t umulhi_u32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#else
+static inline void prefetch_l2(const void *) {}
+static inline uint32_t umulhi_u32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+#endif
 
 // PREMULTIPLIER_MATRIX (src/mpeg1.js:1026-1035) = outer product of these AAN scales, rounded as the
 // reference's table is; kept as a constexpr so that every use folds into an immediate.
@@ -133,9 +145,10 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
 // are data, the instruction stream is the same for every lane.
 // FULLPEL (warp-uniform: no lane has a half-pel component) is the plain copy: one dp4a per sample
 // selects the byte and adds the residual.
+// v = the residual, all zero for a block that is not coded.
 template <bool FULLPEL>
 __device__ __forceinline__ void predict_rows(const uint8_t *__restrict__ splane, int src, int stride, uint32_t weights,
-                                             bool coded, const int (&v)[64], uint8_t *__restrict__ dst) {
+                                             const int (&v)[64], uint8_t *__restrict__ dst) {
 	uint32_t a0, a1, a2;
 	row9(splane, src, a0, a1, a2);
 #pragma unroll
@@ -146,24 +159,29 @@ __device__ __forceinline__ void predict_rows(const uint8_t *__restrict__ splane,
 			if (r < 7) row9(splane, src + (r + 1) * stride, c0, c1, c2);
 #pragma unroll
 			for (int x = 0; x < 4; x++) {
-				s[x] = dp4a_us(a0, 1u << (8 * x), coded ? v[r * 8 + x] : 0);
-				s[4 + x] = dp4a_us(a1, 1u << (8 * x), coded ? v[r * 8 + 4 + x] : 0);
+				s[x] = dp4a_us(a0, 1u << (8 * x), v[r * 8 + x]);
+				s[4 + x] = dp4a_us(a1, 1u << (8 * x), v[r * 8 + 4 + x]);
 			}
 		} else {
 			row9(splane, src + (r + 1) * stride, c0, c1, c2);  // row 8 is inside the plane (checked by the caller)
 			const uint32_t sa0 = __funnelshift_r(a0, a1, 8), sa1 = __funnelshift_r(a1, a2, 8);  // samples 1..4, 5..8
 			const uint32_t sc0 = __funnelshift_r(c0, c1, 8), sc1 = __funnelshift_r(c1, c2, 8);
-			// taps (A, B, C, D) = (row[x], row[x+1], next[x], next[x+1]) as one word per sample
-			s[0] = dp4a_us(__byte_perm(a0, c0, 0x5410), weights, 2);
-			s[1] = dp4a_us(__byte_perm(a0, c0, 0x6521), weights, 2);
-			s[2] = dp4a_us(__byte_perm(a0, c0, 0x7632), weights, 2);
-			s[3] = dp4a_us(__byte_perm(sa0, sc0, 0x7632), weights, 2);
-			s[4] = dp4a_us(__byte_perm(a1, c1, 0x5410), weights, 2);
-			s[5] = dp4a_us(__byte_perm(a1, c1, 0x6521), weights, 2);
-			s[6] = dp4a_us(__byte_perm(a1, c1, 0x7632), weights, 2);
-			s[7] = dp4a_us(__byte_perm(sa1, sc1, 0x7632), weights, 2);
+			// taps (A, B, C, D) = (row[x], row[x+1], next[x], next[x+1]) as one word per sample.  The residual
+			// rides in the accumulator: (sum + 2 + 4 res) >> 2 == ((sum + 2) >> 2) + res exactly, and 4 res + 2
+			// is a multiply-add on the FMA pipe instead of an add on the ALU pipe that bounds this kernel.
+			int acc[8];
 #pragma unroll
-			for (int x = 0; x < 8; x++) s[x] = (s[x] >> 2) + (coded ? v[r * 8 + x] : 0);
+			for (int x = 0; x < 8; x++) acc[x] = v[r * 8 + x] * 4 + 2;
+			s[0] = dp4a_us(__byte_perm(a0, c0, 0x5410), weights, acc[0]);
+			s[1] = dp4a_us(__byte_perm(a0, c0, 0x6521), weights, acc[1]);
+			s[2] = dp4a_us(__byte_perm(a0, c0, 0x7632), weights, acc[2]);
+			s[3] = dp4a_us(__byte_perm(sa0, sc0, 0x7632), weights, acc[3]);
+			s[4] = dp4a_us(__byte_perm(a1, c1, 0x5410), weights, acc[4]);
+			s[5] = dp4a_us(__byte_perm(a1, c1, 0x6521), weights, acc[5]);
+			s[6] = dp4a_us(__byte_perm(a1, c1, 0x7632), weights, acc[6]);
+			s[7] = dp4a_us(__byte_perm(sa1, sc1, 0x7632), weights, acc[7]);
+#pragma unroll
+			for (int x = 0; x < 8; x++) s[x] >>= 2;
 		}
 		uint2 out;
 		out.x = pack_sat_u8x4(s[0], s[1], s[2], s[3]);
@@ -179,16 +197,26 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 static inline uint32_t smem_u32(const void *) { return 0; }
 #endif
 
-// One 8x8 block: slot first_slot + tid of the picture (see above); `stage` = the CTA's staging area
-// (one WARP_STAGE per warp), tid = the thread's index in the CTA.
-// WARP-CONVERGENT: the 32 lanes of a warp call it together (two collectives inside).
-__device__ __forceinline__ void reconstruct_block(const CompactTask &t, int first_slot, int tid, uint8_t *stage) {
+// One 8x8 block: slot first_slot + tid of picture `ty` of the launch (see above); `stage` = the CTA's
+// staging area (one WARP_STAGE per warp), tid = the thread's index in the CTA.
+// WARP-CONVERGENT: the 32 lanes of a warp call it together (collectives inside).
+//
+// Latency plan (round 2; the kernel was stalled on memory it asked for too late -- long-scoreboard 2.7
+// warps per issue at 4.5 resident warps per scheduler, profiles/r2_reconstruct.md):
+//   t0  the coefficient records of a DENSE picture are requested (TMA) before anything is known about
+//       the macroblocks: the address depends on the slot alone;  the header load starts;  the header
+//       and the record of the CTA that will run here two pictures of the launch later are pulled into L2
+//   t1  header there: the nine reference rows of a predicted block are pulled into L2 (no registers)
+//   t2  records there: IDCT (some 700 instructions) -- the reference rows arrive meanwhile
+//   t3  prediction reads hit L2, + residual, store
+__device__ __forceinline__ void reconstruct_block(const ReconParams &params, int ty, int first_slot, int tid, uint8_t *stage) {
+	const CompactTask &t = params.t[ty];
 	const int W = t.mb_width;
 	const int slots_per_row = 6 * W;
 	const int slot = first_slot + tid;
 	const int lane = tid & 31;
 	const bool in_picture = slot < slots_per_row * t.mb_height;
-	const int mb_row = in_picture ? slot / slots_per_row : 0;
+	const int mb_row = in_picture ? (int)umulhi_u32((uint32_t)slot, t.row_magic) : 0;
 	const int s = in_picture ? slot - mb_row * slots_per_row : 0;
 	// [luma top 2W | luma bottom 2W | Cb W | Cr W]
 	int b, mb_col;
@@ -204,9 +232,43 @@ __device__ __forceinline__ void reconstruct_block(const CompactTask &t, int firs
 		b = 4 + second;  // block 4 -> Cb plane, block 5 -> Cr plane (mpeg1.js:829-834)
 	}
 	const int mb = mb_row * W + mb_col;
+	const bool dense = t.flags & RT_DENSE;
+
+	uint8_t *wstage = stage + (tid >> 5) * WARP_STAGE;
+	const uint32_t mbar = smem_u32(wstage + 32 * ROW_PITCH);
+	const uint32_t my_row = smem_u32(wstage + lane * ROW_PITCH);
+	const int16_t *cblk = t.coef + ((size_t)mb * 6 + b) * 64;
+
+	// ---- coefficient records of the warp's blocks: one TMA bulk copy per lane
+	// `want` = this lane's record is copied; warp-uniform `copy_mask` = which lanes' are
+	auto request_records = [&](bool want, unsigned copy_mask) {
+#ifndef JSMPEG_WALK_EMU
+		if (lane == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(128u * (uint32_t)__popc(copy_mask)) : "memory");
+		}
+		__syncwarp();
+		if (want)
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];"
+			             ::"r"(my_row), "l"(cblk), "r"(mbar) : "memory");
+#else
+		(void)mbar; (void)copy_mask;
+		if (want) memcpy(wstage + lane * ROW_PITCH, cblk, 128);  // the emulated "TMA": the lane's record into its staging row
+#endif
+	};
+	const unsigned in_mask = __ballot_sync(0xffffffffu, in_picture);
+	if (dense && in_mask) request_records(in_picture, in_mask);  // t0: before the header is known (uncoded slots hold stale bytes: never used)
 
 	uint2 rec = make_uint2(0, 0);
 	if (in_picture) rec = __ldg(reinterpret_cast<const uint2 *>(t.hdr + mb));
+	if (ty + 2 < params.n_tasks) {  // the CTA that runs on this SM next but one: its header and record, into L2
+		const CompactTask &t2 = params.t[ty + 2];
+		if (in_picture && mb < t2.mb_width * t2.mb_height) {
+			prefetch_l2(t2.hdr + mb);
+			prefetch_l2(t2.coef + ((size_t)mb * 6 + b) * 64);
+		}
+	}
 	const int flags = rec.y & 0xff;
 	const bool present = flags & MBF_PRESENT;  // an untouched macroblock keeps the two-pictures-old content
 	const bool intra = flags & MBF_INTRA;
@@ -215,28 +277,9 @@ __device__ __forceinline__ void reconstruct_block(const CompactTask &t, int firs
 	const bool dc_only = coded && ((rec.y >> 16) & bit);
 	const bool full = coded && !dc_only;
 
-	// ---- coefficient records of the warp's blocks: one TMA bulk copy per lane
-	uint8_t *wstage = stage + (tid >> 5) * WARP_STAGE;
-	const uint32_t mbar = smem_u32(wstage + 32 * ROW_PITCH);
-	const uint32_t my_row = smem_u32(wstage + lane * ROW_PITCH);
-	const int16_t *cblk = t.coef + ((size_t)mb * 6 + b) * 64;
-	const unsigned full_mask = __ballot_sync(0xffffffffu, full);
-	if (full_mask) {  // warp-uniform
-#ifndef JSMPEG_WALK_EMU
-		if (lane == 0) {
-			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(128u * (uint32_t)__popc(full_mask)) : "memory");
-		}
-		__syncwarp();
-		if (full)
-			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];"
-			             ::"r"(my_row), "l"(cblk), "r"(mbar) : "memory");
-#else
-		(void)mbar;
-		if (full) memcpy(wstage + lane * ROW_PITCH, cblk, 128);  // the emulated "TMA": the lane's record into its staging row
-#endif
-	}
+	const unsigned coded_mask = __ballot_sync(0xffffffffu, coded);
+	if (!dense && coded_mask) request_records(coded, coded_mask);  // sparse picture: only what is coded (the DC-only blocks' value too)
+	const bool copying = dense ? in_mask != 0 : coded_mask != 0;   // warp-uniform
 
 	const int stride_y = W * 16;
 	const int ysize = stride_y * t.mb_height * 16;
@@ -250,7 +293,23 @@ __device__ __forceinline__ void reconstruct_block(const CompactTask &t, int firs
 		origin = mb_row * 8 * stride + mb_col * 8;
 	}
 
-	if (full_mask) {  // wait for the warp's copies (phase 0 of a barrier used once)
+	// motion vector of this block's plane, and whether ANY lane of the warp needs half-pel taps
+	int mh = (int)(int16_t)(rec.x & 0xffffu), mv = (int)(int16_t)(rec.x >> 16);
+	if (b >= 4) { mh /= 2; mv /= 2; }  // truncation toward zero (mpeg1.js:562-565, SURVEY Q9)
+	const bool oh = mh & 1, ov = mv & 1;
+	const bool warp_halfpel = __any_sync(0xffffffffu, present && !intra && (oh || ov));
+	const int src = origin + (mv >> 1) * stride + (mh >> 1);  // flat index (mpeg1.js:479, 567)
+	const uint8_t *splane = t.fwd + plane_off;
+	// every tap the prediction USES lies inside the plane.  (What the row loads touch beyond them -- the
+	// rest of the last word, row 8 of a lane without a vertical half -- is inside the allocation: planes
+	// are contiguous and followed by coded_width + 64 readable bytes.)
+	const bool inside = src >= 0 && src + 7 * stride + 7 + (ov ? stride : 0) + (oh ? 1 : 0) < plane_size;
+	if (present && !intra && inside) {  // t1: the reference rows, into L2, while the records travel and the IDCT runs
+#pragma unroll
+		for (int r = 0; r < 9; r++) prefetch_l2(splane + src + r * stride + 4);
+	}
+
+	if (copying) {  // t2: wait for the warp's copies (phase 0 of a barrier used once)
 #ifndef JSMPEG_WALK_EMU
 		uint32_t done = 0;
 		while (!done)
@@ -258,11 +317,6 @@ __device__ __forceinline__ void reconstruct_block(const CompactTask &t, int firs
 			             : "=r"(done) : "r"(mbar) : "memory");
 #endif
 	}
-	// motion vector of this block's plane, and whether ANY lane of the warp needs half-pel taps
-	int mh = (int)(int16_t)(rec.x & 0xffffu), mv = (int)(int16_t)(rec.x >> 16);
-	if (b >= 4) { mh /= 2; mv /= 2; }  // truncation toward zero (mpeg1.js:562-565, SURVEY Q9)
-	const bool oh = mh & 1, ov = mv & 1;
-	const bool warp_halfpel = __any_sync(0xffffffffu, present && !intra && (oh || ov));
 	if (!present) return;
 
 	// ---- residual: 64 values in registers
@@ -287,7 +341,15 @@ __device__ __forceinline__ void reconstruct_block(const CompactTask &t, int firs
 		idct_rows<0>(v);
 	} else {
 		int dc = 0;
-		if (coded) dc = ((int)__ldg(cblk) * PM[0] + 128) >> 8;  // mpeg1.js:838-841, 850-853
+		if (coded) {  // mpeg1.js:838-841, 850-853: the staged record's first value
+			int16_t c0;
+#ifndef JSMPEG_WALK_EMU
+			asm volatile("ld.shared.s16 %0, [%1];" : "=h"(c0) : "r"(my_row));
+#else
+			memcpy(&c0, wstage + lane * ROW_PITCH, 2);
+#endif
+			dc = ((int)c0 * PM[0] + 128) >> 8;
+		}
 #pragma unroll
 		for (int i = 0; i < 64; i++) v[i] = dc;
 	}
@@ -305,13 +367,11 @@ __device__ __forceinline__ void reconstruct_block(const CompactTask &t, int firs
 	}
 
 	// ---- prediction from the forward picture + residual
-	const int src = origin + (mv >> 1) * stride + (mh >> 1);  // flat index (mpeg1.js:479, 567)
-	const uint8_t *splane = t.fwd + plane_off;
-	if (src >= 0 && src + 8 * stride + 8 < plane_size) {
+	if (inside) {
 		// tap weights of this lane: bytes (wA, wB, wC, wD)
 		const uint32_t weights = oh ? (ov ? 0x01010101u : 0x00000202u) : (ov ? 0x00020002u : 0x00000004u);
-		if (warp_halfpel) predict_rows<false>(splane, src, stride, weights, coded, v, dst);
-		else predict_rows<true>(splane, src, stride, weights, coded, v, dst);
+		if (warp_halfpel) predict_rows<false>(splane, src, stride, weights, v, dst);
+		else predict_rows<true>(splane, src, stride, weights, v, dst);
 		return;
 	}
 	// vector leaves the plane: per-tap bounds check, any outside tap zeroes the sample

@@ -207,7 +207,7 @@ def test_stage1_device_code_matches_the_oracle_coefficients(name):
     assert checked > 0
 
 
-def _pipeline_against_oracle_planes(es, name, define=None):
+def _pipeline_against_oracle_planes(es, name, define=None, dense_first=1):
     from jsmpeg_b200 import decoder
     olib = helpers.oracle_lib()
     d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
@@ -219,11 +219,12 @@ def _pipeline_against_oracle_planes(es, name, define=None):
     lib.emu_expand_picture.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.emu_reconstruct_picture.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                            ctypes.c_int, ctypes.c_int]
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int]
     mbw, mbh = stream_geometry(es)
     buf = np.frombuffer(es + b"\0" * 16, dtype=np.uint8).copy()
     ysize = mb * 256
-    planes = [np.zeros(ysize * 3 // 2 + 64, dtype=np.uint8) for _ in range(2)]  # Y | Cr | Cb, ping-pong (mpeg1.js:221-246)
+    # Y | Cr | Cb, ping-pong (mpeg1.js:221-246), with the product's readable slack behind (coded width + 64)
+    planes = [np.zeros(ysize * 3 // 2 + mbw * 16 + 64, dtype=np.uint8) for _ in range(2)]
     cur = 0
     checked = 0
     while d.decode():
@@ -238,7 +239,9 @@ def _pipeline_against_oracle_planes(es, name, define=None):
             continue  # B / D picture or P without f_code: consumed, nothing decoded, no swap (mpeg1.js:181-193)
         lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, park.ctypes.data, coef.ctypes.data,
                                pinfo.ctypes.data)
-        lib.emu_reconstruct_picture(hdr.ctypes.data, coef.ctypes.data, planes[cur].ctypes.data, planes[cur ^ 1].ctypes.data, mbw, mbh)
+        # both record-fetch paths of stage 2 (dense: every slot's record up front; sparse: coded blocks only), alternating
+        lib.emu_reconstruct_picture(hdr.ctypes.data, coef.ctypes.data, planes[cur].ctypes.data, planes[cur ^ 1].ctypes.data, mbw, mbh,
+                                    (checked + dense_first) & 1)
         y, cr, cb = d.planes()
         got = planes[cur]
         assert np.array_equal(got[:ysize], y), f"{name}: picture {checked}: Y differs"
@@ -256,7 +259,9 @@ def test_whole_hot_path_device_code_matches_the_oracle_planes(name):
     (jsmpeg_b200/csrc/recon.cuh, a warp = 32 coroutines, the TMA copy and the packed instructions
     replaced by plain C) with the product's ping-pong planes, against the ORACLE's planes of every
     decoded picture.  Bit-exact, like the GPU parity tests -- which remain the check of the real thing."""
-    _pipeline_against_oracle_planes(open(os.path.join(HERE, "golden", name + ".es"), "rb").read(), name)
+    es = open(os.path.join(HERE, "golden", name + ".es"), "rb").read()
+    _pipeline_against_oracle_planes(es, name)
+    _pipeline_against_oracle_planes(es, name, dense_first=0)  # the other fetch path on every picture
 
 
 def test_whole_hot_path_device_code_on_an_encoder_clip():

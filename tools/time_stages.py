@@ -17,7 +17,8 @@ streams = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 pictures = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 bench.PICTURES = pictures
-clips = bench.load_streams(0, 1)
+distinct = int(os.environ.get("TIME_STAGES_DISTINCT", "8"))
+clips = bench.load_streams([1234 + i for i in range(distinct)])
 bd = BatchDecoder(streams, max_slots=streams * pictures + 8)
 for i in range(streams):
     bd.write(i, clips[i % len(clips)])
