@@ -62,7 +62,17 @@ struct ParseTask {
 	uint2 *park;           // [mb_size][6]: per coded block {bit offset of its first coefficient code, intra dc * 8},
 	                       // the walk's hand-over to stage 1b (a dense side array, written and read as a stream)
 	int32_t mb_width, mb_size;  // copies of the sequence parameters (no dependent load in front of the walk)
+	// lane-parallel walk: staging area for relative macroblock records (walk.cuh, WALK_STAGE): stage_entries
+	// entries of 64 bytes, shared out among the lanes; nullptr = no staging (the walk then makes a second,
+	// storing pass over the bits)
+	uint4 *stage;
+	int32_t stage_entries;
 };
+
+// staging entries per picture: three per macroblock (a lane keeps its macroblocks in its own stretch and a
+// sub-sequence of small macroblocks holds more than the average; a lane that runs out falls back to the
+// second pass) + one per lane for rounding
+constexpr int stage_entries_for(int mb_size) { return 3 * mb_size + 64; }
 
 struct PlaneSet {
 	uint8_t *y, *cr, *cb;

@@ -116,6 +116,7 @@ struct jsmpeg_b200_batch_t {
 	mb_record_t *d_hdr = nullptr;
 	int16_t *d_coef = nullptr;
 	uint2 *d_park = nullptr;
+	uint4 *d_stage = nullptr;  // per slot: stage_entries_for(slot_mb) x 64 B (lane-parallel walk, relative records)
 	picture_info_t *d_info = nullptr, *h_info = nullptr;
 	std::vector<int> free_slots;
 	int lookahead = 1;
@@ -389,13 +390,16 @@ void ensure_pool(Batch *b) {
 	if (b->d_hdr) { CUDA_CHECK(cudaFree(b->d_hdr)); b->d_hdr = nullptr; }
 	if (b->d_coef) { CUDA_CHECK(cudaFree(b->d_coef)); b->d_coef = nullptr; }
 	if (b->d_park) { CUDA_CHECK(cudaFree(b->d_park)); b->d_park = nullptr; }
+	if (b->d_stage) { CUDA_CHECK(cudaFree(b->d_stage)); b->d_stage = nullptr; }
 	if (b->d_info) { CUDA_CHECK(cudaFree(b->d_info)); b->d_info = nullptr; }
 	if (b->h_info) { CUDA_CHECK(cudaFreeHost(b->h_info)); b->h_info = nullptr; }
 	b->slot_mb = 0;
 	b->n_slots = 0;
 	b->free_slots.clear();
-	// per macroblock: 16 B record + 6 x 128 B coefficient blocks + 6 x 8 B {bit offset, dc} side array
-	const size_t slot_bytes = (size_t)need_mb * (sizeof(mb_record_t) + MB_COEF_INT16 * sizeof(int16_t) + 6 * sizeof(uint2));
+	// per macroblock: 16 B record + 6 x 128 B coefficient blocks + 6 x 8 B {bit offset, dc} side array; per picture
+	// the lane-parallel walk's staging entries
+	const size_t slot_bytes = (size_t)need_mb * (sizeof(mb_record_t) + MB_COEF_INT16 * sizeof(int16_t) + 6 * sizeof(uint2)) +
+	                          (size_t)stage_entries_for(need_mb) * 64;
 	size_t n = b->max_slots_req;
 	size_t free_b = 0, total_b = 0;
 	CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
@@ -405,6 +409,7 @@ void ensure_pool(Batch *b) {
 	b->d_hdr = dev_alloc<mb_record_t>(n * need_mb);
 	b->d_coef = dev_alloc<int16_t>(n * need_mb * MB_COEF_INT16);
 	b->d_park = dev_alloc<uint2>(n * need_mb * 6);
+	b->d_stage = dev_alloc<uint4>(n * (size_t)stage_entries_for(need_mb) * 4);
 	b->d_info = dev_alloc<picture_info_t>(n);
 	b->h_info = pinned_alloc<picture_info_t>(n);
 	b->slot_mb = need_mb;
@@ -570,6 +575,8 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			t.info = b->d_info + i;
 			t.mb_width = s.seq.mb_width;
 			t.mb_size = s.seq.mb_size;
+			t.stage = b->d_stage + (size_t)p.slot * stage_entries_for(b->slot_mb) * 4;
+			t.stage_entries = stage_entries_for(b->slot_mb);
 		}
 		if (b->recon_pending) {  // slots freed by the previous round are still being read by its reconstruct launches
 			CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_round, 0));
@@ -837,6 +844,7 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 	if (b->d_hdr) cudaFree(b->d_hdr);
 	if (b->d_coef) cudaFree(b->d_coef);
 	if (b->d_park) cudaFree(b->d_park);
+	if (b->d_stage) cudaFree(b->d_stage);
 	if (b->d_info) cudaFree(b->d_info);
 	if (b->h_info) cudaFreeHost(b->h_info);
 	if (b->h_ptasks) cudaFreeHost(b->h_ptasks);
@@ -1149,6 +1157,7 @@ int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t
 		mb_record_t *d_hdr = dev_alloc<mb_record_t>(n_mb);
 		int16_t *d_coef = dev_alloc<int16_t>(n_mb * MB_COEF_INT16);
 		uint2 *d_park = dev_alloc<uint2>(n_mb * 6);
+		uint4 *d_stage = dev_alloc<uint4>((size_t)stage_entries_for(sp.mb_size) * 4);
 		picture_info_t *d_info = dev_alloc<picture_info_t>(1);
 		ParseTask *d_task = dev_alloc<ParseTask>(1);
 		CUDA_CHECK(cudaMemcpy(d_es, es, es_len, cudaMemcpyHostToDevice));
@@ -1158,6 +1167,7 @@ int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t
 		ParseTask t{};
 		t.es = d_es; t.es_len = es_len; t.start_byte = start_byte; t.seq = d_seq; t.hdr = d_hdr; t.coef = d_coef; t.info = d_info;
 		t.park = d_park; t.mb_width = mb_width; t.mb_size = sp.mb_size;
+		t.stage = d_stage; t.stage_entries = stage_entries_for(sp.mb_size);
 		CUDA_CHECK(cudaMemcpy(d_task, &t, sizeof(t), cudaMemcpyHostToDevice));
 		launch_parse_pictures(d_task, 1, sp.mb_size, 0);
 		CUDA_CHECK(cudaGetLastError());
@@ -1165,7 +1175,7 @@ int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t
 		CUDA_CHECK(cudaMemcpy(info_out, d_info, sizeof(picture_info_t), cudaMemcpyDeviceToHost));
 		CUDA_CHECK(cudaMemcpy(hdr_out, d_hdr, n_mb * sizeof(mb_record_t), cudaMemcpyDeviceToHost));
 		CUDA_CHECK(cudaMemcpy(coef_out, d_coef, n_mb * MB_COEF_INT16 * sizeof(int16_t), cudaMemcpyDeviceToHost));
-		cudaFree(d_es); cudaFree(d_seq); cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_park); cudaFree(d_info); cudaFree(d_task);
+		cudaFree(d_es); cudaFree(d_seq); cudaFree(d_hdr); cudaFree(d_coef); cudaFree(d_park); cudaFree(d_stage); cudaFree(d_info); cudaFree(d_task);
 		return 0;
 	} catch (const std::exception &e) {
 		fprintf(stderr, "%s\n", e.what());

@@ -84,7 +84,15 @@ static inline void sts_s16(uint32_t addr, int v) { const int16_t x = (int16_t)v;
 // 46 %) and the load's latency was the walk's top stall -- 35 % of all warp-stall samples sat on that
 // one instruction (profiles/r2_walk.md).  A 16-byte register cache per lane (loads still on demand) had
 // been measured slower; what was missing was distance, not width.
-template <bool RING>
+// PADDED: the bytes behind the data are known to be zero (the product's ES mirror: ES_PAD zeroed bytes)
+// and no reader runs further than a few words past the end, so neither the test against len nor the mask
+// of the last word is needed.  (Host emulation: exact-size buffers under AddressSanitizer, so never.)
+#ifdef JSMPEG_WALK_EMU
+constexpr bool ES_IS_PADDED = false;
+#else
+constexpr bool ES_IS_PADDED = true;
+#endif
+template <bool RING, bool PADDED = false>
 struct BitReaderT {
 	const uint32_t *words;  // 16-byte aligned base of the ES mirror (cudaMalloc), ES_PAD readable bytes past len
 	const uint8_t *bytes;
@@ -138,6 +146,7 @@ struct BitReaderT {
 			return __byte_perm(ring_word(w), 0, 0x0123);  // first byte -> MSB
 		}
 #endif
+		if (PADDED) return __byte_perm(__ldg(words + w), 0, 0x0123);
 		const uint32_t byte = w * 4u;
 		if (byte >= len) return 0u;
 		return finish_word(__ldg(words + w), byte);
@@ -227,6 +236,7 @@ struct PictureState {
 	int mv_h, mv_v, mv_h_prev, mv_v_prev;
 	int dc_y, dc_b4, dc_b5;  // block 4 / block 5 predictors (the reference's "Cr"/"Cb", mpeg1.js:717)
 	int n_present, n_coded, error;
+	int n_fixup;  // slices of the lane-parallel walk that needed no second pass (staged records + fix-up)
 	// lane-parallel walk only: which parts of a RELATIVE state no longer depend on the state the lane
 	// started from, and whether a case outside the lane-parallel walk's domain was met
 	bool qs_set, dc_abs, mv_abs, anomaly;
@@ -265,11 +275,12 @@ __device__ __forceinline__ uint16_t walk_entry(uint16_t e) {
 // One coded block (bitstream side of src/mpeg1.js:698-811): intra DC with its predictor, then only
 // code lengths.  Leaves {bit offset of the first coefficient code, dc * 8} in the block's slot.
 // head: DC size VLC + differential + predictor (mpeg1.js:705-751), the parked pair, dct_coeff_first
-template <bool DEFER, class BR>
+// RAW_DC (staging): the pair holds the DC predictor's value itself (possibly relative) instead of dc * 8
+template <bool DEFER, bool RAW_DC = false, class BR>
 __device__ __forceinline__ bool walk_block_head(BR &br, uint32_t sbase, PictureState &ps, bool intra, int block,
                                                 uint2 *__restrict__ park, bool store, int &n, bool &defer_first) {
 	n = 0;
-	int dc8 = 0;
+	int dc8 = 0, dc_raw = 0;
 	if (intra) {
 		const uint32_t w = br.peek32();
 		const uint32_t e = block < 4 ? lds_u16(sbase + OFF_DC_LUMA + (w >> 25) * 2u)
@@ -292,10 +303,11 @@ __device__ __forceinline__ bool walk_block_head(BR &br, uint32_t sbase, PictureS
 			}
 		}
 		*pred = dc;
+		dc_raw = dc;
 		dc8 = max(-32768, min(32767, dc * 8));  // x PREMULTIPLIER[0] = dc << 8 in stage 2 (mpeg1.js:747)
 		n = 1;
 	}
-	if (store) *park = make_uint2(br.bitpos(), (uint32_t)dc8 & 0xffffu);
+	if (store) *park = make_uint2(br.bitpos(), RAW_DC ? (uint32_t)dc_raw : (uint32_t)dc8 & 0xffffu);
 	if (DEFER) {
 		defer_first = !intra;  // the caller's first look-up resolves dct_coeff_first (ac_step)
 	} else if (!intra && (br.peek32() >> 31)) {  // dct_coeff_first: a leading '1' is (0, +-1), never end_of_block
@@ -426,12 +438,20 @@ __device__ __forceinline__ uint4 pack_record(int mv_h, int mv_v, int flags, int 
 //                unknown state at the lane's first macroblock (summary pass of the lane-parallel walk)
 //   WALK_ABS     one lane walks it with the true state and stores; cases the lane-parallel walk leaves to
 //                the serial walk set ps.anomaly
-enum { WALK_SERIAL = 0, WALK_REL = 1, WALK_ABS = 2 };
+//   WALK_STAGE   WALK_REL that also leaves every macroblock as a RELATIVE record in the picture's staging
+//                area; a fix-up (no bitstream access) then turns the staged records into the final ones and
+//                the WALK_ABS pass is not needed
+enum { WALK_SERIAL = 0, WALK_REL = 1, WALK_ABS = 2, WALK_STAGE = 3 };
+#define WALK_IS_REL(MODE) ((MODE) == WALK_REL || (MODE) == WALK_STAGE)
 
 struct MbHead {
 	int mb, cbp, mv_h, mv_v, qscale;
 	bool intra;
 	uint32_t bit_pos;
+	// WALK_STAGE only: the run of skipped macroblocks in front of this one
+	int n_skip, skip_first, skip_qs;
+	bool skip_qs_set;
+	uint32_t skip_bit;
 };
 
 // mpeg1.js:294-384, decodeMacroblock up to the blocks.  0: the blocks of h.cbp follow; 1: nothing more
@@ -453,10 +473,10 @@ __device__ __forceinline__ int walk_mb_header(BR &br, uint32_t sbase, PictureSta
 		if (MODE == WALK_ABS && ps.mb_addr + increment >= mb_size) { ps.anomaly = true; return 2; }
 		if (increment > 1) {  // mpeg1.js:323-334
 			ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;
-			if (MODE == WALK_REL) ps.dc_abs = true;
+			if (WALK_IS_REL(MODE)) ps.dc_abs = true;
 			if (ps.picture_type == 2) {
 				ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;
-				if (MODE == WALK_REL) ps.mv_abs = true;
+				if (WALK_IS_REL(MODE)) ps.mv_abs = true;
 			}
 			// skipped macroblocks: predicted copy with the current vector (mpeg1.js:336-346)
 			const int n_skip = increment - 1;
@@ -471,6 +491,10 @@ __device__ __forceinline__ int walk_mb_header(BR &br, uint32_t sbase, PictureSta
 			}
 			if (MODE == WALK_ABS)
 				for (int k = 0; k < n_skip; k++) reinterpret_cast<uint4 *>(t.hdr)[ps.mb_addr + 1 + k] = rec;
+			if (MODE == WALK_STAGE) {
+				h.n_skip = n_skip; h.skip_first = ps.mb_addr + 1; h.skip_qs = ps.qscale; h.skip_qs_set = ps.qs_set;
+				h.skip_bit = br.bitpos();
+			}
 			ps.n_present += n_skip;
 			ps.mb_addr += n_skip;
 		}
@@ -478,7 +502,7 @@ __device__ __forceinline__ int walk_mb_header(BR &br, uint32_t sbase, PictureSta
 	}
 	const int mb = ps.mb_addr;
 	h.mb = mb;
-	if (MODE != WALK_REL && (mb < 0 || mb >= mb_size)) {  // outside the picture: never write there
+	if (!WALK_IS_REL(MODE) && (mb < 0 || mb >= mb_size)) {  // outside the picture: never write there
 		if (MODE == WALK_ABS) ps.anomaly = true;
 		return 2;
 	}
@@ -493,22 +517,22 @@ __device__ __forceinline__ int walk_mb_header(BR &br, uint32_t sbase, PictureSta
 	h.intra = intra;
 	if (type & 0x10) {
 		ps.qscale = (int)br.read(5);
-		if (MODE == WALK_REL) ps.qs_set = true;
+		if (WALK_IS_REL(MODE)) ps.qs_set = true;
 	}
 	h.bit_pos = br.bitpos();
 
 	if (intra) {
 		ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:363-367
-		if (MODE == WALK_REL) ps.mv_abs = true;
+		if (WALK_IS_REL(MODE)) ps.mv_abs = true;
 	} else {
 		ps.dc_y = ps.dc_b4 = ps.dc_b5 = 128;                  // mpeg1.js:370-372
-		if (MODE == WALK_REL) ps.dc_abs = true;
+		if (WALK_IS_REL(MODE)) ps.dc_abs = true;
 		if (type & 0x08) {
 			if (!parse_motion(br, sbase, ps, ps.mv_h_prev, ps.mv_h)) return 2;
 			if (!parse_motion(br, sbase, ps, ps.mv_v_prev, ps.mv_v)) return 2;
 		} else if (ps.picture_type == 2) {
 			ps.mv_h = ps.mv_v = ps.mv_h_prev = ps.mv_v_prev = 0;  // mpeg1.js:452-456
-			if (MODE == WALK_REL) ps.mv_abs = true;
+			if (WALK_IS_REL(MODE)) ps.mv_abs = true;
 		}
 	}
 
@@ -784,21 +808,47 @@ __device__ uint32_t find_slice_end(const BR &br, uint32_t from, int lane) {
 // start code, 2 on anything else; stop_pos = the bit position after the lane's last macroblock.
 // WARP-SYNCHRONOUS like syntax_run: one vote closes the macroblock loop, one every look-up of the
 // coefficient loop.
+// WALK_STAGE: where a lane leaves its macroblocks as relative records: 64-byte entries of the picture's
+// staging area (ParseTask::stage), the lane's own stretch [first, first + cap), in walking order.
+//   word 0      motion predictors after the macroblock's header (int16 h | int16 v << 16); skip entry: the run length
+//   word 1      flags (1 intra, 2 skip entry, 4 motion absolute, 8 DC absolute, 16 quantiser scale set)
+//               | cbp << 8 | dc_only mask << 16 | quantiser scale << 24
+//   word 2      bit_pos      word 3   macroblock address relative to the lane's start (skip entry: the first skipped one)
+//   words 4..15 per block {bit offset of the first coefficient code, DC predictor value (relative unless flag 8)}
+struct StageArea {
+	int first, cap, count;
+	bool ok;  // false: more macroblocks than room -- the summary is still right, the storing pass has to run
+};
+__device__ __forceinline__ uint4 *stage_entry(const ParseTask &t, const StageArea &sa, int k) { return t.stage + (size_t)(sa.first + k) * 4; }
+
 template <int MODE, class BR>
 __device__ int walk_owned(BR &br, uint32_t sbase, PictureState &ls, const ParseTask &t, int mb_size, bool owns,
-                          uint32_t limit, uint32_t end_byte, int lane, uint32_t &stop_pos) {
+                          uint32_t limit, uint32_t end_byte, int lane, uint32_t &stop_pos, StageArea *sa = nullptr) {
 	int how = 0;
 	bool work = owns;
 	if (owns) stop_pos = br.bitpos();
 	while (WK_VOTE(VOTE_OWN_MB, work)) {
 		MbHead h;
 		h.mb = 0; h.cbp = 0; h.mv_h = h.mv_v = h.qscale = 0; h.intra = false; h.bit_pos = 0;
+		h.n_skip = 0; h.skip_first = 0; h.skip_qs = 0; h.skip_qs_set = false; h.skip_bit = 0;
 		bool in_mb = false;
 		if (work) {
 			if (walk_mb_header<MODE>(br, sbase, ls, t, mb_size, lane, h) != 0) { how = 2; work = false; }
 			else in_mb = true;
 		}
 		uint2 *park_mb = t.park + (size_t)(MODE == WALK_ABS ? h.mb : 0) * 6;
+		bool staging = false;
+		if (MODE == WALK_STAGE && in_mb && sa->ok) {
+			if (sa->count + (h.n_skip > 0 ? 2 : 1) > sa->cap) {
+				sa->ok = false;
+			} else {
+				if (h.n_skip > 0)
+					*stage_entry(t, *sa, sa->count++) = make_uint4((uint32_t)h.n_skip, 2u | (h.skip_qs_set ? 16u : 0u) | ((uint32_t)h.skip_qs << 24),
+					                                             h.skip_bit, (uint32_t)h.skip_first);
+				park_mb = reinterpret_cast<uint2 *>(stage_entry(t, *sa, sa->count) + 1);  // the blocks' pairs go straight into the entry
+				staging = true;
+			}
+		}
 		int done = 0, dc_mask = 0;
 		// the coded blocks of the macroblock, one look-up per trip; a block's head (intra DC, the parked
 		// pair) rides on the trip of its first look-up
@@ -811,7 +861,8 @@ __device__ int walk_owned(BR &br, uint32_t sbase, PictureState &ls, const ParseT
 				const int block = __clz((int)rem) - 26;  // mask bit 0x20 >> block
 				bool ok = true;
 				if (at_head) {
-					ok = walk_block_head<true>(br, sbase, ls, h.intra, block, park_mb + block, MODE == WALK_ABS, n, first);
+					ok = MODE == WALK_STAGE ? walk_block_head<true, true>(br, sbase, ls, h.intra, block, park_mb + block, staging, n, first)
+					                        : walk_block_head<true>(br, sbase, ls, h.intra, block, park_mb + block, MODE == WALK_ABS, n, first);
 					at_head = false;
 				}
 				const int r = ok ? ac_step(br, sbase, n, true, first) : 2;
@@ -832,6 +883,12 @@ __device__ int walk_owned(BR &br, uint32_t sbase, PictureState &ls, const ParseT
 			if (MODE == WALK_ABS)
 				reinterpret_cast<uint4 *>(t.hdr)[h.mb] =
 				    pack_record(h.mv_h, h.mv_v, MBF_PRESENT | (h.intra ? MBF_INTRA : 0), done, dc_mask, h.qscale, h.bit_pos);
+			if (MODE == WALK_STAGE && staging) {
+				const uint32_t flags = (h.intra ? 1u : 0u) | (ls.mv_abs ? 4u : 0u) | (ls.dc_abs ? 8u : 0u) | (ls.qs_set ? 16u : 0u);
+				*stage_entry(t, *sa, sa->count++) =
+				    make_uint4(((uint32_t)ls.mv_h_prev & 0xffffu) | ((uint32_t)ls.mv_v_prev << 16),
+				               flags | ((uint32_t)done << 8) | ((uint32_t)dc_mask << 16) | ((uint32_t)h.qscale << 24), h.bit_pos, (uint32_t)h.mb);
+			}
 			ls.n_present++;
 			const uint32_t pos = br.bitpos();
 			const uint32_t i = (pos + 7u) >> 3;
@@ -892,7 +949,13 @@ __device__ bool walk_slice_lanes(BR &br, uint32_t sbase, PictureState &ps, const
 		ls.n_present = ls.n_coded = ls.error = 0;
 	}
 	uint32_t stop_pos = q;
-	how = walk_owned<WALK_REL>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos);
+	if (!owns) ls.n_present = ls.n_coded = ls.error = 0;  // (with the fix-up, this pass's counts are the final ones)
+	StageArea sa;
+	sa.cap = t.stage ? t.stage_entries / K : 0;  // the picture's staging entries, shared out among the lanes in use
+	sa.first = active ? lane * sa.cap : 0;
+	sa.count = 0;
+	sa.ok = sa.cap > 0;
+	how = walk_owned<WALK_STAGE>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos, &sa);
 	const uint32_t next_q = __shfl_down_sync(FULL_MASK, q, 1);
 	if (active && lane < K - 1 && stop_pos != next_q) bad = true;  // the warm-up of lane + 1 had not merged
 	if (owns) {
@@ -916,7 +979,56 @@ __device__ bool walk_slice_lanes(BR &br, uint32_t sbase, PictureState &ps, const
 	const LaneSum before = shfl_up_sum(sum, 1);
 	const LaneSum x = lane == 0 ? x0 : compose(x0, before, ps.f);
 
-	// ---- D: the owned macroblocks again, absolute, storing
+	if (!__any_sync(FULL_MASK, owns && !sa.ok)) {
+		// ---- F: no second walk -- the staged relative records become the final ones.  Every staged value is
+		// cumulative since the lane's start, so each entry only needs the lane's absolute start state `x`.
+		// No bitstream access, no look-ups, all lanes busy: some 40 instructions per macroblock.
+		int k = 0;
+		while (WK_VOTE(VOTE_OWN_MB, k < sa.count)) {
+			if (k < sa.count) {
+				const uint4 *e = stage_entry(t, sa, k);
+				const uint4 w = e[0];
+				const uint32_t flags = w.y & 0xffu;
+				const int qs = (flags & 16u) ? (int)(w.y >> 24) : x.qs;
+				const int mb = x.d_addr + (int)w.w;
+				if (flags & 2u) {  // a run of skipped macroblocks (mpeg1.js:323-346): zero vector, the scale in force
+					const int n_skip = (int)w.x;
+					if (mb < 0 || mb + n_skip > mb_size) bad = true;
+					else {
+						const uint4 rec = pack_record(0, 0, MBF_PRESENT | MBF_SKIPPED, 0, 0, qs, w.z);
+						for (int i = 0; i < n_skip; i++) reinterpret_cast<uint4 *>(t.hdr)[mb + i] = rec;
+					}
+				} else if (mb < 0 || mb >= mb_size) {
+					bad = true;
+				} else {
+					int ph = (int)(int16_t)(w.x & 0xffffu), pv = (int)(int16_t)(w.x >> 16);
+					if (!(flags & 4u)) { ph = wrap_mv(x.mvh + ph, ps.f); pv = wrap_mv(x.mvv + pv, ps.f); }
+					const int cbp = (int)((w.y >> 8) & 0xffu);
+					uint4 pr[3] = {e[1], e[2], e[3]};  // six {bit offset, DC predictor} pairs; uncoded blocks' are stale, never read
+					if (flags & 1u) {  // intra: predictor value -> dc * 8 (x PREMULTIPLIER[0] = dc << 8 in stage 2, mpeg1.js:747)
+						uint32_t *v = reinterpret_cast<uint32_t *>(pr);
+#pragma unroll
+						for (int block = 0; block < 6; block++) {
+							int dc = (int)v[block * 2 + 1];
+							if (!(flags & 8u)) dc += block < 4 ? x.dcy : (block == 4 ? x.dc4 : x.dc5);
+							v[block * 2 + 1] = (uint32_t)max(-32768, min(32767, dc * 8)) & 0xffffu;
+						}
+					} else {
+						pr[0].y = pr[0].w = pr[1].y = pr[1].w = pr[2].y = pr[2].w = 0u;
+					}
+					uint4 *park_mb = reinterpret_cast<uint4 *>(t.park + (size_t)mb * 6);
+					park_mb[0] = pr[0]; park_mb[1] = pr[1]; park_mb[2] = pr[2];
+					reinterpret_cast<uint4 *>(t.hdr)[mb] =
+					    pack_record(ps.full_pel ? ph * 2 : ph, ps.full_pel ? pv * 2 : pv, MBF_PRESENT | ((flags & 1u) ? MBF_INTRA : 0),
+					                cbp, (int)((w.y >> 16) & 0xffu), qs, w.z);
+				}
+				k++;
+			}
+		}
+		if (__any_sync(FULL_MASK, bad)) return false;
+		ps.n_fixup++;
+	} else {
+	// ---- D (a lane ran out of staging room): the owned macroblocks again, absolute, storing
 	ls.n_present = ls.n_coded = ls.error = 0;
 	ls.anomaly = false;
 	if (owns) {
@@ -930,6 +1042,7 @@ __device__ bool walk_slice_lanes(BR &br, uint32_t sbase, PictureState &ps, const
 	const int how_abs = walk_owned<WALK_ABS>(br, sbase, ls, t, mb_size, owns, s_hi, end_byte, lane, stop_pos);
 	if (how_abs != how || ls.anomaly) bad = true;
 	if (__any_sync(FULL_MASK, bad)) return false;
+	}
 	int n_present = ls.n_present, n_coded = ls.n_coded, error = ls.error;
 	for (int d = 16; d > 0; d >>= 1) {
 		n_present += __shfl_xor_sync(FULL_MASK, n_present, d);
@@ -985,6 +1098,7 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane, uint3
 
 		PictureState ps;
 		ps.n_present = ps.n_coded = ps.error = 0;
+		ps.n_fixup = 0;
 		ps.full_pel = 0; ps.r_size = 0; ps.f = 1;
 		ps.qs_set = ps.dc_abs = ps.mv_abs = ps.anomaly = false;
 		int f_code = 0;
@@ -1053,7 +1167,7 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane, uint3
 			info.error = ps.error;
 			info.reserved[0] = (LANES && lanes && go) ? 1 : 0;
 			info.reserved[1] = 0;
-			info.reserved[2] = 0;
+			info.reserved[2] = (LANES && lanes && go) ? ps.n_fixup : 0;
 			*t.info = info;
 		}
 		return;
@@ -1071,7 +1185,7 @@ __device__ __forceinline__ void expand_block(const ParseTask &t, uint32_t rec, u
 	const int qs = (int)(rec >> 24);
 	// quantiser table in coefficient (zig-zag) order: entry n = raster index * 2 | Q[raster index] << 8
 	const uint32_t xq = sbase + EXP_OFF_XQ + (intra ? 0u : 128u);
-	BitReader br;
+	BitReaderT<false, ES_IS_PADDED> br;  // every code of the block was validated by the walk: the reads stay inside data + pad
 	br.words = reinterpret_cast<const uint32_t *>(t.es);
 	br.bytes = t.es;
 	br.len = t.es_len;
@@ -1083,8 +1197,18 @@ __device__ __forceinline__ void expand_block(const ParseTask &t, uint32_t rec, u
 	if (intra) {
 		sts_s16(stile, (int)(int16_t)(parked.y & 0xffffu));  // coefficient 0
 		n = 1;
+	} else if (br.peek32() >> 31) {
+		// dct_coeff_first of a non-intra block: a leading '1' is (run 0, level +-1) with its sign bit, never
+		// end_of_block (mpeg1.js:757-760, 781-787) -- handled here, once, instead of in every trip of the loop
+		int level = (br.peek32() & 0x40000000u) ? -3 : 3;  // 2 level + sign
+		br.consume(2);
+		const uint32_t q = lds_u16(xq);
+		level = (level * qs * (int)(q >> 8)) >> 4;
+		if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
+		level = max(-2048, min(2047, level));
+		sts_s16(stile + (q & 0xffu), level);
+		n = 1;
 	}
-	bool first = !intra;
 	for (;;) {  // mpeg1.js:757-811; the walk has already validated every code of this block
 		const uint32_t w = br.peek32();
 		const int z = min(__clz((int)w), VLC_DCT_MAX_Z);
@@ -1092,12 +1216,6 @@ __device__ __forceinline__ void expand_block(const ParseTask &t, uint32_t rec, u
 		int len = e & 31;
 		int run = (e >> 5) & 31;
 		int level = e >> 10;
-		if (first && z == 0) {  // '1s'
-			len = 1;
-			run = 0;
-			level = 1;
-		}
-		first = false;
 		if (level == 0) {
 			if (run != 0 || len == 0) break;  // end_of_block (or, defensively, an invalid code)
 			// escape (mpeg1.js:767-780)

@@ -50,7 +50,8 @@ for es in streams:
     for s in (starts if limit is None else starts[:3]):
         if limit is not None and count >= limit:
             break
-        walk_exact(es, s, mbw, mbh, 1)
+        walk_exact(es, s, mbw, mbh, 1)  # staged records + fix-up, exact-size staging area
+        walk_exact(es, s, mbw, mbh, 2)  # staging area of 40 entries: lanes run out, second pass
         walk_exact(es, s, mbw, mbh, 0)
         count += 1
 print("asan clean over", count, "pictures")

@@ -156,7 +156,10 @@ extern "C" void emu_set_quant(const uint8_t *intra_q, const uint8_t *non_intra_q
 	memcpy(emu_non_intra_q, non_intra_q, 64);
 }
 
-// park: [mb_size][6] x {bit offset, dc * 8}, the walk's dense hand-over to stage 1b
+// park: [mb_size][6] x {bit offset, dc * 8}, the walk's dense hand-over to stage 1b.
+// lanes: 0 serial walk, 1 lane-parallel walk with its staging area (stage_entries_for(mb_size) entries, the
+// product's size), 2 lane-parallel walk with a staging area of 40 entries (lanes run out: second-pass
+// fall-back), 3 lane-parallel walk without staging area (always the second pass).
 extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t start_byte, int mb_width, int mb_height,
                                 mb_record_t *hdr, uint2 *park, picture_info_t *info, int lanes) {
 	static std::once_flag once;
@@ -175,6 +178,11 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 	ParseTask t;
 	t.es = es; t.es_len = es_len; t.start_byte = start_byte; t.seq = &seq; t.hdr = hdr; t.coef = nullptr; t.info = info;
 	t.park = park; t.mb_width = mb_width; t.mb_size = seq.mb_size;
+	// exact-size staging area on the heap (AddressSanitizer sees any entry outside it)
+	const int entries = lanes == 1 ? stage_entries_for(seq.mb_size) : (lanes == 2 ? 40 : 0);
+	std::vector<uint4> stage((size_t)entries * 4);
+	t.stage = entries ? stage.data() : nullptr;
+	t.stage_entries = entries;
 	static ParseTask task;
 	static int use_lanes;
 	task = t;
@@ -205,6 +213,7 @@ extern "C" int emu_expand_picture(const uint8_t *es, uint32_t es_len, int mb_wid
 	ParseTask t;
 	t.es = es; t.es_len = es_len; t.start_byte = 0; t.seq = &seq; t.hdr = hdr; t.coef = coef; t.info = info;
 	t.park = const_cast<uint2 *>(park); t.mb_width = mb_width; t.mb_size = seq.mb_size;
+	t.stage = nullptr; t.stage_entries = 0;
 	for (int slot_id = 0; slot_id < seq.mb_size * 6; slot_id++) {  // the kernel shell of parse.cu, one thread after the other
 		const int mb = slot_id / 6, block = slot_id - mb * 6;
 		const uint32_t rec = reinterpret_cast<const uint32_t *>(hdr + mb)[1];

@@ -72,11 +72,24 @@ def check_stream(lib, es, what, expect_lanes=None):
     starts = picture_starts(es)
     for k, s in enumerate(starts):
         h0, c0, i0 = walk(lib, buf, len(es), s, mbw, mbh, 0)
-        h1, c1, i1 = walk(lib, buf, len(es), s, mbw, mbh, 1)
-        used += int(i1[9])
-        assert np.array_equal(i0[:9], i1[:9]), f"{what}: picture {k}: info {i0[:9]} vs {i1[:9]}"
-        assert np.array_equal(h0, h1), f"{what}: picture {k}: records differ at mb {np.nonzero((h0 != h1).any(axis=1))[0][:8]}"
-        assert np.array_equal(c0, c1), f"{what}: picture {k}: parked block data differ at slot {np.nonzero((c0 != c1).any(axis=1))[0][:8]}"
+        # 1: staged relative records + fix-up (the product's path); 2: staging area too small, the lanes fall back to
+        # the second, storing pass; 3: no staging area at all
+        for mode in (1, 2, 3):
+            h1, c1, i1 = walk(lib, buf, len(es), s, mbw, mbh, mode)
+            if mode == 1:
+                used += int(i1[9])
+                # with the product's staging area every slice the lane walk takes is finished by the fix-up, not a second pass
+                assert not i1[9] or i1[11] > 0, f"{what}: picture {k}: lane walk without fix-up"
+            elif mode == 3:
+                assert i1[11] == 0
+            coded = np.zeros(len(c0), dtype=bool)  # the pairs of uncoded blocks are never read: only coded ones are compared
+            hb = h0.view(np.uint8).reshape(-1, 16)
+            for blk in range(6):
+                coded[blk::6] = ((hb[:, 4] & 1) != 0) & ((hb[:, 5] & (0x20 >> blk)) != 0)
+            assert np.array_equal(i0[:9], i1[:9]), f"{what}: picture {k} mode {mode}: info {i0[:9]} vs {i1[:9]}"
+            assert np.array_equal(h0, h1), f"{what}: picture {k} mode {mode}: records differ at mb {np.nonzero((h0 != h1).any(axis=1))[0][:8]}"
+            assert np.array_equal(c0[coded], c1[coded]), \
+                f"{what}: picture {k} mode {mode}: parked block data differ at slot {np.nonzero(coded & (c0 != c1).any(axis=1))[0][:8]}"
     if expect_lanes is not None:
         assert used >= expect_lanes, f"{what}: lane-parallel walk used for {used} of {len(starts)} pictures"
     return used, len(starts)
