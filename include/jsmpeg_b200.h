@@ -120,9 +120,12 @@ int jsmpeg_b200_batch_stream_info(jsmpeg_b200_batch_t *b, int stream, int *width
 /* MPEG-TS in, demultiplexed on the GPU (mirror of the reference's host demuxer src/ts.js for a
  * buffer of whole 188-byte packets): the payload of every PES packet with stream id `stream_id`
  * (0xE0 = first video stream, ts.js:213-224) is appended to `stream` exactly as if it had been
- * written with get_write_ptr/did_write.  Returns the number of elementary-stream bytes appended,
- * or -1 when the buffer is not a clean sequence of packets starting with the sync byte (use the
- * host demuxer, which resyncs).  pts_out / offset_out (capacity n_max, may be NULL) receive, per
+ * written with get_write_ptr/did_write.  The buffer need not hold whole packets nor begin on a packet
+ * boundary: what a call leaves over is kept for the next one (ts.js:25-41) and a lost sync byte is
+ * searched for like the reference does (ts.js:155-189); a PID that a later PES header binds to
+ * another stream id stops feeding this stream (ts.js:81-83).  Returns the number of
+ * elementary-stream bytes appended (-1: the decoder is dead).  pts_out / offset_out (capacity n_max,
+ * may be NULL) receive, per
  * PES packet in stream order, its PTS in 90 kHz ticks (0 if absent) and the byte offset of its
  * payload in the stream's buffer -- the table Decoder.Base.write keeps (src/decoder.js:36-47). */
 long jsmpeg_b200_batch_write_ts(jsmpeg_b200_batch_t *b, int stream, const uint8_t *ts, size_t n_bytes, int stream_id,

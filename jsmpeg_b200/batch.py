@@ -109,8 +109,8 @@ class BatchDecoder:
         self.lib.jsmpeg_b200_batch_did_write(self.handle, stream, len(data))
 
     def write_ts(self, stream, ts_bytes, stream_id=0xE0):
-        """MPEG-TS in, demultiplexed on the GPU.  Returns (ES bytes appended, [(payload byte offset,
-        pts seconds), ...] per PES packet) or raises ValueError when the buffer is not packet aligned."""
+        """MPEG-TS in, demultiplexed on the GPU (any chunking, resyncs like src/ts.js).  Returns (ES bytes
+        appended, [(payload byte offset, pts seconds), ...] per PES packet of `stream_id` that starts in it)."""
         ts_bytes = bytes(ts_bytes)
         n_max = len(ts_bytes) // 188 + 1
         pts = np.zeros(n_max, np.uint64)
@@ -119,7 +119,7 @@ class BatchDecoder:
         total = self.lib.jsmpeg_b200_batch_write_ts(self.handle, stream, ts_bytes, len(ts_bytes), stream_id,
                                                     pts.ctypes.data, off.ctypes.data, n_max, ctypes.byref(n))
         if total < 0:
-            raise ValueError("not a clean sequence of 188-byte TS packets (use jsmpeg_b200.ts.TS, which resyncs)")
+            raise RuntimeError(self.last_error() or "jsmpeg_b200_batch_write_ts failed")
         return total, [(int(off[i]), float(pts[i]) / 90000.0) for i in range(n.value)]
 
     def get_index(self, stream):

@@ -113,6 +113,5 @@ void launch_rgba(const ReconTask *tasks, int n_tasks, int max_width, int max_hei
 struct TsScratch;
 TsScratch *ts_scratch_create();
 void ts_scratch_destroy(TsScratch *s);
-long ts_demux_measure(TsScratch *s, const uint8_t *ts_host, size_t ts_bytes, int stream_id, uint8_t *bound, cudaStream_t st);
-int ts_demux_gather(TsScratch *s, size_t ts_bytes, uint8_t *es, uint32_t es_base, uint64_t *pts_out,
-                    uint32_t *offset_out, int n_max, cudaStream_t st);
+long ts_demux_measure(TsScratch *s, const uint8_t *ts_host, size_t ts_bytes, int stream_id, int16_t *bound, size_t *consumed, cudaStream_t st);
+int ts_demux_gather(TsScratch *s, uint8_t *es, uint32_t es_base, uint64_t *pts_out, uint32_t *offset_out, int n_max, cudaStream_t st);

@@ -93,7 +93,8 @@ struct Stream {
 	uint8_t *h_planes[HOST_RING] = {};
 	int h_head = -1;
 	uint8_t *d_rgba = nullptr;
-	std::vector<uint8_t> ts_bound;  // device TS demux: PIDs already bound to the stream id (ts.js pidsToStreamIds)
+	std::vector<int16_t> ts_bound;     // device TS demux: the stream id every PID is bound to, 0 = none (ts.js pidsToStreamIds)
+	std::vector<uint8_t> ts_leftover;  // ... and the bytes the last write_ts left over (ts.js leftoverBytes)
 	// parsed-ahead pictures, consecutive, front = next picture decode() consumes
 	std::deque<Parsed> cache;
 };
@@ -993,8 +994,18 @@ long jsmpeg_b200_batch_write_ts(jsmpeg_b200_batch_t *b, int stream, const uint8_
 		Stream &s = b->streams[stream];
 		if (!b->ts) b->ts = ts_scratch_create();
 		if (s.ts_bound.empty()) s.ts_bound.assign(8192, 0);
-		const long total = ts_demux_measure(b->ts, ts, n_bytes, stream_id, s.ts_bound.data(), b->st_main);
-		if (total <= 0) return total;
+		// what the previous call left over comes first (a partial packet, a resync that wanted more data: ts.js:25-41)
+		const uint8_t *data = ts;
+		size_t n_data = n_bytes;
+		if (!s.ts_leftover.empty()) {
+			s.ts_leftover.insert(s.ts_leftover.end(), ts, ts + n_bytes);
+			data = s.ts_leftover.data();
+			n_data = s.ts_leftover.size();
+		}
+		size_t consumed = 0;
+		const long total = ts_demux_measure(b->ts, data, n_data, stream_id, s.ts_bound.data(), &consumed, b->st_main);
+		std::vector<uint8_t> rest(data + consumed, data + n_data);  // (data may alias ts_leftover)
+		if (total <= 0) { s.ts_leftover.swap(rest); return total; }
 		// room in the host bit buffer (the reference's write protocol, may expand or evict) and in HBM
 		uint8_t *hdst = static_cast<uint8_t *>(stream_get_write_ptr(b, s, (uint32_t)total));
 		reserve_device_es(b, s, s.bb.length + (uint32_t)total);
@@ -1003,9 +1014,10 @@ long jsmpeg_b200_batch_write_ts(jsmpeg_b200_batch_t *b, int stream, const uint8_
 			b->stats.h2d_bytes += s.bb.length - s.d_valid;
 			s.d_valid = s.bb.length;
 		}
-		const int count = ts_demux_gather(b->ts, n_bytes, s.d_es, s.bb.length, pts_out, offset_out, n_max, b->st_main);
-		b->stats.kernel_launches += 4;
-		b->stats.h2d_bytes += n_bytes;
+		const int count = ts_demux_gather(b->ts, s.d_es, s.bb.length, pts_out, offset_out, n_max, b->st_main);
+		s.ts_leftover.swap(rest);
+		b->stats.kernel_launches += 7;
+		b->stats.h2d_bytes += n_data;
 		// the host keeps a mirror of the ES (sequence header parse, EVICT bookkeeping): copy the new bytes back
 		CUDA_CHECK(cudaMemcpyAsync(hdst, s.d_es + s.bb.length, (size_t)total, cudaMemcpyDeviceToHost, b->st_main));
 		CUDA_CHECK(cudaMemsetAsync(s.d_es + s.bb.length + total, 0, ES_PAD, b->st_main));

@@ -101,8 +101,8 @@ struct BitReaderT {
 	uint32_t nextw;  // prefetched
 	uint64_t win;    // left-aligned window
 	int nbits;       // valid bits in win, >= 32 between calls
-	uint32_t ring;   // RING: shared-window address of this lane's ring (4 chunks of 16 bytes, chunk q in slot q & 3)
-	uint32_t qhead;  // RING: chunks below qhead have been requested
+	uint32_t ring;   // RING: shared-window address of this lane's ring (4 chunks of 16 bytes, chunk q in slot q & 3).
+	                 // Invariant between calls: the chunks up to (chunk of word wpos) + 3 have been requested.
 
 	__device__ __forceinline__ uint32_t finish_word(uint32_t raw, uint32_t byte) const {
 		uint32_t v = __byte_perm(raw, 0, 0x0123);  // first byte -> MSB
@@ -139,8 +139,8 @@ struct BitReaderT {
 			// No test against len and no tail mask here: the mirror is followed by zeroed bytes (ES_PAD), a chunk
 			// past them is fetched from the pad too (ring_request), and no walk runs more than a macroblock
 			// header past the end of the data before it stops.
-			if ((w & 3u) == 0u) {  // first word of chunk q: chunk q - 1 is consumed; exactly one request keeps qhead = q + 4
-				ring_request(qhead++);
+			if ((w & 3u) == 0u) {  // first word of chunk q: chunk q - 1 is consumed, its slot takes chunk q + 3
+				ring_request((w >> 2) + 3u);
 				asm volatile("cp.async.wait_group 3;" ::: "memory");  // everything but the three newest chunks has landed
 			}
 			return __byte_perm(ring_word(w), 0, 0x0123);  // first byte -> MSB
@@ -158,7 +158,6 @@ struct BitReaderT {
 			asm volatile("cp.async.wait_all;" ::: "memory");  // nothing requested for the old position may still be landing
 			const uint32_t q0 = w >> 2;
 			ring_request(q0); ring_request(q0 + 1u); ring_request(q0 + 2u); ring_request(q0 + 3u);
-			qhead = q0 + 4u;
 			asm volatile("cp.async.wait_all;" ::: "memory");
 			auto raw = [&](uint32_t x) { return __byte_perm(ring_word(x), 0, 0x0123); };
 			win = ((uint64_t)raw(w) << 32) | raw(w + 1);
@@ -166,8 +165,8 @@ struct BitReaderT {
 			nextw = raw(wpos);
 			// w .. w + 2 lie in chunks q0, q0 + 1.  If they reach into q0 + 1, chunk q0 is consumed and that
 			// chunk's turn to extend the ring (load_word, first word of a chunk) is taken here -- after the
-			// reads, the new chunk goes into q0's slot -- so that qhead = (chunk of the next word) + 4 holds
-			if (((w + 2u) >> 2) != q0) ring_request(qhead++);
+			// reads, the new chunk goes into q0's slot -- so that the invariant holds
+			if (((w + 2u) >> 2) != q0) ring_request(q0 + 4u);
 		} else
 #endif
 		{
@@ -287,6 +286,9 @@ __device__ __forceinline__ bool walk_block_head(BR &br, uint32_t sbase, PictureS
 		                             : lds_u16(sbase + OFF_DC_CHROMA + (w >> 24) * 2u);
 		const int len = e & 31, size = e >> 5;
 		if (len == 0) return false;
+		// (The pointer sends the three predictors to local memory, 5 % of the lane walk's stall samples sit on
+		// those loads.  Selects instead were measured: the state then competes for the 64 registers, spill
+		// instructions went from 12 M to 390 M per wave and the walk from 11.6 to 12.6 ms.)
 		int *pred = block < 4 ? &ps.dc_y : (block == 4 ? &ps.dc_b4 : &ps.dc_b5);
 		int dc = *pred;
 		if (DEFER) {  // code and differential (at most 8 + 8 bits) sit in the same 32-bit peek: the window moves once
@@ -623,6 +625,10 @@ constexpr uint32_t MIN_SUBSEQ_BITS = 2048;  // shorter sub-sequences are not wor
 #define JSMPEG_WARMUP_BITS 8192
 #endif
 constexpr uint32_t WARMUP_BITS = JSMPEG_WARMUP_BITS;  // how far before its sub-sequence a lane starts guessing
+#ifndef JSMPEG_WARMUP_MBS
+#define JSMPEG_WARMUP_MBS 48
+#endif
+constexpr uint32_t WARMUP_MBS = JSMPEG_WARMUP_MBS;    // ... or this many average macroblocks, whichever is longer
 
 struct SliceConst {
 	int picture_type, r_size, f;
@@ -921,7 +927,7 @@ __device__ bool walk_slice_lanes(BR &br, uint32_t sbase, PictureState &ps, const
 
 	// ---- W: warm-up to the first macroblock that starts in the sub-sequence.  Chains merge within a few
 	// macroblocks, so the warm-up is WARMUP_BITS or 48 average macroblocks, whichever is longer
-	const uint32_t warm = max(WARMUP_BITS, total / (uint32_t)mb_size * 48u);
+	const uint32_t warm = max(WARMUP_BITS, total / (uint32_t)mb_size * WARMUP_MBS);
 	uint32_t st = PH_MBA;
 	if (active) {
 		if (lane == 0 || s_lo - p_start <= warm) {
@@ -987,6 +993,9 @@ __device__ bool walk_slice_lanes(BR &br, uint32_t sbase, PictureState &ps, const
 		while (WK_VOTE(VOTE_OWN_MB, k < sa.count)) {
 			if (k < sa.count) {
 				const uint4 *e = stage_entry(t, sa, k);
+#ifndef JSMPEG_WALK_EMU
+				if (k + 2 < sa.count) asm volatile("prefetch.global.L1 [%0];" ::"l"(e + 8));  // the entry after next (written by this lane, sits in L2)
+#endif
 				const uint4 w = e[0];
 				const uint32_t flags = w.y & 0xffu;
 				const int qs = (flags & 16u) ? (int)(w.y >> 24) : x.qs;
@@ -1093,7 +1102,6 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane, uint3
 		br.bytes = t.es;
 		br.len = t.es_len;
 		br.ring = ring;
-		br.qhead = 0;
 		br.seek_byte(t.start_byte);
 
 		PictureState ps;
@@ -1190,7 +1198,6 @@ __device__ __forceinline__ void expand_block(const ParseTask &t, uint32_t rec, u
 	br.bytes = t.es;
 	br.len = t.es_len;
 	br.ring = 0;
-	br.qhead = 0;
 	br.seek_bit(parked.x);
 
 	int n = 0;

@@ -15,13 +15,14 @@ from __future__ import annotations
 
 
 class _PesInfo:
-    __slots__ = ("destination", "current_length", "total_length", "pts", "buffers")
+    __slots__ = ("destination", "current_length", "total_length", "pts", "pts_ticks", "buffers")
 
     def __init__(self, destination):
         self.destination = destination
         self.current_length = 0
         self.total_length = 0
         self.pts = 0.0
+        self.pts_ticks = 0  # the same in 90 kHz ticks (what the device demuxer reports)
         self.buffers = []
 
 
@@ -54,9 +55,15 @@ class TS:
             pass
         self.leftover = data[self._pos:] if self._pos < n else b""
 
-    # -- src/ts.js:43-153
+    def _rd(self, i):
+        """bits.read past the end of the buffer: `undefined & mask` = 0 (src/buffer.js:152-170)"""
+        return self._bytes[i] if i < len(self._bytes) else 0
+
+    # -- src/ts.js:43-153.  Positions are byte positions in the whole buffer (the reference reads through
+    # its bit buffer, which knows nothing of packet boundaries: a header field that lies behind the packet's
+    # end is read from the next packet's bytes, one behind the buffer's end reads as 0).
     def _parse_packet(self):
-        b = self._bytes
+        b, rd = self._bytes, self._rd
         p = self._pos
         if b[p] != 0x47:
             self._pos = p + 1
@@ -66,9 +73,9 @@ class TS:
         else:
             p += 1
         end = p + 187
-        payload_start = (b[p] >> 6) & 1
-        pid = ((b[p] & 0x1F) << 8) | b[p + 1]
-        adaptation_field = (b[p + 2] >> 4) & 3
+        payload_start = (rd(p) >> 6) & 1
+        pid = ((rd(p) & 0x1F) << 8) | rd(p + 1)
+        adaptation_field = (rd(p + 2) >> 4) & 3
         p += 3
 
         stream_id = self.pids_to_stream_ids.get(pid)
@@ -79,23 +86,26 @@ class TS:
 
         if adaptation_field & 1:
             if adaptation_field & 2:
-                p += 1 + b[p]
-            if payload_start and p + 2 < len(b) and b[p] == 0 and b[p + 1] == 0 and b[p + 2] == 1:
-                stream_id = b[p + 3]
+                p += 1 + rd(p)
+            # nextBytesAreStartCode (src/buffer.js:141-150): true at the very end of the BUFFER as well
+            if payload_start and (p >= len(b) or (rd(p) == 0 and p + 2 < len(b) and b[p + 1] == 0 and b[p + 2] == 1)):
+                stream_id = rd(p + 3)
                 self.pids_to_stream_ids[pid] = stream_id
-                packet_length = (b[p + 4] << 8) | b[p + 5]
-                pts_dts_flag = b[p + 7] >> 6
-                header_length = b[p + 8]
+                packet_length = (rd(p + 4) << 8) | rd(p + 5)
+                pts_dts_flag = rd(p + 7) >> 6
+                header_length = rd(p + 8)
                 payload_begin = p + 9 + header_length
                 pi = self.pes_packet_info.get(stream_id)
                 if pi is not None:
                     pts = 0.0
+                    pts_ticks = 0
                     if pts_dts_flag & 2:
                         q = p + 9
-                        p32_30 = (b[q] >> 1) & 7
-                        p29_15 = (b[q + 1] << 7) | (b[q + 2] >> 1)
-                        p14_0 = (b[q + 3] << 7) | (b[q + 4] >> 1)
-                        pts = (p32_30 * 1073741824 + p29_15 * 32768 + p14_0) / 90000.0
+                        p32_30 = (rd(q) >> 1) & 7
+                        p29_15 = (rd(q + 1) << 7) | (rd(q + 2) >> 1)
+                        p14_0 = (rd(q + 3) << 7) | (rd(q + 4) >> 1)
+                        pts_ticks = p32_30 * 1073741824 + p29_15 * 32768 + p14_0
+                        pts = pts_ticks / 90000.0
                         self.current_time = pts
                         if self.start_time == -1:
                             self.start_time = pts
@@ -103,12 +113,13 @@ class TS:
                     pi.total_length = payload_length
                     pi.current_length = 0
                     pi.pts = pts
+                    pi.pts_ticks = pts_ticks
                 p = payload_begin
             if stream_id:
                 pi = self.pes_packet_info.get(stream_id)
                 if pi is not None:
-                    start = min(p, end)
-                    pi.buffers.append(bytes(b[start:end]))
+                    start = p
+                    pi.buffers.append(bytes(b[start:end]) if start < end else b"")  # subarray(start, end)
                     pi.current_length += end - start
                     complete = pi.total_length != 0 and pi.current_length >= pi.total_length
                     has_padding = (not payload_start) and (adaptation_field & 2)

@@ -326,12 +326,27 @@ def test_device_ts_demux_matches_host_demuxer_and_decodes_bit_exact():
     bd.close()
 
 
-def test_device_ts_demux_rejects_unaligned_input():
+def test_device_ts_demux_resyncs_on_unaligned_input_and_decodes_bit_exact():
+    """Three bytes of garbage in front of the clip, an odd chunking: the device demuxer finds the packet grid the
+    way src/ts.js:155-189 does, carries partial packets over (ts.js:25-41), and the pictures decode bit-exact."""
     import gen_streams
+    from jsmpeg_b200 import ts
     data = gen_streams.make_clip_ts(176, 144, 6, seed=3, noise=4)
+    packets = ts.demux_video_es(data)
+    es = b"".join(p for _, p in packets)
+    dirty = b"\x00\x01\x02" + data
     bd = BatchDecoder(1)
-    with pytest.raises(ValueError):
-        bd.write_ts(0, b"\x00\x01\x02" + data)
+    total = 0
+    for o in range(0, len(dirty), 1777):
+        total += bd.write_ts(0, dirty[o:o + 1777])[0]
+    assert total == len(es)
+    exp_frames, exp_idx, od = decode_all(oracle_lib(), packets)
+    n = 0
+    while bd.decode(1, OUT_DEVICE):
+        assert_frames_equal([bd.read_planes(0)], [exp_frames[n]], f"resynced TS picture {n}")
+        n += 1
+    assert n == len(exp_frames) and bd.get_index(0) == exp_idx[-1]
+    od.destroy()
     bd.close()
 
 
