@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["engine.cu", "parse.cu", "recon.cu", "scan.cu", "rgba.cu", "tsdemux.cu"]
+SOURCES = ["engine.cu", "parse.cu", "recon.cu", "scan.cu", "tsdemux.cu"]
 OUT = os.path.join(HERE, "libjsmpeg_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -107,7 +107,8 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 int parse_group_count(int n_tasks, bool forked);
 // `tasks_host` is read on the host at launch time: the table travels in the kernel parameters
 void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream);
-void launch_rgba(const ReconTask *tasks, int n_tasks, int max_width, int max_height, cudaStream_t stream);
+// the same with the planar -> RGBA conversion fused in (tasks' rgba / width / height)
+void launch_reconstruct_rgba(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream);
 
 // device MPEG-TS demux (tsdemux.cu)
 struct TsScratch;

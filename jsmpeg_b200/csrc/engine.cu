@@ -673,7 +673,10 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 					t.n_coded_blocks = e.info.n_coded_blocks;
 					t.rgba = nullptr;
 					if (flags & JSMPEG_B200_OUT_RGBA) {
-						if (!s.d_rgba) s.d_rgba = dev_alloc<uint8_t>((size_t)s.width * s.height * 4);
+						if (!s.d_rgba) {  // opaque white, like the canvas the reference creates (canvas2d.js:24-29): the odd edge keeps it
+							s.d_rgba = dev_alloc<uint8_t>((size_t)s.width * s.height * 4);
+							CUDA_CHECK(cudaMemsetAsync(s.d_rgba, 0xff, (size_t)s.width * s.height * 4, b->st_recon));
+						}
 						t.rgba = s.d_rgba;
 					}
 					if ((int)steps.size() <= step) { steps.emplace_back(); step_streams.emplace_back(); }
@@ -699,11 +702,6 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 		ensure_task_caps(b, 0, (int)total);
 		size_t off = 0;
 		for (auto &v : steps) { memcpy(b->h_rtasks + off, v.data(), v.size() * sizeof(ReconTask)); off += v.size(); }
-		if (flags & JSMPEG_B200_OUT_RGBA) {  // only the RGBA epilogue reads the task table from HBM
-			CUDA_CHECK(cudaStreamSynchronize(b->st_recon));  // the previous chunk's epilogue reads the same table
-			CUDA_CHECK(cudaMemcpyAsync(b->d_rtasks, b->h_rtasks, total * sizeof(ReconTask), cudaMemcpyHostToDevice, b->st_recon));
-			b->stats.h2d_bytes += total * sizeof(ReconTask);
-		}
 		CUDA_CHECK(cudaEventRecord(b->ev_rec0[rec_chunks], b->st_recon));
 		off = 0;
 		for (size_t f = 0; f < steps.size(); f++) {
@@ -712,15 +710,10 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			// (the copy stream is in order, so that covers every earlier one).
 			if ((flags & JSMPEG_B200_OUT_HOST) && b->copy_steps >= 2)
 				CUDA_CHECK(cudaStreamWaitEvent(b->st_recon, b->ev_copied[b->copy_steps & 1], 0));
-			launch_reconstruct(b->h_rtasks + off, (int)steps[f].size(), b->st_recon);
-			b->stats.kernel_launches++;
+			if (flags & JSMPEG_B200_OUT_RGBA) launch_reconstruct_rgba(b->h_rtasks + off, (int)steps[f].size(), b->st_recon);  // conversion fused in
+			else launch_reconstruct(b->h_rtasks + off, (int)steps[f].size(), b->st_recon);
+			b->stats.kernel_launches += ((int)steps[f].size() + (flags & JSMPEG_B200_OUT_RGBA ? 59 : 79)) / (flags & JSMPEG_B200_OUT_RGBA ? 60 : 80);
 			b->stats.recon_launches++;
-			if (flags & JSMPEG_B200_OUT_RGBA) {
-				int mw = 0, mh = 0;
-				for (auto &t : steps[f]) { mw = std::max(mw, t.width); mh = std::max(mh, t.height); }
-				launch_rgba(b->d_rtasks + off, (int)steps[f].size(), mw, mh, b->st_recon);
-				b->stats.kernel_launches++;
-			}
 			if (flags & JSMPEG_B200_OUT_HOST) copy_out_step(b, steps[f], step_streams[f]);  // while the next step reconstructs
 			off += steps[f].size();
 		}

@@ -43,6 +43,36 @@ reconstruct_kernel(const __grid_constant__ ReconParams params) {
 	reconstruct_block(params, blockIdx.y, blockIdx.x * THREADS, threadIdx.x, stage);
 }
 
+// OUT_RGBA: the same reconstruction with the planar -> RGBA conversion fused in (recon.cuh)
+struct ReconRgbaParams {
+	ReconParamsT<MAX_TASKS_RGBA> p;
+	RgbaTarget out[MAX_TASKS_RGBA];
+};
+static_assert(sizeof(ReconRgbaParams) <= 4096, "kernel parameters");
+
+__global__ void __launch_bounds__(RGBA_THREADS)
+reconstruct_rgba_kernel(const __grid_constant__ ReconRgbaParams params) {
+	__shared__ __align__(16) uint8_t stage[(RGBA_THREADS / 32) * WARP_STAGE];
+	__shared__ __align__(16) uint8_t chroma[2][8][RGBA_MBS * 8];
+	reconstruct_rgba_block(params.p, params.out[blockIdx.z], blockIdx.z, blockIdx.y, blockIdx.x * RGBA_MBS, threadIdx.x, stage, chroma);
+}
+
+void fill_task(CompactTask &c, const ReconTask &t) {
+	c.hdr = t.hdr;
+	c.coef = t.coef;
+	c.cur = t.cur.y;   // planes are contiguous: Y | Cr | Cb (engine.cu plane_set)
+	c.fwd = t.fwd.y;
+	c.mb_width = t.mb_width;
+	c.mb_height = t.mb_size / t.mb_width;
+	c.row_magic = (uint32_t)(0x100000000ull / (uint64_t)(6 * t.mb_width)) + 1u;
+	// dense: at least 3 of 4 block slots carry a coded block -- fetching every slot's record before the
+	// header is known costs at most a third more record bytes and takes one memory latency off the chain
+	// (JSMPEG_B200_RECON_DENSE=0 / 1 forces one path: tests, A/B)
+	static const int force_dense = [] { const char *e = getenv("JSMPEG_B200_RECON_DENSE"); return e && *e ? atoi(e) : -1; }();
+	const bool dense = force_dense >= 0 ? force_dense != 0 : (int64_t)t.n_coded_blocks * 4 >= (int64_t)t.mb_size * 6 * 3;
+	c.flags = dense ? RT_DENSE : 0;
+}
+
 }  // namespace
 
 void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream) {
@@ -52,23 +82,30 @@ void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t s
 		int max_slots = 0;
 		for (int i = 0; i < n; i++) {
 			const ReconTask &t = tasks_host[first + i];
-			p.t[i].hdr = t.hdr;
-			p.t[i].coef = t.coef;
-			p.t[i].cur = t.cur.y;   // planes are contiguous: Y | Cr | Cb (engine.cu plane_set)
-			p.t[i].fwd = t.fwd.y;
-			p.t[i].mb_width = t.mb_width;
-			p.t[i].mb_height = t.mb_size / t.mb_width;
-			p.t[i].row_magic = (uint32_t)(0x100000000ull / (uint64_t)(6 * t.mb_width)) + 1u;
-			// dense: at least 3 of 4 block slots carry a coded block -- fetching every slot's record before the
-			// header is known costs at most a third more record bytes and takes one memory latency off the chain
-			// (JSMPEG_B200_RECON_DENSE=0 / 1 forces one path: tests, A/B)
-			static const int force_dense = [] { const char *e = getenv("JSMPEG_B200_RECON_DENSE"); return e && *e ? atoi(e) : -1; }();
-			const bool dense = force_dense >= 0 ? force_dense != 0 : (int64_t)t.n_coded_blocks * 4 >= (int64_t)t.mb_size * 6 * 3;
-			p.t[i].flags = dense ? RT_DENSE : 0;
+			fill_task(p.t[i], t);
 			max_slots = max_slots > t.mb_size * 6 ? max_slots : t.mb_size * 6;
 		}
 		p.n_tasks = n;
 		dim3 grid((max_slots + THREADS - 1) / THREADS, n);
 		reconstruct_kernel<<<grid, THREADS, 0, stream>>>(p);
+	}
+}
+
+void launch_reconstruct_rgba(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream) {
+	for (int first = 0; first < n_tasks; first += MAX_TASKS_RGBA) {
+		const int n = n_tasks - first < MAX_TASKS_RGBA ? n_tasks - first : MAX_TASKS_RGBA;
+		ReconRgbaParams p;
+		int max_w = 0, max_h = 0;
+		for (int i = 0; i < n; i++) {
+			const ReconTask &t = tasks_host[first + i];
+			fill_task(p.p.t[i], t);
+			p.out[i] = RgbaTarget{t.rgba, t.width, t.height};
+			max_w = max_w > t.mb_width ? max_w : t.mb_width;
+			const int h = t.mb_size / t.mb_width;
+			max_h = max_h > h ? max_h : h;
+		}
+		p.p.n_tasks = n;
+		dim3 grid((max_w + RGBA_MBS - 1) / RGBA_MBS, max_h, n);
+		reconstruct_rgba_kernel<<<grid, RGBA_THREADS, 0, stream>>>(p);
 	}
 }

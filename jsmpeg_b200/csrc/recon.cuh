@@ -13,7 +13,8 @@ namespace {
 constexpr int THREADS = 128;
 constexpr int ROW_PITCH = 144;                       // bytes per staged block: 128 + 16 (bank spread)
 constexpr int WARP_STAGE = 32 * ROW_PITCH + 16;      // + the warp's mbarrier
-constexpr int MAX_TASKS = 80;  // per launch; (80 * 48 B) + 16 < 4 KB of kernel parameters
+constexpr int MAX_TASKS = 80;       // per launch; (80 * 48 B) + 16 < 4 KB of kernel parameters
+constexpr int MAX_TASKS_RGBA = 60;  // the RGBA variant's parameters: (60 * (48 + 16) B) + 16 < 4 KB
 
 enum { RT_DENSE = 1 };  // CompactTask::flags
 
@@ -27,10 +28,12 @@ struct CompactTask {
 	uint32_t flags;      // RT_DENSE: almost every block is coded -- all coefficient records are requested before the header is known
 };
 
-struct ReconParams {
-	CompactTask t[MAX_TASKS];
+template <int N>
+struct ReconParamsT {
+	CompactTask t[N];
 	int32_t n_tasks;
 };
+using ReconParams = ReconParamsT<MAX_TASKS>;
 
 #ifndef JSMPEG_WALK_EMU
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -146,9 +149,10 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
 // FULLPEL (warp-uniform: no lane has a half-pel component) is the plain copy: one dp4a per sample
 // selects the byte and adds the residual.
 // v = the residual, all zero for a block that is not coded.
-template <bool FULLPEL>
+// KEEP: the packed rows are also handed back (the fused RGBA epilogue converts them).
+template <bool FULLPEL, bool KEEP>
 __device__ __forceinline__ void predict_rows(const uint8_t *__restrict__ splane, int src, int stride, uint32_t weights,
-                                             const int (&v)[64], uint8_t *__restrict__ dst) {
+                                             const int (&v)[64], uint8_t *__restrict__ dst, uint2 (&rows)[8]) {
 	uint32_t a0, a1, a2;
 	row9(splane, src, a0, a1, a2);
 #pragma unroll
@@ -187,6 +191,7 @@ __device__ __forceinline__ void predict_rows(const uint8_t *__restrict__ splane,
 		out.x = pack_sat_u8x4(s[0], s[1], s[2], s[3]);
 		out.y = pack_sat_u8x4(s[4], s[5], s[6], s[7]);
 		*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+		if (KEEP) rows[r] = out;
 		a0 = c0; a1 = c1; a2 = c2;
 	}
 }
@@ -209,32 +214,17 @@ static inline uint32_t smem_u32(const void *) { return 0; }
 //   t1  header there: the nine reference rows of a predicted block are pulled into L2 (no registers)
 //   t2  records there: IDCT (some 700 instructions) -- the reference rows arrive meanwhile
 //   t3  prediction reads hit L2, + residual, store
-__device__ __forceinline__ void reconstruct_block(const ReconParams &params, int ty, int first_slot, int tid, uint8_t *stage) {
+// block (mb_row, mb_col, b) of picture `ty`; the 32 lanes of the warp call it together, wstage = the warp's staging
+// area.  KEEP: the block's eight packed output rows come back in `rows` (also for a macroblock that is not present:
+// the samples it keeps).
+template <bool KEEP, class PARAMS>
+__device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int mb_row, int mb_col, int b, bool in_picture,
+                                               int lane, uint8_t *wstage, uint2 (&rows)[8]) {
 	const CompactTask &t = params.t[ty];
 	const int W = t.mb_width;
-	const int slots_per_row = 6 * W;
-	const int slot = first_slot + tid;
-	const int lane = tid & 31;
-	const bool in_picture = slot < slots_per_row * t.mb_height;
-	const int mb_row = in_picture ? (int)umulhi_u32((uint32_t)slot, t.row_magic) : 0;
-	const int s = in_picture ? slot - mb_row * slots_per_row : 0;
-	// [luma top 2W | luma bottom 2W | Cb W | Cr W]
-	int b, mb_col;
-	if (s < 4 * W) {
-		const int by = s >= 2 * W;
-		const int bx = s - by * 2 * W;
-		mb_col = bx >> 1;
-		b = by * 2 + (bx & 1);
-	} else {
-		const int c = s - 4 * W;
-		const int second = c >= W;
-		mb_col = c - second * W;
-		b = 4 + second;  // block 4 -> Cb plane, block 5 -> Cr plane (mpeg1.js:829-834, SURVEY Q8)
-	}
 	const int mb = mb_row * W + mb_col;
 	const bool dense = t.flags & RT_DENSE;
 
-	uint8_t *wstage = stage + (tid >> 5) * WARP_STAGE;
 	const uint32_t mbar = smem_u32(wstage + 32 * ROW_PITCH);
 	const uint32_t my_row = smem_u32(wstage + lane * ROW_PITCH);
 	const int16_t *cblk = t.coef + ((size_t)mb * 6 + b) * 64;
@@ -245,7 +235,10 @@ __device__ __forceinline__ void reconstruct_block(const ReconParams &params, int
 #ifndef JSMPEG_WALK_EMU
 		if (lane == 0) {
 			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			// the initialised barrier must be visible to the async proxy (the TMA unit) before the copies name it:
+			// the proxy fence of the CUDA guide's single-CTA pattern.  (fence.mbarrier_init.release.cluster, used
+			// until round 2, is cluster-scoped: ptxas adds CCTL.IVALL to it, an invalidation of the SM's whole L1.)
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(128u * (uint32_t)__popc(copy_mask)) : "memory");
 		}
 		__syncwarp();
@@ -319,7 +312,15 @@ __device__ __forceinline__ void reconstruct_block(const ReconParams &params, int
 			             : "=r"(done) : "r"(mbar) : "memory");
 #endif
 	}
-	if (!present) return;
+	uint8_t *dst = t.cur + plane_off + origin;
+	auto reload_rows = [&]() {  // what is in the plane now (rare paths of the RGBA variant)
+#pragma unroll
+		for (int r = 0; r < 8; r++) rows[r] = *reinterpret_cast<const uint2 *>(dst + r * stride);
+	};
+	if (!present) {
+		if (KEEP && in_picture) reload_rows();
+		return;
+	}
 
 	// ---- residual: 64 values in registers
 	int v[64];
@@ -356,7 +357,6 @@ __device__ __forceinline__ void reconstruct_block(const ReconParams &params, int
 		for (int i = 0; i < 64; i++) v[i] = dc;
 	}
 
-	uint8_t *dst = t.cur + plane_off + origin;
 	if (intra) {
 #pragma unroll
 		for (int r = 0; r < 8; r++) {
@@ -364,6 +364,7 @@ __device__ __forceinline__ void reconstruct_block(const ReconParams &params, int
 			out.x = pack_sat_u8x4(v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
 			out.y = pack_sat_u8x4(v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
 			*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+			if (KEEP) rows[r] = out;
 		}
 		return;
 	}
@@ -372,8 +373,8 @@ __device__ __forceinline__ void reconstruct_block(const ReconParams &params, int
 	if (inside) {
 		// tap weights of this lane: bytes (wA, wB, wC, wD)
 		const uint32_t weights = oh ? (ov ? 0x01010101u : 0x00000202u) : (ov ? 0x00020002u : 0x00000004u);
-		if (warp_halfpel) predict_rows<false>(splane, src, stride, weights, v, dst);
-		else predict_rows<true>(splane, src, stride, weights, v, dst);
+		if (warp_halfpel) predict_rows<false, KEEP>(splane, src, stride, weights, v, dst, rows);
+		else predict_rows<true, KEEP>(splane, src, stride, weights, v, dst, rows);
 		return;
 	}
 	// vector leaves the plane: per-tap bounds check, any outside tap zeroes the sample
@@ -412,6 +413,110 @@ __device__ __forceinline__ void reconstruct_block(const ReconParams &params, int
 			out.x = p[0]; out.y = p[1];
 		}
 		*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+	}
+	if (KEEP) reload_rows();
+}
+
+// The plain kernel's numbering: slot first_slot + tid of picture `ty`; `stage` = the CTA's staging area (one
+// WARP_STAGE per warp).  The 32 lanes of a warp hold 32 horizontally adjacent blocks of one plane row:
+// [luma top 2W | luma bottom 2W | Cb W | Cr W] per macroblock row.
+__device__ __forceinline__ void reconstruct_block(const ReconParams &params, int ty, int first_slot, int tid, uint8_t *stage) {
+	const CompactTask &t = params.t[ty];
+	const int W = t.mb_width;
+	const int slots_per_row = 6 * W;
+	const int slot = first_slot + tid;
+	const bool in_picture = slot < slots_per_row * t.mb_height;
+	const int mb_row = in_picture ? (int)umulhi_u32((uint32_t)slot, t.row_magic) : 0;
+	const int s = in_picture ? slot - mb_row * slots_per_row : 0;
+	int b, mb_col;
+	if (s < 4 * W) {
+		const int by = s >= 2 * W;
+		const int bx = s - by * 2 * W;
+		mb_col = bx >> 1;
+		b = by * 2 + (bx & 1);
+	} else {
+		const int c = s - 4 * W;
+		const int second = c >= W;
+		mb_col = c - second * W;
+		b = 4 + second;  // block 4 -> Cb plane, block 5 -> Cr plane (mpeg1.js:829-834, SURVEY Q8)
+	}
+	uint2 unused[8];
+	reconstruct_at<false>(params, ty, mb_row, mb_col, b, in_picture, tid & 31, stage + (tid >> 5) * WARP_STAGE, unused);
+}
+
+// ---- fused planar -> RGBA epilogue (src/canvas2d.js:53-122) ------------------------------------
+// A CTA of three warps owns 16 macroblocks of one macroblock row: warp 0 their 32 top luma blocks, warp 1 the 32
+// bottom ones, warp 2 the 16 Cb and the 16 Cr blocks.  All reconstruct (and write their planes, the next picture
+// needs them); the chroma warp also leaves its 16 x 8 x 8 samples twice in shared memory; after one barrier the
+// luma threads convert their own 8 x 8 samples, still in registers, with the 4 x 4 chroma samples that cover them,
+// and write 8 rows of 32 RGBA bytes.  The planes are never read back.
+//     r = Cr + (Cr * 103 >> 8) - 179,  g = (Cb * 88 >> 8) - 44 + (Cr * 183 >> 8) - 91,  b = Cb + (Cb * 198 >> 8) - 227
+//     R = clamp(Y + r), G = clamp(Y - g), B = clamp(Y + b), A = 255
+// (canvas2d.js names its parameters (y, cb, cr) but is CALLED with (Y, Cr, Cb), mpeg1.js:217 -- its `ccb` is a Cr
+// sample)  Only (width >> 1) x (height >> 1) quads are converted (canvas2d.js:77-78); the odd edge of
+// the image keeps the opaque white the buffer is created with (canvas2d.js:24-29).
+constexpr int RGBA_THREADS = 96, RGBA_MBS = 16;
+
+struct RgbaTarget {
+	uint8_t *rgba;          // display size, RGBA8888
+	int32_t width, height;  // display size
+};
+
+__device__ __forceinline__ uint32_t rgba_px(int y, int r, int g, int b) {
+	auto c = [](int v) { return (uint32_t)min(255, max(0, v)); };  // Uint8ClampedArray
+	return c(y + r) | (c(y - g) << 8) | (c(y + b) << 16) | 0xff000000u;
+}
+
+template <class PARAMS>
+__device__ __forceinline__ void reconstruct_rgba_block(const PARAMS &params, const RgbaTarget &out, int ty, int mb_row, int first_mb_col,
+                                                       int tid, uint8_t *stage, uint8_t (*chroma)[8][RGBA_MBS * 8]) {
+	const CompactTask &t = params.t[ty];
+	const int warp = tid >> 5, lane = tid & 31;
+	int b, local;  // local = macroblock within the CTA's 16
+	if (warp < 2) { b = warp * 2 + (lane & 1); local = lane >> 1; }
+	else { b = 4 + (lane >> 4); local = lane & 15; }
+	const int mb_col = first_mb_col + local;
+	const bool in_picture = mb_col < t.mb_width;
+	uint2 rows[8];
+#pragma unroll
+	for (int r = 0; r < 8; r++) rows[r] = make_uint2(0u, 0u);
+	reconstruct_at<true>(params, ty, mb_row, in_picture ? mb_col : 0, b, in_picture, lane, stage + warp * WARP_STAGE, rows);
+	if (warp == 2) {
+		// plane 0 = Cb (block 4), plane 1 = Cr (block 5)
+#pragma unroll
+		for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(&chroma[b - 4][r][local * 8]) = rows[r];
+	}
+	__syncthreads();
+	if (warp == 2 || !in_picture || !out.rgba) return;
+	const int x0 = mb_col * 16 + (b & 1) * 8, y0 = mb_row * 16 + (b >> 1) * 8;  // this block's top-left sample
+	const int cx0 = local * 8 + (b & 1) * 4, cy0 = (b >> 1) * 4;                  // its chroma samples in the CTA's tile
+	const int xlim = (out.width >> 1) * 2, ylim = (out.height >> 1) * 2;
+	if (x0 >= xlim || y0 >= ylim) return;
+	const bool whole = x0 + 8 <= xlim && (out.width & 3) == 0;  // 16-byte stores need aligned rows
+#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		if (y0 + r >= ylim) break;
+		const uint32_t cb4 = *reinterpret_cast<const uint32_t *>(&chroma[0][cy0 + (r >> 1)][cx0]);
+		const uint32_t cr4 = *reinterpret_cast<const uint32_t *>(&chroma[1][cy0 + (r >> 1)][cx0]);
+		uint32_t px[8];
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			const int cb = (int)((cb4 >> (8 * (i >> 1))) & 255u), cr = (int)((cr4 >> (8 * (i >> 1))) & 255u);
+			const int rr = (cr + ((cr * 103) >> 8)) - 179;
+			const int gg = ((cb * 88) >> 8) - 44 + ((cr * 183) >> 8) - 91;
+			const int bb = (cb + ((cb * 198) >> 8)) - 227;
+			const int yy = (int)(((i < 4 ? rows[r].x : rows[r].y) >> (8 * (i & 3))) & 255u);
+			px[i] = rgba_px(yy, rr, gg, bb);
+		}
+		uint32_t *dstp = reinterpret_cast<uint32_t *>(out.rgba) + (size_t)(y0 + r) * out.width + x0;
+		if (whole) {
+			reinterpret_cast<uint4 *>(dstp)[0] = make_uint4(px[0], px[1], px[2], px[3]);
+			reinterpret_cast<uint4 *>(dstp)[1] = make_uint4(px[4], px[5], px[6], px[7]);
+		} else {
+#pragma unroll
+			for (int i = 0; i < 8; i++)
+				if (x0 + i < xlim) dstp[i] = px[i];
+		}
 	}
 }
 

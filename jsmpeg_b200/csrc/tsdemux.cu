@@ -11,7 +11,7 @@
 // What "packet complete" means in the reference (:65-70, :143-146, :201) only decides how the
 // payload is CHUNKED into destination.write() calls; the decoder concatenates the chunks, so the
 // elementary stream is the concatenation of the accepted payloads.  The host mirror
-// (jsmpeg_b200/ts.py) reproduces the chunking too; both are pinned by tests/golden/ts_cases.json.
+// (jsmpeg_b200/ts.py) reproduces the chunking too; both are pinned by tests/fixtures/ts_cases.json.
 //
 // Decomposition.  The only serial thing in a transport stream is where the packets ARE once sync was
 // lost; everything else is per packet:

@@ -1,5 +1,5 @@
 """SURVEY 8f rank 1 pinned to the TEXT of the reference's src/ts.js: the hand-derived cases of
-tools/make_ts_cases.py (tests/golden/ts_cases.json; every expected delivery is a list of (packet, first
+tools/make_ts_cases.py (tests/fixtures/ts_cases.json; every expected delivery is a list of (packet, first
 payload byte) pairs worked out from ts.js by hand -- the reference's JS cannot run in this image).
 
   * the host mirror jsmpeg_b200/ts.py must make exactly those destination.write(pts, buffers) calls
@@ -19,7 +19,7 @@ import pytest
 import helpers
 from jsmpeg_b200 import ts
 
-CASES = json.load(open(os.path.join(helpers.ROOT, "tests", "golden", "ts_cases.json")))["cases"]
+CASES = json.load(open(os.path.join(helpers.ROOT, "tests", "fixtures", "ts_cases.json")))["cases"]
 
 
 class Recorder:
@@ -49,7 +49,7 @@ def test_host_mirror_makes_the_hand_derived_deliveries(case):
 
 
 def test_fixture_file_is_what_the_generator_writes():
-    before = open(os.path.join(helpers.ROOT, "tests", "golden", "ts_cases.json")).read()
+    before = open(os.path.join(helpers.ROOT, "tests", "fixtures", "ts_cases.json")).read()
     sys.path.insert(0, os.path.join(helpers.ROOT, "tools"))
     import make_ts_cases
     now = json.dumps({"generator": "tools/make_ts_cases.py (hand-derived from src/ts.js; see the comments there)",

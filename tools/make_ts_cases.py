@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Hand-derived MPEG-TS demux cases -> tests/golden/ts_cases.json (pins SURVEY 8f rank 1 to the TEXT of
+"""Hand-derived MPEG-TS demux cases -> tests/fixtures/ts_cases.json (pins SURVEY 8f rank 1 to the TEXT of
 the reference's src/ts.js, which cannot be executed in this image).
 
 Every case is a handful of 188-byte packets built field by field below, one or more write() calls, and
@@ -11,7 +11,7 @@ slice that is off by one byte is a different byte string.
 The expected byte strings in the JSON are nothing but `packet[k][start:188]` concatenated in the stated
 order; no demuxer of ours is involved in producing them (tools/make_ts_cases.py imports none).
 
-    python tools/make_ts_cases.py        # rewrites tests/golden/ts_cases.json
+    python tools/make_ts_cases.py        # rewrites tests/fixtures/ts_cases.json
 """
 import json
 import os
@@ -148,7 +148,7 @@ def build():
 
 
 def main():
-    out = os.path.join(ROOT, "tests", "golden", "ts_cases.json")
+    out = os.path.join(ROOT, "tests", "fixtures", "ts_cases.json")
     with open(out, "w") as f:
         json.dump({"generator": "tools/make_ts_cases.py (hand-derived from src/ts.js; see the comments there)", "cases": build()}, f, indent=1)
     print(out)
