@@ -67,6 +67,11 @@ struct ParseTask {
 	// storing pass over the bits)
 	uint4 *stage;
 	int32_t stage_entries;
+	// the stream's start-code prefixes (byte positions of 00 00 01, sorted, all of them up to es_len) and the
+	// index of this picture's own start code in that list: a slice ends at the first prefix at or after its
+	// first macroblock, so the walk looks the position up instead of searching the bytes.  nullptr = search.
+	const uint32_t *codes;
+	uint32_t n_codes, code_hint;
 };
 
 // staging entries per picture: three per macroblock (a lane keeps its macroblocks in its own stretch and a

@@ -82,8 +82,12 @@ struct Stream {
 	// ES mirror in HBM + start-code index
 	uint8_t *d_es = nullptr;
 	uint32_t d_capacity = 0, d_valid = 0;
-	std::vector<uint32_t> pics;  // sorted byte positions of picture start codes
-	uint32_t scanned = 0;        // every start code with pos + 3 < scanned is in `pics`
+	std::vector<uint32_t> pics;  // sorted byte positions of picture start codes (00 00 01 00)
+	std::vector<uint32_t> codes, pic_code;  // every start-code prefix (00 00 01), sorted; pics[k] == codes[pic_code[k]]
+	uint32_t codes_classified = 0;          // codes[0 .. codes_classified) have had their fourth byte looked at
+	uint32_t *d_codes = nullptr;            // the device's copy of `codes` (ParseTask::codes)
+	uint32_t d_codes_cap = 0;
+	uint32_t scanned = 0;        // every prefix with pos + 2 < scanned is in `codes`
 	uint32_t *d_scan = nullptr, *h_scan = nullptr;  // [0] = count, [1..] = positions
 	uint32_t scan_cap = 0, scan_from = 0;
 	bool scan_pending = false;
@@ -123,6 +127,9 @@ struct jsmpeg_b200_batch_t {
 	int lookahead = 1;
 	int chunk_pictures = 0;      // G of the pipeline; 0 = the whole wave is one chunk
 	int chunk_min_wave = 256;    // waves with fewer new pictures stay whole
+	int chunk_streams = 3;       // chunks are parsed on this many streams in turn (1 = on the main stream, forked into size groups)
+	cudaStream_t st_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t ev_fed = nullptr, ev_chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
 	bool recon_pending = false;  // reconstruct launches of an earlier round may still read record slots
 	// task staging
 	ParseTask *h_ptasks = nullptr, *d_ptasks = nullptr;
@@ -178,6 +185,9 @@ void flush_cache(Batch *b, Stream &s) {
 void forget_index(Batch *b, Stream &s) {
 	flush_cache(b, s);
 	s.pics.clear();
+	s.codes.clear();
+	s.pic_code.clear();
+	s.codes_classified = 0;
 	s.scanned = 0;
 	s.d_valid = 0;
 }
@@ -322,10 +332,11 @@ void begin_upload(Batch *b, Stream &s) {
 		CUDA_CHECK(cudaMemsetAsync(s.d_es + s.bb.length, 0, ES_PAD, b->st_main));
 	}
 	if (s.scanned < s.bb.length) {
-		s.scan_from = s.scanned >= 3 ? s.scanned - 3 : 0;
-		// room for one picture per 2 KiB (real streams: one per tens of KiB).  A stream that packs them
-		// denser overflows the list; the scan is then repeated with the count it reported (upload_all).
-		reserve_scan(s, std::max<uint32_t>(4096u, (s.bb.length - s.scan_from) / 2048u + 16u));
+		s.scan_from = s.scanned >= 2 ? s.scanned - 2 : 0;  // a prefix needs its three bytes: those from scanned - 2 on were not complete
+		// room for one start code per 512 bytes (FFmpeg streams: two per picture of tens of KiB; a slice per
+		// macroblock row: ~70 per picture).  A stream that packs them denser overflows the list; the scan is
+		// then repeated with the count it reported (upload_all).
+		reserve_scan(s, std::max<uint32_t>(4096u, (s.bb.length - s.scan_from) / 512u + 16u));
 		launch_scan(b, s);
 		s.scan_pending = true;
 	}
@@ -333,7 +344,7 @@ void begin_upload(Batch *b, Stream &s) {
 
 long upload_all(Batch *b) {
 	CUDA_CHECK(cudaEventRecord(b->ev_a, b->st_main));
-	bool any = false;
+	bool any = false, copied = false;
 	for (auto &s : b->streams) {
 		begin_upload(b, s);
 		any |= s.scan_pending;
@@ -367,14 +378,42 @@ long upload_all(Batch *b) {
 			if (!s.scan_pending) continue;
 			const uint32_t n = s.h_scan[0];
 			std::sort(s.h_scan + 1, s.h_scan + 1 + n);
-			// the rescanned window starts 3 bytes before the old frontier, so nothing is reported twice
-			for (uint32_t i = 1; i <= n; i++) s.pics.push_back(s.h_scan[i]);
+			// the rescanned window starts 2 bytes before the old frontier, so nothing is reported twice
+			const uint32_t old = (uint32_t)s.codes.size();
+			s.codes.insert(s.codes.end(), s.h_scan + 1, s.h_scan + 1 + n);
+			if (n) {  // the device's copy, for the lane-parallel walk's slice ends
+				if (old + n > s.d_codes_cap) {
+					const uint32_t cap = std::max<uint32_t>(2 * s.d_codes_cap, old + n + 1024u);
+					uint32_t *grown = dev_alloc<uint32_t>(cap);
+					if (s.d_codes) {
+						if (old) CUDA_CHECK(cudaMemcpyAsync(grown, s.d_codes, old * sizeof(uint32_t), cudaMemcpyDeviceToDevice, b->st_main));
+						CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+						CUDA_CHECK(cudaFree(s.d_codes));
+					}
+					s.d_codes = grown;
+					s.d_codes_cap = cap;
+				}
+				CUDA_CHECK(cudaMemcpyAsync(s.d_codes + old, s.h_scan + 1, n * sizeof(uint32_t), cudaMemcpyHostToDevice, b->st_main));
+				b->stats.h2d_bytes += n * sizeof(uint32_t);
+				copied = true;
+			}
 			s.scanned = s.bb.length;
 			s.scan_pending = false;
 		}
 	}
+	if (copied) CUDA_CHECK(cudaStreamSynchronize(b->st_main));  // the pinned lists are reused by the next scan
+	// picture start codes = prefixes whose fourth byte is 00 and inside the buffer (findStartCode, buffer.js:130-139).
+	// Only the very last prefix can still be waiting for its fourth byte.
 	long total = 0;
-	for (auto &s : b->streams) total += (long)s.pics.size();
+	for (auto &s : b->streams) {
+		while (s.codes_classified < s.codes.size()) {
+			const uint32_t p = s.codes[s.codes_classified];
+			if (p + 3u >= s.bb.length) break;
+			if (s.bb.bytes[p + 3u] == 0) { s.pics.push_back(p); s.pic_code.push_back(s.codes_classified); }
+			s.codes_classified++;
+		}
+		total += (long)s.pics.size();
+	}
 	return total;
 }
 
@@ -511,7 +550,7 @@ void copy_out_step(Batch *b, const std::vector<ReconTask> &tasks, const std::vec
 long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &progress, std::vector<char> &more, int flags) {
 	const int S = (int)b->streams.size();
 	// ---- 1. plan the parse wave
-	struct NewParse { int stream; size_t cache_idx; uint32_t bytes; int chunk; };
+	struct NewParse { int stream; size_t cache_idx; uint32_t bytes; int chunk; uint32_t pic; };
 	std::vector<NewParse> fresh;
 	for (int si = 0; si < S; si++) {
 		Stream &s = b->streams[si];
@@ -539,7 +578,7 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			b->free_slots.pop_back();
 			s.cache.push_back(p);
 			++next;
-			fresh.push_back({si, s.cache.size() - 1, (next < s.pics.end() ? *next : s.bb.length) - p.pos, 0});
+			fresh.push_back({si, s.cache.size() - 1, (next < s.pics.end() ? *next : s.bb.length) - p.pos, 0, (uint32_t)(next - 1 - s.pics.begin())});
 		}
 	}
 	// ---- 2. chunks by picture ordinal (position in the stream's look-ahead); a small wave stays whole
@@ -578,6 +617,9 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			t.mb_size = s.seq.mb_size;
 			t.stage = b->d_stage + (size_t)p.slot * stage_entries_for(b->slot_mb) * 4;
 			t.stage_entries = stage_entries_for(b->slot_mb);
+			t.codes = s.d_codes;
+			t.n_codes = (uint32_t)s.codes.size();
+			t.code_hint = s.pic_code[fresh[i].pic];
 		}
 		if (b->recon_pending) {  // slots freed by the previous round are still being read by its reconstruct launches
 			CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_round, 0));
@@ -585,18 +627,37 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 		}
 		CUDA_CHECK(cudaMemcpyAsync(b->d_ptasks, b->h_ptasks, fresh.size() * sizeof(ParseTask), cudaMemcpyHostToDevice, b->st_main));
 		CUDA_CHECK(cudaEventRecord(b->ev_a, b->st_main));
+		// Chunks are parsed on a few streams in turn: the walk of chunk c + 1 starts while chunk c is still walking or
+		// expanding (a chunk's walk costs its latency floor whatever its size; in a row on one stream the floors add up).
+		const int n_cs = (G > 0 && n_chunks > 1) ? std::min(std::max(b->chunk_streams, 1), 4) : 1;
+		if (n_cs > 1) {
+			for (int k = 0; k < n_cs; k++)
+				if (!b->st_chunk[k]) {
+					CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_chunk[k], cudaStreamNonBlocking));
+					CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_chunk_done[k], cudaEventDisableTiming));
+				}
+			if (!b->ev_fed) CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_fed, cudaEventDisableTiming));
+			CUDA_CHECK(cudaEventRecord(b->ev_fed, b->st_main));  // tasks uploaded, the previous round's reconstruction waited for
+		}
 		bool mid_recorded = false;
 		for (int c = 0; c < n_chunks; c++) {
 			const int lo = chunk_off[c], n = chunk_off[c + 1] - lo;
+			cudaStream_t st = n_cs > 1 ? b->st_chunk[c % n_cs] : b->st_main;
+			if (n_cs > 1 && c < n_cs) CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_fed, 0));
 			if (n > 0) {
-				launch_parse_pictures(b->d_ptasks + lo, n, b->slot_mb, b->st_main, mid_recorded ? nullptr : b->ev_mid, &b->fork);
+				launch_parse_pictures(b->d_ptasks + lo, n, b->slot_mb, st, mid_recorded ? nullptr : b->ev_mid, n_cs > 1 ? nullptr : &b->fork);
 				mid_recorded = true;
-				b->stats.kernel_launches += 2 * parse_group_count(n, true);  // walk + expand per size group
-				CUDA_CHECK(cudaMemcpyAsync(b->h_info + lo, b->d_info + lo, n * sizeof(picture_info_t), cudaMemcpyDeviceToHost, b->st_main));
+				b->stats.kernel_launches += 2 * parse_group_count(n, n_cs == 1);  // walk + expand per size group
+				CUDA_CHECK(cudaMemcpyAsync(b->h_info + lo, b->d_info + lo, n * sizeof(picture_info_t), cudaMemcpyDeviceToHost, st));
 			}
-			if (c == n_chunks - 1) CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
-			CUDA_CHECK(cudaEventRecord(b->ev_info[c], b->st_main));
+			CUDA_CHECK(cudaEventRecord(b->ev_info[c], st));
 		}
+		if (n_cs > 1)  // everything queued later on the main stream comes after the whole wave
+			for (int k = 0; k < n_cs; k++) {
+				CUDA_CHECK(cudaEventRecord(b->ev_chunk_done[k], b->st_chunk[k]));
+				CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_chunk_done[k], 0));
+			}
+		CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
 		b->stats.h2d_bytes += fresh.size() * sizeof(ParseTask);
 		b->stats.d2h_bytes += fresh.size() * sizeof(picture_info_t);
 	}
@@ -799,6 +860,7 @@ jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigne
 	b->max_slots_req = max_slots;
 	b->chunk_pictures = std::max(0, env_int("JSMPEG_B200_CHUNK", 0));
 	b->chunk_min_wave = std::max(1, env_int("JSMPEG_B200_CHUNK_MIN_WAVE", 256));
+	b->chunk_streams = std::min(std::max(1, env_int("JSMPEG_B200_CHUNK_STREAMS", 3)), 4);
 	try {
 		use_device(b);
 		CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
@@ -830,6 +892,7 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 		if (s.d_seq) cudaFree(s.d_seq);
 		if (s.d_es) cudaFree(s.d_es);
 		if (s.d_scan) cudaFree(s.d_scan);
+		if (s.d_codes) cudaFree(s.d_codes);
 		if (s.h_scan) cudaFreeHost(s.h_scan);
 		if (s.d_rgba) cudaFree(s.d_rgba);
 		for (auto p : s.d_planes) if (p) cudaFree(p);
@@ -853,7 +916,8 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 		if (b->fork.join[i]) cudaEventDestroy(b->fork.join[i]);
 		if (b->fork.side[i]) cudaStreamDestroy(b->fork.side[i]);
 	}
-	for (auto st : {b->st_main, b->st_recon, b->st_copy}) if (st) cudaStreamDestroy(st);
+	for (auto st : {b->st_main, b->st_recon, b->st_copy, b->st_chunk[0], b->st_chunk[1], b->st_chunk[2], b->st_chunk[3]}) if (st) cudaStreamDestroy(st);
+	for (auto e : {b->ev_fed, b->ev_chunk_done[0], b->ev_chunk_done[1], b->ev_chunk_done[2], b->ev_chunk_done[3]}) if (e) cudaEventDestroy(e);
 	(void)cudaGetLastError();
 	delete b;
 }
@@ -864,6 +928,7 @@ int jsmpeg_b200_batch_set_option(jsmpeg_b200_batch_t *b, const char *name, int v
 	if (!b || !name) return -1;
 	if (!strcmp(name, "chunk_pictures")) { b->chunk_pictures = std::max(0, value); return 0; }
 	if (!strcmp(name, "chunk_min_wave")) { b->chunk_min_wave = std::max(1, value); return 0; }
+	if (!strcmp(name, "chunk_streams")) { b->chunk_streams = std::min(std::max(1, value), 4); return 0; }
 	if (!strcmp(name, "lookahead")) { b->lookahead = std::max(1, value); return 0; }
 	return -1;
 }
@@ -914,6 +979,9 @@ void jsmpeg_b200_batch_rewind(jsmpeg_b200_batch_t *b) {
 	for (auto &s : b->streams) {
 		flush_cache(b, s);
 		s.pics.clear();
+		s.codes.clear();
+		s.pic_code.clear();
+		s.codes_classified = 0;
 		s.scanned = 0;
 		s.bb.index = s.has_seq ? s.seq_end_index : 0;  // where did_write left it (mpeg1.c:812-819)
 	}
@@ -1173,6 +1241,7 @@ int jsmpeg_b200_debug_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t
 		t.es = d_es; t.es_len = es_len; t.start_byte = start_byte; t.seq = d_seq; t.hdr = d_hdr; t.coef = d_coef; t.info = d_info;
 		t.park = d_park; t.mb_width = mb_width; t.mb_size = sp.mb_size;
 		t.stage = d_stage; t.stage_entries = stage_entries_for(sp.mb_size);
+		t.codes = nullptr; t.n_codes = 0; t.code_hint = 0;  // this hook lets the walk search the slice end itself
 		CUDA_CHECK(cudaMemcpy(d_task, &t, sizeof(t), cudaMemcpyHostToDevice));
 		launch_parse_pictures(d_task, 1, sp.mb_size, 0);
 		CUDA_CHECK(cudaGetLastError());

@@ -444,6 +444,7 @@ __device__ __forceinline__ void reconstruct_block(const ReconParams &params, int
 	reconstruct_at<false>(params, ty, mb_row, mb_col, b, in_picture, tid & 31, stage + (tid >> 5) * WARP_STAGE, unused);
 }
 
+#ifndef JSMPEG_WALK_EMU  // (a CTA-wide barrier: outside what the one-warp host emulation runs)
 // ---- fused planar -> RGBA epilogue (src/canvas2d.js:53-122) ------------------------------------
 // A CTA of three warps owns 16 macroblocks of one macroblock row: warp 0 their 32 top luma blocks, warp 1 the 32
 // bottom ones, warp 2 the 16 Cb and the 16 Cr blocks.  All reconstruct (and write their planes, the next picture
@@ -519,5 +520,7 @@ __device__ __forceinline__ void reconstruct_rgba_block(const PARAMS &params, con
 		}
 	}
 }
+
+#endif
 
 }  // namespace

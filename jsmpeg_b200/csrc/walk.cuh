@@ -792,8 +792,13 @@ __device__ __forceinline__ LaneSum shfl_up_sum(const LaneSum &s, int d) {
 // The byte index of the first start code prefix (00 00 01) at or after `from`, or len: where
 // nextBytesAreStartCode (buffer.js:141-150) first becomes true.  The warp scans 128 bytes per step.
 template <class BR>
-__device__ uint32_t find_slice_end(const BR &br, uint32_t from, int lane) {
+__device__ uint32_t find_slice_end(const BR &br, uint32_t from, int lane, const ParseTask &t) {
 	const uint32_t len = br.len;
+	if (t.codes) {  // the host's sorted list of every prefix in the stream: a few steps from this picture's own start code
+		uint32_t i = t.code_hint;
+		while (i < t.n_codes && __ldg(t.codes + i) < from) i++;
+		return i < t.n_codes ? __ldg(t.codes + i) : len;
+	}
 	for (uint32_t base = from >> 2; base * 4u < len; base += 32u) {
 		const uint32_t wi = base + (uint32_t)lane;
 		const uint64_t x = ((uint64_t)br.load_word_direct(wi) << 32) | br.load_word_direct(wi + 1u);  // bytes 4 wi .. 4 wi + 7
@@ -912,7 +917,7 @@ __device__ int walk_owned(BR &br, uint32_t sbase, PictureState &ls, const ParseT
 template <class BR>
 __device__ bool walk_slice_lanes(BR &br, uint32_t sbase, PictureState &ps, const ParseTask &t, int mb_size, int lane) {
 	const uint32_t p_start = br.bitpos();
-	const uint32_t end_byte = find_slice_end(br, (p_start + 7u) >> 3, lane);
+	const uint32_t end_byte = find_slice_end(br, (p_start + 7u) >> 3, lane, t);
 	if (((p_start + 7u) >> 3) >= end_byte) return false;
 	const uint32_t end_bit = end_byte * 8u;
 	const uint32_t total = end_bit - p_start;

@@ -183,6 +183,18 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 	std::vector<uint4> stage((size_t)entries * 4);
 	t.stage = entries ? stage.data() : nullptr;
 	t.stage_entries = entries;
+	// the start-code prefix list the host hands the product's walk (engine.cu): every 00 00 01 with its three bytes inside
+	// the data.  lanes == 3 walks without it (the in-kernel search).
+	std::vector<uint32_t> codes;
+	uint32_t hint = 0;
+	for (uint32_t p = 0; p + 2 < es_len; p++)
+		if (es[p] == 0 && es[p + 1] == 0 && es[p + 2] == 1) {
+			if (p + 4 == start_byte) hint = (uint32_t)codes.size();
+			codes.push_back(p);
+		}
+	t.codes = lanes == 3 ? nullptr : codes.data();
+	t.n_codes = (uint32_t)codes.size();
+	t.code_hint = hint;
 	static ParseTask task;
 	static int use_lanes;
 	task = t;
@@ -214,6 +226,7 @@ extern "C" int emu_expand_picture(const uint8_t *es, uint32_t es_len, int mb_wid
 	t.es = es; t.es_len = es_len; t.start_byte = 0; t.seq = &seq; t.hdr = hdr; t.coef = coef; t.info = info;
 	t.park = const_cast<uint2 *>(park); t.mb_width = mb_width; t.mb_size = seq.mb_size;
 	t.stage = nullptr; t.stage_entries = 0;
+	t.codes = nullptr; t.n_codes = 0; t.code_hint = 0;
 	for (int slot_id = 0; slot_id < seq.mb_size * 6; slot_id++) {  // the kernel shell of parse.cu, one thread after the other
 		const int mb = slot_id / 6, block = slot_id - mb * 6;
 		const uint32_t rec = reinterpret_cast<const uint32_t *>(hdr + mb)[1];

@@ -3,6 +3,7 @@
 
     python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv          > profiles/r1_launches.md
     python tools/summarize_ncu.py kernel   gpurun_out/prof_recon_r1.ncu-rep    > profiles/r1_reconstruct.md
+    python tools/summarize_ncu.py lines    gpurun_out/prof_walk_r2.ncu-rep 25  >> profiles/r2_walk.md   # hottest source lines
 """
 import csv
 import io
@@ -59,6 +60,12 @@ def kernel(path):
         if k in hdr:
             i = hdr.index(k)
             print(f"| {k} | {units[i]} | " + " | ".join(r[i] for r in data) + " |")
+    print("\nwarps stalled per issued instruction, by reason (smsp__average_warps_issue_stalled_*_per_issue_active, > 0.2):\n")
+    for i, h in enumerate(hdr):
+        if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h:
+            v = [float(r[i] or 0) for r in data]
+            if max(v) > 0.2:
+                print("* " + h.split("stalled_")[1].replace("_per_issue_active.ratio", "") + ": " + ", ".join(f"{x:.2f}" for x in v))
     print("\nwarp issue stall reasons (% of active warps, > 3 %):\n")
     for i, h in enumerate(hdr):
         if "warp_issue_stalled" in h and h.endswith("per_warp_active.pct"):
@@ -67,5 +74,34 @@ def kernel(path):
                 print("* " + h.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", "") + ": " + ", ".join(f"{x:.1f}" for x in v))
 
 
+def lines(path, top=25):
+    """The source lines (needs -lineinfo + --import-source on) with the most warp-stall samples, summed over the launches."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    keys = ["# Samples", "Instructions Executed", "stall_long_sb", "stall_wait", "stall_short_sb", "stall_branch_resolving", "stall_math",
+            "stall_barrier", "stall_not_selected"]
+    cur, hdr, agg = None, None, {}
+    for r in rows:
+        if len(r) == 2 and r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+        elif len(r) > 5 and r[0] == "Line No":
+            hdr = r
+        elif hdr and len(r) == len(hdr) and r[0] != "":
+            d = dict(zip(hdr, r))
+            try:
+                v = [int(d[k]) for k in keys]
+            except (KeyError, ValueError):
+                continue
+            k = (cur, r[0], r[1].strip()[:110])
+            agg[k] = [a + b for a, b in zip(agg.get(k, [0] * len(keys)), v)]
+    tot = sum(v[0] for v in agg.values()) or 1
+    toti = sum(v[1] for v in agg.values()) or 1
+    print(f"\nhottest source lines of {path} (share of warp-stall samples | of warp instructions | dominant stall reasons in samples):\n")
+    print("| samples | instr | long sb | wait | short sb | branch | math | barrier | not sel | line |")
+    print("|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(top)]:
+        print(f"| {100 * v[0] / tot:.1f} % | {100 * v[1] / toti:.1f} % | " + " | ".join(str(x) for x in v[2:]) + f" | `{k[0]}:{k[1]}` `{k[2]}` |")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "lines": lines}[sys.argv[1]](*sys.argv[2:])
