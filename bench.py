@@ -558,21 +558,28 @@ def main():
     # NCCL is used for the barrier / counter reduction only; keep its banner off stdout (one JSON line)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
+    # this rank's share of the host: the cgroup quota (or the CPU set) divided among the ranks of the node
+    per_rank_cores = max(1, cores["usable"] // max(1, local_world))
+    # the clips are encoded (worker PROCESSES, cv2) before anything touches CUDA: nothing CUDA is ever forked
+    seeds = rank_seeds(rank)
+    streams = load_streams(sorted(set(seeds)), workers=per_rank_cores)
+    by_seed = dict(zip(sorted(set(seeds)), streams))
+    streams = [by_seed[s] for s in seeds]
+    streams_720 = None
+    if world == 1 and EXTRAS and not args.no_extras:
+        s2 = load_streams(sorted(set(seeds)), 1280, 720, workers=per_rank_cores)
+        by2 = dict(zip(sorted(set(seeds)), s2))
+        streams_720 = [by2[s] for s in seeds]
     # this rank's host side lives on its GPU's NUMA node: threads, pinned bit buffers and plane rings
     from jsmpeg_b200 import capi
     numa = capi.bind_host_to_device(local_rank)
     cores_rank = host_cores()
-    per_rank_cores = max(1, cores_rank["usable"] // max(1, local_world) if cores_rank["cgroup_quota_cpus"] else cores_rank["usable"])
+    cores_rank["per_rank"] = per_rank_cores
     import torch
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-
-    seeds = rank_seeds(rank)
-    streams = load_streams(sorted(set(seeds)), workers=per_rank_cores)
-    by_seed = dict(zip(sorted(set(seeds)), streams))
-    streams = [by_seed[s] for s in seeds]
     if world > 1:
         dist.barrier()
     e2e_groups = max(1, min(E2E_GROUPS, per_rank_cores))
@@ -631,9 +638,7 @@ def main():
     if world == 1 and EXTRAS and not args.no_extras:
         # BASELINE configs[1]: 1280x720, the same legs
         w2, h2 = 1280, 720
-        streams2 = load_streams(sorted(set(seeds)), w2, h2, workers=per_rank_cores)
-        by2 = dict(zip(sorted(set(seeds)), streams2))
-        legs2 = Legs([by2[s] for s in seeds], w2, h2, local_rank, 1, e2e_groups)
+        legs2 = Legs(streams_720, w2, h2, local_rank, 1, e2e_groups)
         f2, dt2, st2, _ = legs2.timed(legs2.run_device, args.steps, args.warmup, legs2.value_decoders)
         v2 = legs2.verify(seeds, per_rank_cores) if not args.no_verify else {"verified": None}
         if args.no_e2e:

@@ -93,7 +93,6 @@ struct ReconTask {
 	int32_t coded_width, coded_height;
 	uint8_t *rgba;  // optional fused epilogue target (display size, RGBA8888) or nullptr
 	int32_t width, height;
-	int32_t n_coded_blocks;  // from the picture info: decides whether stage 2 requests every record up front
 };
 
 // kernel launchers (defined in scan.cu / parse.cu / recon.cu)

@@ -731,7 +731,6 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 					t.coded_height = s.seq.coded_height;
 					t.width = s.width;
 					t.height = s.height;
-					t.n_coded_blocks = e.info.n_coded_blocks;
 					t.rgba = nullptr;
 					if (flags & JSMPEG_B200_OUT_RGBA) {
 						if (!s.d_rgba) {  // opaque white, like the canvas the reference creates (canvas2d.js:24-29): the odd edge keeps it
@@ -1282,12 +1281,6 @@ int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, 
 		t.fwd = PlaneSet{d_fwd, d_fwd + ysz, d_fwd + ysz + csz};
 		t.mb_width = mb_width; t.mb_size = (int)n_mb;
 		t.coded_width = mb_width * 16; t.coded_height = mb_height * 16;
-		{  // the count the walk would have reported
-			const mb_record_t *h = static_cast<const mb_record_t *>(hdr);
-			int n = 0;
-			for (size_t i = 0; i < n_mb; i++) if (h[i].flags & MBF_PRESENT) n += __builtin_popcount(h[i].cbp & 0x3f);
-			t.n_coded_blocks = n;
-		}
 		launch_reconstruct(&t, 1, 0);
 		CUDA_CHECK(cudaGetLastError());
 		CUDA_CHECK(cudaDeviceSynchronize());

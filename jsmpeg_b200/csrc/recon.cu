@@ -65,12 +65,7 @@ void fill_task(CompactTask &c, const ReconTask &t) {
 	c.mb_width = t.mb_width;
 	c.mb_height = t.mb_size / t.mb_width;
 	c.row_magic = (uint32_t)(0x100000000ull / (uint64_t)(6 * t.mb_width)) + 1u;
-	// dense: at least 3 of 4 block slots carry a coded block -- fetching every slot's record before the
-	// header is known costs at most a third more record bytes and takes one memory latency off the chain
-	// (JSMPEG_B200_RECON_DENSE=0 / 1 forces one path: tests, A/B)
-	static const int force_dense = [] { const char *e = getenv("JSMPEG_B200_RECON_DENSE"); return e && *e ? atoi(e) : -1; }();
-	const bool dense = force_dense >= 0 ? force_dense != 0 : (int64_t)t.n_coded_blocks * 4 >= (int64_t)t.mb_size * 6 * 3;
-	c.flags = dense ? RT_DENSE : 0;
+	c.flags = 0;
 }
 
 }  // namespace

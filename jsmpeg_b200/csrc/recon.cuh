@@ -16,7 +16,6 @@ constexpr int WARP_STAGE = 32 * ROW_PITCH + 16;      // + the warp's mbarrier
 constexpr int MAX_TASKS = 80;       // per launch; (80 * 48 B) + 16 < 4 KB of kernel parameters
 constexpr int MAX_TASKS_RGBA = 60;  // the RGBA variant's parameters: (60 * (48 + 16) B) + 16 < 4 KB
 
-enum { RT_DENSE = 1 };  // CompactTask::flags
 
 struct CompactTask {
 	const mb_record_t *hdr;
@@ -25,7 +24,7 @@ struct CompactTask {
 	const uint8_t *fwd;
 	int32_t mb_width, mb_height;
 	uint32_t row_magic;  // floor(2^32 / (6 mb_width)) + 1: slot / (6 mb_width) == umulhi(slot, row_magic) for every slot of a picture
-	uint32_t flags;      // RT_DENSE: almost every block is coded -- all coefficient records are requested before the header is known
+	uint32_t flags;      // (none defined)
 };
 
 template <int N>
@@ -208,9 +207,11 @@ static inline uint32_t smem_u32(const void *) { return 0; }
 //
 // Latency plan (round 2; the kernel was stalled on memory it asked for too late -- long-scoreboard 2.7
 // warps per issue at 4.5 resident warps per scheduler, profiles/r2_reconstruct.md):
-//   t0  the coefficient records of a DENSE picture are requested (TMA) before anything is known about
-//       the macroblocks: the address depends on the slot alone;  the header load starts;  the header
-//       and the record of the CTA that will run here two pictures of the launch later are pulled into L2
+//   t0  the header load starts;  the header and the coefficient record of the CTA that will run here two
+//       pictures of the launch later are pulled into L2
+//   t0' header there: the records of the coded blocks are requested (TMA).  (Requesting every slot's record
+//       before the header is known, for pictures with most blocks coded, was built and measured: 11.90 ms per
+//       60 launches against 11.92 -- nothing, for 3.5 % more DRAM traffic; removed.)
 //   t1  header there: the nine reference rows of a predicted block are pulled into L2 (no registers)
 //   t2  records there: IDCT (some 700 instructions) -- the reference rows arrive meanwhile
 //   t3  prediction reads hit L2, + residual, store
@@ -223,7 +224,6 @@ __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int
 	const CompactTask &t = params.t[ty];
 	const int W = t.mb_width;
 	const int mb = mb_row * W + mb_col;
-	const bool dense = t.flags & RT_DENSE;
 
 	const uint32_t mbar = smem_u32(wstage + 32 * ROW_PITCH);
 	const uint32_t my_row = smem_u32(wstage + lane * ROW_PITCH);
@@ -250,9 +250,6 @@ __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int
 		if (want) memcpy(wstage + lane * ROW_PITCH, cblk, 128);  // the emulated "TMA": the lane's record into its staging row
 #endif
 	};
-	const unsigned in_mask = __ballot_sync(0xffffffffu, in_picture);
-	if (dense && in_mask) request_records(in_picture, in_mask);  // t0: before the header is known (uncoded slots hold stale bytes: never used)
-
 	uint2 rec = make_uint2(0, 0);
 	if (in_picture) rec = __ldg(reinterpret_cast<const uint2 *>(t.hdr + mb));
 	if (ty + 2 < params.n_tasks) {  // the CTA that runs on this SM next but one: its header and record, into L2
@@ -271,8 +268,8 @@ __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int
 	const bool full = coded && !dc_only;
 
 	const unsigned coded_mask = __ballot_sync(0xffffffffu, coded);
-	if (!dense && coded_mask) request_records(coded, coded_mask);  // sparse picture: only what is coded (the DC-only blocks' value too)
-	const bool copying = dense ? in_mask != 0 : coded_mask != 0;   // warp-uniform
+	if (coded_mask) request_records(coded, coded_mask);  // only what is coded (the DC-only blocks' value too)
+	const bool copying = coded_mask != 0;                 // warp-uniform
 
 	const int stride_y = W * 16;
 	const int ysize = stride_y * t.mb_height * 16;

@@ -241,17 +241,16 @@ extern "C" int emu_expand_picture(const uint8_t *es, uint32_t es_len, int mb_wid
 
 // Stage 2: every block slot of the picture through reconstruct_block (jsmpeg_b200/csrc/recon.cuh), a
 // warp of 32 consecutive slots at a time.  cur / fwd: Y | Cr | Cb contiguous, like the product's plane sets.
-// dense: the RT_DENSE path (every slot's record is requested before the header is read) or the sparse one.
 // Planes need mb_width * 16 + 64 readable bytes past their end, like the product's.
 extern "C" int emu_reconstruct_picture(const mb_record_t *hdr, const int16_t *coef, uint8_t *cur, const uint8_t *fwd,
-                                       int mb_width, int mb_height, int dense) {
+                                       int mb_width, int mb_height) {
 	static ReconParams params;
 	static int first_slot;
 	static uint8_t wstage[WARP_STAGE];
 	CompactTask &task = params.t[0];
 	task.hdr = hdr; task.coef = coef; task.cur = cur; task.fwd = fwd; task.mb_width = mb_width; task.mb_height = mb_height;
 	task.row_magic = (uint32_t)(0x100000000ull / (uint64_t)(6 * mb_width)) + 1u;  // as launch_reconstruct (recon.cu)
-	task.flags = dense ? RT_DENSE : 0;
+	task.flags = 0;
 	params.n_tasks = 1;
 	const int slots = mb_width * mb_height * 6;
 	for (first_slot = 0; first_slot < slots; first_slot += 32)

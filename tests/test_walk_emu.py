@@ -220,7 +220,7 @@ def test_stage1_device_code_matches_the_oracle_coefficients(name):
     assert checked > 0
 
 
-def _pipeline_against_oracle_planes(es, name, define=None, dense_first=1):
+def _pipeline_against_oracle_planes(es, name, define=None):
     from jsmpeg_b200 import decoder
     olib = helpers.oracle_lib()
     d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
@@ -232,7 +232,7 @@ def _pipeline_against_oracle_planes(es, name, define=None, dense_first=1):
     lib.emu_expand_picture.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.emu_reconstruct_picture.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                            ctypes.c_int, ctypes.c_int, ctypes.c_int]
+                                            ctypes.c_int, ctypes.c_int]
     mbw, mbh = stream_geometry(es)
     buf = np.frombuffer(es + b"\0" * 16, dtype=np.uint8).copy()
     ysize = mb * 256
@@ -252,9 +252,7 @@ def _pipeline_against_oracle_planes(es, name, define=None, dense_first=1):
             continue  # B / D picture or P without f_code: consumed, nothing decoded, no swap (mpeg1.js:181-193)
         lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, park.ctypes.data, coef.ctypes.data,
                                pinfo.ctypes.data)
-        # both record-fetch paths of stage 2 (dense: every slot's record up front; sparse: coded blocks only), alternating
-        lib.emu_reconstruct_picture(hdr.ctypes.data, coef.ctypes.data, planes[cur].ctypes.data, planes[cur ^ 1].ctypes.data, mbw, mbh,
-                                    (checked + dense_first) & 1)
+        lib.emu_reconstruct_picture(hdr.ctypes.data, coef.ctypes.data, planes[cur].ctypes.data, planes[cur ^ 1].ctypes.data, mbw, mbh)
         y, cr, cb = d.planes()
         got = planes[cur]
         assert np.array_equal(got[:ysize], y), f"{name}: picture {checked}: Y differs"
@@ -272,9 +270,7 @@ def test_whole_hot_path_device_code_matches_the_oracle_planes(name):
     (jsmpeg_b200/csrc/recon.cuh, a warp = 32 coroutines, the TMA copy and the packed instructions
     replaced by plain C) with the product's ping-pong planes, against the ORACLE's planes of every
     decoded picture.  Bit-exact, like the GPU parity tests -- which remain the check of the real thing."""
-    es = open(os.path.join(HERE, "golden", name + ".es"), "rb").read()
-    _pipeline_against_oracle_planes(es, name)
-    _pipeline_against_oracle_planes(es, name, dense_first=0)  # the other fetch path on every picture
+    _pipeline_against_oracle_planes(open(os.path.join(HERE, "golden", name + ".es"), "rb").read(), name)
 
 
 def test_whole_hot_path_device_code_on_an_encoder_clip():
