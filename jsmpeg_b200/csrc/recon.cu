@@ -37,7 +37,10 @@
 
 namespace {
 
-__global__ void __launch_bounds__(THREADS, 5)
+#ifndef JSMPEG_RECON_MIN_CTAS
+#define JSMPEG_RECON_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(THREADS, JSMPEG_RECON_MIN_CTAS)
 reconstruct_kernel(const __grid_constant__ ReconParams params) {
 	__shared__ __align__(16) uint8_t stage[(THREADS / 32) * WARP_STAGE];
 	reconstruct_block(params, blockIdx.y, blockIdx.x * THREADS, threadIdx.x, stage);

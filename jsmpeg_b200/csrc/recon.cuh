@@ -266,6 +266,7 @@ __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int
 	const bool coded = present && ((rec.y >> 8) & bit);
 	const bool dc_only = coded && ((rec.y >> 16) & bit);
 	const bool full = coded && !dc_only;
+	const bool warp_full = __any_sync(0xffffffffu, full);  // warp-uniform: some lane needs the transform
 
 	const unsigned coded_mask = __ballot_sync(0xffffffffu, coded);
 	if (coded_mask) request_records(coded, coded_mask);  // only what is coded (the DC-only blocks' value too)
@@ -320,13 +321,28 @@ __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int
 	}
 
 	// ---- residual: 64 values in registers
+	// One path per WARP.  A block with nothing but coefficient 0 takes the reference's scalar shortcut
+	// (mpeg1.js:838-853: every sample = (block[0] + 128) >> 8) -- and the full transform of such a block gives
+	// exactly that: column 0 comes out as eight copies of block[0], every row then as (block[0] + 128) >> 8
+	// (all other terms are (0 * k + 128) >> 8 = 0).  An uncoded block is the transform of zeros.  So in a warp
+	// with at least one block that needs the transform, every lane runs it -- the DC-only lanes on their staged
+	// record (zeros behind coefficient 0, the expand kernel writes whole records), the uncoded lanes on a row
+	// they zero themselves -- instead of the warp running the transform AND the 64-register fill one after the other.
 	int v[64];
-	if (full) {
+	if (warp_full) {
+		if (!coded) {  // present, nothing coded: a residual of zeros
+#ifndef JSMPEG_WALK_EMU
+#pragma unroll
+			for (int i = 0; i < 8; i++) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(my_row + i * 16), "r"(0u) : "memory");
+#else
+			memset(wstage + lane * ROW_PITCH, 0, 128);
+#endif
+		}
 #pragma unroll
 		for (int i = 0; i < 8; i++) {
 			uint4 q;
 #ifndef JSMPEG_WALK_EMU
-			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(my_row + i * 16));
+			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(my_row + i * 16) : "memory");
 #else
 			(void)my_row;
 			memcpy(&q, wstage + lane * ROW_PITCH + i * 16, 16);

@@ -4,8 +4,8 @@
     python tools/ab_variants.py                      # builds variants/lib_<name>.so for the candidates below
     gpurun -- '<the printed command>'                # tools/time_stages.py once per library (JSMPEG_B200_LIB)
 
-The candidates are the macro-gated code paths of jsmpeg_b200/csrc/walk.cuh that the host emulation has
-verified but no GPU run has measured yet.  The in-tree library is left alone.
+The candidates are compile-time tuning constants (CTA sizes, occupancy bounds); round 1's macro-gated code
+paths were measured and deleted (profiles/r2_variants.md).  The in-tree library is left alone.
 """
 import os
 import shutil
@@ -18,11 +18,9 @@ from jsmpeg_b200 import build  # noqa: E402
 
 CANDIDATES = {
     "default": "",
-    "fixup": "-DJSMPEG_LANES_FIXUP",
-    "emit": "-DJSMPEG_WALK_EMITS_BLOCKS",
-    "wide": "-DJSMPEG_WIDE_REFILL",
-    "fixup_wide": "-DJSMPEG_LANES_FIXUP -DJSMPEG_WIDE_REFILL",
-    "emit_wide": "-DJSMPEG_WALK_EMITS_BLOCKS -DJSMPEG_WIDE_REFILL",
+    "expand128": "-DJSMPEG_EXPAND_THREADS=128",
+    "expand512": "-DJSMPEG_EXPAND_THREADS=512",
+    "recon6": "-DJSMPEG_RECON_MIN_CTAS=6",
 }
 
 
