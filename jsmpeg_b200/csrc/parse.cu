@@ -69,40 +69,66 @@ WALK_KERNEL(walk_pictures_lanes_kernel, true, LANES_BOUNDS)
 
 // ==================================================================================================
 // 1b: expand every coded block (one thread per block slot, grid.y = picture)
+//
+// A CTA stages the tables once and then takes EXPAND_GROUPS runs of CTA_THREADS consecutive slots, one after
+// the other: the warps go through their runs independently (tiles are per thread, the tables read-only, so
+// the one barrier is the one after staging), and a thread asks for the next run's inputs before it expands
+// the current block -- the staging, the barrier and the exposed load latency at the start of a CTA were a
+// fifth of the kernel's stall samples when every CTA did one run (profiles/r2_expand.md).
+#ifndef JSMPEG_EXPAND_GROUPS
+#define JSMPEG_EXPAND_GROUPS 4  // measured: 1 -> 4: 8.2 -> 7.5 ms; 8: the same
+#endif
+constexpr int EXPAND_GROUPS = JSMPEG_EXPAND_GROUPS;
 
 __global__ void __launch_bounds__(CTA_THREADS)
 expand_blocks_kernel(const ParseTask *__restrict__ tasks) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const ParseTask &t = tasks[blockIdx.y];
-	const int slot_id = blockIdx.x * CTA_THREADS + threadIdx.x;  // mb * 6 + block
-	const bool in_picture = slot_id < t.mb_size * 6;
-	// this thread's inputs are requested before the tables are staged: one exposed latency, not two.
+	const int n_slots = t.mb_size * 6;
+	// a thread's inputs: the macroblock record's second word and the pair the walk parked for the block.
 	// (A picture that was not decoded has no present macroblock: the walk clears the records first.)
-	const int mb = in_picture ? slot_id / 6 : 0;
-	uint32_t rec = 0;
-	uint2 parked = make_uint2(0u, 0u);
-	if (in_picture) {
-		rec = __ldg(reinterpret_cast<const uint32_t *>(t.hdr + mb) + 1);
-		parked = __ldg(t.park + slot_id);
-	}
+	auto fetch = [&](int slot_id, uint32_t &rec, uint2 &parked) {
+		rec = 0;
+		parked = make_uint2(0u, 0u);
+		if (slot_id < n_slots) {
+			rec = __ldg(reinterpret_cast<const uint32_t *>(t.hdr + slot_id / 6) + 1);
+			parked = __ldg(t.park + slot_id);
+		}
+	};
+	int slot_id = blockIdx.x * (CTA_THREADS * EXPAND_GROUPS) + threadIdx.x;  // mb * 6 + block
+	uint32_t rec;
+	uint2 parked;
+	fetch(slot_id, rec, parked);  // requested before the tables are staged: one exposed latency, not two
 	{
-		// tables: the DCT code table with values (768 B, 16 bytes per thread), the picture's two quantiser
-		// tables in zig-zag order (256 B, one entry per thread), and this thread's zeroed tile
-		if (threadIdx.x < (VLC_DCT_MAX_Z + 1) * 4)
-			reinterpret_cast<uint4 *>(smem + EXP_OFF_DCT)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(VLC_DCT_COEFF) + threadIdx.x);
-		reinterpret_cast<uint16_t *>(smem + EXP_OFF_XQ)[threadIdx.x] = __ldg(&t.seq->xq[0][0] + threadIdx.x);
-		uint4 *tile = reinterpret_cast<uint4 *>(smem + EXP_OFF_TILES + threadIdx.x * TILE_PITCH);
-#pragma unroll
-		for (int i = 0; i < (int)(TILE_PITCH / 16); i++) tile[i] = make_uint4(0u, 0u, 0u, 0u);
+		// tables: the two DCT code tables of stage 1b (1536 + 1024 B, 16 bytes per thread each) and the picture's
+		// two quantiser tables in zig-zag order (256 B, one entry per thread)
+		static_assert(CTA_THREADS >= (VLC_DCT_MAX_Z + 1) * 8 && CTA_THREADS >= 128, "one pass stages the tables");
+		if (threadIdx.x < (VLC_DCT_MAX_Z + 1) * 8)
+			reinterpret_cast<uint4 *>(smem + EXP_OFF_DCT)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(VLC_DCT_EXPAND) + threadIdx.x);
+		if (threadIdx.x < 64)
+			reinterpret_cast<uint4 *>(smem + EXP_OFF_TOP8)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(VLC_DCT_EXPAND_TOP8) + threadIdx.x);
+		if (threadIdx.x < 128)
+			reinterpret_cast<uint16_t *>(smem + EXP_OFF_XQ)[threadIdx.x] = __ldg(&t.seq->xq[0][0] + threadIdx.x);
 	}
 	__syncthreads();
-	const int block = slot_id - mb * 6;
-	if (!in_picture || !(rec & MBF_PRESENT) || !((rec >> 8) & (0x20u >> block))) return;
 	const uint32_t sbase = smem_base(smem);
 	// this thread's 64 x int16 tile, linear (it leaves as one bulk copy); tiles are 144 bytes apart so
 	// that lanes writing the same coefficient index spread over the banks
-	expand_block(t, rec, parked, reinterpret_cast<uint4 *>(t.coef) + (size_t)slot_id * 8, sbase,
-	             sbase + EXP_OFF_TILES + threadIdx.x * TILE_PITCH);
+	uint4 *tile = reinterpret_cast<uint4 *>(smem + EXP_OFF_TILES + threadIdx.x * TILE_PITCH);
+#pragma unroll 1
+	for (int g = 0; g < EXPAND_GROUPS; g++) {
+		const uint32_t rec_now = rec;
+		const uint2 parked_now = parked;
+		const int slot_now = slot_id;
+		slot_id += CTA_THREADS;
+		if (g + 1 < EXPAND_GROUPS) fetch(slot_id, rec, parked);  // the next run's, while this block is expanded
+		const int block = slot_now % 6;
+		if (slot_now >= n_slots || !(rec_now & MBF_PRESENT) || !((rec_now >> 8) & (0x20u >> block))) continue;
+#pragma unroll
+		for (int i = 0; i < 8; i++) tile[i] = make_uint4(0u, 0u, 0u, 0u);  // (the last bulk store has read the tile: expand_block waits)
+		expand_block(t, rec_now, parked_now, reinterpret_cast<uint4 *>(t.coef) + (size_t)slot_now * 8, sbase,
+		             sbase + EXP_OFF_TILES + threadIdx.x * TILE_PITCH);
+	}
 }
 
 }  // namespace
@@ -176,7 +202,7 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 			walk_pictures_kernel<<<(n + per_cta - 1) / per_cta, WALK_THREADS, walk_smem, st>>>(
 			    tasks + lo, n, reinterpret_cast<const uint4 *>(ms));
 		if (g == 0 && walk_done) CUDA_CHECK(cudaEventRecord(walk_done, st));
-		dim3 grid((max_mb_size * 6 + CTA_THREADS - 1) / CTA_THREADS, n);
+		dim3 grid((max_mb_size * 6 + CTA_THREADS * EXPAND_GROUPS - 1) / (CTA_THREADS * EXPAND_GROUPS), n);
 		expand_blocks_kernel<<<grid, CTA_THREADS, EXPAND_SMEM, st>>>(tasks + lo);
 		if (g > 0) {
 			CUDA_CHECK(cudaEventRecord(fork->join[g], st));

@@ -49,9 +49,11 @@ constexpr uint32_t OFF_TYPE_P = OFF_TYPE_I + 8;                        // uint16
 static_assert(OFF_TYPE_P + 128 <= OFF_MS, "the per-symbol tables end before the multi-symbol table");
 // stage 1b (its own kernel, its own shared memory): the DCT table with values, the two quantiser tables
 // in zig-zag order (SeqParams::xq), one 64 x int16 tile per thread
-constexpr uint32_t EXP_OFF_DCT = 0;                                    // uint16[384]
-constexpr uint32_t EXP_OFF_XQ = EXP_OFF_DCT + (VLC_DCT_MAX_Z + 1) * 64;  // uint16[2][64]
+constexpr uint32_t EXP_OFF_DCT = 0;                                     // uint32[384]: VLC_DCT_EXPAND (clz-indexed)
+constexpr uint32_t EXP_OFF_TOP8 = EXP_OFF_DCT + (VLC_DCT_MAX_Z + 1) * 128;  // uint32[256]: VLC_DCT_EXPAND_TOP8 (next 8 bits)
+constexpr uint32_t EXP_OFF_XQ = EXP_OFF_TOP8 + 1024;                    // uint16[2][64]
 constexpr uint32_t EXP_OFF_TILES = (EXP_OFF_XQ + 256 + 127) & ~127u;
+constexpr uint32_t EXP_TABLE_BYTES = EXP_OFF_XQ;                        // the two code tables, contiguous
 
 #ifndef JSMPEG_WALK_EMU
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
@@ -64,6 +66,11 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 	asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
 __device__ __forceinline__ void sts_s16(uint32_t addr, int v) {
 	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
 }
@@ -73,6 +80,7 @@ constexpr uint32_t EMU_EXPAND_BASE = (WALK_SMEM_LANES + 127u) & ~127u;  // a sec
 static uint8_t emu_smem[EMU_EXPAND_BASE + 8192];
 static inline uint32_t lds_u16(uint32_t addr) { uint16_t v; memcpy(&v, emu_smem + addr, 2); return v; }
 static inline uint32_t lds_u8(uint32_t addr) { return emu_smem[addr]; }
+static inline uint32_t lds_u32(uint32_t addr) { uint32_t v; memcpy(&v, emu_smem + addr, 4); return v; }
 static inline void sts_s16(uint32_t addr, int v) { const int16_t x = (int16_t)v; memcpy(emu_smem + addr, &x, 2); }
 #endif
 // MSB-first bit window over a byte span (src/buffer.js:152-187); one copy per thread.
@@ -1192,73 +1200,100 @@ __device__ void walk_picture(const ParseTask &t, uint32_t sbase, int lane, uint3
 // rec = the macroblock record's second word (flags | cbp << 8 | dc_only << 16 | quantiser scale << 24),
 // parked = {bit offset of the block's first coefficient code, intra dc * 8} from the walk's dense side
 // array, stile = the shared-memory address of this thread's (zeroed) 128-byte tile.
+//
+// The kernel is bound by the integer ALU pipe (87 % busy, profiles/r2_expand.md), so the loop is built to need
+// few ALU instructions per code:
+//  * no bit window to maintain: the 32 bits at the current bit POSITION are two word loads (L1 hits: the
+//    blocks of a warp lie side by side in the stream) and one funnel shift -- the loads go to the LSU, the
+//    address to the FMA pipe; the window's shifts, counters and predicated refill were a quarter of the loop.
+//    (Keeping the three words around the position in registers and loading one word per crossing -- the
+//    load off the chain from code to code -- was measured: 8.2 ms against 7.9, the predicated register
+//    moves cost more than the L1 hits.)
+//  * the frequent codes (at most 8 bits) come from a table indexed by the next 8 bits (VLC_DCT_EXPAND_TOP8),
+//    no clz and no second shift; entries hold what a trip needs: bits to consume, run + 1, 2 * level
+//  * dequantisation in sign-magnitude form.  The reference (mpeg1.js:794-807): level <<= 1;
+//    if (!intra) level += level < 0 ? -1 : 1;  level = (level * qs * Q) >> 4;  if even: level -= level > 0 ? 1 : -1;
+//    clamp to [-2048, 2047].  With m = 2 |level| + (intra ? 0 : 1) and p = m * qs * Q >= 0: the arithmetic
+//    shift is floor, so the product's magnitude is t = p >> 4 for a positive level and t = (p + 15) >> 4 for a
+//    negative one; "make odd, toward zero" is (t - 1) | 1 for t >= 1, and t = 0 becomes +1 WHATEVER the sign
+//    (0 is even and not > 0); the clamp is min(., 2047 + negative).  The multiplies run on the FMA pipe.
+//    (tests/test_expand_arith.py: all of it against the reference's statements, exhaustively.)
+__device__ __forceinline__ int dequant_sm(int mag2_plus, int neg, int qs, uint32_t q) {
+	// mag2_plus = 2 |level| + (intra ? 0 : 1), neg = 0 / 1, q = raster index * 2 | Q << 8
+	const int p = mag2_plus * (qs * (int)(q >> 8)) + neg * 15;
+	const int t = p >> 4;
+	const int r = min(max((t - 1) | 1, 1), 2047 + neg);
+	return (neg && t != 0) ? -r : r;
+}
 __device__ __forceinline__ void expand_block(const ParseTask &t, uint32_t rec, uint2 parked, uint4 *__restrict__ slot,
                                              uint32_t sbase, uint32_t stile) {
 	const bool intra = rec & MBF_INTRA;
+	const int ni = intra ? 0 : 1;
 	const int qs = (int)(rec >> 24);
 	// quantiser table in coefficient (zig-zag) order: entry n = raster index * 2 | Q[raster index] << 8
 	const uint32_t xq = sbase + EXP_OFF_XQ + (intra ? 0u : 128u);
-	BitReaderT<false, ES_IS_PADDED> br;  // every code of the block was validated by the walk: the reads stay inside data + pad
-	br.words = reinterpret_cast<const uint32_t *>(t.es);
+	BitReaderT<false, ES_IS_PADDED> br;  // for its word loads only; every code of the block was validated by the walk:
+	br.words = reinterpret_cast<const uint32_t *>(t.es);  // the reads stay inside data + pad
 	br.bytes = t.es;
 	br.len = t.es_len;
 	br.ring = 0;
-	br.seek_bit(parked.x);
+	auto window = [&](uint32_t pos) {  // the 32 bits at bit position pos, MSB first
+		const uint32_t i = pos >> 5;
+		return __funnelshift_l(br.load_word(i + 1u), br.load_word(i), pos);  // (shifts by pos & 31)
+	};
+	uint32_t pos = parked.x;
+	uint32_t w = window(pos);
 
 	int n = 0;
 	if (intra) {
 		sts_s16(stile, (int)(int16_t)(parked.y & 0xffffu));  // coefficient 0
 		n = 1;
-	} else if (br.peek32() >> 31) {
+	} else if (w >> 31) {
 		// dct_coeff_first of a non-intra block: a leading '1' is (run 0, level +-1) with its sign bit, never
 		// end_of_block (mpeg1.js:757-760, 781-787) -- handled here, once, instead of in every trip of the loop
-		int level = (br.peek32() & 0x40000000u) ? -3 : 3;  // 2 level + sign
-		br.consume(2);
 		const uint32_t q = lds_u16(xq);
-		level = (level * qs * (int)(q >> 8)) >> 4;
-		if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
-		level = max(-2048, min(2047, level));
-		sts_s16(stile + (q & 0xffu), level);
+		sts_s16(stile + (q & 0xffu), dequant_sm(3, (int)((w >> 30) & 1u), qs, q));
+		pos += 2u;
+		w = window(pos);
 		n = 1;
 	}
 	for (;;) {  // mpeg1.js:757-811; the walk has already validated every code of this block
-		const uint32_t w = br.peek32();
-		const int z = min(__clz((int)w), VLC_DCT_MAX_Z);
-		const uint32_t e = lds_u16(sbase + EXP_OFF_DCT + (((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) * 2u);
-		int len = e & 31;
-		int run = (e >> 5) & 31;
-		int level = e >> 10;
-		if (level == 0) {
-			if (run != 0 || len == 0) break;  // end_of_block (or, defensively, an invalid code)
-			// escape (mpeg1.js:767-780)
-			run = (w >> 20) & 63;
-			const int l8 = (w >> 12) & 255;
+		uint32_t x = lds_u32(sbase + EXP_OFF_TOP8 + ((w >> 24) << 2));
+		if (x == 0u) {  // a code of more than 8 bits (or none)
+			const int z = min(__clz((int)w), VLC_DCT_MAX_Z);
+			x = lds_u32(sbase + EXP_OFF_DCT + ((((uint32_t)z << 5) | ((w << (z + 1)) >> 27)) << 2));
+		}
+		int mag2 = (int)((x >> 16) & 0xffu);
+		uint32_t nb = x & 63u;
+		int run1 = (int)((x >> 8) & 63u);
+		int neg;
+		if (mag2 == 0) {
+			if (!(x >> 30)) break;  // end_of_block (or, defensively, not a code)
+			// escape (mpeg1.js:767-780): 6-bit run, 8 (+8) bit level
+			run1 = (int)((w >> 20) & 63u) + 1;
+			const int l8 = (int)((w >> 12) & 255u);
+			int level;
 			if ((l8 & 127) == 0) {
-				level = (int)((w >> 4) & 255) - (l8 << 1);  // l8 == 128: second byte - 256
-				br.consume(28);
+				level = (int)((w >> 4) & 255u) - (l8 << 1);  // l8 == 128: second byte - 256
+				nb = 28u;
 			} else {
 				level = l8 > 128 ? l8 - 256 : l8;
-				br.consume(20);
+				nb = 20u;
 			}
+			neg = level < 0;
+			mag2 = 2 * abs(level);
 		} else {
-			if ((w >> (31 - len)) & 1u) level = -level;
-			br.consume(len + 1);
+			neg = (int)((w >> (32u - nb)) & 1u);  // the sign is the last bit consumed
 		}
-		n += run;
-		if (n > 63) {  // JS: ZIG_ZAG[n] undefined -> the store is a no-op (the walk flagged the picture)
-			if (n > 4096) break;
-			n++;
+		pos += nb;
+		w = window(pos);  // (requested before the arithmetic of this code)
+		n += run1;        // one past this coefficient's index
+		if (n > 64) {     // JS: ZIG_ZAG[n] undefined -> the store is a no-op (the walk flagged the picture)
+			if (n > 4097) break;
 			continue;
 		}
-		const uint32_t q = lds_u16(xq + (uint32_t)n * 2u);
-		n++;
-		// dequantise, oddify toward zero, clip (mpeg1.js:794-807)
-		level <<= 1;
-		if (!intra) level += level < 0 ? -1 : 1;
-		level = (level * qs * (int)(q >> 8)) >> 4;
-		if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
-		level = max(-2048, min(2047, level));
-		sts_s16(stile + (q & 0xffu), level);
+		const uint32_t q = lds_u16(xq + (uint32_t)(n - 1) * 2u);
+		sts_s16(stile + (q & 0xffu), dequant_sm(mag2 + ni, neg, qs, q));
 	}
 	// The finished block leaves as ONE 128-byte TMA bulk store (shared -> global, SASS UBLKCP): whole
 	// lines reach L2, whereas eight 16-byte stores per thread half-fill 32-byte sectors and made L2

@@ -90,6 +90,7 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {  // P
 	}
 	return r;
 }
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((((uint64_t)hi << 32) | lo) << (sh & 31u))) >> 32); }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
 static inline int __dp2a_lo(int a, int b, int c) {  // c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (all signed)
 	return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)(b & 0xff) + (int)(int16_t)((uint32_t)a >> 16) * (int)(int8_t)((b >> 8) & 0xff);
@@ -211,8 +212,8 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 extern "C" int emu_expand_picture(const uint8_t *es, uint32_t es_len, int mb_width, int mb_height,
                                   mb_record_t *hdr, const uint2 *park, int16_t *coef, picture_info_t *info) {
 	if (info->status != PIC_DECODED) return 0;
-	uint16_t *s16 = reinterpret_cast<uint16_t *>(emu_smem + EMU_EXPAND_BASE);
-	for (int i = 0; i < (VLC_DCT_MAX_Z + 1) * 32; i++) s16[EXP_OFF_DCT / 2 + i] = VLC_DCT_COEFF[i];
+	memcpy(emu_smem + EMU_EXPAND_BASE + EXP_OFF_DCT, VLC_DCT_EXPAND, sizeof(VLC_DCT_EXPAND));  // as the kernel shell stages them
+	memcpy(emu_smem + EMU_EXPAND_BASE + EXP_OFF_TOP8, VLC_DCT_EXPAND_TOP8, sizeof(VLC_DCT_EXPAND_TOP8));
 	SeqParams seq;
 	memset(&seq, 0, sizeof(seq));
 	seq.mb_width = mb_width;
@@ -256,4 +257,29 @@ extern "C" int emu_reconstruct_picture(const mb_record_t *hdr, const int16_t *co
 	for (first_slot = 0; first_slot < slots; first_slot += 32)
 		run_warp([](int l) { reconstruct_block(params, 0, first_slot, l, wstage); });
 	return 0;
+}
+
+// Stage 1b's sign-magnitude dequantisation (dequant_sm, walk.cuh) against the reference's statements
+// (src/mpeg1.js:794-807, src/wasm/mpeg1.c decode_block), every level an escape or a table code can carry,
+// every quantiser scale (0 included: a corrupt stream can carry it), every matrix entry, intra and not.
+// Returns the number of mismatches; first_bad = {level, qs, Q, intra, got, want} of the first one.
+extern "C" long emu_check_dequant(int *first_bad) {
+	long bad = 0;
+	for (int intra = 0; intra < 2; intra++)
+		for (int qs = 0; qs < 32; qs++)
+			for (int Q = 0; Q < 256; Q++)
+				for (int lv = -255; lv <= 255; lv++) {
+					int level = lv;  // the reference, statement for statement
+					level <<= 1;
+					if (!intra) level += (level < 0 ? -1 : 1);
+					level = (level * qs * Q) >> 4;
+					if ((level & 1) == 0) level -= level > 0 ? 1 : -1;
+					if (level > 2047) level = 2047;
+					else if (level < -2048) level = -2048;
+					const int got = dequant_sm(2 * abs(lv) + (intra ? 0 : 1), lv < 0, qs, (uint32_t)Q << 8);
+					if (got != level && bad++ == 0 && first_bad) {
+						first_bad[0] = lv; first_bad[1] = qs; first_bad[2] = Q; first_bad[3] = intra; first_bad[4] = got; first_bad[5] = level;
+					}
+				}
+	return bad;
 }

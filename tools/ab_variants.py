@@ -18,9 +18,8 @@ from jsmpeg_b200 import build  # noqa: E402
 
 CANDIDATES = {
     "default": "",
-    "expand128": "-DJSMPEG_EXPAND_THREADS=128",
-    "expand512": "-DJSMPEG_EXPAND_THREADS=512",
-    "recon6": "-DJSMPEG_RECON_MIN_CTAS=6",
+    "groups4": "-DJSMPEG_EXPAND_GROUPS=4",
+    "groups8": "-DJSMPEG_EXPAND_GROUPS=8",
 }
 
 
