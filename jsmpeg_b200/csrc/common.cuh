@@ -96,8 +96,15 @@ struct ReconTask {
 };
 
 // kernel launchers (defined in scan.cu / parse.cu / recon.cu)
-void launch_scan_start_codes(const uint8_t *es, uint32_t from, uint32_t len, uint32_t *positions,
-                             uint32_t capacity, uint32_t *count, cudaStream_t stream);
+// Stage 0, all streams of a batch in one launch: span k = bytes [from, len) of the ES mirror `es`; its hits
+// (byte positions of 00 00 01, unsorted) go to positions[k * capacity ...], their number to counts[k] (it keeps
+// counting past `capacity`: the host sees an overflow and repeats the scan with room).
+struct ScanSpan {
+	const uint8_t *es;
+	uint32_t from, len;
+};
+void launch_scan_start_codes(const ScanSpan *spans, int n_spans, uint32_t longest_span, uint32_t *positions,
+                             uint32_t capacity, uint32_t *counts, cudaStream_t stream);
 // Helper streams/events with which stage 1 forks the (size-sorted) wave into groups: the expand of
 // a group of small pictures runs while the walk of the bigger pictures is still going.
 constexpr int PARSE_GROUPS = 8;

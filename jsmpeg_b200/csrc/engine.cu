@@ -85,11 +85,8 @@ struct Stream {
 	std::vector<uint32_t> pics;  // sorted byte positions of picture start codes (00 00 01 00)
 	std::vector<uint32_t> codes, pic_code;  // every start-code prefix (00 00 01), sorted; pics[k] == codes[pic_code[k]]
 	uint32_t codes_classified = 0;          // codes[0 .. codes_classified) have had their fourth byte looked at
-	uint32_t *d_codes = nullptr;            // the device's copy of `codes` (ParseTask::codes)
-	uint32_t d_codes_cap = 0;
 	uint32_t scanned = 0;        // every prefix with pos + 2 < scanned is in `codes`
-	uint32_t *d_scan = nullptr, *h_scan = nullptr;  // [0] = count, [1..] = positions
-	uint32_t scan_cap = 0, scan_from = 0;
+	uint32_t scan_from = 0;      // the span a pending scan covers starts here
 	bool scan_pending = false;
 	// planes: two sets in HBM (ping-pong like mpeg1.js:221-246), a host ring for OUT_HOST
 	uint8_t *d_planes[2] = {nullptr, nullptr};
@@ -111,6 +108,13 @@ struct jsmpeg_b200_batch_t {
 	std::string error;
 	std::vector<uint8_t> dead_scratch;  // where get_write_ptr points a caller's memcpy once dead
 	std::vector<Stream> streams;
+	// start-code scan of all streams in one launch (scan.cu): span list, per-span hit counts and positions;
+	// and the device's copy of every stream's sorted prefix list (ParseTask::codes), one row per stream
+	ScanSpan *d_spans = nullptr, *h_spans = nullptr;
+	uint32_t *d_scan_counts = nullptr, *h_scan_counts = nullptr, *d_scan_pos = nullptr, *h_scan_pos = nullptr;
+	uint32_t scan_rows = 0, scan_seg = 0;       // room: spans, positions per span
+	uint32_t *d_codes = nullptr, *h_codes = nullptr;
+	uint32_t codes_rows = 0, codes_stride = 0;  // rows = streams, stride = entries per row
 	cudaStream_t st_main = nullptr, st_recon = nullptr, st_copy = nullptr;  // uploads + scan + parse | reconstruct | copy-out
 	cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_mid = nullptr, ev_step = nullptr, ev_round = nullptr, ev_copied[2] = {nullptr, nullptr};
 	std::vector<cudaEvent_t> ev_info;            // per chunk: its picture infos are on the host
@@ -300,23 +304,57 @@ void reserve_device_es(Batch *b, Stream &s, uint32_t need) {
 	s.d_capacity = (uint32_t)cap;
 }
 
-void launch_scan(Batch *b, Stream &s) {
-	CUDA_CHECK(cudaMemsetAsync(s.d_scan, 0, sizeof(uint32_t), b->st_main));
-	launch_scan_start_codes(s.d_es, s.scan_from, s.bb.length, s.d_scan + 1, s.scan_cap - 1, s.d_scan, b->st_main);
-	b->stats.kernel_launches++;
-	CUDA_CHECK(cudaMemcpyAsync(s.h_scan, s.d_scan, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->st_main));
+// Room for `rows` spans with `seg` positions each (contents are per scan: nothing to keep).
+void reserve_scan(Batch *b, uint32_t rows, uint32_t seg) {
+	if (rows <= b->scan_rows && seg <= b->scan_seg) return;
+	rows = std::max(rows, b->scan_rows);
+	seg = std::max(seg, b->scan_seg);
+	if (b->d_spans) CUDA_CHECK(cudaFree(b->d_spans));
+	if (b->d_scan_counts) CUDA_CHECK(cudaFree(b->d_scan_counts));
+	if (b->d_scan_pos) CUDA_CHECK(cudaFree(b->d_scan_pos));
+	if (b->h_spans) CUDA_CHECK(cudaFreeHost(b->h_spans));
+	if (b->h_scan_counts) CUDA_CHECK(cudaFreeHost(b->h_scan_counts));
+	if (b->h_scan_pos) CUDA_CHECK(cudaFreeHost(b->h_scan_pos));
+	b->d_spans = nullptr; b->d_scan_counts = nullptr; b->d_scan_pos = nullptr;
+	b->h_spans = nullptr; b->h_scan_counts = nullptr; b->h_scan_pos = nullptr;
+	b->scan_rows = b->scan_seg = 0;
+	b->d_spans = dev_alloc<ScanSpan>(rows);
+	b->h_spans = pinned_alloc<ScanSpan>(rows);
+	b->d_scan_counts = dev_alloc<uint32_t>(rows);
+	b->h_scan_counts = pinned_alloc<uint32_t>(rows);
+	b->d_scan_pos = dev_alloc<uint32_t>((size_t)rows * seg);
+	b->h_scan_pos = pinned_alloc<uint32_t>((size_t)rows * seg);
+	b->scan_rows = rows;
+	b->scan_seg = seg;
 }
 
-void reserve_scan(Stream &s, uint32_t entries) {
-	if (entries + 1 <= s.scan_cap) return;
-	if (s.d_scan) CUDA_CHECK(cudaFree(s.d_scan));
-	s.d_scan = nullptr;
-	if (s.h_scan) CUDA_CHECK(cudaFreeHost(s.h_scan));
-	s.h_scan = nullptr;
-	s.scan_cap = 0;
-	s.d_scan = dev_alloc<uint32_t>(entries + 1);
-	s.h_scan = pinned_alloc<uint32_t>(entries + 1);
-	s.scan_cap = entries + 1;
+// One launch over the pending spans (h_spans[0 .. n)); the counts come back to h_scan_counts.
+void launch_scan(Batch *b, int n, uint32_t longest) {
+	CUDA_CHECK(cudaMemcpyAsync(b->d_spans, b->h_spans, n * sizeof(ScanSpan), cudaMemcpyHostToDevice, b->st_main));
+	CUDA_CHECK(cudaMemsetAsync(b->d_scan_counts, 0, n * sizeof(uint32_t), b->st_main));
+	launch_scan_start_codes(b->d_spans, n, longest, b->d_scan_pos, b->scan_seg, b->d_scan_counts, b->st_main);
+	b->stats.kernel_launches++;
+	CUDA_CHECK(cudaMemcpyAsync(b->h_scan_counts, b->d_scan_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->st_main));
+}
+
+// The device's copy of every stream's prefix list: row si = streams[si].codes.  The host has them all, so a
+// change of geometry (more streams, a longer list) just stages everything again.  Returns true if rebuilt.
+bool reserve_codes(Batch *b, uint32_t rows, uint32_t entries) {
+	if (rows == b->codes_rows && entries <= b->codes_stride) return false;
+	const uint32_t stride = std::max<uint32_t>(std::max<uint32_t>(2 * b->codes_stride, entries + 256u), 1024u);
+	if (b->d_codes) {
+		CUDA_CHECK(cudaStreamSynchronize(b->st_main));  // (tasks of an earlier round may still name the old rows)
+		CUDA_CHECK(cudaStreamSynchronize(b->st_recon));
+		CUDA_CHECK(cudaFree(b->d_codes));
+	}
+	if (b->h_codes) CUDA_CHECK(cudaFreeHost(b->h_codes));
+	b->d_codes = nullptr; b->h_codes = nullptr;
+	b->codes_rows = b->codes_stride = 0;
+	b->d_codes = dev_alloc<uint32_t>((size_t)rows * stride);
+	b->h_codes = pinned_alloc<uint32_t>((size_t)rows * stride);
+	b->codes_rows = rows;
+	b->codes_stride = stride;
+	return true;
 }
 
 void begin_upload(Batch *b, Stream &s) {
@@ -333,75 +371,90 @@ void begin_upload(Batch *b, Stream &s) {
 	}
 	if (s.scanned < s.bb.length) {
 		s.scan_from = s.scanned >= 2 ? s.scanned - 2 : 0;  // a prefix needs its three bytes: those from scanned - 2 on were not complete
-		// room for one start code per 512 bytes (FFmpeg streams: two per picture of tens of KiB; a slice per
-		// macroblock row: ~70 per picture).  A stream that packs them denser overflows the list; the scan is
-		// then repeated with the count it reported (upload_all).
-		reserve_scan(s, std::max<uint32_t>(4096u, (s.bb.length - s.scan_from) / 512u + 16u));
-		launch_scan(b, s);
-		s.scan_pending = true;
+		s.scan_pending = true;  // (upload_all scans all pending spans in one launch)
 	}
 }
 
 long upload_all(Batch *b) {
 	CUDA_CHECK(cudaEventRecord(b->ev_a, b->st_main));
-	bool any = false, copied = false;
-	for (auto &s : b->streams) {
+	const int S = (int)b->streams.size();
+	std::vector<int> pending;
+	uint32_t longest = 0, seg = 4096u;
+	for (int si = 0; si < S; si++) {
+		Stream &s = b->streams[si];
 		begin_upload(b, s);
-		any |= s.scan_pending;
+		if (!s.scan_pending) continue;
+		pending.push_back(si);
+		const uint32_t span = s.bb.length - (s.scan_from & ~15u);
+		longest = std::max(longest, span);
+		// room for one start code per 512 bytes (FFmpeg streams: two per picture of tens of KiB; a slice per
+		// macroblock row: ~70 per picture).  A stream that packs them denser overflows its list; the scan is
+		// then repeated with the count it reported.
+		seg = std::max(seg, span / 512u + 16u);
 	}
-	if (any) {
+	if (!pending.empty()) {
+		const int n = (int)pending.size();
+		reserve_scan(b, (uint32_t)n, seg);
+		for (int k = 0; k < n; k++) {
+			const Stream &s = b->streams[pending[k]];
+			b->h_spans[k] = ScanSpan{s.d_es, s.scan_from, s.bb.length};
+		}
+		launch_scan(b, n, longest);
 		CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
 		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
 		float ms = 0;
 		CUDA_CHECK(cudaEventElapsedTime(&ms, b->ev_a, b->ev_b));
 		b->stats.scan_ms += ms;
-		// a list that overflowed (hostile input: start codes cannot overlap, so at most length / 4 of them)
-		// is scanned again with room for the count the kernel reported
-		bool again = false;
-		for (auto &s : b->streams) {
-			if (!s.scan_pending || s.h_scan[0] <= s.scan_cap - 1) continue;
-			reserve_scan(s, s.h_scan[0] + 16u);
-			launch_scan(b, s);
-			again = true;
-		}
-		if (again) CUDA_CHECK(cudaStreamSynchronize(b->st_main));
-		for (auto &s : b->streams) {
-			if (!s.scan_pending) continue;
-			if (s.h_scan[0] > s.scan_cap - 1) throw std::runtime_error("jsmpeg_b200: start-code index overflow after a rescan");
-			if (s.h_scan[0]) {
-				CUDA_CHECK(cudaMemcpyAsync(s.h_scan + 1, s.d_scan + 1, s.h_scan[0] * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->st_main));
-				b->stats.d2h_bytes += s.h_scan[0] * sizeof(uint32_t);
+		uint32_t most = *std::max_element(b->h_scan_counts, b->h_scan_counts + n);
+		if (most > b->scan_seg) {
+			// a list overflowed (hostile input: start codes cannot overlap, so at most length / 3 of them): once
+			// more, with room for the count the kernel reported
+			reserve_scan(b, (uint32_t)n, most + 16u);
+			for (int k = 0; k < n; k++) {  // (the pinned span list was reallocated)
+				const Stream &s = b->streams[pending[k]];
+				b->h_spans[k] = ScanSpan{s.d_es, s.scan_from, s.bb.length};
 			}
+			launch_scan(b, n, longest);
+			CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+			most = *std::max_element(b->h_scan_counts, b->h_scan_counts + n);
+			if (most > b->scan_seg) throw std::runtime_error("jsmpeg_b200: start-code index overflow after a rescan");
 		}
-		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
-		for (auto &s : b->streams) {
-			if (!s.scan_pending) continue;
-			const uint32_t n = s.h_scan[0];
-			std::sort(s.h_scan + 1, s.h_scan + 1 + n);
+		if (most) {  // the positions of all spans in one (strided) copy
+			CUDA_CHECK(cudaMemcpy2DAsync(b->h_scan_pos, (size_t)b->scan_seg * sizeof(uint32_t), b->d_scan_pos,
+			                             (size_t)b->scan_seg * sizeof(uint32_t), (size_t)most * sizeof(uint32_t), (size_t)n,
+			                             cudaMemcpyDeviceToHost, b->st_main));
+			b->stats.d2h_bytes += (uint64_t)most * n * sizeof(uint32_t);
+			CUDA_CHECK(cudaStreamSynchronize(b->st_main));
+		}
+		bool grew = false;
+		for (int k = 0; k < n; k++) {
+			Stream &s = b->streams[pending[k]];
+			uint32_t *hits = b->h_scan_pos + (size_t)k * b->scan_seg;
+			const uint32_t cnt = b->h_scan_counts[k];
+			std::sort(hits, hits + cnt);
 			// the rescanned window starts 2 bytes before the old frontier, so nothing is reported twice
-			const uint32_t old = (uint32_t)s.codes.size();
-			s.codes.insert(s.codes.end(), s.h_scan + 1, s.h_scan + 1 + n);
-			if (n) {  // the device's copy, for the lane-parallel walk's slice ends
-				if (old + n > s.d_codes_cap) {
-					const uint32_t cap = std::max<uint32_t>(2 * s.d_codes_cap, old + n + 1024u);
-					uint32_t *grown = dev_alloc<uint32_t>(cap);
-					if (s.d_codes) {
-						if (old) CUDA_CHECK(cudaMemcpyAsync(grown, s.d_codes, old * sizeof(uint32_t), cudaMemcpyDeviceToDevice, b->st_main));
-						CUDA_CHECK(cudaStreamSynchronize(b->st_main));
-						CUDA_CHECK(cudaFree(s.d_codes));
-					}
-					s.d_codes = grown;
-					s.d_codes_cap = cap;
-				}
-				CUDA_CHECK(cudaMemcpyAsync(s.d_codes + old, s.h_scan + 1, n * sizeof(uint32_t), cudaMemcpyHostToDevice, b->st_main));
-				b->stats.h2d_bytes += n * sizeof(uint32_t);
-				copied = true;
-			}
+			s.codes.insert(s.codes.end(), hits, hits + cnt);
+			grew |= cnt != 0;
 			s.scanned = s.bb.length;
 			s.scan_pending = false;
 		}
+		if (grew) {  // the device's copy, for the lane-parallel walk's slice ends: every row that changed, in one copy
+			size_t longest_list = 0;
+			for (auto &s : b->streams) longest_list = std::max(longest_list, s.codes.size());
+			const bool rebuilt = reserve_codes(b, (uint32_t)S, (uint32_t)longest_list);
+			for (int si = 0; si < S; si++) {
+				const Stream &s = b->streams[si];
+				// (a rewound stream's list starts over: staging whole rows keeps this free of bookkeeping; they are short)
+				if (!s.codes.empty() && (rebuilt || std::find(pending.begin(), pending.end(), si) != pending.end()))
+					memcpy(b->h_codes + (size_t)si * b->codes_stride, s.codes.data(), s.codes.size() * sizeof(uint32_t));
+			}
+			CUDA_CHECK(cudaMemcpy2DAsync(b->d_codes, (size_t)b->codes_stride * sizeof(uint32_t), b->h_codes,
+			                             (size_t)b->codes_stride * sizeof(uint32_t), longest_list * sizeof(uint32_t), (size_t)S,
+			                             cudaMemcpyHostToDevice, b->st_main));
+			b->stats.h2d_bytes += (uint64_t)longest_list * S * sizeof(uint32_t);
+			CUDA_CHECK(cudaStreamSynchronize(b->st_main));  // the pinned staging is written again by the next scan
+		}
 	}
-	if (copied) CUDA_CHECK(cudaStreamSynchronize(b->st_main));  // the pinned lists are reused by the next scan
 	// picture start codes = prefixes whose fourth byte is 00 and inside the buffer (findStartCode, buffer.js:130-139).
 	// Only the very last prefix can still be waiting for its fourth byte.
 	long total = 0;
@@ -617,7 +670,7 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			t.mb_size = s.seq.mb_size;
 			t.stage = b->d_stage + (size_t)p.slot * stage_entries_for(b->slot_mb) * 4;
 			t.stage_entries = stage_entries_for(b->slot_mb);
-			t.codes = s.d_codes;
+			t.codes = b->d_codes ? b->d_codes + (size_t)fresh[i].stream * b->codes_stride : nullptr;
 			t.n_codes = (uint32_t)s.codes.size();
 			t.code_hint = s.pic_code[fresh[i].pic];
 		}
@@ -890,13 +943,18 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 		if (s.bb.bytes) cudaFreeHost(s.bb.bytes);
 		if (s.d_seq) cudaFree(s.d_seq);
 		if (s.d_es) cudaFree(s.d_es);
-		if (s.d_scan) cudaFree(s.d_scan);
-		if (s.d_codes) cudaFree(s.d_codes);
-		if (s.h_scan) cudaFreeHost(s.h_scan);
 		if (s.d_rgba) cudaFree(s.d_rgba);
 		for (auto p : s.d_planes) if (p) cudaFree(p);
 		for (auto p : s.h_planes) if (p) cudaFreeHost(p);
 	}
+	if (b->d_spans) cudaFree(b->d_spans);
+	if (b->h_spans) cudaFreeHost(b->h_spans);
+	if (b->d_scan_counts) cudaFree(b->d_scan_counts);
+	if (b->h_scan_counts) cudaFreeHost(b->h_scan_counts);
+	if (b->d_scan_pos) cudaFree(b->d_scan_pos);
+	if (b->h_scan_pos) cudaFreeHost(b->h_scan_pos);
+	if (b->d_codes) cudaFree(b->d_codes);
+	if (b->h_codes) cudaFreeHost(b->h_codes);
 	if (b->d_hdr) cudaFree(b->d_hdr);
 	if (b->d_coef) cudaFree(b->d_coef);
 	if (b->d_park) cudaFree(b->d_park);

@@ -14,10 +14,12 @@
 
 namespace {
 
-__global__ void scan_start_codes_kernel(const uint8_t *__restrict__ es, uint32_t from, uint32_t len,
-                                        uint32_t *__restrict__ positions, uint32_t capacity,
-                                        uint32_t *__restrict__ count) {
-	// `es` is 16-byte aligned; thread handles byte positions [base, base + 16)
+__global__ void scan_start_codes_kernel(const ScanSpan *__restrict__ spans, uint32_t *__restrict__ positions, uint32_t capacity,
+                                        uint32_t *__restrict__ counts) {
+	// blockIdx.y = the span; `es` is 16-byte aligned; a thread handles byte positions [base, base + 16)
+	const ScanSpan sp = spans[blockIdx.y];
+	const uint8_t *__restrict__ es = sp.es;
+	const uint32_t from = sp.from, len = sp.len;
 	const uint32_t first = from & ~15u;
 	const uint32_t base = first + (blockIdx.x * blockDim.x + threadIdx.x) * 16u;
 	if (base >= len) return;
@@ -32,20 +34,20 @@ __global__ void scan_start_codes_kernel(const uint8_t *__restrict__ es, uint32_t
 		// 00 00 01 -> low three bytes 0x010000; all three bytes must be inside the buffer (the fourth, the code,
 		// is looked at by the host once it is there)
 		if ((q & 0x00ffffffu) == 0x00010000u && pos >= from && pos + 2u < len) {
-			const uint32_t slot = atomicAdd(count, 1u);
-			if (slot < capacity) positions[slot] = pos;
+			const uint32_t slot = atomicAdd(counts + blockIdx.y, 1u);
+			if (slot < capacity) positions[(size_t)blockIdx.y * capacity + slot] = pos;
 		}
 	}
 }
 
 }  // namespace
 
-void launch_scan_start_codes(const uint8_t *es, uint32_t from, uint32_t len, uint32_t *positions,
-                             uint32_t capacity, uint32_t *count, cudaStream_t stream) {
-	if (from >= len) return;
-	const uint32_t first = from & ~15u;
-	const uint32_t n_threads = (len - first + 15u) / 16u;
+// longest_span = the largest len - (from & ~15) of the spans: the grid covers it, shorter spans' surplus threads leave at once
+void launch_scan_start_codes(const ScanSpan *spans, int n_spans, uint32_t longest_span, uint32_t *positions,
+                             uint32_t capacity, uint32_t *counts, cudaStream_t stream) {
+	if (n_spans <= 0 || longest_span == 0) return;
+	const uint32_t n_threads = (longest_span + 15u) / 16u;
 	const int block = 256;
-	const uint32_t grid = (n_threads + block - 1) / block;
-	scan_start_codes_kernel<<<grid, block, 0, stream>>>(es, from, len, positions, capacity, count);
+	const dim3 grid((n_threads + block - 1) / block, (unsigned)n_spans);
+	scan_start_codes_kernel<<<grid, block, 0, stream>>>(spans, positions, capacity, counts);
 }
