@@ -27,6 +27,11 @@
 #define MBF_PRESENT 0x01 /* macroblock was decoded (coded or skipped-predicted): stage 2 writes it   */
 #define MBF_INTRA   0x02 /* intra macroblock: blocks overwrite; otherwise predict from forward + add */
 #define MBF_SKIPPED 0x04 /* produced by an address increment > 1 (informational)                     */
+/* B pictures only (the opt-in extension; the reference skips B pictures, mpeg1.js:181-184): which of the two
+ * references a non-intra macroblock is predicted from -- both set = the rounded average of the two predictions
+ * (ISO 11172-2 2.4.4.3).  In I and P records both bits are 0 and a non-intra macroblock predicts from forward. */
+#define MBF_MOTION_BWD 0x08 /* from the backward (future) reference, vector mv_bwd */
+#define MBF_MOTION_FWD 0x10 /* from the forward (past) reference, vector mv_h / mv_v */
 
 typedef struct mb_record_t {
 	int16_t mv_h;       /* forward motion vector, luma half-pel units, after full_pel doubling  */
@@ -36,7 +41,7 @@ typedef struct mb_record_t {
 	uint8_t dc_only;    /* same bit order: block takes the n==1 scalar shortcut (mpeg1.js:838-841,850-853) */
 	uint8_t qscale;     /* quantiser_scale in force (informational)                              */
 	uint32_t bit_pos;   /* bit offset of the macroblock inside the picture's ES span (diagnostic) */
-	uint32_t reserved;
+	uint32_t mv_bwd;    /* B pictures: backward vector, (uint16)h | (uint16)v << 16, same units; else 0 */
 } mb_record_t;
 
 #define MB_COEF_INT16 (6 * 64) /* int16 per macroblock in the coefficient plane */
@@ -44,12 +49,15 @@ typedef struct mb_record_t {
 /* Picture-level result of stage 1 (one per picture start code that decode() consumes). */
 #define PIC_DECODED 1 /* I or P picture: reconstruct + swap (mpeg1.js:216-246)                  */
 #define PIC_IGNORED 2 /* B / D / unknown type, or P with forward_f_code == 0 (mpeg1.js:181-193) */
+/* With the B-picture extension switched on, a B picture (type 3) is PIC_DECODED too: it is reconstructed from
+ * the two most recent I/P pictures into a set of its own and does NOT become a reference (no plane swap);
+ * reserved[1] then holds full_pel_backward << 4 | backward_f_code. */
 
 typedef struct picture_info_t {
 	uint32_t start_byte;    /* first byte after the 00 00 01 00 start code                      */
 	uint32_t end_bit;       /* bit index at which the reference's decode_picture returns         */
 	int32_t  status;        /* PIC_*                                                             */
-	int32_t  picture_type;  /* 1 = I, 2 = P                                                      */
+	int32_t  picture_type;  /* 1 = I, 2 = P (3 = B with the extension)                           */
 	int32_t  full_pel;
 	int32_t  f_code;
 	int32_t  n_present;     /* macroblocks with MBF_PRESENT                                      */

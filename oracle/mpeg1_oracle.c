@@ -16,6 +16,14 @@
  * compiled in place) on FFmpeg-encoded clips and on the synthetic syntax-corner streams, and
  * tests/golden/ holds plane checksums produced by that reference build.
  *
+ * B pictures.  The reference skips them (mpeg1.js:181-184) and so does this file by default.  With
+ * oracle_set_decode_b(1) -- the opt-in extension of the product, SURVEY 8(f) rank 4 -- a B picture is decoded
+ * after ISO/IEC 11172-2 (2.4.3.6 macroblock layer, 2.4.4.2/2.4.4.3 skipped macroblocks and bidirectional
+ * prediction, table B.2d = the reference's unused MACROBLOCK_TYPE_B, mpeg1.js:1152-1175) with the reference's own
+ * building blocks (same bit reader, vector arithmetic, dequantisation, IDCT, flat-index prediction).  PARITY OF
+ * THAT PART IS UNPINNED BY THE REFERENCE (there is nothing to run); it is checked against FFmpeg's mpeg1video
+ * decoder by PSNR (tests/test_b_pictures.py), which proves the prediction structure, not bit-exactness.
+ *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library.
  * It deliberately decodes VLCs a different way (bit-by-bit trie built from the ISO-form code
  * lists) than the product (clz-indexed LUTs).
@@ -34,7 +42,7 @@
 typedef struct { int16_t child[2]; int value; bool leaf; } trie_node_t;
 typedef struct { trie_node_t *nodes; int count; } trie_t;
 
-enum { T_MBA, T_TYPE_I, T_TYPE_P, T_CBP, T_MOTION, T_DC_LUMA, T_DC_CHROMA, T_DCT, T_COUNT };
+enum { T_MBA, T_TYPE_I, T_TYPE_P, T_TYPE_B, T_CBP, T_MOTION, T_DC_LUMA, T_DC_CHROMA, T_DCT, T_COUNT };
 static trie_t g_trie[T_COUNT];
 static bool g_tries_ready = false;
 #define VLC_INVALID (-999999)
@@ -61,6 +69,7 @@ static void tries_init(void) {
 	trie_build(&g_trie[T_MBA], ORACLE_MACROBLOCK_ADDRESS_INCREMENT);
 	trie_build(&g_trie[T_TYPE_I], ORACLE_MACROBLOCK_TYPE_INTRA);
 	trie_build(&g_trie[T_TYPE_P], ORACLE_MACROBLOCK_TYPE_PREDICTIVE);
+	trie_build(&g_trie[T_TYPE_B], ORACLE_MACROBLOCK_TYPE_B);
 	trie_build(&g_trie[T_CBP], ORACLE_CODE_BLOCK_PATTERN);
 	trie_build(&g_trie[T_MOTION], ORACLE_MOTION);
 	trie_build(&g_trie[T_DC_LUMA], ORACLE_DCT_DC_SIZE_LUMINANCE);
@@ -143,10 +152,21 @@ typedef struct {
 	bool slice_begin;
 	int mv_h, mv_v, mv_h_prev, mv_v_prev;
 	int dc_pred[3]; /* Y, then the predictor used by block 4, then the one used by block 5 */
+	/* B pictures: the backward vector with its own f_code, and how the last macroblock was predicted */
+	int full_pel_b, r_size_b, f_b;
+	int mvb_h, mvb_v, mvb_h_prev, mvb_v_prev;
+	uint8_t last_motion; /* MBF_MOTION_FWD | MBF_MOTION_BWD of the previous macroblock (a skipped one repeats it) */
 } parse_t;
 
+static int g_decode_b = 0;
+/* the B-picture extension: 0 (default) = B pictures are skipped like the reference does */
+void oracle_set_decode_b(int on) { g_decode_b = on; }
+
 static void reset_dc(parse_t *p) { p->dc_pred[0] = p->dc_pred[1] = p->dc_pred[2] = 128; }
-static void reset_mv(parse_t *p) { p->mv_h = p->mv_v = p->mv_h_prev = p->mv_v_prev = 0; }
+static void reset_mv(parse_t *p) {
+	p->mv_h = p->mv_v = p->mv_h_prev = p->mv_v_prev = 0;
+	p->mvb_h = p->mvb_v = p->mvb_h_prev = p->mvb_v_prev = 0; /* (unused outside B pictures) */
+}
 
 static int16_t sat16(int v) { return (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
 
@@ -215,20 +235,23 @@ static bool parse_block(parse_t *p, int mb, int block, bool intra, uint8_t *dc_o
 }
 
 /* mpeg1.js:395-457, one component */
-static bool parse_motion_component(parse_t *p, int *prev, int *mv) {
+static bool parse_motion_component_f(parse_t *p, int r_size, int f, int full_pel, int *prev, int *mv) {
 	int code = read_vlc(&p->bits, T_MOTION);
 	if (code == VLC_INVALID) return false;
 	int d = code;
-	if (code != 0 && p->f != 1) {
-		int r = bits_read(&p->bits, p->r_size);
-		d = ((abs(code) - 1) << p->r_size) + r + 1;
+	if (code != 0 && f != 1) {
+		int r = bits_read(&p->bits, r_size);
+		d = ((abs(code) - 1) << r_size) + r + 1;
 		if (code < 0) d = -d;
 	}
 	*prev += d;
-	if (*prev > (p->f << 4) - 1) *prev -= p->f << 5;
-	else if (*prev < -(p->f << 4)) *prev += p->f << 5;
-	*mv = p->full_pel ? *prev * 2 : *prev;
+	if (*prev > (f << 4) - 1) *prev -= f << 5;
+	else if (*prev < -(f << 4)) *prev += f << 5;
+	*mv = full_pel ? *prev * 2 : *prev;
 	return true;
+}
+static bool parse_motion_component(parse_t *p, int *prev, int *mv) {
+	return parse_motion_component_f(p, p->r_size, p->f, p->full_pel, prev, mv);
 }
 
 static void emit_predicted(parse_t *p, int addr, uint8_t extra_flags) {
@@ -239,6 +262,11 @@ static void emit_predicted(parse_t *p, int addr, uint8_t extra_flags) {
 	r->flags = MBF_PRESENT | extra_flags;
 	r->qscale = (uint8_t)p->qscale;
 	r->bit_pos = p->bits.index;
+	if (p->picture_type == 3) { /* ISO 11172-2 2.4.4.2: same prediction and vectors as the macroblock before */
+		r->flags |= p->last_motion;
+		if (!(p->last_motion & MBF_MOTION_FWD)) r->mv_h = r->mv_v = 0;
+		if (p->last_motion & MBF_MOTION_BWD) r->mv_bwd = ((uint32_t)p->mvb_h & 0xffffu) | ((uint32_t)p->mvb_v << 16);
+	}
 	p->info->n_present++;
 }
 
@@ -258,7 +286,7 @@ static bool parse_macroblock(parse_t *p) {
 		if (p->mb_addr + increment >= p->seq->mb_size) return true; /* mpeg1.js:319-322 (loop goes on) */
 		if (increment > 1) { /* mpeg1.js:323-334 */
 			reset_dc(p);
-			if (p->picture_type == 2) reset_mv(p);
+			if (p->picture_type == 2) reset_mv(p); /* (B pictures keep their vectors: ISO 11172-2 2.4.4.2) */
 		}
 		while (increment > 1) { /* skipped macroblocks: predicted copy, mpeg1.js:336-346 */
 			p->mb_addr++;
@@ -270,14 +298,17 @@ static bool parse_macroblock(parse_t *p) {
 	int mb = p->mb_addr;
 	if (mb < 0 || mb >= p->seq->mb_size) return false; /* out of the picture: memory safety */
 
-	int type = read_vlc(&p->bits, p->picture_type == 1 ? T_TYPE_I : T_TYPE_P);
+	int type = read_vlc(&p->bits, p->picture_type == 1 ? T_TYPE_I : (p->picture_type == 2 ? T_TYPE_P : T_TYPE_B));
 	if (type == VLC_INVALID) return false;
 	bool intra = type & 0x01;
 	if (type & 0x10) p->qscale = bits_read(&p->bits, 5);
 
 	uint32_t mb_bit_pos = p->bits.index;
 	if (intra) {
-		reset_mv(p); /* mpeg1.js:363-367 */
+		reset_mv(p); /* mpeg1.js:363-367 (B: both predictors, ISO 11172-2 2.4.4.3) */
+		/* (a skipped macroblock must not follow an intra one in a B picture; if a stream does it anyway it is
+		 * predicted forward with the reset, i.e. zero, vector) */
+		p->last_motion = MBF_MOTION_FWD;
 	} else {
 		reset_dc(p); /* mpeg1.js:370-372 */
 		if (type & 0x08) {
@@ -285,6 +316,13 @@ static bool parse_macroblock(parse_t *p) {
 			if (!parse_motion_component(p, &p->mv_v_prev, &p->mv_v)) return false;
 		} else if (p->picture_type == 2) {
 			reset_mv(p); /* mpeg1.js:452-456 */
+		}
+		if (p->picture_type == 3) { /* a direction that is not used keeps its predictor */
+			if (type & 0x04) {
+				if (!parse_motion_component_f(p, p->r_size_b, p->f_b, p->full_pel_b, &p->mvb_h_prev, &p->mvb_h)) return false;
+				if (!parse_motion_component_f(p, p->r_size_b, p->f_b, p->full_pel_b, &p->mvb_v_prev, &p->mvb_v)) return false;
+			}
+			p->last_motion = (uint8_t)(((type & 0x08) ? MBF_MOTION_FWD : 0) | ((type & 0x04) ? MBF_MOTION_BWD : 0));
 		}
 	}
 
@@ -299,6 +337,12 @@ static bool parse_macroblock(parse_t *p) {
 	r->flags = MBF_PRESENT | (intra ? MBF_INTRA : 0);
 	r->qscale = (uint8_t)p->qscale;
 	r->bit_pos = mb_bit_pos;
+	if (p->picture_type == 3 && !intra) {
+		r->flags |= p->last_motion;
+		/* a vector that is not used is stored as zero (the record then does not depend on stale predictors) */
+		if (!(p->last_motion & MBF_MOTION_FWD)) r->mv_h = r->mv_v = 0;
+		if (p->last_motion & MBF_MOTION_BWD) r->mv_bwd = ((uint32_t)p->mvb_h & 0xffffu) | ((uint32_t)p->mvb_v << 16);
+	}
 	uint8_t dc_only = 0;
 	bool ok = true;
 	for (int block = 0; block < 6 && ok; block++) {
@@ -317,6 +361,7 @@ static void parse_slice(parse_t *p, int slice) {
 	p->mb_addr = (slice - 1) * p->seq->mb_width - 1;
 	reset_mv(p);
 	reset_dc(p);
+	p->last_motion = MBF_MOTION_FWD;
 	p->qscale = bits_read(&p->bits, 5);
 	while (bits_read(&p->bits, 1)) bits_skip(&p->bits, 8);
 	do {
@@ -345,14 +390,22 @@ void oracle_parse_picture(const uint8_t *es, uint32_t es_len, uint32_t start_bit
 	bits_skip(&p.bits, 16);
 	info->picture_type = p.picture_type;
 	info->status = PIC_IGNORED;
-	if (p.picture_type <= 0 || p.picture_type >= 3) { info->end_bit = p.bits.index; return; }
-	if (p.picture_type == 2) {
+	if (p.picture_type <= 0 || p.picture_type > 3 || (p.picture_type == 3 && !g_decode_b)) { info->end_bit = p.bits.index; return; }
+	if (p.picture_type >= 2) {
 		p.full_pel = bits_read(&p.bits, 1);
 		int f_code = bits_read(&p.bits, 3);
 		info->full_pel = p.full_pel; info->f_code = f_code;
 		if (f_code == 0) { info->end_bit = p.bits.index; return; }
 		p.r_size = f_code - 1;
 		p.f = 1 << p.r_size;
+	}
+	if (p.picture_type == 3) { /* ISO 11172-2 2.4.2.5: full_pel_backward_vector, backward_f_code */
+		p.full_pel_b = bits_read(&p.bits, 1);
+		int f_code_b = bits_read(&p.bits, 3);
+		info->reserved[1] = p.full_pel_b << 4 | f_code_b;
+		if (f_code_b == 0) { info->end_bit = p.bits.index; return; }
+		p.r_size_b = f_code_b - 1;
+		p.f_b = 1 << p.r_size_b;
 	}
 	info->status = PIC_DECODED;
 
@@ -420,22 +473,64 @@ static void predict_plane(uint8_t *dst, const uint8_t *src, int stride, int plan
 }
 
 typedef struct { uint8_t *y, *cr, *cb; } planes_t;
+static void free_planes(planes_t *p) { free(p->y); free(p->cr); free(p->cb); }
 
-void oracle_reconstruct(const seq_params_t *seq, int coded_width, int coded_height,
-                        const mb_record_t *hdr, const int16_t *coef,
-                        const planes_t *fwd, planes_t *cur) {
+/* One macroblock's prediction from one reference into `cur` (the three planes). */
+static void predict_macroblock(const seq_params_t *seq, int cw, int ysize, int mb, int mh, int mv,
+                               const planes_t *ref, planes_t *cur) {
+	int hw = cw >> 1, csize = ysize >> 2;
+	int row = mb / seq->mb_width, col = mb % seq->mb_width;
+	predict_plane(cur->y, ref->y, cw, ysize, row, col, 16, mh, mv);
+	/* chroma vector: (mv / 2) truncated toward zero, mpeg1.js:562-565 */
+	predict_plane(cur->cr, ref->cr, hw, csize, row, col, 8, mh / 2, mv / 2);
+	predict_plane(cur->cb, ref->cb, hw, csize, row, col, 8, mh / 2, mv / 2);
+}
+
+/* ISO 11172-2 2.4.4.3: a macroblock with both vectors is the average of the two predictions, "//" = rounded
+ * to the nearest integer, halves away from zero: (a + b + 1) >> 1 on samples.  `a` holds the forward
+ * prediction of the macroblock on entry and the average on exit; `b` the backward prediction. */
+static void average_macroblock(const seq_params_t *seq, int cw, int mb, planes_t *a, const planes_t *b) {
+	int hw = cw >> 1;
+	int row = mb / seq->mb_width, col = mb % seq->mb_width;
+	for (int y = 0; y < 16; y++)
+		for (int x = 0; x < 16; x++) {
+			int i = (row * 16 + y) * cw + col * 16 + x;
+			a->y[i] = (uint8_t)((a->y[i] + b->y[i] + 1) >> 1);
+		}
+	for (int y = 0; y < 8; y++)
+		for (int x = 0; x < 8; x++) {
+			int i = (row * 8 + y) * hw + col * 8 + x;
+			a->cr[i] = (uint8_t)((a->cr[i] + b->cr[i] + 1) >> 1);
+			a->cb[i] = (uint8_t)((a->cb[i] + b->cb[i] + 1) >> 1);
+		}
+}
+
+/* I and P pictures: bwd == NULL, every non-intra macroblock predicts from fwd (mpeg1.js:336-346, 459-687).
+ * B pictures (the extension): fwd = the older, bwd = the newer of the two most recent I/P pictures; the record's
+ * MBF_MOTION_* bits say which are used. */
+static void reconstruct_picture(const seq_params_t *seq, int coded_width, int coded_height,
+                                const mb_record_t *hdr, const int16_t *coef,
+                                const planes_t *fwd, const planes_t *bwd, planes_t *cur) {
 	int cw = coded_width, hw = coded_width >> 1;
 	int ysize = coded_width * coded_height, csize = ysize >> 2;
+	planes_t tmp = { 0, 0, 0 };
+	if (bwd) { tmp.y = (uint8_t *)calloc(ysize, 1); tmp.cr = (uint8_t *)calloc(csize, 1); tmp.cb = (uint8_t *)calloc(csize, 1); }
 	for (int mb = 0; mb < seq->mb_size; mb++) {
 		const mb_record_t *r = &hdr[mb];
 		if (!(r->flags & MBF_PRESENT)) continue; /* untouched: keeps the 2-frames-old content */
 		int row = mb / seq->mb_width, col = mb % seq->mb_width;
 		bool intra = r->flags & MBF_INTRA;
-		if (!intra) {
-			predict_plane(cur->y, fwd->y, cw, ysize, row, col, 16, r->mv_h, r->mv_v);
-			/* chroma vector: (mv / 2) truncated toward zero, mpeg1.js:562-565 */
-			predict_plane(cur->cr, fwd->cr, hw, csize, row, col, 8, r->mv_h / 2, r->mv_v / 2);
-			predict_plane(cur->cb, fwd->cb, hw, csize, row, col, 8, r->mv_h / 2, r->mv_v / 2);
+		if (!intra && !bwd) {
+			predict_macroblock(seq, cw, ysize, mb, r->mv_h, r->mv_v, fwd, cur);
+		} else if (!intra) {
+			int bh = (int16_t)(r->mv_bwd & 0xffffu), bv = (int16_t)(r->mv_bwd >> 16);
+			bool use_f = r->flags & MBF_MOTION_FWD, use_b = r->flags & MBF_MOTION_BWD;
+			if (use_f || !use_b) predict_macroblock(seq, cw, ysize, mb, r->mv_h, r->mv_v, fwd, cur);
+			if (use_b && !use_f) predict_macroblock(seq, cw, ysize, mb, bh, bv, bwd, cur);
+			if (use_b && use_f) {
+				predict_macroblock(seq, cw, ysize, mb, bh, bv, bwd, &tmp);
+				average_macroblock(seq, cw, mb, cur, &tmp);
+			}
 		}
 		for (int block = 0; block < 6; block++) {
 			if (!(r->cbp & (0x20 >> block))) continue;
@@ -464,6 +559,20 @@ void oracle_reconstruct(const seq_params_t *seq, int coded_width, int coded_heig
 				}
 		}
 	}
+	if (bwd) free_planes(&tmp);
+}
+
+void oracle_reconstruct(const seq_params_t *seq, int coded_width, int coded_height,
+                        const mb_record_t *hdr, const int16_t *coef,
+                        const planes_t *fwd, planes_t *cur) {
+	reconstruct_picture(seq, coded_width, coded_height, hdr, coef, fwd, NULL, cur);
+}
+
+/* B picture (extension): see reconstruct_picture */
+void oracle_reconstruct_b(const seq_params_t *seq, int coded_width, int coded_height,
+                          const mb_record_t *hdr, const int16_t *coef,
+                          const planes_t *fwd, const planes_t *bwd, planes_t *cur) {
+	reconstruct_picture(seq, coded_width, coded_height, hdr, coef, fwd, bwd, cur);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -476,6 +585,8 @@ typedef struct mpeg1_decoder_t {
 	int width, height, coded_width, coded_height, coded_size;
 	seq_params_t seq;
 	planes_t current, forward;
+	planes_t bout;     /* B-picture extension: where a B picture is reconstructed (it is no reference) */
+	bool last_was_b;
 	mb_record_t *hdr; int16_t *coef;
 	picture_info_t last;
 } mpeg1_decoder_t;
@@ -488,11 +599,9 @@ mpeg1_decoder_t *mpeg1_decoder_create(unsigned int buffer_size, int mode) {
 	return d;
 }
 
-static void free_planes(planes_t *p) { free(p->y); free(p->cr); free(p->cb); }
-
 void mpeg1_decoder_destroy(mpeg1_decoder_t *d) {
 	free(d->bytes);
-	if (d->has_sequence_header) { free_planes(&d->current); free_planes(&d->forward); free(d->hdr); free(d->coef); }
+	if (d->has_sequence_header) { free_planes(&d->current); free_planes(&d->forward); free_planes(&d->bout); free(d->hdr); free(d->coef); }
 	free(d);
 }
 
@@ -543,6 +652,7 @@ static void parse_sequence_header(mpeg1_decoder_t *d, bits_t *b) {
 	d->coded_size = d->coded_width * d->coded_height;
 	d->current = alloc_planes(d->coded_size);
 	d->forward = alloc_planes(d->coded_size);
+	d->bout = alloc_planes(d->coded_size);
 	d->hdr = (mb_record_t *)calloc(d->seq.mb_size, sizeof(mb_record_t));
 	d->coef = (int16_t *)calloc((size_t)d->seq.mb_size * MB_COEF_INT16, sizeof(int16_t));
 	d->has_sequence_header = true;
@@ -564,9 +674,9 @@ int mpeg1_decoder_get_coded_size(mpeg1_decoder_t *d) { return d->coded_size; }
 int mpeg1_decoder_get_width(mpeg1_decoder_t *d) { return d->width; }
 int mpeg1_decoder_get_height(mpeg1_decoder_t *d) { return d->height; }
 /* most recently decoded picture = forward after the swap (mpeg1.c:841-851) */
-void *mpeg1_decoder_get_y_ptr(mpeg1_decoder_t *d) { return d->forward.y; }
-void *mpeg1_decoder_get_cr_ptr(mpeg1_decoder_t *d) { return d->forward.cr; }
-void *mpeg1_decoder_get_cb_ptr(mpeg1_decoder_t *d) { return d->forward.cb; }
+void *mpeg1_decoder_get_y_ptr(mpeg1_decoder_t *d) { return d->last_was_b ? d->bout.y : d->forward.y; }
+void *mpeg1_decoder_get_cr_ptr(mpeg1_decoder_t *d) { return d->last_was_b ? d->bout.cr : d->forward.cr; }
+void *mpeg1_decoder_get_cb_ptr(mpeg1_decoder_t *d) { return d->last_was_b ? d->bout.cb : d->forward.cb; }
 
 /* mpeg1.c:853-864 + decode_picture :947-995 */
 bool mpeg1_decoder_decode(mpeg1_decoder_t *d) {
@@ -578,9 +688,16 @@ bool mpeg1_decoder_decode(mpeg1_decoder_t *d) {
 	memset(d->hdr, 0, (size_t)d->seq.mb_size * sizeof(mb_record_t));
 	oracle_parse_picture(d->bytes, d->length, d->index, &d->seq, &d->last, d->hdr, d->coef);
 	d->index = d->last.end_bit;
-	if (d->last.status == PIC_DECODED) {
+	if (d->last.status == PIC_DECODED && d->last.picture_type == 3) {
+		/* extension: after the swaps `current` holds the older and `forward` the newer of the two most recent
+		 * I/P pictures = the B picture's forward (past) and backward (future) reference.  Pictures leave in
+		 * CODED order; no swap, a B picture is never a reference. */
+		oracle_reconstruct_b(&d->seq, d->coded_width, d->coded_height, d->hdr, d->coef, &d->current, &d->forward, &d->bout);
+		d->last_was_b = true;
+	} else if (d->last.status == PIC_DECODED) {
 		oracle_reconstruct(&d->seq, d->coded_width, d->coded_height, d->hdr, d->coef, &d->forward, &d->current);
 		planes_t t = d->forward; d->forward = d->current; d->current = t;
+		d->last_was_b = false;
 	}
 	return true;
 }

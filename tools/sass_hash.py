@@ -27,6 +27,6 @@ def sass_hash(cu, flags=()):
 
 
 if __name__ == "__main__":
-    for cu in ("parse.cu", "recon.cu", "scan.cu", "rgba.cu", "tsdemux.cu"):
+    for cu in ("parse.cu", "recon.cu", "scan.cu", "tsdemux.cu"):
         h, n = sass_hash(cu, sys.argv[1:])
         print(f"{cu:12s} {h}  ({n} instructions)")

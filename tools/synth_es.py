@@ -33,6 +33,7 @@ _inv = lambda table: {v: k for k, v in table.items()}  # noqa: E731
 MBA_CODE = _inv(V.MBA_INCREMENT)
 TYPE_I_CODE = _inv(V.MB_TYPE_INTRA)
 TYPE_P_CODE = _inv(V.MB_TYPE_PREDICTIVE)
+TYPE_B_CODE = _inv(V.MB_TYPE_B)
 CBP_CODE = _inv(V.CODE_BLOCK_PATTERN)
 MOTION_CODE = _inv(V.MOTION)
 DC_LUMA_CODE = _inv(V.DCT_DC_SIZE_LUMINANCE)
@@ -96,6 +97,14 @@ class Knobs:
         self.ignored_pictures = False
         self.repeat_sequence_header = False
         self.gop_headers = True
+        # B pictures (the opt-in extension; the reference skips them): b_frames > 0 puts that many B pictures
+        # behind every I/P picture in CODED order (I B B P B B ...: the first ones have one reference only,
+        # an open GOP), `gop` then counts I/P pictures.  0 = none, and no random numbers are drawn for them:
+        # the streams of the committed cases stay byte-identical.
+        self.b_frames = 0
+        self.b_skip_prob = 0.2
+        self.b_intra_prob = 0.08
+        self.b_f_codes = (1, 2, 3)
         self.__dict__.update(kw)
 
 
@@ -137,7 +146,7 @@ class SynthStream:
         w.put(1, 1)   # closed gop
         w.put(0, 1)   # broken link
 
-    def picture_header(self, temporal, ptype, full_pel=0, f_code=1):
+    def picture_header(self, temporal, ptype, full_pel=0, f_code=1, full_pel_b=0, f_code_b=1):
         w = self.out
         w.start_code(0x00)
         w.put(temporal & 1023, 10)
@@ -147,8 +156,8 @@ class SynthStream:
             w.put(full_pel, 1)
             w.put(f_code, 3)
         if ptype == 3:
-            w.put(0, 1)
-            w.put(1, 3)
+            w.put(full_pel_b, 1)
+            w.put(f_code_b, 3)
         w.put(0, 1)  # extra_bit_picture
         if self.k.extension_user_data and self.rng.random() < 0.5:
             w.start_code(0xB5)
@@ -250,28 +259,31 @@ class SynthStream:
         """A predictor value (in the units the bitstream carries) whose luma AND chroma footprints
         stay inside the coded planes."""
         rng = self.rng
-        cw, ch = self.mbw * 16, self.mbh * 16
         lo, hi = -16 * f, 16 * f - 1
         scale = 2 if full_pel else 1
         for _ in range(50):
             vx = int(rng.integers(max(lo, -24), min(hi, 24) + 1))
             vy = int(rng.integers(max(lo, -24), min(hi, 24) + 1))
-            mx, my = vx * scale, vy * scale
-            x0 = mb_col * 16 + (mx >> 1)
-            y0 = mb_row * 16 + (my >> 1)
-            x1 = x0 + 16 + (mx & 1)
-            y1 = y0 + 16 + (my & 1)
-            if x0 < 0 or y0 < 0 or x1 > cw or y1 > ch:
-                continue
-            cx, cy = int(mx / 2), int(my / 2)  # truncation toward zero (mpeg1.js:562-565)
-            x0 = mb_col * 8 + (cx >> 1)
-            y0 = mb_row * 8 + (cy >> 1)
-            x1 = x0 + 8 + (cx & 1)
-            y1 = y0 + 8 + (cy & 1)
-            if x0 < 0 or y0 < 0 or x1 > cw // 2 or y1 > ch // 2:
-                continue
-            return vx, vy
+            if self.footprint_inside(mb_col, mb_row, vx * scale, vy * scale):
+                return vx, vy
         return 0, 0
+
+    def footprint_inside(self, mb_col, mb_row, mx, my):
+        """Vector (mx, my) in luma half-pel units at macroblock (mb_col, mb_row): the luma and the chroma
+        footprint both stay inside the coded planes."""
+        cw, ch = self.mbw * 16, self.mbh * 16
+        x0 = mb_col * 16 + (mx >> 1)
+        y0 = mb_row * 16 + (my >> 1)
+        x1 = x0 + 16 + (mx & 1)
+        y1 = y0 + 16 + (my & 1)
+        if x0 < 0 or y0 < 0 or x1 > cw or y1 > ch:
+            return False
+        cx, cy = int(mx / 2), int(my / 2)  # truncation toward zero (mpeg1.js:562-565)
+        x0 = mb_col * 8 + (cx >> 1)
+        y0 = mb_row * 8 + (cy >> 1)
+        x1 = x0 + 8 + (cx & 1)
+        y1 = y0 + 8 + (cy & 1)
+        return not (x0 < 0 or y0 < 0 or x1 > cw // 2 or y1 > ch // 2)
 
     # ---------------------------------------------------------------- slices
     def address_increment(self, w, inc):
@@ -283,12 +295,15 @@ class SynthStream:
             inc -= 33
         w.code(MBA_CODE[inc])
 
-    def slice(self, ptype, first_mb, last_mb, f_code, full_pel):
+    def slice(self, ptype, first_mb, last_mb, f_code, full_pel, f_code_b=1, full_pel_b=0):
         """Macroblocks first_mb..last_mb (inclusive, raster addresses) as one slice whose start
         code is the row of first_mb + 1.  Returns the slice bytes (re-rolled on start-code emulation)."""
         for _attempt in range(20):
             w = BitWriter()
-            data = self._slice_once(w, ptype, first_mb, last_mb, f_code, full_pel)
+            if ptype == 3:
+                data = self._slice_once_b(w, first_mb, last_mb, f_code, full_pel, f_code_b, full_pel_b)
+            else:
+                data = self._slice_once(w, ptype, first_mb, last_mb, f_code, full_pel)
             body = data[4:]
             bad = any(body[i] == 0 and body[i + 1] == 0 and body[i + 2] <= 1 for i in range(len(body) - 2))
             if not bad and not (len(body) >= 2 and body[-1] == 0 and body[-2] == 0) and not (len(body) >= 1 and body[-1] == 0):
@@ -363,11 +378,89 @@ class SynthStream:
         w.align()
         return w.tobytes()
 
+    def _slice_once_b(self, w, first_mb, last_mb, f_code, full_pel, f_code_b, full_pel_b):
+        """A slice of a B picture (ISO 11172-2 2.4.3.6, 2.4.4.2, 2.4.4.3; types: table B.2d)."""
+        rng = self.rng
+        mbw = self.mbw
+        row = first_mb // mbw
+        w.start_code(row + 1)
+        qscale = int(rng.integers(1, 32))
+        w.put(qscale, 5)
+        w.put(0, 1)
+        f, r_size = 1 << (f_code - 1), f_code - 1
+        fb, r_size_b = 1 << (f_code_b - 1), f_code_b - 1
+        sf, sb = (2 if full_pel else 1), (2 if full_pel_b else 1)
+        pf = [0, 0]   # forward predictors (bitstream units), kept by macroblocks that do not use them
+        pb = [0, 0]
+        last = None   # (uses forward, uses backward) of the previous macroblock; None = intra / slice start
+        dc = [128, 128, 128]
+        addr = row * mbw - 1
+        mb = first_mb
+        first = True
+        while mb <= last_mb:
+            skipped = 0
+            if not first and last is not None and rng.random() < self.k.b_skip_prob and mb < last_mb:
+                # skipped macroblocks repeat the previous one's prediction: its vectors must fit where they land
+                want = int(min(rng.integers(1, self.k.max_skip + 1), last_mb - mb))
+                while skipped < want:
+                    r2, c2 = divmod(mb + skipped, mbw)
+                    if last[0] and not self.footprint_inside(c2, r2, pf[0] * sf, pf[1] * sf):
+                        break
+                    if last[1] and not self.footprint_inside(c2, r2, pb[0] * sb, pb[1] * sb):
+                        break
+                    skipped += 1
+                mb += skipped
+            if skipped:
+                dc = [128, 128, 128]
+            self.address_increment(w, mb - addr)
+            addr = mb
+            first = False
+            mb_row, mb_col = divmod(mb, mbw)
+            if rng.random() < self.k.b_intra_prob:
+                mtype = 0x11 if rng.random() < self.k.quant_change_prob else 0x01
+            else:
+                mtype = int(rng.choice([0x0C, 0x0E, 0x04, 0x06, 0x08, 0x0A, 0x1E, 0x1A, 0x16]))
+            w.code(TYPE_B_CODE[mtype])
+            if mtype & 0x10:
+                qscale = int(rng.integers(1, 32))
+                w.put(qscale, 5)
+            intra = mtype & 0x01
+            if intra:
+                pf = [0, 0]
+                pb = [0, 0]
+                last = None
+            else:
+                dc = [128, 128, 128]
+                if mtype & 0x08:
+                    th, tv = self.pick_vector(mb_col, mb_row, f, full_pel)
+                    pf[0] = self.motion_component(w, th, pf[0], f, r_size)
+                    pf[1] = self.motion_component(w, tv, pf[1], f, r_size)
+                if mtype & 0x04:
+                    th, tv = self.pick_vector(mb_col, mb_row, fb, full_pel_b)
+                    pb[0] = self.motion_component(w, th, pb[0], fb, r_size_b)
+                    pb[1] = self.motion_component(w, tv, pb[1], fb, r_size_b)
+                last = (bool(mtype & 0x08), bool(mtype & 0x04))
+            if mtype & 0x02:
+                cbp = int(rng.integers(1, 64))
+                w.code(CBP_CODE[cbp])
+            else:
+                cbp = 0x3F if intra else 0
+            for blk in range(6):
+                if cbp & (0x20 >> blk):
+                    which = 0 if blk < 4 else blk - 3
+                    dc[which] = self.block(w, intra, blk < 4, dc[which])
+            mb += 1
+        w.align()
+        return w.tobytes()
+
     # ---------------------------------------------------------------- pictures
     def picture(self, index):
         rng = self.rng
         k = self.k
         ptype = 1 if index % k.gop == 0 else 2
+        if k.b_frames:  # coded order: a reference picture, then the B pictures shown before it
+            ref, pos = divmod(index, k.b_frames + 1)
+            ptype = 3 if pos else (1 if ref % k.gop == 0 else 2)
         if ptype == 1 and k.gop_headers:
             self.gop_header()
         if k.repeat_sequence_header and index and ptype == 1:
@@ -387,7 +480,11 @@ class SynthStream:
                 self.out.bits.extend(BitWriter_bits(self.slice(1, 0, self.mbw - 1, 1, 0)))
         f_code = int(rng.choice(k.f_codes))
         full_pel = int(rng.random() < k.full_pel_prob)
-        self.picture_header(index, ptype, full_pel, f_code)
+        f_code_b, full_pel_b = 1, 0
+        if ptype == 3:
+            f_code_b = int(rng.choice(k.b_f_codes))
+            full_pel_b = int(rng.random() < k.full_pel_prob)
+        self.picture_header(index, ptype, full_pel, f_code, full_pel_b, f_code_b)
         total = self.mbw * self.mbh
         if k.slices == "one":
             spans = [(0, total - 1)]
@@ -406,7 +503,7 @@ class SynthStream:
                     at = min(total, at + int(rng.integers(1, self.mbw)))
         self.out.align()
         for (a, b) in spans:
-            self.out.bits.extend(BitWriter_bits(self.slice(ptype, a, b, f_code, full_pel)))
+            self.out.bits.extend(BitWriter_bits(self.slice(ptype, a, b, f_code, full_pel, f_code_b, full_pel_b)))
 
     def generate(self):
         self.sequence_header()
@@ -438,13 +535,24 @@ CASES = {
     "odd_size": dict(knobs=dict(width=100, height=50, pictures=6, gop=3, slices="random"), seed=18),
 }
 
+# B-picture streams (the opt-in extension; the reference skips every B picture of them).  Not part of CASES:
+# the golden vectors of tests/golden/ come from the compiled reference, which cannot decode these.
+B_CASES = {
+    "b_rows": dict(knobs=dict(width=96, height=64, pictures=13, gop=2, slices="rows", b_frames=2), seed=21),
+    "b_one_slice_fcodes": dict(knobs=dict(width=176, height=144, pictures=10, gop=3, slices="one", b_frames=2, f_codes=(1, 2, 3, 4),
+                                          b_f_codes=(1, 2, 3, 4, 5), full_pel_prob=0.3, b_skip_prob=0.35), seed=22),
+    "b_random_slices": dict(knobs=dict(width=112, height=80, pictures=9, gop=2, slices="random", b_frames=1, stuffing_prob=0.2,
+                                       escape_prob=0.3, custom_matrices=True), seed=23),
+    "b_three": dict(knobs=dict(width=64, height=48, pictures=12, gop=1, slices="one", b_frames=3, b_intra_prob=0.3), seed=24),
+}
+
 
 def make_case(name):
-    spec = CASES[name]
+    spec = CASES[name] if name in CASES else B_CASES[name]
     return SynthStream(Knobs(**spec["knobs"]), spec["seed"]).generate()
 
 
 if __name__ == "__main__":
-    for name in CASES:
+    for name in list(CASES) + list(B_CASES):
         es = make_case(name)
         print(f"{name}: {len(es)} bytes")
