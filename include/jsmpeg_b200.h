@@ -105,7 +105,14 @@ const char *jsmpeg_b200_batch_last_error(jsmpeg_b200_batch_t *b);
 /* Tuning knobs, 0 on success.  "chunk_pictures" G: a parse wave is queued in chunks of G pictures per
  * stream and chunk k is reconstructed while chunk k+1 is being parsed (0 = one chunk, no overlap;
  * default from the environment variable JSMPEG_B200_CHUNK, else 0).  "lookahead": pictures parsed
- * ahead per stream beyond the ones a decode call asks for. */
+ * ahead per stream beyond the ones a decode call asks for.
+ * "decode_b" (default 0, or the environment variable JSMPEG_B200_DECODE_B; also honoured by decoders made with
+ * mpeg1_decoder_create): the B-PICTURE EXTENSION.  The reference skips B pictures (src/mpeg1.js:181-184:
+ * decode() returns true, nothing is rendered) and so does this library by default.  With 1, a B picture is
+ * decoded after ISO/IEC 11172-2 from the two most recent I/P pictures; decode() still consumes pictures in
+ * CODED order, the planes of a B picture are what get_planes / get_host_planes / the reference ABI's
+ * get_{y,cr,cb}_ptr return after it, and jsmpeg_b200_batch_last_picture tells type and temporal_reference so
+ * that a player can put pictures into display order.  No reference implementation exists for this part. */
 int jsmpeg_b200_batch_set_option(jsmpeg_b200_batch_t *b, const char *name, int value);
 
 /* per-stream twins of the reference ABI */
@@ -159,6 +166,10 @@ int jsmpeg_b200_batch_read_rgba(jsmpeg_b200_batch_t *b, int stream, void *rgba);
 /* Synchronous copy of the most recent picture's planes into caller memory (coded size). */
 int jsmpeg_b200_batch_read_planes(jsmpeg_b200_batch_t *b, int stream, void *y, void *cr, void *cb);
 
+/* picture_coding_type (1 I, 2 P, 3 B, 4 D) and temporal_reference (ISO 11172-2 2.4.2.5) of the picture the
+ * stream's last decode() consumed, decoded or skipped; -1 before the first one.  Either pointer may be NULL. */
+int jsmpeg_b200_batch_last_picture(jsmpeg_b200_batch_t *b, int stream, int *picture_type, int *temporal_reference);
+
 void jsmpeg_b200_batch_get_stats(jsmpeg_b200_batch_t *b, jsmpeg_b200_stats_t *out);
 void jsmpeg_b200_batch_reset_stats(jsmpeg_b200_batch_t *b);
 
@@ -178,6 +189,11 @@ int jsmpeg_b200_debug_reconstruct(int mb_width, int mb_height, const void *hdr, 
 
 /* NULL while the decoder works, else why it is dead (see mpeg1_decoder_create). */
 const char *jsmpeg_b200_decoder_last_error(mpeg1_decoder_t *self);
+
+/* jsmpeg_b200_batch_set_option / jsmpeg_b200_batch_last_picture for a decoder of the reference ABI (which has no
+ * option call): "decode_b" switches the B-picture extension on, "lookahead" sets the pictures parsed ahead. */
+int jsmpeg_b200_decoder_set_option(mpeg1_decoder_t *self, const char *name, int value);
+int jsmpeg_b200_decoder_last_picture(mpeg1_decoder_t *self, int *picture_type, int *temporal_reference);
 
 /* CUDA device for decoders created through the reference ABI from now on (the reference ABI has no
  * device argument; the JS/Python class passes its `device` option here). */

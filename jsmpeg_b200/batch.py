@@ -49,6 +49,7 @@ _BATCH_ABI = {
     "jsmpeg_b200_batch_get_rgba": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP)]),
     "jsmpeg_b200_batch_read_planes": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP]),
     "jsmpeg_b200_batch_read_rgba": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
+    "jsmpeg_b200_batch_last_picture": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "jsmpeg_b200_batch_get_stats": (None, [_VP, ctypes.POINTER(Stats)]),
     "jsmpeg_b200_batch_reset_stats": (None, [_VP]),
     "jsmpeg_b200_debug_parse_picture": (ctypes.c_int, [_VP, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
@@ -58,6 +59,8 @@ _BATCH_ABI = {
     "jsmpeg_b200_batch_last_error": (ctypes.c_char_p, [_VP]),
     "jsmpeg_b200_batch_set_option": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_int]),
     "jsmpeg_b200_decoder_last_error": (ctypes.c_char_p, [_VP]),
+    "jsmpeg_b200_decoder_set_option": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_int]),
+    "jsmpeg_b200_decoder_last_picture": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "jsmpeg_b200_bind_host_to_device": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "jsmpeg_b200_version": (ctypes.c_char_p, []),
 }
@@ -74,7 +77,7 @@ def bind_batch_abi(lib):
 class BatchDecoder:
     """``n_streams`` independent MPEG-1 video decoders on one B200."""
 
-    def __init__(self, n_streams, device=0, max_slots=0, lib=None, chunk_pictures=None):
+    def __init__(self, n_streams, device=0, max_slots=0, lib=None, chunk_pictures=None, decode_b=None):
         from . import capi
         self.lib = lib if lib is not None else capi.product_library()
         self.n_streams = n_streams
@@ -85,6 +88,8 @@ class BatchDecoder:
             raise RuntimeError(err.decode(errors="replace"))
         if chunk_pictures is not None:
             self.set_option("chunk_pictures", chunk_pictures)
+        if decode_b is not None:  # the B-picture extension (the reference skips B pictures, and so does the default)
+            self.set_option("decode_b", decode_b)
 
     def close(self):
         if self.handle:
@@ -179,6 +184,13 @@ class BatchDecoder:
         if self.lib.jsmpeg_b200_batch_read_rgba(self.handle, stream, out.ctypes.data) != 0:
             raise RuntimeError("no RGBA picture (decode with OUT_RGBA first)")
         return out
+
+    def last_picture(self, stream):
+        """(picture_coding_type, temporal_reference) of the picture the stream's last decode() consumed, or None."""
+        t, r = ctypes.c_int(), ctypes.c_int()
+        if self.lib.jsmpeg_b200_batch_last_picture(self.handle, stream, t, r) != 0:
+            return None
+        return t.value, r.value
 
     def stats(self):
         st = Stats()

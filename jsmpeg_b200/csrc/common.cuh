@@ -88,11 +88,12 @@ struct ReconTask {
 	const mb_record_t *hdr;
 	const int16_t *coef;
 	PlaneSet cur;   // written
-	PlaneSet fwd;   // read (previous I/P picture)
+	PlaneSet fwd;   // read (previous I/P picture; B picture: the older of the two most recent I/P pictures)
 	int32_t mb_width, mb_size;
 	int32_t coded_width, coded_height;
 	uint8_t *rgba;  // optional fused epilogue target (display size, RGBA8888) or nullptr
 	int32_t width, height;
+	PlaneSet bwd;   // B picture (the opt-in extension): the newer of the two most recent I/P pictures
 };
 
 // kernel launchers (defined in scan.cu / parse.cu / recon.cu)
@@ -120,6 +121,11 @@ int parse_group_count(int n_tasks, bool forked);
 void launch_reconstruct(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream);
 // the same with the planar -> RGBA conversion fused in (tasks' rgba / width / height)
 void launch_reconstruct_rgba(const ReconTask *tasks_host, int n_tasks, cudaStream_t stream);
+// B pictures (every task has `bwd`): prediction from two references; `rgba` = with the fused conversion.
+// Returns the number of kernels launched.
+int launch_reconstruct_b(const ReconTask *tasks_host, int n_tasks, bool rgba, cudaStream_t stream);
+// stage 1 for B pictures: the serial walk with the B-picture macroblock layer (walk_b.cuh) + the same expand
+void launch_parse_pictures_b(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream);
 
 // device MPEG-TS demux (tsdemux.cu)
 struct TsScratch;

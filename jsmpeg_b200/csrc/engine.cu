@@ -93,6 +93,12 @@ struct Stream {
 	int cur = 0;  // set written by the next I/P picture; forward = 1 - cur
 	uint8_t *h_planes[HOST_RING] = {};
 	int h_head = -1;
+	// B-picture extension ("decode_b"): two more sets in HBM, written in turn -- a B picture is no reference, the
+	// ping-pong above is untouched by it; d_last = the set holding the most recently decoded picture
+	uint8_t *d_planes_b[2] = {nullptr, nullptr};
+	int b_cur = 0;
+	uint8_t *d_last = nullptr;
+	int last_type = 0, last_temporal = 0;  // picture_coding_type / temporal_reference of the last picture decode() consumed
 	uint8_t *d_rgba = nullptr;
 	std::vector<int16_t> ts_bound;     // device TS demux: the stream id every PID is bound to, 0 = none (ts.js pidsToStreamIds)
 	std::vector<uint8_t> ts_leftover;  // ... and the bytes the last write_ts left over (ts.js leftoverBytes)
@@ -129,6 +135,7 @@ struct jsmpeg_b200_batch_t {
 	picture_info_t *d_info = nullptr, *h_info = nullptr;
 	std::vector<int> free_slots;
 	int lookahead = 1;
+	bool decode_b = false;       // the B-picture extension: off = B pictures are skipped like the reference does (mpeg1.js:181-184)
 	int chunk_pictures = 0;      // G of the pipeline; 0 = the whole wave is one chunk
 	int chunk_min_wave = 256;    // waves with fewer new pictures stay whole
 	int chunk_streams = 3;       // chunks are parsed on this many streams in turn (1 = on the main stream, forked into size groups)
@@ -603,7 +610,7 @@ void copy_out_step(Batch *b, const std::vector<ReconTask> &tasks, const std::vec
 long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &progress, std::vector<char> &more, int flags) {
 	const int S = (int)b->streams.size();
 	// ---- 1. plan the parse wave
-	struct NewParse { int stream; size_t cache_idx; uint32_t bytes; int chunk; uint32_t pic; };
+	struct NewParse { int stream; size_t cache_idx; uint32_t bytes; int chunk; uint32_t pic; bool is_b; };
 	std::vector<NewParse> fresh;
 	for (int si = 0; si < S; si++) {
 		Stream &s = b->streams[si];
@@ -631,7 +638,10 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			b->free_slots.pop_back();
 			s.cache.push_back(p);
 			++next;
-			fresh.push_back({si, s.cache.size() - 1, (next < s.pics.end() ? *next : s.bb.length) - p.pos, 0, (uint32_t)(next - 1 - s.pics.begin())});
+			// the extension: a picture whose header says type 3 (ISO 11172-2 2.4.2.5: 10 bits temporal_reference, 3 bits
+			// picture_coding_type) goes to the B-picture walk; everything else, and everything without it, to the I/P walk
+			const bool is_b = b->decode_b && (uint64_t)p.pos + 5 < s.bb.length && ((s.bb.bytes[p.pos + 5] >> 3) & 7) == 3;
+			fresh.push_back({si, s.cache.size() - 1, (next < s.pics.end() ? *next : s.bb.length) - p.pos, 0, (uint32_t)(next - 1 - s.pics.begin()), is_b});
 		}
 	}
 	// ---- 2. chunks by picture ordinal (position in the stream's look-ahead); a small wave stays whole
@@ -648,8 +658,9 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 	if (!fresh.empty()) {
 		// Within a chunk, longest pictures first: a CTA's warps, and consecutive CTAs (which land on different
 		// SMs), then carry similar amounts of work and the chunk's walk ends without a long tail.
+		// (B pictures, if the extension decodes them, behind the chunk's I/P pictures: they have their own walk kernel)
 		std::stable_sort(fresh.begin(), fresh.end(), [](const NewParse &x, const NewParse &y) {
-			return x.chunk != y.chunk ? x.chunk < y.chunk : x.bytes > y.bytes;
+			return x.chunk != y.chunk ? x.chunk < y.chunk : (x.is_b != y.is_b ? y.is_b : x.bytes > y.bytes);
 		});
 		for (auto &f : fresh) chunk_off[f.chunk + 1]++;
 		for (int c = 0; c < n_chunks; c++) chunk_off[c + 1] += chunk_off[c];
@@ -698,9 +709,18 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			cudaStream_t st = n_cs > 1 ? b->st_chunk[c % n_cs] : b->st_main;
 			if (n_cs > 1 && c < n_cs) CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_fed, 0));
 			if (n > 0) {
-				launch_parse_pictures(b->d_ptasks + lo, n, b->slot_mb, st, mid_recorded ? nullptr : b->ev_mid, n_cs > 1 ? nullptr : &b->fork);
-				mid_recorded = true;
-				b->stats.kernel_launches += 2 * parse_group_count(n, n_cs == 1);  // walk + expand per size group
+				int n_b = 0;  // the chunk's B pictures sit at its end
+				while (n_b < n && fresh[lo + n - 1 - n_b].is_b) n_b++;
+				const int n_ip = n - n_b;
+				if (n_ip > 0) {
+					launch_parse_pictures(b->d_ptasks + lo, n_ip, b->slot_mb, st, mid_recorded ? nullptr : b->ev_mid, n_cs > 1 ? nullptr : &b->fork);
+					mid_recorded = true;
+					b->stats.kernel_launches += 2 * parse_group_count(n_ip, n_cs == 1);  // walk + expand per size group
+				}
+				if (n_b > 0) {
+					launch_parse_pictures_b(b->d_ptasks + lo + n_ip, n_b, b->slot_mb, st);
+					b->stats.kernel_launches += 2;
+				}
 				CUDA_CHECK(cudaMemcpyAsync(b->h_info + lo, b->d_info + lo, n * sizeof(picture_info_t), cudaMemcpyDeviceToHost, st));
 			}
 			CUDA_CHECK(cudaEventRecord(b->ev_info[c], st));
@@ -710,6 +730,7 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 				CUDA_CHECK(cudaEventRecord(b->ev_chunk_done[k], b->st_chunk[k]));
 				CUDA_CHECK(cudaStreamWaitEvent(b->st_main, b->ev_chunk_done[k], 0));
 			}
+		if (!mid_recorded) CUDA_CHECK(cudaEventRecord(b->ev_mid, b->st_main));  // (a wave of B pictures only)
 		CUDA_CHECK(cudaEventRecord(b->ev_b, b->st_main));
 		b->stats.h2d_bytes += fresh.size() * sizeof(ParseTask);
 		b->stats.d2h_bytes += fresh.size() * sizeof(picture_info_t);
@@ -772,12 +793,31 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 				consumed++;
 				b->stats.pictures++;
 				b->stats.es_bytes += (e.info.end_bit >> 3) - e.pos;
+				s.last_type = e.info.picture_type;
+				s.last_temporal = (uint64_t)e.pos + 5 < s.bb.length ? (s.bb.bytes[e.pos + 4] << 2 | s.bb.bytes[e.pos + 5] >> 6) : 0;
 				if (e.info.status == PIC_DECODED) {
+					const bool is_b = e.info.picture_type == 3;  // (only the extension's walk answers PIC_DECODED for one)
 					ReconTask t{};
 					t.hdr = b->d_hdr + (size_t)e.slot * b->slot_mb;
 					t.coef = b->d_coef + (size_t)e.slot * b->slot_mb * MB_COEF_INT16;
-					t.cur = plane_set(s, s.d_planes[s.cur]);
-					t.fwd = plane_set(s, s.d_planes[1 - s.cur]);
+					if (is_b) {
+						// after the swaps `cur` holds the older and `1 - cur` the newer of the two most recent I/P pictures:
+						// the B picture's forward (past) and backward (future) reference.  It goes to a set of its own.
+						if (!s.d_planes_b[0]) {
+							const size_t bytes = (size_t)s.coded_size * 3 / 2 + s.seq.coded_width + 64;
+							for (auto &pb : s.d_planes_b) {
+								pb = dev_alloc<uint8_t>(bytes);
+								CUDA_CHECK(cudaMemsetAsync(pb, 0, bytes, b->st_recon));
+							}
+						}
+						t.cur = plane_set(s, s.d_planes_b[s.b_cur]);
+						t.fwd = plane_set(s, s.d_planes[s.cur]);
+						t.bwd = plane_set(s, s.d_planes[1 - s.cur]);
+					} else {
+						t.cur = plane_set(s, s.d_planes[s.cur]);
+						t.fwd = plane_set(s, s.d_planes[1 - s.cur]);
+					}
+					s.d_last = t.cur.y;
 					t.mb_width = s.seq.mb_width;
 					t.mb_size = s.seq.mb_size;
 					t.coded_width = s.seq.coded_width;
@@ -796,12 +836,13 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 					steps[step].push_back(t);
 					step_streams[step].push_back(si);
 					step++;
-					s.cur ^= 1;  // mpeg1.js:221-246: the picture just decoded becomes `forward`
+					if (is_b) s.b_cur ^= 1;  // no reference: the I/P ping-pong stays as it is
+					else s.cur ^= 1;         // mpeg1.js:221-246: the picture just decoded becomes `forward`
 					b->stats.pictures_decoded++;
 					b->stats.coded_blocks += e.info.n_coded_blocks;
 					b->stats.macroblocks += e.info.n_present;
 					const uint64_t planes = (uint64_t)s.coded_size * 3 / 2;
-					b->stats.algorithmic_bytes += planes + (e.info.picture_type == 2 ? planes : 0) +
+					b->stats.algorithmic_bytes += planes + (e.info.picture_type == 2 ? planes : (is_b ? 2 * planes : 0)) +
 					                              (uint64_t)s.seq.mb_size * sizeof(mb_record_t) + (uint64_t)e.info.n_coded_blocks * 128;
 				}
 				release_slot(b, e.slot);  // reused by the NEXT round's parse, which waits for this round's reconstruction (ev_round)
@@ -814,7 +855,25 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 		for (auto &v : steps) total += v.size();
 		ensure_task_caps(b, 0, (int)total);
 		size_t off = 0;
-		for (auto &v : steps) { memcpy(b->h_rtasks + off, v.data(), v.size() * sizeof(ReconTask)); off += v.size(); }
+		std::vector<int> step_n_b(steps.size(), 0);
+		for (size_t f = 0; f < steps.size(); f++) {
+			auto &v = steps[f];
+			// the step's B pictures (extension) behind its I/P pictures: they take the two-reference kernel
+			int n_b = 0;
+			for (auto &t : v) n_b += t.bwd.y != nullptr;
+			if (n_b) {
+				std::vector<ReconTask> tv;
+				std::vector<int> sv;
+				for (int pass = 0; pass < 2; pass++)
+					for (size_t i = 0; i < v.size(); i++)
+						if ((v[i].bwd.y != nullptr) == (pass == 1)) { tv.push_back(v[i]); sv.push_back(step_streams[f][i]); }
+				v.swap(tv);
+				step_streams[f].swap(sv);
+			}
+			step_n_b[f] = n_b;
+			memcpy(b->h_rtasks + off, v.data(), v.size() * sizeof(ReconTask));
+			off += v.size();
+		}
 		CUDA_CHECK(cudaEventRecord(b->ev_rec0[rec_chunks], b->st_recon));
 		off = 0;
 		for (size_t f = 0; f < steps.size(); f++) {
@@ -823,9 +882,14 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			// (the copy stream is in order, so that covers every earlier one).
 			if ((flags & JSMPEG_B200_OUT_HOST) && b->copy_steps >= 2)
 				CUDA_CHECK(cudaStreamWaitEvent(b->st_recon, b->ev_copied[b->copy_steps & 1], 0));
-			if (flags & JSMPEG_B200_OUT_RGBA) launch_reconstruct_rgba(b->h_rtasks + off, (int)steps[f].size(), b->st_recon);  // conversion fused in
-			else launch_reconstruct(b->h_rtasks + off, (int)steps[f].size(), b->st_recon);
-			b->stats.kernel_launches += ((int)steps[f].size() + (flags & JSMPEG_B200_OUT_RGBA ? 59 : 79)) / (flags & JSMPEG_B200_OUT_RGBA ? 60 : 80);
+			const int n_ip = (int)steps[f].size() - step_n_b[f];
+			if (n_ip > 0) {
+				if (flags & JSMPEG_B200_OUT_RGBA) launch_reconstruct_rgba(b->h_rtasks + off, n_ip, b->st_recon);  // conversion fused in
+				else launch_reconstruct(b->h_rtasks + off, n_ip, b->st_recon);
+				b->stats.kernel_launches += (n_ip + (flags & JSMPEG_B200_OUT_RGBA ? 59 : 79)) / (flags & JSMPEG_B200_OUT_RGBA ? 60 : 80);
+			}
+			if (step_n_b[f] > 0)
+				b->stats.kernel_launches += launch_reconstruct_b(b->h_rtasks + off + n_ip, step_n_b[f], (flags & JSMPEG_B200_OUT_RGBA) != 0, b->st_recon);
 			b->stats.recon_launches++;
 			if (flags & JSMPEG_B200_OUT_HOST) copy_out_step(b, steps[f], step_streams[f]);  // while the next step reconstructs
 			off += steps[f].size();
@@ -913,6 +977,7 @@ jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigne
 	b->chunk_pictures = std::max(0, env_int("JSMPEG_B200_CHUNK", 0));
 	b->chunk_min_wave = std::max(1, env_int("JSMPEG_B200_CHUNK_MIN_WAVE", 256));
 	b->chunk_streams = std::min(std::max(1, env_int("JSMPEG_B200_CHUNK_STREAMS", 3)), 4);
+	b->decode_b = env_int("JSMPEG_B200_DECODE_B", 0) != 0;
 	try {
 		use_device(b);
 		CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
@@ -945,6 +1010,7 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 		if (s.d_es) cudaFree(s.d_es);
 		if (s.d_rgba) cudaFree(s.d_rgba);
 		for (auto p : s.d_planes) if (p) cudaFree(p);
+		for (auto p : s.d_planes_b) if (p) cudaFree(p);
 		for (auto p : s.h_planes) if (p) cudaFreeHost(p);
 	}
 	if (b->d_spans) cudaFree(b->d_spans);
@@ -987,6 +1053,12 @@ int jsmpeg_b200_batch_set_option(jsmpeg_b200_batch_t *b, const char *name, int v
 	if (!strcmp(name, "chunk_min_wave")) { b->chunk_min_wave = std::max(1, value); return 0; }
 	if (!strcmp(name, "chunk_streams")) { b->chunk_streams = std::min(std::max(1, value), 4); return 0; }
 	if (!strcmp(name, "lookahead")) { b->lookahead = std::max(1, value); return 0; }
+	if (!strcmp(name, "decode_b")) {
+		if (b->decode_b != (value != 0))
+			for (auto &st : b->streams) flush_cache(b, st);  // what was parsed ahead was parsed under the other rule
+		b->decode_b = value != 0;
+		return 0;
+	}
 	return -1;
 }
 
@@ -1052,9 +1124,14 @@ void jsmpeg_b200_batch_reset(jsmpeg_b200_batch_t *b) {
 			s.bb.length = 0;
 			s.bb.index = 0;
 			s.cur = 0;
+			s.b_cur = 0;
+			s.d_last = nullptr;
+			s.last_type = s.last_temporal = 0;
 			s.h_head = -1;
-			if (s.has_seq)
+			if (s.has_seq) {
 				for (auto p : s.d_planes) CUDA_CHECK(cudaMemsetAsync(p, 0, (size_t)s.coded_size * 3 / 2, b->st_main));
+				for (auto p : s.d_planes_b) if (p) CUDA_CHECK(cudaMemsetAsync(p, 0, (size_t)s.coded_size * 3 / 2, b->st_main));
+			}
 		}
 		CUDA_CHECK(cudaStreamSynchronize(b->st_main));
 	});
@@ -1067,7 +1144,8 @@ long jsmpeg_b200_batch_decode(jsmpeg_b200_batch_t *b, int n_pictures, int flags)
 int jsmpeg_b200_batch_get_planes(jsmpeg_b200_batch_t *b, int stream, void **y, void **cr, void **cb) {
 	const Stream &s = b->streams[stream];
 	if (!s.has_seq) return -1;
-	PlaneSet p = plane_set(s, s.d_planes[1 - s.cur]);  // most recent picture = forward (mpeg1.c:841-851)
+	// most recent picture = forward (mpeg1.c:841-851); with the B-picture extension it may be a B picture's own set
+	PlaneSet p = plane_set(s, s.d_last ? s.d_last : s.d_planes[1 - s.cur]);
 	if (y) *y = p.y;
 	if (cr) *cr = p.cr;
 	if (cb) *cb = p.cb;
@@ -1096,7 +1174,7 @@ int jsmpeg_b200_batch_read_planes(jsmpeg_b200_batch_t *b, int stream, void *y, v
 		use_device(b);
 		const Stream &s = b->streams[stream];
 		if (!s.has_seq) return -1;
-		PlaneSet p = plane_set(s, s.d_planes[1 - s.cur]);
+		PlaneSet p = plane_set(s, s.d_last ? s.d_last : s.d_planes[1 - s.cur]);
 		if (y) CUDA_CHECK(cudaMemcpy(y, p.y, s.coded_size, cudaMemcpyDeviceToHost));
 		if (cr) CUDA_CHECK(cudaMemcpy(cr, p.cr, s.coded_size >> 2, cudaMemcpyDeviceToHost));
 		if (cb) CUDA_CHECK(cudaMemcpy(cb, p.cb, s.coded_size >> 2, cudaMemcpyDeviceToHost));
@@ -1163,6 +1241,13 @@ int jsmpeg_b200_batch_read_rgba(jsmpeg_b200_batch_t *b, int stream, void *rgba) 
 		CUDA_CHECK(cudaMemcpy(rgba, s.d_rgba, (size_t)s.width * s.height * 4, cudaMemcpyDeviceToHost));
 		return 0;
 	});
+}
+
+int jsmpeg_b200_batch_last_picture(jsmpeg_b200_batch_t *b, int stream, int *picture_type, int *temporal_reference) {
+	const Stream &s = b->streams[stream];
+	if (picture_type) *picture_type = s.last_type;
+	if (temporal_reference) *temporal_reference = s.last_temporal;
+	return s.last_type ? 0 : -1;
 }
 
 void jsmpeg_b200_batch_get_stats(jsmpeg_b200_batch_t *b, jsmpeg_b200_stats_t *out) { *out = b->stats; }
@@ -1241,6 +1326,12 @@ void mpeg1_decoder_destroy(mpeg1_decoder_t *self) {
 }
 
 const char *jsmpeg_b200_decoder_last_error(mpeg1_decoder_t *self) { return self ? jsmpeg_b200_batch_last_error(self->b) : nullptr; }
+int jsmpeg_b200_decoder_set_option(mpeg1_decoder_t *self, const char *name, int value) {
+	return self ? jsmpeg_b200_batch_set_option(self->b, name, value) : -1;
+}
+int jsmpeg_b200_decoder_last_picture(mpeg1_decoder_t *self, int *picture_type, int *temporal_reference) {
+	return self ? jsmpeg_b200_batch_last_picture(self->b, 0, picture_type, temporal_reference) : -1;
+}
 
 void *mpeg1_decoder_get_write_ptr(mpeg1_decoder_t *self, unsigned int byte_size) {
 	return jsmpeg_b200_batch_get_write_ptr(self->b, 0, byte_size);

@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "walk.cuh"
+#include "walk_b.cuh"
 
 namespace {
 
@@ -66,6 +67,18 @@ constexpr uint32_t EXPAND_SMEM = EXP_OFF_TILES + CTA_THREADS * TILE_PITCH;
 	}
 WALK_KERNEL(walk_pictures_kernel, false, __launch_bounds__(WALK_THREADS))
 WALK_KERNEL(walk_pictures_lanes_kernel, true, LANES_BOUNDS)
+
+// B pictures (the opt-in extension, walk_b.cuh): the serial walk with the B-picture macroblock layer
+__global__ void __launch_bounds__(WALK_THREADS)
+walk_pictures_b_kernel(const ParseTask *__restrict__ tasks, int n_tasks, const uint4 *__restrict__ ms_table) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	walk_tables_init(smem, threadIdx.x, WALK_THREADS, ms_table, false);
+	__syncthreads();
+	const int task_id = blockIdx.x * (WALK_THREADS / 32) + (threadIdx.x >> 5);
+	if (task_id >= n_tasks) return;
+	const ParseTask t = tasks[task_id];
+	walk_picture_b(t, smem_base(smem), threadIdx.x & 31);
+}
 
 // ==================================================================================================
 // 1b: expand every coded block (one thread per block slot, grid.y = picture)
@@ -145,6 +158,8 @@ static const uint16_t *ms_table_for_current_device() {
 	                                (int)WALK_SMEM_SERIAL));  // per device, once
 	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                (int)WALK_SMEM_LANES));
+	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                (int)WALK_SMEM_SERIAL));
 	std::vector<uint16_t> dct((VLC_DCT_MAX_Z + 1) * 32);
 	CUDA_CHECK(cudaMemcpyFromSymbol(dct.data(), VLC_DCT_COEFF, dct.size() * sizeof(uint16_t)));
 	std::vector<uint16_t> ms(MS_TABLE_ENTRIES);
@@ -209,4 +224,15 @@ void launch_parse_pictures(const ParseTask *tasks, int n_tasks, int max_mb_size,
 			CUDA_CHECK(cudaStreamWaitEvent(stream, fork->join[g], 0));
 		}
 	}
+}
+
+// B pictures: one walk + one expand launch on `stream` (no size groups: B pictures are the small ones of a stream)
+void launch_parse_pictures_b(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream) {
+	if (n_tasks <= 0) return;
+	const uint16_t *ms = ms_table_for_current_device();
+	const int per_cta = WALK_THREADS / 32;
+	walk_pictures_b_kernel<<<(n_tasks + per_cta - 1) / per_cta, WALK_THREADS, WALK_SMEM_SERIAL, stream>>>(
+	    tasks, n_tasks, reinterpret_cast<const uint4 *>(ms));
+	dim3 grid((max_mb_size * 6 + CTA_THREADS * EXPAND_GROUPS - 1) / (CTA_THREADS * EXPAND_GROUPS), n_tasks);
+	expand_blocks_kernel<<<grid, CTA_THREADS, EXPAND_SMEM, stream>>>(tasks);
 }

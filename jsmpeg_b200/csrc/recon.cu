@@ -60,6 +60,27 @@ reconstruct_rgba_kernel(const __grid_constant__ ReconRgbaParams params) {
 	reconstruct_rgba_block(params.p, params.out[blockIdx.z], blockIdx.z, blockIdx.y, blockIdx.x * RGBA_MBS, threadIdx.x, stage, chroma);
 }
 
+// B pictures (the opt-in extension): the same two kernels instantiated for two references
+__global__ void __launch_bounds__(THREADS, JSMPEG_RECON_MIN_CTAS)
+reconstruct_b_kernel(const __grid_constant__ ReconParamsB params) {
+	__shared__ __align__(16) uint8_t stage[(THREADS / 32) * WARP_STAGE];
+	reconstruct_block<true>(params, blockIdx.y, blockIdx.x * THREADS, threadIdx.x, stage);
+}
+
+constexpr int MAX_TASKS_RGBA_B = 48;  // (48 * (56 + 16) B) + 16 < 4 KB
+struct ReconRgbaParamsB {
+	struct { CompactTaskB t[MAX_TASKS_RGBA_B]; int32_t n_tasks; } p;
+	RgbaTarget out[MAX_TASKS_RGBA_B];
+};
+static_assert(sizeof(ReconParamsB) <= 4096 && sizeof(ReconRgbaParamsB) <= 4096, "kernel parameters");
+
+__global__ void __launch_bounds__(RGBA_THREADS)
+reconstruct_rgba_b_kernel(const __grid_constant__ ReconRgbaParamsB params) {
+	__shared__ __align__(16) uint8_t stage[(RGBA_THREADS / 32) * WARP_STAGE];
+	__shared__ __align__(16) uint8_t chroma[2][8][RGBA_MBS * 8];
+	reconstruct_rgba_block<true>(params.p, params.out[blockIdx.z], blockIdx.z, blockIdx.y, blockIdx.x * RGBA_MBS, threadIdx.x, stage, chroma);
+}
+
 void fill_task(CompactTask &c, const ReconTask &t) {
 	c.hdr = t.hdr;
 	c.coef = t.coef;
@@ -106,4 +127,43 @@ void launch_reconstruct_rgba(const ReconTask *tasks_host, int n_tasks, cudaStrea
 		dim3 grid((max_w + RGBA_MBS - 1) / RGBA_MBS, max_h, n);
 		reconstruct_rgba_kernel<<<grid, RGBA_THREADS, 0, stream>>>(p);
 	}
+}
+
+int launch_reconstruct_b(const ReconTask *tasks_host, int n_tasks, bool rgba, cudaStream_t stream) {
+	int launches = 0;
+	const int per = rgba ? MAX_TASKS_RGBA_B : MAX_TASKS_B;
+	for (int first = 0; first < n_tasks; first += per, launches++) {
+		const int n = n_tasks - first < per ? n_tasks - first : per;
+		int max_slots = 0, max_w = 0, max_h = 0;
+		for (int i = 0; i < n; i++) {
+			const ReconTask &t = tasks_host[first + i];
+			max_slots = max_slots > t.mb_size * 6 ? max_slots : t.mb_size * 6;
+			max_w = max_w > t.mb_width ? max_w : t.mb_width;
+			const int h = t.mb_size / t.mb_width;
+			max_h = max_h > h ? max_h : h;
+		}
+		if (rgba) {
+			ReconRgbaParamsB p;
+			for (int i = 0; i < n; i++) {
+				const ReconTask &t = tasks_host[first + i];
+				fill_task(p.p.t[i], t);
+				p.p.t[i].bwd = t.bwd.y;
+				p.out[i] = RgbaTarget{t.rgba, t.width, t.height};
+			}
+			p.p.n_tasks = n;
+			dim3 grid((max_w + RGBA_MBS - 1) / RGBA_MBS, max_h, n);
+			reconstruct_rgba_b_kernel<<<grid, RGBA_THREADS, 0, stream>>>(p);
+		} else {
+			ReconParamsB p;
+			for (int i = 0; i < n; i++) {
+				const ReconTask &t = tasks_host[first + i];
+				fill_task(p.t[i], t);
+				p.t[i].bwd = t.bwd.y;
+			}
+			p.n_tasks = n;
+			dim3 grid((max_slots + THREADS - 1) / THREADS, n);
+			reconstruct_b_kernel<<<grid, THREADS, 0, stream>>>(p);
+		}
+	}
+	return launches;
 }

@@ -34,6 +34,17 @@ struct ReconParamsT {
 };
 using ReconParams = ReconParamsT<MAX_TASKS>;
 
+// B pictures (the opt-in extension; the reference skips them, mpeg1.js:181-184): a second reference.
+// fwd = the older, bwd = the newer of the stream's two most recent I/P pictures.
+struct CompactTaskB : CompactTask {
+	const uint8_t *bwd;
+};
+constexpr int MAX_TASKS_B = 64;  // (64 * 56 B) + 16 < 4 KB of kernel parameters
+struct ReconParamsB {
+	CompactTaskB t[MAX_TASKS_B];
+	int32_t n_tasks;
+};
+
 #ifndef JSMPEG_WALK_EMU
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t umulhi_u32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
@@ -195,6 +206,84 @@ __device__ __forceinline__ void predict_rows(const uint8_t *__restrict__ splane,
 	}
 }
 
+// ---- B pictures: prediction from two references (ISO 11172-2 2.4.4.3) ------------------------------------------
+// per byte (a + b + 1) >> 1: the "//" of the standard on samples (halves rounded up)
+__device__ __forceinline__ uint32_t avg_round_u8x4(uint32_t a, uint32_t b) {
+#ifndef JSMPEG_WALK_EMU
+	return __vavgu4(a, b);
+#else
+	uint32_t r = 0;
+	for (int i = 0; i < 4; i++) r |= ((((a >> (8 * i)) & 255u) + ((b >> (8 * i)) & 255u) + 1u) >> 1) << (8 * i);
+	return r;
+#endif
+}
+
+// One row of 8 predicted samples (packed) from rows a (this row) and c (the next one) of one reference with the
+// lane's tap weights -- the formula of predict_rows, without residual: (wA*A + wB*B + wC*C + wD*D + 2) >> 2.
+__device__ __forceinline__ uint2 predict_row_packed(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                    uint32_t weights) {
+	const uint32_t sa0 = __funnelshift_r(a0, a1, 8), sa1 = __funnelshift_r(a1, a2, 8);
+	const uint32_t sc0 = __funnelshift_r(c0, c1, 8), sc1 = __funnelshift_r(c1, c2, 8);
+	int s[8];
+	s[0] = dp4a_us(__byte_perm(a0, c0, 0x5410), weights, 2);
+	s[1] = dp4a_us(__byte_perm(a0, c0, 0x6521), weights, 2);
+	s[2] = dp4a_us(__byte_perm(a0, c0, 0x7632), weights, 2);
+	s[3] = dp4a_us(__byte_perm(sa0, sc0, 0x7632), weights, 2);
+	s[4] = dp4a_us(__byte_perm(a1, c1, 0x5410), weights, 2);
+	s[5] = dp4a_us(__byte_perm(a1, c1, 0x6521), weights, 2);
+	s[6] = dp4a_us(__byte_perm(a1, c1, 0x7632), weights, 2);
+	s[7] = dp4a_us(__byte_perm(sa1, sc1, 0x7632), weights, 2);
+	uint2 out;  // (sums of at most four bytes + 2) >> 2 fit a byte: plain packing
+	out.x = (uint32_t)(s[0] >> 2) | (uint32_t)(s[1] >> 2) << 8 | (uint32_t)(s[2] >> 2) << 16 | (uint32_t)(s[3] >> 2) << 24;
+	out.y = (uint32_t)(s[4] >> 2) | (uint32_t)(s[5] >> 2) << 8 | (uint32_t)(s[6] >> 2) << 16 | (uint32_t)(s[7] >> 2) << 24;
+	return out;
+}
+
+// The 8 rows of one block of a B picture: forward and / or backward prediction (each rounded on its own, like
+// copyMacroblock, mpeg1.js:481-556), their rounded average when both are used, + residual, saturate, store.
+// A direction that is not used is read at the block's own position (in bounds) and ignored.
+template <bool KEEP>
+__device__ __forceinline__ void predict_rows_b(const uint8_t *__restrict__ fplane, int fsrc, uint32_t fweights, bool use_f,
+                                               const uint8_t *__restrict__ bplane, int bsrc, uint32_t bweights, bool use_b,
+                                               int stride, const int (&v)[64], uint8_t *__restrict__ dst, uint2 (&rows)[8]) {
+	uint32_t f0, f1, f2, b0, b1, b2;
+	row9(fplane, fsrc, f0, f1, f2);
+	row9(bplane, bsrc, b0, b1, b2);
+#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		uint32_t g0, g1, g2, c0, c1, c2;
+		row9(fplane, fsrc + (r + 1) * stride, g0, g1, g2);  // row 8 is inside the allocation (checked by the caller / the pad)
+		row9(bplane, bsrc + (r + 1) * stride, c0, c1, c2);
+		const uint2 pf = predict_row_packed(f0, f1, f2, g0, g1, g2, fweights);
+		const uint2 pb = predict_row_packed(b0, b1, b2, c0, c1, c2, bweights);
+		uint2 p;
+		p.x = use_f ? (use_b ? avg_round_u8x4(pf.x, pb.x) : pf.x) : pb.x;
+		p.y = use_f ? (use_b ? avg_round_u8x4(pf.y, pb.y) : pf.y) : pb.y;
+		uint2 out;
+		out.x = add_sat4(p.x, v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
+		out.y = add_sat4(p.y, v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+		*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+		if (KEEP) rows[r] = out;
+		f0 = g0; f1 = g1; f2 = g2;
+		b0 = c0; b1 = c1; b2 = c2;
+	}
+}
+
+// one predicted sample by flat index with per-tap bounds check: any tap outside the plane zeroes it
+__device__ __forceinline__ int tap_px(const uint8_t *__restrict__ plane, int i, int stride, bool oh, bool ov, int plane_size) {
+	const int taps[4] = {i, i + 1, i + stride, i + stride + 1};
+	const bool use[4] = {true, oh, ov, oh && ov};
+	int sum = 0, n = 0;
+	bool in = true;
+	for (int k = 0; k < 4; k++) {
+		if (!use[k]) continue;
+		if (taps[k] < 0 || taps[k] >= plane_size) { in = false; continue; }
+		sum += plane[taps[k]];
+		n++;
+	}
+	return !in ? 0 : (n == 4 ? (sum + 2) >> 2 : (n == 2 ? (sum + 1) >> 1 : sum));
+}
+
 #ifndef JSMPEG_WALK_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 #else
@@ -218,10 +307,12 @@ static inline uint32_t smem_u32(const void *) { return 0; }
 // block (mb_row, mb_col, b) of picture `ty`; the 32 lanes of the warp call it together, wstage = the warp's staging
 // area.  KEEP: the block's eight packed output rows come back in `rows` (also for a macroblock that is not present:
 // the samples it keeps).
-template <bool KEEP, class PARAMS>
+// BIDIR (B pictures, PARAMS = ReconParamsB): the record's MBF_MOTION_* bits say which of t.fwd / t.bwd a predicted
+// block uses; everything up to the prediction is the same code.
+template <bool KEEP, bool BIDIR = false, class PARAMS>
 __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int mb_row, int mb_col, int b, bool in_picture,
                                                int lane, uint8_t *wstage, uint2 (&rows)[8]) {
-	const CompactTask &t = params.t[ty];
+	const auto &t = params.t[ty];
 	const int W = t.mb_width;
 	const int mb = mb_row * W + mb_col;
 
@@ -251,9 +342,18 @@ __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int
 #endif
 	};
 	uint2 rec = make_uint2(0, 0);
-	if (in_picture) rec = __ldg(reinterpret_cast<const uint2 *>(t.hdr + mb));
+	uint32_t rec_bwd = 0;  // BIDIR: the backward vector (mb_record_t::mv_bwd)
+	if constexpr (BIDIR) {
+		if (in_picture) {
+			const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(t.hdr + mb));
+			rec = make_uint2(r4.x, r4.y);
+			rec_bwd = r4.w;
+		}
+	} else {
+		if (in_picture) rec = __ldg(reinterpret_cast<const uint2 *>(t.hdr + mb));
+	}
 	if (ty + 2 < params.n_tasks) {  // the CTA that runs on this SM next but one: its header and record, into L2
-		const CompactTask &t2 = params.t[ty + 2];
+		const auto &t2 = params.t[ty + 2];
 		if (in_picture && mb < t2.mb_width * t2.mb_height) {
 			prefetch_l2(t2.hdr + mb);
 			prefetch_l2(t2.coef + ((size_t)mb * 6 + b) * 64);
@@ -295,7 +395,25 @@ __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int
 	// rest of the last word, row 8 of a lane without a vertical half -- is inside the allocation: planes
 	// are contiguous and followed by coded_width + 64 readable bytes.)
 	const bool inside = src >= 0 && src + 7 * stride + 7 + (ov ? stride : 0) + (oh ? 1 : 0) < plane_size;
-	if (present && !intra && inside) {  // t1: the reference rows, into L2, while the records travel and the IDCT runs
+	// BIDIR: which references the block uses (a record with neither bit predicts forward, like the oracle), and the
+	// same geometry for the backward one
+	const bool use_b = BIDIR && (flags & MBF_MOTION_BWD);
+	const bool use_f = !use_b || (flags & MBF_MOTION_FWD);
+	int src_b = origin;
+	bool ohb = false, ovb = false, inside_b = true;
+	if constexpr (BIDIR) {
+		int bh = (int)(int16_t)(rec_bwd & 0xffffu), bv = (int)(int16_t)(rec_bwd >> 16);
+		if (b >= 4) { bh /= 2; bv /= 2; }
+		if (!use_b) bh = bv = 0;
+		ohb = bh & 1; ovb = bv & 1;
+		src_b = origin + (bv >> 1) * stride + (bh >> 1);
+		inside_b = src_b >= 0 && src_b + 7 * stride + 7 + (ovb ? stride : 0) + (ohb ? 1 : 0) < plane_size;
+		if (present && !intra && use_b && inside_b) {
+#pragma unroll
+			for (int r = 0; r < 9; r++) prefetch_l2(t.bwd + plane_off + src_b + r * stride + 4);
+		}
+	}
+	if (present && !intra && inside && (!BIDIR || use_f)) {  // t1: the reference rows, into L2, while the records travel and the IDCT runs
 		// (Sharing the rows out among the lanes -- lane l asks for row l & 7 of its own block, two instructions
 		// instead of nine -- was measured: 12.03 ms per 60 launches against 11.87, the neighbours' vectors differ too often.)
 #pragma unroll
@@ -382,6 +500,43 @@ __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int
 		return;
 	}
 
+	if constexpr (BIDIR) {
+		// ---- B picture: forward and / or backward prediction (+ their rounded average) + residual
+		const uint8_t *bplane = t.bwd + plane_off;
+		const int fsrc = use_f ? src : origin;  // (an unused direction is read at the block's own position and ignored)
+		if ((!use_f || inside) && (!use_b || inside_b)) {
+			const uint32_t fw = (use_f && oh) ? (ov ? 0x01010101u : 0x00000202u) : ((use_f && ov) ? 0x00020002u : 0x00000004u);
+			const uint32_t bw = ohb ? (ovb ? 0x01010101u : 0x00000202u) : (ovb ? 0x00020002u : 0x00000004u);
+			predict_rows_b<KEEP>(splane, fsrc, fw, use_f, bplane, src_b, bw, use_b, stride, v, dst, rows);
+			return;
+		}
+		// a vector leaves its plane: per-tap bounds check, any outside tap zeroes that prediction's sample
+#pragma unroll 1
+		for (int r = 0; r < 8; r++) {
+			uint32_t p[2] = {0, 0};
+			for (int x = 0; x < 8; x++) {
+				const int pf = use_f ? tap_px(splane, src + r * stride + x, stride, oh, ov, plane_size) : 0;
+				const int pb = use_b ? tap_px(bplane, src_b + r * stride + x, stride, ohb, ovb, plane_size) : 0;
+				const int px = (use_f && use_b) ? (pf + pb + 1) >> 1 : (use_b ? pb : pf);
+				p[x >> 2] |= (uint32_t)px << (8 * (x & 3));
+			}
+			int rr[8];
+#pragma unroll
+			for (int x = 0; x < 8; x++) {
+				int acc = 0;
+#pragma unroll
+				for (int q = 0; q < 8; q++) acc = (q == r) ? v[q * 8 + x] : acc;
+				rr[x] = acc;
+			}
+			uint2 out;
+			out.x = add_sat4(p[0], rr[0], rr[1], rr[2], rr[3]);
+			out.y = add_sat4(p[1], rr[4], rr[5], rr[6], rr[7]);
+			*reinterpret_cast<uint2 *>(dst + r * stride) = out;
+		}
+		if (KEEP) reload_rows();
+		return;
+	}
+
 	// ---- prediction from the forward picture + residual
 	if (inside) {
 		// tap weights of this lane: bytes (wA, wB, wC, wD)
@@ -433,8 +588,9 @@ __device__ __forceinline__ void reconstruct_at(const PARAMS &params, int ty, int
 // The plain kernel's numbering: slot first_slot + tid of picture `ty`; `stage` = the CTA's staging area (one
 // WARP_STAGE per warp).  The 32 lanes of a warp hold 32 horizontally adjacent blocks of one plane row:
 // [luma top 2W | luma bottom 2W | Cb W | Cr W] per macroblock row.
-__device__ __forceinline__ void reconstruct_block(const ReconParams &params, int ty, int first_slot, int tid, uint8_t *stage) {
-	const CompactTask &t = params.t[ty];
+template <bool BIDIR = false, class PARAMS>
+__device__ __forceinline__ void reconstruct_block(const PARAMS &params, int ty, int first_slot, int tid, uint8_t *stage) {
+	const auto &t = params.t[ty];
 	const int W = t.mb_width;
 	const int slots_per_row = 6 * W;
 	const int slot = first_slot + tid;
@@ -454,7 +610,7 @@ __device__ __forceinline__ void reconstruct_block(const ReconParams &params, int
 		b = 4 + second;  // block 4 -> Cb plane, block 5 -> Cr plane (mpeg1.js:829-834)
 	}
 	uint2 unused[8];
-	reconstruct_at<false>(params, ty, mb_row, mb_col, b, in_picture, tid & 31, stage + (tid >> 5) * WARP_STAGE, unused);
+	reconstruct_at<false, BIDIR>(params, ty, mb_row, mb_col, b, in_picture, tid & 31, stage + (tid >> 5) * WARP_STAGE, unused);
 }
 
 #ifndef JSMPEG_WALK_EMU  // (a CTA-wide barrier: outside what the one-warp host emulation runs)
@@ -481,10 +637,10 @@ __device__ __forceinline__ uint32_t rgba_px(int y, int r, int g, int b) {
 	return c(y + r) | (c(y - g) << 8) | (c(y + b) << 16) | 0xff000000u;
 }
 
-template <class PARAMS>
+template <bool BIDIR = false, class PARAMS>
 __device__ __forceinline__ void reconstruct_rgba_block(const PARAMS &params, const RgbaTarget &out, int ty, int mb_row, int first_mb_col,
                                                        int tid, uint8_t *stage, uint8_t (*chroma)[8][RGBA_MBS * 8]) {
-	const CompactTask &t = params.t[ty];
+	const auto &t = params.t[ty];
 	const int warp = tid >> 5, lane = tid & 31;
 	int b, local;  // local = macroblock within the CTA's 16
 	if (warp < 2) { b = warp * 2 + (lane & 1); local = lane >> 1; }
@@ -494,7 +650,7 @@ __device__ __forceinline__ void reconstruct_rgba_block(const PARAMS &params, con
 	uint2 rows[8];
 #pragma unroll
 	for (int r = 0; r < 8; r++) rows[r] = make_uint2(0u, 0u);
-	reconstruct_at<true>(params, ty, mb_row, in_picture ? mb_col : 0, b, in_picture, lane, stage + warp * WARP_STAGE, rows);
+	reconstruct_at<true, BIDIR>(params, ty, mb_row, in_picture ? mb_col : 0, b, in_picture, lane, stage + warp * WARP_STAGE, rows);
 	if (warp == 2) {
 		// plane 0 = Cb (block 4), plane 1 = Cr (block 5)
 #pragma unroll

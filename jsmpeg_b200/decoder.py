@@ -4,7 +4,9 @@
 (reference src/decoder.js:3-106, src/mpeg1.js:6-64, src/mpeg1-wasm.js:1-132):
 
     ctor(options)  keys: videoBufferSize, streaming, decodeFirstFrame, onVideoDecode
-                   (+ our extension `device`: CUDA device index)
+                   (+ our extensions `device`: CUDA device index; `decodeBPictures`: decode B pictures, which
+                   the reference skips (src/mpeg1.js:181-184), in coded order -- `lastPicture()` tells type and
+                   temporal_reference)
     connect(destination) / destroy()
     bufferGetIndex() / bufferSetIndex(i) / bufferWrite(buffers)
     write(pts, buffers) / seek(time) / decode() -> bool
@@ -63,6 +65,10 @@ class MPEG1Video:
             if err:
                 self.destroy()
                 raise RuntimeError(err.decode(errors="replace"))
+        if options.get("decodeBPictures"):
+            if not hasattr(self.functions, "jsmpeg_b200_decoder_set_option"):
+                raise ValueError("decodeBPictures: this library has no B-picture extension")
+            self.functions.jsmpeg_b200_decoder_set_option(self.decoder, b"decode_b", 1)
 
     # ---- src/decoder.js:19-35 / src/mpeg1-wasm.js:32-50
     def destroy(self):
@@ -145,6 +151,13 @@ class MPEG1Video:
         if self.onDecodeCallback:
             self.onDecodeCallback(self, (time.perf_counter() - t0) * 1000.0)
         return True
+
+    def lastPicture(self):
+        """(picture_coding_type, temporal_reference) of the picture the last decode() consumed (extension)."""
+        t, r = ctypes.c_int(), ctypes.c_int()
+        if self.functions.jsmpeg_b200_decoder_last_picture(self.decoder, ctypes.byref(t), ctypes.byref(r)) != 0:
+            return None
+        return t.value, r.value
 
     def planes(self):
         """Zero-copy views of the most recently decoded picture (borrowed; valid until the next

@@ -585,7 +585,11 @@ typedef struct mpeg1_decoder_t {
 	int width, height, coded_width, coded_height, coded_size;
 	seq_params_t seq;
 	planes_t current, forward;
-	planes_t bout;     /* B-picture extension: where a B picture is reconstructed (it is no reference) */
+	/* B-picture extension: where B pictures are reconstructed (they are no references) -- two sets written in
+	 * turn, like the product's (its copy-out of one B picture overlaps the reconstruction of the next): a
+	 * macroblock no slice covers keeps what the B picture before the previous one left there */
+	planes_t bout[2];
+	int b_cur;
 	bool last_was_b;
 	mb_record_t *hdr; int16_t *coef;
 	picture_info_t last;
@@ -601,7 +605,7 @@ mpeg1_decoder_t *mpeg1_decoder_create(unsigned int buffer_size, int mode) {
 
 void mpeg1_decoder_destroy(mpeg1_decoder_t *d) {
 	free(d->bytes);
-	if (d->has_sequence_header) { free_planes(&d->current); free_planes(&d->forward); free_planes(&d->bout); free(d->hdr); free(d->coef); }
+	if (d->has_sequence_header) { free_planes(&d->current); free_planes(&d->forward); free_planes(&d->bout[0]); free_planes(&d->bout[1]); free(d->hdr); free(d->coef); }
 	free(d);
 }
 
@@ -652,7 +656,8 @@ static void parse_sequence_header(mpeg1_decoder_t *d, bits_t *b) {
 	d->coded_size = d->coded_width * d->coded_height;
 	d->current = alloc_planes(d->coded_size);
 	d->forward = alloc_planes(d->coded_size);
-	d->bout = alloc_planes(d->coded_size);
+	d->bout[0] = alloc_planes(d->coded_size);
+	d->bout[1] = alloc_planes(d->coded_size);
 	d->hdr = (mb_record_t *)calloc(d->seq.mb_size, sizeof(mb_record_t));
 	d->coef = (int16_t *)calloc((size_t)d->seq.mb_size * MB_COEF_INT16, sizeof(int16_t));
 	d->has_sequence_header = true;
@@ -674,9 +679,9 @@ int mpeg1_decoder_get_coded_size(mpeg1_decoder_t *d) { return d->coded_size; }
 int mpeg1_decoder_get_width(mpeg1_decoder_t *d) { return d->width; }
 int mpeg1_decoder_get_height(mpeg1_decoder_t *d) { return d->height; }
 /* most recently decoded picture = forward after the swap (mpeg1.c:841-851) */
-void *mpeg1_decoder_get_y_ptr(mpeg1_decoder_t *d) { return d->last_was_b ? d->bout.y : d->forward.y; }
-void *mpeg1_decoder_get_cr_ptr(mpeg1_decoder_t *d) { return d->last_was_b ? d->bout.cr : d->forward.cr; }
-void *mpeg1_decoder_get_cb_ptr(mpeg1_decoder_t *d) { return d->last_was_b ? d->bout.cb : d->forward.cb; }
+void *mpeg1_decoder_get_y_ptr(mpeg1_decoder_t *d) { return d->last_was_b ? d->bout[d->b_cur ^ 1].y : d->forward.y; }
+void *mpeg1_decoder_get_cr_ptr(mpeg1_decoder_t *d) { return d->last_was_b ? d->bout[d->b_cur ^ 1].cr : d->forward.cr; }
+void *mpeg1_decoder_get_cb_ptr(mpeg1_decoder_t *d) { return d->last_was_b ? d->bout[d->b_cur ^ 1].cb : d->forward.cb; }
 
 /* mpeg1.c:853-864 + decode_picture :947-995 */
 bool mpeg1_decoder_decode(mpeg1_decoder_t *d) {
@@ -692,7 +697,8 @@ bool mpeg1_decoder_decode(mpeg1_decoder_t *d) {
 		/* extension: after the swaps `current` holds the older and `forward` the newer of the two most recent
 		 * I/P pictures = the B picture's forward (past) and backward (future) reference.  Pictures leave in
 		 * CODED order; no swap, a B picture is never a reference. */
-		oracle_reconstruct_b(&d->seq, d->coded_width, d->coded_height, d->hdr, d->coef, &d->current, &d->forward, &d->bout);
+		oracle_reconstruct_b(&d->seq, d->coded_width, d->coded_height, d->hdr, d->coef, &d->current, &d->forward, &d->bout[d->b_cur]);
+		d->b_cur ^= 1;
 		d->last_was_b = true;
 	} else if (d->last.status == PIC_DECODED) {
 		oracle_reconstruct(&d->seq, d->coded_width, d->coded_height, d->hdr, d->coef, &d->forward, &d->current);

@@ -117,6 +117,7 @@ extern "C" void emu_vote_counters(uint64_t *trips, uint64_t *lanes, int reset) {
 
 #define VLC_TABLE_QUALIFIER static const
 #include "../../jsmpeg_b200/csrc/walk.cuh"
+#include "../../jsmpeg_b200/csrc/walk_b.cuh"
 #include "../../jsmpeg_b200/csrc/recon.cuh"
 
 // Runs `body(lane)` as the 32 lanes of one warp.  Every collective is executed by all 32 lanes (the
@@ -207,6 +208,23 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 	return 0;
 }
 
+// The B-picture walk (jsmpeg_b200/csrc/walk_b.cuh, the opt-in extension): one warp, all lanes on one chain.
+extern "C" int emu_walk_picture_b(const uint8_t *es, uint32_t es_len, uint32_t start_byte, int mb_width, int mb_height,
+                                  mb_record_t *hdr, uint2 *park, picture_info_t *info) {
+	static std::once_flag once;
+	static std::vector<uint16_t> ms(MS_TABLE_ENTRIES);
+	std::call_once(once, [] {
+		build_ms_table(VLC_DCT_COEFF, ms.data());
+		walk_tables_init(emu_smem, 0, 1, reinterpret_cast<const uint4 *>(ms.data()), true);
+	});
+	static ParseTask task;
+	memset(&task, 0, sizeof(task));
+	task.es = es; task.es_len = es_len; task.start_byte = start_byte; task.hdr = hdr; task.info = info;
+	task.park = park; task.mb_width = mb_width; task.mb_size = mb_width * mb_height;
+	run_warp([](int l) { walk_picture_b(task, 0, l); });
+	return 0;
+}
+
 // Stage 1b on the records the walk left: every block slot of the picture through expand_block
 // (jsmpeg_b200/csrc/walk.cuh), one "thread" after the other with its own zeroed tile.
 extern "C" int emu_expand_picture(const uint8_t *es, uint32_t es_len, int mb_width, int mb_height,
@@ -256,6 +274,23 @@ extern "C" int emu_reconstruct_picture(const mb_record_t *hdr, const int16_t *co
 	const int slots = mb_width * mb_height * 6;
 	for (first_slot = 0; first_slot < slots; first_slot += 32)
 		run_warp([](int l) { reconstruct_block(params, 0, first_slot, l, wstage); });
+	return 0;
+}
+
+// Stage 2 of a B picture (reconstruct_block<true>): fwd = the older, bwd = the newer reference.
+extern "C" int emu_reconstruct_picture_b(const mb_record_t *hdr, const int16_t *coef, uint8_t *cur, const uint8_t *fwd,
+                                         const uint8_t *bwd, int mb_width, int mb_height) {
+	static ReconParamsB params;
+	static int first_slot;
+	static uint8_t wstage[WARP_STAGE];
+	CompactTaskB &task = params.t[0];
+	task.hdr = hdr; task.coef = coef; task.cur = cur; task.fwd = fwd; task.bwd = bwd; task.mb_width = mb_width; task.mb_height = mb_height;
+	task.row_magic = (uint32_t)(0x100000000ull / (uint64_t)(6 * mb_width)) + 1u;
+	task.flags = 0;
+	params.n_tasks = 1;
+	const int slots = mb_width * mb_height * 6;
+	for (first_slot = 0; first_slot < slots; first_slot += 32)
+		run_warp([](int l) { reconstruct_block<true>(params, 0, first_slot, l, wstage); });
 	return 0;
 }
 

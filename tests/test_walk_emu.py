@@ -26,7 +26,7 @@ CSRC = os.path.join(HERE, "..", "jsmpeg_b200", "csrc")
 def emu_lib(define=None):
     """The emulation library; `define` builds a variant with -D<define>."""
     out = EMU_LIB if define is None else EMU_LIB.replace(".so", "_" + define.lower() + ".so")
-    deps = [EMU_SRC] + [os.path.join(CSRC, f) for f in ("walk.cuh", "recon.cuh", "common.cuh", "records.h", "vlc_tables.h")]
+    deps = [EMU_SRC] + [os.path.join(CSRC, f) for f in ("walk.cuh", "walk_b.cuh", "recon.cuh", "common.cuh", "records.h", "vlc_tables.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         tmp = out + ".%d.tmp" % os.getpid()
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-attributes", "-Wno-unknown-pragmas",
