@@ -9,9 +9,10 @@ The reference skips B pictures (src/mpeg1.js:181-184), so there is nothing to ru
     on the syntax-level generator's B cases (tools/synth_es.py: all macroblock types of table B.2d, skipped
     runs, both f_codes, full-pel vectors, several slices);
   * with the extension off, oracle and product treat a B picture exactly as before (consumed, nothing decoded).
-The GPU twin is tests/test_gpu_b_pictures.py.
+The GPU twin is tests/test_gpu_zz_b_pictures.py.
 """
 import ctypes
+import functools
 import os
 
 import numpy as np
@@ -57,7 +58,9 @@ def oracle_b():
     lib.oracle_set_decode_b(0)
 
 
+@functools.lru_cache(maxsize=None)
 def natural_clip(width=176, height=144, frames=13, b_frames=2, seed=1234):
+    """(ES bytes, picture types in coded order, display index per coded picture, macroblock statistics)."""
     import mini_enc
     return mini_enc.make_b_clip(width, height, frames, b_frames, seed)
 
@@ -194,6 +197,16 @@ def test_b_device_code_matches_the_oracle_on_a_natural_clip(oracle_b):
     es, types, order, stats = natural_clip()
     checked, n_b = _emulated_b_pipeline(es, "mini_enc 176x144")
     assert checked == len(types) and n_b == types.count(3)
+
+
+FIXTURE_720P = os.path.join(HERE, "fixtures", "b_clip_1280x720.m1v")  # tools/mini_enc.py: make_b_clip(1280, 720, 13, 2, seed=1234)
+
+
+def test_b_device_code_matches_the_oracle_at_720p(oracle_b):
+    """The committed 1280x720 I/P/B clip (the one tools/time_b.py times on the GPU): 13 pictures, 8 of them B."""
+    es = open(FIXTURE_720P, "rb").read()
+    checked, n_b = _emulated_b_pipeline(es, "fixture 720p")
+    assert (checked, n_b) == (13, 8)
 
 
 def test_b_walk_on_damaged_streams_matches_the_oracle(oracle_b):
