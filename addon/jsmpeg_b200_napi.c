@@ -104,6 +104,28 @@ static napi_value js_decode(napi_env env, napi_callback_info info) {
 	return out;
 }
 
+/* Extension (not in the reference, which skips B pictures -- src/mpeg1.js:181-184): setDecodeB(decoder, on)
+ * switches the B-picture decode on; lastPictureType(decoder) = picture_coding_type of the picture the last
+ * decode() consumed (1 I, 2 P, 3 B), so that a player can put pictures into display order. */
+static napi_value js_set_decode_b(napi_env env, napi_callback_info info) {
+	napi_value argv[2];
+	uint32_t on = 0;
+	mpeg1_decoder_t *d = decoder_arg(env, info, 2, argv);
+	if (!d) return NULL;
+	napi_get_value_uint32(env, argv[1], &on);
+	jsmpeg_b200_decoder_set_option(d, "decode_b", (int)on);
+	return NULL;
+}
+static napi_value js_last_picture_type(napi_env env, napi_callback_info info) {
+	napi_value argv[1], out;
+	int type = 0;
+	mpeg1_decoder_t *d = decoder_arg(env, info, 1, argv);
+	if (!d) return NULL;
+	jsmpeg_b200_decoder_last_picture(d, &type, NULL);
+	NAPI_OK(napi_create_int32(env, type, &out));
+	return out;
+}
+
 /* planes(decoder) -> {y, cr, cb}: zero-copy Uint8Arrays over the pinned host planes of the most
  * recently decoded picture; valid until the next decode() (src/mpeg1-wasm.js:110-118). */
 static napi_value plane_view(napi_env env, void *ptr, size_t n) {
@@ -132,6 +154,7 @@ static napi_value init(napi_env env, napi_value exports) {
 		{"hasSequenceHeader", js_has_sequence_header}, {"getFrameRate", js_get_frame_rate},
 		{"getCodedSize", js_get_coded_size}, {"getWidth", js_get_width}, {"getHeight", js_get_height},
 		{"decode", js_decode}, {"planes", js_planes},
+		{"setDecodeB", js_set_decode_b}, {"lastPictureType", js_last_picture_type},
 	};
 	for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); i++) {
 		napi_value fn;

@@ -18,6 +18,9 @@ var MPEG1B200 = function(options) {
 	var bufferSize = options.videoBufferSize || 512*1024;
 	var bufferMode = options.streaming ? 1 /* EVICT */ : 2 /* EXPAND */;
 	this.decoder = native.create(bufferSize, bufferMode);
+	// extension: decode B pictures (the reference skips them, src/mpeg1.js:181-184); pictures then arrive in
+	// CODED order, native.lastPictureType(this.decoder) tells a renderer which ones to hold back
+	if (options.decodeBPictures) { native.setDecodeB(this.decoder, 1); }
 	this.decodeFirstFrame = options.decodeFirstFrame !== false;
 	this.hasSequenceHeader = false;
 };
