@@ -209,6 +209,22 @@ def test_b_device_code_matches_the_oracle_at_720p(oracle_b):
     assert (checked, n_b) == (13, 8)
 
 
+def test_fixture_hashes_are_the_oracles(oracle_b):
+    """tests/fixtures/b_clip_1280x720.json (what bench.py's b_pictures_720p leg and tools/time_b.py compare the GPU's
+    pictures with) holds the oracle's picture hashes and bit indices."""
+    import json
+
+    import bench
+    meta = json.load(open(FIXTURE_720P.replace(".m1v", ".json")))
+    es = open(FIXTURE_720P, "rb").read()
+    frames, idx, d = helpers.decode_all(oracle_b, [(0, es)])
+    assert picture_types(es) == meta["picture_types"] and idx == meta["bit_index_after"]
+    if bench.ref_library() is None:
+        pytest.skip("oracle/_ref (the hash helper lives there) not built")
+    assert [format(bench.fnv1a64_planes(*f), "016x") for f in frames] == meta["fnv1a64"]
+    d.destroy()
+
+
 def test_b_walk_on_damaged_streams_matches_the_oracle(oracle_b):
     """Bit flips and a truncation in B-picture streams: the walk stops where the oracle's stops (same records, same
     end_bit, same error), stage 2 stays inside its planes."""
