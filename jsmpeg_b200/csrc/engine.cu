@@ -139,6 +139,8 @@ struct jsmpeg_b200_batch_t {
 	int chunk_pictures = 0;      // G of the pipeline; 0 = the whole wave is one chunk
 	int chunk_min_wave = 256;    // waves with fewer new pictures stay whole
 	int chunk_streams = 3;       // chunks are parsed on this many streams in turn (1 = on the main stream, forked into size groups)
+	cudaStream_t st_bpic = nullptr;  // B-picture extension: its walk runs beside the I/P pictures' walk
+	cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
 	cudaStream_t st_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev_fed = nullptr, ev_chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
 	bool recon_pending = false;  // reconstruct launches of an earlier round may still read record slots
@@ -712,14 +714,30 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 				int n_b = 0;  // the chunk's B pictures sit at its end
 				while (n_b < n && fresh[lo + n - 1 - n_b].is_b) n_b++;
 				const int n_ip = n - n_b;
+				// B pictures have a walk kernel of their own (one warp per picture, latency-bound like every walk): beside the
+				// I/P pictures' walk, on its own stream, forked before that walk is queued and joined before the infos are read
+				const bool b_beside = n_b > 0 && n_ip > 0;
+				if (b_beside) {
+					if (!b->st_bpic) {
+						CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_bpic, cudaStreamNonBlocking));
+						CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_bfork, cudaEventDisableTiming));
+						CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_bjoin, cudaEventDisableTiming));
+					}
+					CUDA_CHECK(cudaEventRecord(b->ev_bfork, st));
+					CUDA_CHECK(cudaStreamWaitEvent(b->st_bpic, b->ev_bfork, 0));
+				}
 				if (n_ip > 0) {
 					launch_parse_pictures(b->d_ptasks + lo, n_ip, b->slot_mb, st, mid_recorded ? nullptr : b->ev_mid, n_cs > 1 ? nullptr : &b->fork);
 					mid_recorded = true;
 					b->stats.kernel_launches += 2 * parse_group_count(n_ip, n_cs == 1);  // walk + expand per size group
 				}
 				if (n_b > 0) {
-					launch_parse_pictures_b(b->d_ptasks + lo + n_ip, n_b, b->slot_mb, st);
+					launch_parse_pictures_b(b->d_ptasks + lo + n_ip, n_b, b->slot_mb, b_beside ? b->st_bpic : st);
 					b->stats.kernel_launches += 2;
+					if (b_beside) {
+						CUDA_CHECK(cudaEventRecord(b->ev_bjoin, b->st_bpic));
+						CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_bjoin, 0));
+					}
 				}
 				CUDA_CHECK(cudaMemcpyAsync(b->h_info + lo, b->d_info + lo, n * sizeof(picture_info_t), cudaMemcpyDeviceToHost, st));
 			}
@@ -1039,8 +1057,8 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 		if (b->fork.join[i]) cudaEventDestroy(b->fork.join[i]);
 		if (b->fork.side[i]) cudaStreamDestroy(b->fork.side[i]);
 	}
-	for (auto st : {b->st_main, b->st_recon, b->st_copy, b->st_chunk[0], b->st_chunk[1], b->st_chunk[2], b->st_chunk[3]}) if (st) cudaStreamDestroy(st);
-	for (auto e : {b->ev_fed, b->ev_chunk_done[0], b->ev_chunk_done[1], b->ev_chunk_done[2], b->ev_chunk_done[3]}) if (e) cudaEventDestroy(e);
+	for (auto st : {b->st_main, b->st_recon, b->st_copy, b->st_bpic, b->st_chunk[0], b->st_chunk[1], b->st_chunk[2], b->st_chunk[3]}) if (st) cudaStreamDestroy(st);
+	for (auto e : {b->ev_fed, b->ev_bfork, b->ev_bjoin, b->ev_chunk_done[0], b->ev_chunk_done[1], b->ev_chunk_done[2], b->ev_chunk_done[3]}) if (e) cudaEventDestroy(e);
 	(void)cudaGetLastError();
 	delete b;
 }
