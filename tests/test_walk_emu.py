@@ -133,8 +133,8 @@ def test_truncated_and_corrupt_streams_fall_back_identically():
 
 
 def test_walks_are_memory_safe_under_address_sanitizer():
-    """Both walks on exact-size heap buffers (clean, bit-flipped and truncated streams) with the
-    emulation library built with -fsanitize=address: no read or write outside the ES, the record
+    """Both walks -- and the B-picture extension's walk, stage 1b and two-reference stage 2 -- on exact-size heap
+    buffers (clean, bit-flipped and truncated streams) with the emulation library built with -fsanitize=address: no read or write outside the ES, the record
     arrays or the picture info.  (compute-sanitizer covers the same on the GPU when there is budget.)"""
     asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not asan or not os.path.exists(asan):
@@ -147,7 +147,7 @@ def test_walks_are_memory_safe_under_address_sanitizer():
                ASAN_CHECK_PICTURES=os.environ.get("ASAN_CHECK_PICTURES", "60"))
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "asan_check.py"), lib], env=env, capture_output=True, text=True,
                        timeout=1200)
-    assert r.returncode == 0 and "asan clean over" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "asan clean over" in r.stdout and " B pictures" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 @pytest.mark.parametrize("name", GOLDEN)
