@@ -6,7 +6,8 @@
     ctor(options)  keys: videoBufferSize, streaming, decodeFirstFrame, onVideoDecode
                    (+ our extensions `device`: CUDA device index; `decodeBPictures`: decode B pictures, which
                    the reference skips (src/mpeg1.js:181-184), in coded order -- `lastPicture()` tells type and
-                   temporal_reference)
+                   temporal_reference; with `displayOrder` the destination gets them in DISPLAY order: an I/P
+                   picture is held back (a copy) until the next I/P picture arrives, `flush()` renders the last)
     connect(destination) / destroy()
     bufferGetIndex() / bufferSetIndex(i) / bufferWrite(buffers)
     write(pts, buffers) / seek(time) / decode() -> bool
@@ -65,10 +66,13 @@ class MPEG1Video:
             if err:
                 self.destroy()
                 raise RuntimeError(err.decode(errors="replace"))
+        self.displayOrder = False
+        self._held = None  # displayOrder: the I/P picture waiting for the B pictures shown before it
         if options.get("decodeBPictures"):
             if not hasattr(self.functions, "jsmpeg_b200_decoder_set_option"):
                 raise ValueError("decodeBPictures: this library has no B-picture extension")
             self.functions.jsmpeg_b200_decoder_set_option(self.decoder, b"decode_b", 1)
+            self.displayOrder = bool(options.get("displayOrder"))
 
     # ---- src/decoder.js:19-35 / src/mpeg1-wasm.js:32-50
     def destroy(self):
@@ -145,12 +149,35 @@ class MPEG1Video:
         if not self.functions.mpeg1_decoder_decode(self.decoder):
             return False
         self.currentY, self.currentCr, self.currentCb = self.planes()
-        if self.destination is not None:
+        if self.displayOrder:
+            self._render_in_display_order()
+        elif self.destination is not None:
             self.destination.render(self.currentY, self.currentCr, self.currentCb, False)
         self.advanceDecodedTime(1.0 / self.frameRate if self.frameRate else 0.0)
         if self.onDecodeCallback:
             self.onDecodeCallback(self, (time.perf_counter() - t0) * 1000.0)
         return True
+
+    def _render_in_display_order(self):
+        """Extension (decodeBPictures + displayOrder): a B picture is shown at once, an I/P picture when the next
+        I/P picture arrives -- the B pictures that follow it in the stream come before it on the screen
+        (ISO 11172-2 2.4.1: pictures are transmitted in decoding order).  The planes the library hands out are
+        borrowed until the next decode(), so the held picture is a copy."""
+        kind = self.lastPicture()
+        if kind is None or kind[0] not in (1, 2, 3):
+            return  # a D picture / unknown type: nothing was decoded (mpeg1.js:181-184)
+        if kind[0] == 3:
+            if self.destination is not None:
+                self.destination.render(self.currentY, self.currentCr, self.currentCb, False)
+            return
+        self.flush()
+        self._held = (self.currentY.copy(), self.currentCr.copy(), self.currentCb.copy())
+
+    def flush(self):
+        """displayOrder: render the I/P picture still held back (end of stream, or before a seek)."""
+        if self._held is not None and self.destination is not None:
+            self.destination.render(*self._held, False)
+        self._held = None
 
     def lastPicture(self):
         """(picture_coding_type, temporal_reference) of the picture the last decode() consumed (extension)."""

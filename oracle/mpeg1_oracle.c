@@ -708,6 +708,23 @@ bool mpeg1_decoder_decode(mpeg1_decoder_t *d) {
 	return true;
 }
 
+/* The product's two extension entry points under the same names (include/jsmpeg_b200.h), so that the shared host
+ * class (jsmpeg_b200/decoder.py) drives this checker exactly like the product.  "decode_b" is process-wide here. */
+int jsmpeg_b200_decoder_set_option(mpeg1_decoder_t *d, const char *name, int value) {
+	(void)d;
+	if (strcmp(name, "decode_b") == 0) { g_decode_b = value; return 0; }
+	return -1;
+}
+int jsmpeg_b200_decoder_last_picture(mpeg1_decoder_t *d, int *picture_type, int *temporal_reference) {
+	if (!d->last.picture_type) return -1;
+	if (picture_type) *picture_type = d->last.picture_type;
+	if (temporal_reference) { /* 10 bits right after the picture start code */
+		uint32_t p = d->last.start_byte;
+		*temporal_reference = p + 1 < d->length ? (d->bytes[p] << 2 | d->bytes[p + 1] >> 6) : 0;
+	}
+	return 0;
+}
+
 /* test hooks */
 void oracle_idct(int *block) { /* the 2-D transform alone, for unit parity against the reference's idct() */
 	for (int k = 0; k < 8; k++) idct_pass(block + k, 8, false);

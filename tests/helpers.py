@@ -50,6 +50,11 @@ def oracle_lib():
         lib.oracle_last_coefficients.argtypes = [ctypes.c_void_p]
         lib.oracle_seq_params.restype = ctypes.POINTER(SeqParamsOracle)
         lib.oracle_seq_params.argtypes = [ctypes.c_void_p]
+        # the product's extension entry points, same names (B pictures: decodeBPictures / lastPicture of the host class)
+        lib.jsmpeg_b200_decoder_set_option.restype = ctypes.c_int
+        lib.jsmpeg_b200_decoder_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        lib.jsmpeg_b200_decoder_last_picture.restype = ctypes.c_int
+        lib.jsmpeg_b200_decoder_last_picture.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
         _oracle = lib
     return _oracle
 

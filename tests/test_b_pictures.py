@@ -94,6 +94,39 @@ def test_oracle_b_pictures_against_ffmpeg(oracle_b, tmp_path, b_frames, frames):
     d.destroy()
 
 
+def test_display_order_rendering_against_ffmpeg(oracle_b, tmp_path):
+    """The host class with decodeBPictures + displayOrder hands the destination the pictures in the order a screen
+    shows them -- the order FFmpeg's decoder returns them in: compared picture for picture (PSNR, as above), and the
+    temporal_reference the library reports counts the display positions."""
+    cv2 = pytest.importorskip("cv2")
+    from jsmpeg_b200 import decoder
+    es, types, order, _ = natural_clip()
+    d = decoder.MPEG1Video({"decodeFirstFrame": False, "decodeBPictures": True, "displayOrder": True}, lib=oracle_b)
+    rec = decoder.PlaneRecorder()
+    d.connect(rec)
+    d.write(0, [es])
+    seen = []
+    while d.decode():
+        seen.append(d.lastPicture())
+    d.flush()
+    assert [t for t, _ in seen] == types and [r for _, r in seen] == order  # (one GOP header: temporal_reference = display index)
+    w, h = d.width, d.height
+    path = str(tmp_path / "clip.m1v")
+    with open(path, "wb") as f:
+        f.write(es)
+    cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG)
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    k = 0
+    while True:
+        ok, frame = cap.read()
+        if not ok:
+            break
+        assert psnr(rec.frames[k][0].reshape(-1, w)[:h], frame[:h, :w]) > 50.0, f"display picture {k}"
+        k += 1
+    assert k == len(rec.frames) == len(types)
+    d.destroy()
+
+
 def test_extension_off_b_pictures_are_consumed_and_not_decoded():
     lib = helpers.oracle_lib()
     lib.oracle_set_decode_b(0)

@@ -48,6 +48,27 @@ def test_reference_abi_decodes_b_pictures_bit_exact(oracle_b, name):
     gd.destroy()
 
 
+def test_display_order_rendering(oracle_b):
+    """decodeBPictures + displayOrder of the host class over the CUDA library: the destination receives the oracle's
+    pictures in display order, lastPicture() reports the same (type, temporal_reference) sequence."""
+    from jsmpeg_b200 import decoder
+    es, types, order, _ = natural_clip()
+    runs = []
+    for lib in (oracle_b, capi.product_library()):
+        d = decoder.MPEG1Video({"decodeFirstFrame": False, "decodeBPictures": True, "displayOrder": True}, lib=lib)
+        rec = decoder.PlaneRecorder()
+        d.connect(rec)
+        d.write(0, [es])
+        seen = []
+        while d.decode():
+            seen.append(d.lastPicture())
+        d.flush()
+        runs.append((seen, rec.frames))
+        d.destroy()
+    assert runs[0][0] == runs[1][0] == list(zip(types, order))
+    assert_frames_equal(runs[1][1], runs[0][1], "display order: CUDA vs oracle")
+
+
 def test_extension_off_is_the_reference_behaviour():
     """Default: a B picture is consumed and nothing is decoded -- identical to the compiled reference."""
     es = synth_es.make_case("b_rows")
