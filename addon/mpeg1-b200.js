@@ -21,6 +21,10 @@ var MPEG1B200 = function(options) {
 	// extension: decode B pictures (the reference skips them, src/mpeg1.js:181-184); pictures then arrive in
 	// CODED order, native.lastPictureType(this.decoder) tells a renderer which ones to hold back
 	if (options.decodeBPictures) { native.setDecodeB(this.decoder, 1); }
+	// ... and with displayOrder an I/P picture is held back (a copy: the planes are borrowed until the next
+	// decode) until the next I/P picture arrives; flush() renders the last one
+	this.displayOrder = !!(options.decodeBPictures && options.displayOrder);
+	this.held = null;
 	this.decodeFirstFrame = options.decodeFirstFrame !== false;
 	this.hasSequenceHeader = false;
 };
@@ -65,13 +69,27 @@ MPEG1B200.prototype.decode = function() {
 	if (this.destination) {
 		var p = native.planes(this.decoder);
 		this.currentY = p.y; this.currentCr = p.cr; this.currentCb = p.cb;
-		this.destination.render(p.y, p.cr, p.cb, false);
+		var type = this.displayOrder ? native.lastPictureType(this.decoder) : 3;
+		if (type === 3) {
+			this.destination.render(p.y, p.cr, p.cb, false);
+		}
+		else if (type === 1 || type === 2) {
+			this.flush();
+			this.held = {y: p.y.slice(), cr: p.cr.slice(), cb: p.cb.slice()};
+		}
 	}
 	this.advanceDecodedTime(1/this.frameRate);
 	if (this.onDecodeCallback) {
 		this.onDecodeCallback(this, JSMpeg.Now() - startTime);
 	}
 	return true;
+};
+
+MPEG1B200.prototype.flush = function() {
+	if (this.held && this.destination) {
+		this.destination.render(this.held.y, this.held.cr, this.held.cb, false);
+	}
+	this.held = null;
 };
 
 return MPEG1B200;
