@@ -178,3 +178,35 @@ def test_switching_the_extension_between_calls(oracle_b):
         assert bd.decode(1, OUT_DEVICE) == 1
         assert_frames_equal([bd.read_planes(0)], [exp[k]], f"picture {k} after switching the extension on")
     bd.close()
+
+
+def test_bench_shape_64_streams_720p_every_picture():
+    """The shape bench.py's b_pictures_720p leg and tools/time_b.py time: 64 streams of the committed 1280x720 I/P/B
+    clip.  Picture by picture (13 steps: I/P launches and B launches), every stream's planes against the hashes the
+    oracle gave (tests/fixtures/b_clip_1280x720.json); then the whole clip in one call after a rewind."""
+    import json
+    import os
+
+    import bench
+    from test_b_pictures import FIXTURE_720P
+    if bench.ref_library() is None:
+        pytest.skip("oracle/_ref (the hash helper lives there) not built")
+    meta = json.load(open(FIXTURE_720P.replace(".m1v", ".json")))
+    es = open(FIXTURE_720P, "rb").read()
+    n_streams = int(os.environ.get("B_TEST_STREAMS", "64"))
+    bd = BatchDecoder(n_streams, max_slots=n_streams * 13 + 8, decode_b=1)
+    for s in range(n_streams):
+        bd.write(s, es)
+    for k, want in enumerate(meta["fnv1a64"]):
+        assert bd.decode(1, OUT_DEVICE) == n_streams
+        for s in range(n_streams):
+            assert format(bench.fnv1a64_planes(*bd.read_planes(s)), "016x") == want, f"stream {s} picture {k}"
+            assert bd.last_picture(s) == (meta["picture_types"][k], [0, 3, 1, 2, 6, 4, 5, 9, 7, 8, 12, 10, 11][k])
+    assert bd.decode(1, OUT_DEVICE) == 0
+    bd.rewind()
+    assert bd.decode(13, OUT_DEVICE) == 13 * n_streams
+    for s in range(n_streams):
+        assert format(bench.fnv1a64_planes(*bd.read_planes(s)), "016x") == meta["fnv1a64"][-1]
+    st = bd.stats()
+    assert st["parse_errors"] == 0
+    bd.close()
