@@ -59,16 +59,22 @@ def oracle_b():
 
 
 @functools.lru_cache(maxsize=None)
-def natural_clip(width=176, height=144, frames=13, b_frames=2, seed=1234):
+def natural_clip(width=176, height=144, frames=13, b_frames=2, seed=1234, f_codes=(3, 3), full_pel=(0, 0)):
     """(ES bytes, picture types in coded order, display index per coded picture, macroblock statistics)."""
     import mini_enc
-    return mini_enc.make_b_clip(width, height, frames, b_frames, seed)
+    return mini_enc.make_b_clip(width, height, frames, b_frames, seed, f_codes=f_codes, full_pel=full_pel)
 
 
-@pytest.mark.parametrize("b_frames,frames", [(2, 13), (1, 9), (3, 9)])
-def test_oracle_b_pictures_against_ffmpeg(oracle_b, tmp_path, b_frames, frames):
+# (forward_f_code, backward_f_code), (full_pel_forward_vector, full_pel_backward_vector): each direction with its own
+# vector range and unit (ISO 11172-2 2.4.2.5; mpeg1.js:395-457 once per direction)
+VECTOR_FORMS = [((3, 3), (0, 0)), ((2, 4), (0, 1)), ((4, 2), (1, 0))]
+
+
+@pytest.mark.parametrize("b_frames,frames,form", [(2, 13, 0), (1, 9, 0), (3, 9, 0), (2, 10, 1), (2, 10, 2)])
+def test_oracle_b_pictures_against_ffmpeg(oracle_b, tmp_path, b_frames, frames, form):
     cv2 = pytest.importorskip("cv2")
-    es, types, order, stats = natural_clip(frames=frames, b_frames=b_frames)
+    f_codes, full_pel = VECTOR_FORMS[form]
+    es, types, order, stats = natural_clip(frames=frames, b_frames=b_frames, f_codes=f_codes, full_pel=full_pel)
     assert types.count(3) >= 4 and all(stats[k] > 0 for k in ("fwd", "bwd", "bi", "intra", "skipped")), stats
     got, _, d = helpers.decode_all(oracle_b, [(0, es)])
     w, h = d.width, d.height
@@ -225,10 +231,12 @@ def test_b_device_code_matches_the_oracle_on_syntax_cases(oracle_b, name):
     assert checked == len(picture_starts(es)) and n_b == picture_types(es).count(3) > 0
 
 
-def test_b_device_code_matches_the_oracle_on_a_natural_clip(oracle_b):
+@pytest.mark.parametrize("form", range(len(VECTOR_FORMS)))
+def test_b_device_code_matches_the_oracle_on_a_natural_clip(oracle_b, form):
     pytest.importorskip("cv2")
-    es, types, order, stats = natural_clip()
-    checked, n_b = _emulated_b_pipeline(es, "mini_enc 176x144")
+    f_codes, full_pel = VECTOR_FORMS[form]
+    es, types, order, stats = natural_clip(frames=13 if form == 0 else 10, f_codes=f_codes, full_pel=full_pel)
+    checked, n_b = _emulated_b_pipeline(es, f"mini_enc 176x144 {f_codes} {full_pel}")
     assert checked == len(types) and n_b == types.count(3)
 
 

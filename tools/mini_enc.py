@@ -75,13 +75,16 @@ def predict(ref, x, y, size, mx, my):
 
 
 class Encoder:
-    def __init__(self, width, height, b_frames=2, gop_refs=4, qscale=(6, 8, 10), search=7, seed=1):
+    def __init__(self, width, height, b_frames=2, gop_refs=4, qscale=(6, 8, 10), search=7, seed=1,
+                 f_codes=(3, 3), full_pel=(0, 0)):
         assert width % 16 == 0 and height % 16 == 0
         self.w, self.h = width, height
         self.mbw, self.mbh = width // 16, height // 16
         self.b_frames, self.gop_refs = b_frames, gop_refs
         self.qs = dict(zip((1, 2, 3), qscale))
         self.search = search
+        self.f_codes = f_codes    # (forward_f_code, backward_f_code): vectors in [-16 f, 16 f - 1] of their unit
+        self.full_pel = full_pel  # (full_pel_forward_vector, full_pel_backward_vector): unit = a whole sample
         self.rng = np.random.default_rng(seed)
         self.out = BitWriter()
         self.stats = {"intra": 0, "fwd": 0, "bwd": 0, "bi": 0, "skipped": 0}
@@ -96,9 +99,9 @@ class Encoder:
         x0, y0 = mb_col * 8 + (cx >> 1), mb_row * 8 + (cy >> 1)
         return not (x0 < 0 or y0 < 0 or x0 + 8 + (cx & 1) > self.w // 2 or y0 + 8 + (cy & 1) > self.h // 2)
 
-    def best_vector(self, cur_y, ref_y, mb_col, mb_row, limit):
-        """Luma block matching: full-pel in +-search, then the eight half-pel neighbours.  Vector in half-pel
-        units, |component| <= limit, footprint inside the planes."""
+    def best_vector(self, cur_y, ref_y, mb_col, mb_row, limit, full_only=False):
+        """Luma block matching: full-pel in +-search, then (unless full_only) the eight half-pel neighbours.
+        Vector in half-pel units, |component| <= limit, footprint inside the planes."""
         x, y = mb_col * 16, mb_row * 16
         blk = cur_y[y:y + 16, x:x + 16].astype(np.int32)
         best = (None, 1 << 30)
@@ -111,6 +114,8 @@ class Encoder:
                 if sad < best[1]:
                     best = ((mx, my), sad)
         (bx, by), _ = best
+        if full_only:
+            return best
         for hy in (-1, 0, 1):
             for hx in (-1, 0, 1):
                 mx, my = bx + hx, by + hy
@@ -222,19 +227,21 @@ class Encoder:
     def picture(self, ptype, temporal, cur, fwd, bwd):
         """Encodes `cur` (Y, Cb, Cr); fwd / bwd = reconstructed references.  Returns the reconstruction."""
         w = self.out
-        f_code = 3  # vectors in [-64, 63] half-pel units
-        f, r_size = 1 << (f_code - 1), f_code - 1
-        limit = 16 * f - 2
+        (fc_f, fc_b), (fp_f, fp_b) = self.f_codes, self.full_pel
+        f, r_size = 1 << (fc_f - 1), fc_f - 1
+        fb, r_size_b = 1 << (fc_b - 1), fc_b - 1
+        sc_f, sc_b = (2 if fp_f else 1), (2 if fp_b else 1)  # half-pel units per bitstream unit
+        limit, limit_b = (16 * f - 2) * sc_f, (16 * fb - 2) * sc_b
         w.start_code(0x00)
         w.put(temporal & 1023, 10)
         w.put(ptype, 3)
         w.put(0xFFFF, 16)
         if ptype >= 2:
-            w.put(0, 1)
-            w.put(f_code, 3)
+            w.put(fp_f, 1)
+            w.put(fc_f, 3)
         if ptype == 3:
-            w.put(0, 1)
-            w.put(f_code, 3)
+            w.put(fp_b, 1)
+            w.put(fc_b, 3)
         w.put(0, 1)
         w.align()
         qs = self.qs[ptype]
@@ -256,10 +263,10 @@ class Encoder:
                 mode, mvf, mvb, pred = "intra", (0, 0), (0, 0), None
                 if ptype >= 2:
                     cands = []
-                    vf, sf = self.best_vector(cur[0], fwd[0], col, row, limit)
+                    vf, sf = self.best_vector(cur[0], fwd[0], col, row, limit, bool(fp_f))
                     cands.append(("fwd", vf, (0, 0), sf))
                     if ptype == 3:
-                        vb, sb = self.best_vector(cur[0], bwd[0], col, row, limit)
+                        vb, sb = self.best_vector(cur[0], bwd[0], col, row, limit_b, bool(fp_b))
                         cands.append(("bwd", (0, 0), vb, sb))
                         bi = (predict(fwd[0], col * 16, row * 16, 16, *vf) + predict(bwd[0], col * 16, row * 16, 16, *vb) + 1) >> 1
                         cands.append(("bi", vf, vb, int(np.abs(src[0] - bi).sum())))
@@ -282,6 +289,12 @@ class Encoder:
                     can_skip = mvf == (0, 0)
                 elif can_skip:
                     can_skip = last_mode == (mode, mvf if mode != "bwd" else None, mvb if mode != "fwd" else None)
+                    # No skipped macroblock in a direction coded with full_pel vectors: FFmpeg's decoder -- the cross-check
+                    # these streams are written for -- repeats the vector of the macroblock before WITHOUT the full-pel
+                    # doubling there (it keeps last_mv in bitstream units), where ISO 11172-2 2.4.4.2 says "the same
+                    # vector".  (The syntax generator, tools/synth_es.py, does write that case: oracle vs CUDA.)
+                    if (mode != "bwd" and fp_f) or (mode != "fwd" and fp_b):
+                        can_skip = False
                 self.trace.append((ptype, temporal, mb, mode, mvf, mvb, cbp, bool(can_skip)))
                 if can_skip:
                     self.stats["skipped"] += 1
@@ -307,14 +320,14 @@ class Encoder:
                         last_mode = None
                     else:
                         dc = [128, 128, 128]
-                        if mode in ("fwd", "bi"):
-                            pf[0] = self.write_motion(mw, mvf[0], pf[0], f, r_size)
-                            pf[1] = self.write_motion(mw, mvf[1], pf[1], f, r_size)
+                        if mode in ("fwd", "bi"):  # (the bitstream carries the vector in its own unit: mpeg1.js:421-424)
+                            pf[0] = self.write_motion(mw, mvf[0] // sc_f, pf[0], f, r_size)
+                            pf[1] = self.write_motion(mw, mvf[1] // sc_f, pf[1], f, r_size)
                         elif ptype == 2:
                             pf = [0, 0]
                         if mode in ("bwd", "bi"):
-                            pb[0] = self.write_motion(mw, mvb[0], pb[0], f, r_size)
-                            pb[1] = self.write_motion(mw, mvb[1], pb[1], f, r_size)
+                            pb[0] = self.write_motion(mw, mvb[0] // sc_b, pb[0], fb, r_size_b)
+                            pb[1] = self.write_motion(mw, mvb[1] // sc_b, pb[1], fb, r_size_b)
                         last_mode = (mode, mvf if mode != "bwd" else None, mvb if mode != "fwd" else None)
                         if cbp:
                             mw.code(CBP_CODE[cbp])
