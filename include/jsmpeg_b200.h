@@ -106,6 +106,9 @@ const char *jsmpeg_b200_batch_last_error(jsmpeg_b200_batch_t *b);
  * stream and chunk k is reconstructed while chunk k+1 is being parsed (0 = one chunk, no overlap;
  * default from the environment variable JSMPEG_B200_CHUNK, else 0).  "lookahead": pictures parsed
  * ahead per stream beyond the ones a decode call asks for.
+ * "slice_walk" (default 0, or JSMPEG_B200_SLICE_WALK): I/P pictures with at least four slices are parsed by a
+ * walk kernel that gives every slice a lane of its own instead of cutting one slice's bits into 32 (streams with a
+ * slice per macroblock row); the results are the same bit for bit, only the speed differs.
  * "decode_b" (default 0, or the environment variable JSMPEG_B200_DECODE_B; also honoured by decoders made with
  * mpeg1_decoder_create): the B-PICTURE EXTENSION.  The reference skips B pictures (src/mpeg1.js:181-184:
  * decode() returns true, nothing is rendered) and so does this library by default.  With 1, a B picture is

@@ -126,6 +126,10 @@ void launch_reconstruct_rgba(const ReconTask *tasks_host, int n_tasks, cudaStrea
 int launch_reconstruct_b(const ReconTask *tasks_host, int n_tasks, bool rgba, cudaStream_t stream);
 // stage 1 for B pictures: the serial walk with the B-picture macroblock layer (walk_b.cuh) + the same expand
 void launch_parse_pictures_b(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream);
+// stage 1 for I/P pictures of many slices (opt-in, walk_slices.cuh): a lane per slice + the same expand
+void launch_parse_pictures_slices(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream);
+// the host routes an I/P picture to it when it has at least this many slices
+constexpr int SLICE_WALK_MIN_SLICES = 4;
 
 // device MPEG-TS demux (tsdemux.cu)
 struct TsScratch;

@@ -136,11 +136,14 @@ struct jsmpeg_b200_batch_t {
 	std::vector<int> free_slots;
 	int lookahead = 1;
 	bool decode_b = false;       // the B-picture extension: off = B pictures are skipped like the reference does (mpeg1.js:181-184)
+	bool slice_walk = false;     // I/P pictures of >= SLICE_WALK_MIN_SLICES slices go to the one-lane-per-slice walk (walk_slices.cuh)
 	int chunk_pictures = 0;      // G of the pipeline; 0 = the whole wave is one chunk
 	int chunk_min_wave = 256;    // waves with fewer new pictures stay whole
 	int chunk_streams = 3;       // chunks are parsed on this many streams in turn (1 = on the main stream, forked into size groups)
-	cudaStream_t st_bpic = nullptr;  // B-picture extension: its walk runs beside the I/P pictures' walk
-	cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
+	// pictures with a walk kernel of their own (B pictures; with "slice_walk", I/P pictures of many slices) are
+	// walked beside the others, on these streams
+	cudaStream_t st_side[2] = {nullptr, nullptr};
+	cudaEvent_t ev_sfork = nullptr, ev_sjoin[2] = {nullptr, nullptr};
 	cudaStream_t st_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev_fed = nullptr, ev_chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
 	bool recon_pending = false;  // reconstruct launches of an earlier round may still read record slots
@@ -612,7 +615,8 @@ void copy_out_step(Batch *b, const std::vector<ReconTask> &tasks, const std::vec
 long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &progress, std::vector<char> &more, int flags) {
 	const int S = (int)b->streams.size();
 	// ---- 1. plan the parse wave
-	struct NewParse { int stream; size_t cache_idx; uint32_t bytes; int chunk; uint32_t pic; bool is_b; };
+	// kind: which walk kernel takes the picture -- 0 the lane-parallel walk, 1 the slice walk, 2 the B-picture walk
+	struct NewParse { int stream; size_t cache_idx; uint32_t bytes; int chunk; uint32_t pic; int kind; };
 	std::vector<NewParse> fresh;
 	for (int si = 0; si < S; si++) {
 		Stream &s = b->streams[si];
@@ -642,8 +646,19 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			++next;
 			// the extension: a picture whose header says type 3 (ISO 11172-2 2.4.2.5: 10 bits temporal_reference, 3 bits
 			// picture_coding_type) goes to the B-picture walk; everything else, and everything without it, to the I/P walk
-			const bool is_b = b->decode_b && (uint64_t)p.pos + 5 < s.bb.length && ((s.bb.bytes[p.pos + 5] >> 3) & 7) == 3;
-			fresh.push_back({si, s.cache.size() - 1, (next < s.pics.end() ? *next : s.bb.length) - p.pos, 0, (uint32_t)(next - 1 - s.pics.begin()), is_b});
+			const int type = (uint64_t)p.pos + 5 < s.bb.length ? (s.bb.bytes[p.pos + 5] >> 3) & 7 : 0;
+			const uint32_t pic = (uint32_t)(next - 1 - s.pics.begin());
+			int kind = (b->decode_b && type == 3) ? 2 : 0;
+			if (b->slice_walk && (type == 1 || type == 2)) {  // enough slice start codes between this picture's and the next one's?
+				const uint32_t hi = pic + 1 < s.pic_code.size() ? s.pic_code[pic + 1] : (uint32_t)s.codes.size();
+				int n_slices = 0;
+				for (uint32_t k = s.pic_code[pic] + 1; k < hi && n_slices < SLICE_WALK_MIN_SLICES; k++) {
+					const uint32_t q = s.codes[k];
+					if (q + 3u < s.bb.length && s.bb.bytes[q + 3u] >= 0x01 && s.bb.bytes[q + 3u] <= 0xAF) n_slices++;
+				}
+				if (n_slices >= SLICE_WALK_MIN_SLICES) kind = 1;
+			}
+			fresh.push_back({si, s.cache.size() - 1, (next < s.pics.end() ? *next : s.bb.length) - p.pos, 0, pic, kind});
 		}
 	}
 	// ---- 2. chunks by picture ordinal (position in the stream's look-ahead); a small wave stays whole
@@ -660,9 +675,9 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 	if (!fresh.empty()) {
 		// Within a chunk, longest pictures first: a CTA's warps, and consecutive CTAs (which land on different
 		// SMs), then carry similar amounts of work and the chunk's walk ends without a long tail.
-		// (B pictures, if the extension decodes them, behind the chunk's I/P pictures: they have their own walk kernel)
+		// (and grouped by the walk kernel that takes them)
 		std::stable_sort(fresh.begin(), fresh.end(), [](const NewParse &x, const NewParse &y) {
-			return x.chunk != y.chunk ? x.chunk < y.chunk : (x.is_b != y.is_b ? y.is_b : x.bytes > y.bytes);
+			return x.chunk != y.chunk ? x.chunk < y.chunk : (x.kind != y.kind ? x.kind < y.kind : x.bytes > y.bytes);
 		});
 		for (auto &f : fresh) chunk_off[f.chunk + 1]++;
 		for (int c = 0; c < n_chunks; c++) chunk_off[c + 1] += chunk_off[c];
@@ -711,32 +726,47 @@ long decode_round(Batch *b, const std::vector<int> &want, std::vector<int> &prog
 			cudaStream_t st = n_cs > 1 ? b->st_chunk[c % n_cs] : b->st_main;
 			if (n_cs > 1 && c < n_cs) CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_fed, 0));
 			if (n > 0) {
-				int n_b = 0;  // the chunk's B pictures sit at its end
-				while (n_b < n && fresh[lo + n - 1 - n_b].is_b) n_b++;
-				const int n_ip = n - n_b;
-				// B pictures have a walk kernel of their own (one warp per picture, latency-bound like every walk): beside the
-				// I/P pictures' walk, on its own stream, forked before that walk is queued and joined before the infos are read
-				const bool b_beside = n_b > 0 && n_ip > 0;
-				if (b_beside) {
-					if (!b->st_bpic) {
-						CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_bpic, cudaStreamNonBlocking));
-						CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_bfork, cudaEventDisableTiming));
-						CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_bjoin, cudaEventDisableTiming));
+				// the chunk's pictures by walk kernel: [lo, lo + cnt[0]) lane-parallel walk, then the slice walk's, then the B pictures
+				int cnt[3] = {0, 0, 0};
+				for (int i = lo; i < lo + n; i++) cnt[fresh[i].kind]++;
+				const int off[3] = {lo, lo + cnt[0], lo + cnt[0] + cnt[1]};
+				// The first kind present stays on `st`; the others have walk kernels of their own (one warp per picture,
+				// latency-bound like every walk) and run beside it on side streams, forked before anything is queued and
+				// joined before the infos are read.
+				int primary = 0;
+				while (cnt[primary] == 0) primary++;
+				const bool side = cnt[0] + cnt[1] + cnt[2] > cnt[primary];
+				if (side) {
+					if (!b->ev_sfork) {
+						CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sfork, cudaEventDisableTiming));
+						for (int j = 0; j < 2; j++) {
+							CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_side[j], cudaStreamNonBlocking));
+							CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sjoin[j], cudaEventDisableTiming));
+						}
 					}
-					CUDA_CHECK(cudaEventRecord(b->ev_bfork, st));
-					CUDA_CHECK(cudaStreamWaitEvent(b->st_bpic, b->ev_bfork, 0));
+					CUDA_CHECK(cudaEventRecord(b->ev_sfork, st));
 				}
-				if (n_ip > 0) {
-					launch_parse_pictures(b->d_ptasks + lo, n_ip, b->slot_mb, st, mid_recorded ? nullptr : b->ev_mid, n_cs > 1 ? nullptr : &b->fork);
-					mid_recorded = true;
-					b->stats.kernel_launches += 2 * parse_group_count(n_ip, n_cs == 1);  // walk + expand per size group
-				}
-				if (n_b > 0) {
-					launch_parse_pictures_b(b->d_ptasks + lo + n_ip, n_b, b->slot_mb, b_beside ? b->st_bpic : st);
-					b->stats.kernel_launches += 2;
-					if (b_beside) {
-						CUDA_CHECK(cudaEventRecord(b->ev_bjoin, b->st_bpic));
-						CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_bjoin, 0));
+				int n_side = 0;
+				for (int kind = 0; kind < 3; kind++) {
+					if (cnt[kind] == 0) continue;
+					cudaStream_t sk = st;
+					if (kind != primary) {
+						sk = b->st_side[n_side];
+						CUDA_CHECK(cudaStreamWaitEvent(sk, b->ev_sfork, 0));
+					}
+					if (kind == 0) {
+						launch_parse_pictures(b->d_ptasks + off[0], cnt[0], b->slot_mb, sk, mid_recorded ? nullptr : b->ev_mid, n_cs > 1 ? nullptr : &b->fork);
+						mid_recorded = true;
+						b->stats.kernel_launches += 2 * parse_group_count(cnt[0], n_cs == 1);  // walk + expand per size group
+					} else {
+						if (kind == 1) launch_parse_pictures_slices(b->d_ptasks + off[1], cnt[1], b->slot_mb, sk);
+						else launch_parse_pictures_b(b->d_ptasks + off[2], cnt[2], b->slot_mb, sk);
+						b->stats.kernel_launches += 2;
+					}
+					if (kind != primary) {
+						CUDA_CHECK(cudaEventRecord(b->ev_sjoin[n_side], sk));
+						CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_sjoin[n_side], 0));
+						n_side++;
 					}
 				}
 				CUDA_CHECK(cudaMemcpyAsync(b->h_info + lo, b->d_info + lo, n * sizeof(picture_info_t), cudaMemcpyDeviceToHost, st));
@@ -996,6 +1026,7 @@ jsmpeg_b200_batch_t *jsmpeg_b200_batch_create(int n_streams, int device, unsigne
 	b->chunk_min_wave = std::max(1, env_int("JSMPEG_B200_CHUNK_MIN_WAVE", 256));
 	b->chunk_streams = std::min(std::max(1, env_int("JSMPEG_B200_CHUNK_STREAMS", 3)), 4);
 	b->decode_b = env_int("JSMPEG_B200_DECODE_B", 0) != 0;
+	b->slice_walk = env_int("JSMPEG_B200_SLICE_WALK", 0) != 0;
 	try {
 		use_device(b);
 		CUDA_CHECK(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
@@ -1057,8 +1088,8 @@ void jsmpeg_b200_batch_destroy(jsmpeg_b200_batch_t *b) {
 		if (b->fork.join[i]) cudaEventDestroy(b->fork.join[i]);
 		if (b->fork.side[i]) cudaStreamDestroy(b->fork.side[i]);
 	}
-	for (auto st : {b->st_main, b->st_recon, b->st_copy, b->st_bpic, b->st_chunk[0], b->st_chunk[1], b->st_chunk[2], b->st_chunk[3]}) if (st) cudaStreamDestroy(st);
-	for (auto e : {b->ev_fed, b->ev_bfork, b->ev_bjoin, b->ev_chunk_done[0], b->ev_chunk_done[1], b->ev_chunk_done[2], b->ev_chunk_done[3]}) if (e) cudaEventDestroy(e);
+	for (auto st : {b->st_main, b->st_recon, b->st_copy, b->st_side[0], b->st_side[1], b->st_chunk[0], b->st_chunk[1], b->st_chunk[2], b->st_chunk[3]}) if (st) cudaStreamDestroy(st);
+	for (auto e : {b->ev_fed, b->ev_sfork, b->ev_sjoin[0], b->ev_sjoin[1], b->ev_chunk_done[0], b->ev_chunk_done[1], b->ev_chunk_done[2], b->ev_chunk_done[3]}) if (e) cudaEventDestroy(e);
 	(void)cudaGetLastError();
 	delete b;
 }
@@ -1071,6 +1102,7 @@ int jsmpeg_b200_batch_set_option(jsmpeg_b200_batch_t *b, const char *name, int v
 	if (!strcmp(name, "chunk_min_wave")) { b->chunk_min_wave = std::max(1, value); return 0; }
 	if (!strcmp(name, "chunk_streams")) { b->chunk_streams = std::min(std::max(1, value), 4); return 0; }
 	if (!strcmp(name, "lookahead")) { b->lookahead = std::max(1, value); return 0; }
+	if (!strcmp(name, "slice_walk")) { b->slice_walk = value != 0; return 0; }  // (same records either way: nothing to flush)
 	if (!strcmp(name, "decode_b")) {
 		if (b->decode_b != (value != 0))
 			for (auto &st : b->streams) flush_cache(b, st);  // what was parsed ahead was parsed under the other rule

@@ -36,6 +36,7 @@
 
 #include "walk.cuh"
 #include "walk_b.cuh"
+#include "walk_slices.cuh"
 
 namespace {
 
@@ -78,6 +79,19 @@ walk_pictures_b_kernel(const ParseTask *__restrict__ tasks, int n_tasks, const u
 	if (task_id >= n_tasks) return;
 	const ParseTask t = tasks[task_id];
 	walk_picture_b(t, smem_base(smem), threadIdx.x & 31);
+}
+
+// pictures of many slices (opt-in, walk_slices.cuh): one lane per slice, serial walk as in-kernel fall-back
+__global__ void LANES_BOUNDS
+walk_pictures_slices_kernel(const ParseTask *__restrict__ tasks, int n_tasks, const uint4 *__restrict__ ms_table) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	walk_tables_init(smem, threadIdx.x, WALK_THREADS, ms_table, true);
+	__syncthreads();
+	const int task_id = blockIdx.x * (WALK_THREADS / 32) + (threadIdx.x >> 5);
+	if (task_id >= n_tasks) return;
+	const ParseTask t = tasks[task_id];
+	const uint32_t sbase = smem_base(smem);
+	walk_picture_slices(t, sbase, threadIdx.x & 31, sbase + OFF_RING + threadIdx.x * RING_BYTES);
 }
 
 // ==================================================================================================
@@ -160,6 +174,8 @@ static const uint16_t *ms_table_for_current_device() {
 	                                (int)WALK_SMEM_LANES));
 	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                (int)WALK_SMEM_SERIAL));
+	CUDA_CHECK(cudaFuncSetAttribute(walk_pictures_slices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                (int)WALK_SMEM_LANES));
 	std::vector<uint16_t> dct((VLC_DCT_MAX_Z + 1) * 32);
 	CUDA_CHECK(cudaMemcpyFromSymbol(dct.data(), VLC_DCT_COEFF, dct.size() * sizeof(uint16_t)));
 	std::vector<uint16_t> ms(MS_TABLE_ENTRIES);
@@ -232,6 +248,17 @@ void launch_parse_pictures_b(const ParseTask *tasks, int n_tasks, int max_mb_siz
 	const uint16_t *ms = ms_table_for_current_device();
 	const int per_cta = WALK_THREADS / 32;
 	walk_pictures_b_kernel<<<(n_tasks + per_cta - 1) / per_cta, WALK_THREADS, WALK_SMEM_SERIAL, stream>>>(
+	    tasks, n_tasks, reinterpret_cast<const uint4 *>(ms));
+	dim3 grid((max_mb_size * 6 + CTA_THREADS * EXPAND_GROUPS - 1) / (CTA_THREADS * EXPAND_GROUPS), n_tasks);
+	expand_blocks_kernel<<<grid, CTA_THREADS, EXPAND_SMEM, stream>>>(tasks);
+}
+
+// Pictures of many slices (opt-in): one walk (a lane per slice) + one expand launch on `stream`
+void launch_parse_pictures_slices(const ParseTask *tasks, int n_tasks, int max_mb_size, cudaStream_t stream) {
+	if (n_tasks <= 0) return;
+	const uint16_t *ms = ms_table_for_current_device();
+	const int per_cta = WALK_THREADS / 32;
+	walk_pictures_slices_kernel<<<(n_tasks + per_cta - 1) / per_cta, WALK_THREADS, WALK_SMEM_LANES, stream>>>(
 	    tasks, n_tasks, reinterpret_cast<const uint4 *>(ms));
 	dim3 grid((max_mb_size * 6 + CTA_THREADS * EXPAND_GROUPS - 1) / (CTA_THREADS * EXPAND_GROUPS), n_tasks);
 	expand_blocks_kernel<<<grid, CTA_THREADS, EXPAND_SMEM, stream>>>(tasks);

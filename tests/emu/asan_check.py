@@ -53,6 +53,7 @@ for es in streams:
         walk_exact(es, s, mbw, mbh, 1)  # staged records + fix-up, exact-size staging area
         walk_exact(es, s, mbw, mbh, 2)  # staging area of 40 entries: lanes run out, second pass
         walk_exact(es, s, mbw, mbh, 0)
+        walk_exact(es, s, mbw, mbh, 4)  # the slice walk: a lane per slice, serial fall-back
         count += 1
 
 # ---- the B-picture extension's device code (walk_b.cuh, stage 1b, recon.cuh<BIDIR>) on exact-size buffers:

@@ -118,6 +118,7 @@ extern "C" void emu_vote_counters(uint64_t *trips, uint64_t *lanes, int reset) {
 #define VLC_TABLE_QUALIFIER static const
 #include "../../jsmpeg_b200/csrc/walk.cuh"
 #include "../../jsmpeg_b200/csrc/walk_b.cuh"
+#include "../../jsmpeg_b200/csrc/walk_slices.cuh"
 #include "../../jsmpeg_b200/csrc/recon.cuh"
 
 // Runs `body(lane)` as the 32 lanes of one warp.  Every collective is executed by all 32 lanes (the
@@ -161,7 +162,8 @@ extern "C" void emu_set_quant(const uint8_t *intra_q, const uint8_t *non_intra_q
 // park: [mb_size][6] x {bit offset, dc * 8}, the walk's dense hand-over to stage 1b.
 // lanes: 0 serial walk, 1 lane-parallel walk with its staging area (stage_entries_for(mb_size) entries, the
 // product's size), 2 lane-parallel walk with a staging area of 40 entries (lanes run out: second-pass
-// fall-back), 3 lane-parallel walk without staging area (always the second pass).
+// fall-back), 3 lane-parallel walk without staging area (always the second pass), 4 the slice walk (walk_slices.cuh:
+// a lane per slice, serial fall-back).
 extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t start_byte, int mb_width, int mb_height,
                                 mb_record_t *hdr, uint2 *park, picture_info_t *info, int lanes) {
 	static std::once_flag once;
@@ -202,7 +204,8 @@ extern "C" int emu_walk_picture(const uint8_t *es, uint32_t es_len, uint32_t sta
 	task = t;
 	use_lanes = lanes;
 	run_warp([](int l) {
-		if (use_lanes) walk_picture<true>(task, 0, l, 0);
+		if (use_lanes == 4) walk_picture_slices(task, 0, l, 0);
+		else if (use_lanes) walk_picture<true>(task, 0, l, 0);
 		else walk_picture<false>(task, 0, l, 0);
 	});
 	return 0;

@@ -26,7 +26,7 @@ CSRC = os.path.join(HERE, "..", "jsmpeg_b200", "csrc")
 def emu_lib(define=None):
     """The emulation library; `define` builds a variant with -D<define>."""
     out = EMU_LIB if define is None else EMU_LIB.replace(".so", "_" + define.lower() + ".so")
-    deps = [EMU_SRC] + [os.path.join(CSRC, f) for f in ("walk.cuh", "walk_b.cuh", "recon.cuh", "common.cuh", "records.h", "vlc_tables.h")]
+    deps = [EMU_SRC] + [os.path.join(CSRC, f) for f in ("walk.cuh", "walk_b.cuh", "walk_slices.cuh", "recon.cuh", "common.cuh", "records.h", "vlc_tables.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         tmp = out + ".%d.tmp" % os.getpid()
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-attributes", "-Wno-unknown-pragmas",
@@ -65,7 +65,7 @@ def walk(lib, buf, n, start, mbw, mbh, lanes):
     return hdr.reshape(mb, 4), park.reshape(mb * 6, 2), info
 
 
-def check_stream(lib, es, what, expect_lanes=None):
+def check_stream(lib, es, what, expect_lanes=None, slice_walk_used=None):
     mbw, mbh = stream_geometry(es)
     buf = np.frombuffer(es + b"\0" * 16, dtype=np.uint8).copy()  # 4-byte aligned base, padded like the ES mirror
     used = 0
@@ -73,9 +73,11 @@ def check_stream(lib, es, what, expect_lanes=None):
     for k, s in enumerate(starts):
         h0, c0, i0 = walk(lib, buf, len(es), s, mbw, mbh, 0)
         # 1: staged relative records + fix-up (the product's path); 2: staging area too small, the lanes fall back to
-        # the second, storing pass; 3: no staging area at all
-        for mode in (1, 2, 3):
+        # the second, storing pass; 3: no staging area at all; 4: the slice walk (a lane per slice, walk_slices.cuh)
+        for mode in (1, 2, 3, 4):
             h1, c1, i1 = walk(lib, buf, len(es), s, mbw, mbh, mode)
+            if mode == 4 and slice_walk_used is not None and i1[2] == 1:
+                slice_walk_used.append(int(i1[9]) == 2)
             if mode == 1:
                 used += int(i1[9])
                 # with the product's staging area every slice the lane walk takes is finished by the fix-up, not a second pass
@@ -117,6 +119,43 @@ def test_encoder_clips_use_the_lane_walk(size, frames):
     es = b"".join(p for _, p in helpers.clip_packets(size[0], size[1], frames))
     used, n = check_stream(emu_lib(), es, f"clip {size}")
     assert used == n, f"lane-parallel walk fell back on {n - used} of {n} clean pictures"
+
+
+def test_slice_walk_takes_clean_multi_slice_pictures():
+    """walk_slices.cuh (a lane per slice): on clean streams it finishes every decoded picture itself (info.reserved[0]
+    == 2) -- a slice per macroblock row, slices starting mid-row, gaps between slices, one slice per picture, 45 slices
+    of a natural 720p clip -- and its records equal the serial walk's (check_stream compares them)."""
+    import synth_es
+    lib = emu_lib()
+    for name in ("rows_ip", "fcodes_fullpel", "random_slices_gaps", "odd_size", "i_only_320x240", "escapes_matrices"):
+        took = []
+        check_stream(lib, synth_es.make_case(name), name, slice_walk_used=took)
+        assert took and all(took), f"{name}: slice walk fell back on {took.count(False)} of {len(took)} clean pictures"
+    es = open(os.path.join(HERE, "fixtures", "b_clip_1280x720.m1v"), "rb").read()  # 45 slices per picture; B pictures are ignored here
+    took = []
+    check_stream(lib, es, "720p fixture", slice_walk_used=took)
+    assert len(took) == 5 and all(took)
+
+
+def test_slice_walk_falls_back_on_overlapping_slices():
+    """Two slices claiming the same macroblock row: the reference decodes them one after the other and the second one
+    wins; the slice walk must notice (address ranges not strictly increasing) and leave the picture to the serial walk."""
+    import synth_es
+    es = bytearray(synth_es.make_case("rows_ip"))
+    starts = picture_starts(bytes(es))
+    # the slices of the first picture: make the third one carry the second one's row number
+    p = starts[0]
+    codes = []
+    i = p
+    while len(codes) < 3:
+        i = bytes(es).find(b"\x00\x00\x01", i)
+        if 1 <= es[i + 3] <= 0xAF:
+            codes.append(i)
+        i += 3
+    es[codes[2] + 3] = es[codes[1] + 3]
+    took = []
+    check_stream(emu_lib(), bytes(es), "overlapping slices", slice_walk_used=took)
+    assert took[0] is False and all(took[1:4])
 
 
 def test_truncated_and_corrupt_streams_fall_back_identically():
@@ -220,7 +259,7 @@ def test_stage1_device_code_matches_the_oracle_coefficients(name):
     assert checked > 0
 
 
-def _pipeline_against_oracle_planes(es, name, define=None):
+def _pipeline_against_oracle_planes(es, name, define=None, walk_mode=1):
     from jsmpeg_b200 import decoder
     olib = helpers.oracle_lib()
     d = decoder.MPEG1Video({"decodeFirstFrame": False}, lib=olib)
@@ -247,7 +286,7 @@ def _pipeline_against_oracle_planes(es, name, define=None):
         coef = np.zeros(mb * 6 * 32, dtype=np.uint32)
         pinfo = np.zeros(12, dtype=np.int32)
         lib.emu_walk_picture(buf.ctypes.data, len(es), info.start_byte, mbw, mbh, hdr.ctypes.data, park.ctypes.data,
-                             pinfo.ctypes.data, 1)
+                             pinfo.ctypes.data, walk_mode)
         if pinfo[2] != 1:
             continue  # B / D picture or P without f_code: consumed, nothing decoded, no swap (mpeg1.js:181-193)
         lib.emu_expand_picture(buf.ctypes.data, len(es), mbw, mbh, hdr.ctypes.data, park.ctypes.data, coef.ctypes.data,
@@ -271,6 +310,13 @@ def test_whole_hot_path_device_code_matches_the_oracle_planes(name):
     replaced by plain C) with the product's ping-pong planes, against the ORACLE's planes of every
     decoded picture.  Bit-exact, like the GPU parity tests -- which remain the check of the real thing."""
     _pipeline_against_oracle_planes(open(os.path.join(HERE, "golden", name + ".es"), "rb").read(), name)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_whole_hot_path_with_the_slice_walk_matches_the_oracle_planes(name):
+    """The same with stage 1a = the slice walk (walk_slices.cuh, a lane per slice; its serial fall-back where a
+    picture is outside its clean domain)."""
+    _pipeline_against_oracle_planes(open(os.path.join(HERE, "golden", name + ".es"), "rb").read(), name, walk_mode=4)
 
 
 def test_whole_hot_path_device_code_on_an_encoder_clip():
