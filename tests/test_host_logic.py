@@ -178,3 +178,29 @@ def test_napi_addon_source_parses():
                         "-I", os.path.join(helpers.ROOT, "tests", "stubs"), "-I", os.path.join(helpers.ROOT, "include"), src],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_kernels_are_the_measured_ones():
+    """profiles/r2_sass_hashes.txt lists an md5 of every kernel's SASS on the build the round's last GPU runs used
+    (tools/sass_hash.py).  Recompiling the tree must give the same machine code: nobody edits a kernel after it was
+    measured without this test saying so."""
+    import shutil
+    import sys
+    if not (shutil.which("nvcc") and shutil.which("cuobjdump")):
+        pytest.skip("nvcc / cuobjdump not available")
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tools"))
+    import sass_hash
+    recorded = {}
+    for line in open(os.path.join(helpers.ROOT, "profiles", "r2_sass_hashes.txt")):
+        parts = line.split()
+        if len(parts) >= 3 and parts[0].endswith(".cu") and parts[1].endswith("_kernel"):
+            recorded[parts[1]] = next(p for p in parts[2:] if len(p) == 32)
+    assert {"walk_pictures_lanes_kernel", "expand_blocks_kernel", "reconstruct_kernel", "reconstruct_b_kernel",
+            "walk_pictures_b_kernel", "walk_pictures_slices_kernel", "scan_start_codes_kernel"} <= set(recorded)
+    now = {}
+    for cu in ("parse.cu", "recon.cu", "scan.cu"):
+        for name, (md5, _) in sass_hash.kernel_hashes(cu).items():
+            now[sass_hash.demangle(name)] = md5
+    changed = {k: (recorded[k], now.get(k)) for k in recorded if k in now and now[k] != recorded[k]}
+    assert not changed, changed
+    assert all(k in now for k in recorded if not k.startswith("ts_"))
