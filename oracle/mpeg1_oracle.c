@@ -122,13 +122,16 @@ static bool bits_next_bytes_are_start_code(const bits_t *b) {
 }
 
 /* mpeg1.js:66-72 readHuffman, as a trie walk.  The reference has no defined result for an
- * invalid code; we return VLC_INVALID and the caller abandons the slice. */
+ * invalid code; we return VLC_INVALID and the caller abandons the slice, with the bit index still at the
+ * start of that code -- where the search for the next start code then begins (the CUDA walk does the same, so
+ * the two agree record for record on damaged streams too; only the reference's own behaviour is undefined there). */
 static int read_vlc(bits_t *b, int which) {
 	const trie_t *t = &g_trie[which];
+	const uint32_t start = b->index;
 	int at = 0;
 	for (;;) {
 		at = t->nodes[at].child[bits_read(b, 1)];
-		if (!at) return VLC_INVALID;
+		if (!at) { b->index = start; return VLC_INVALID; } /* (nothing of an invalid code is consumed: the product's rule) */
 		if (t->nodes[at].leaf) return t->nodes[at].value;
 	}
 }
