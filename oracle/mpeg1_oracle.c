@@ -631,6 +631,12 @@ void *mpeg1_decoder_get_write_ptr(mpeg1_decoder_t *d, unsigned int n) {
 			}
 		}
 	}
+	/* buffer.c's sizing can leave less room than it promises (a partly full buffer and a large write: the C build then
+	 * writes past its allocation, the JS build throws).  A checker must not corrupt its own heap: make the room. */
+	if (d->capacity - d->length < n) {
+		d->capacity = d->length + n;
+		d->bytes = (uint8_t *)realloc(d->bytes, d->capacity);
+	}
 	return d->bytes + d->length;
 }
 
