@@ -59,10 +59,10 @@ def oracle_b():
 
 
 @functools.lru_cache(maxsize=None)
-def natural_clip(width=176, height=144, frames=13, b_frames=2, seed=1234, f_codes=(3, 3), full_pel=(0, 0)):
+def natural_clip(width=176, height=144, frames=13, b_frames=2, seed=1234, f_codes=(3, 3), full_pel=(0, 0), one_slice=False):
     """(ES bytes, picture types in coded order, display index per coded picture, macroblock statistics)."""
     import mini_enc
-    return mini_enc.make_b_clip(width, height, frames, b_frames, seed, f_codes=f_codes, full_pel=full_pel)
+    return mini_enc.make_b_clip(width, height, frames, b_frames, seed, f_codes=f_codes, full_pel=full_pel, one_slice=one_slice)
 
 
 # (forward_f_code, backward_f_code), (full_pel_forward_vector, full_pel_backward_vector): each direction with its own
@@ -70,11 +70,13 @@ def natural_clip(width=176, height=144, frames=13, b_frames=2, seed=1234, f_code
 VECTOR_FORMS = [((3, 3), (0, 0)), ((2, 4), (0, 1)), ((4, 2), (1, 0))]
 
 
-@pytest.mark.parametrize("b_frames,frames,form", [(2, 13, 0), (1, 9, 0), (3, 9, 0), (2, 10, 1), (2, 10, 2)])
-def test_oracle_b_pictures_against_ffmpeg(oracle_b, tmp_path, b_frames, frames, form):
+# (b_frames, display pictures, vector form, one slice per picture -- what FFmpeg itself writes -- instead of one per row)
+@pytest.mark.parametrize("b_frames,frames,form,one_slice", [(2, 13, 0, False), (1, 9, 0, False), (3, 9, 0, False), (2, 10, 1, False),
+                                                            (2, 10, 2, False), (2, 10, 0, True)])
+def test_oracle_b_pictures_against_ffmpeg(oracle_b, tmp_path, b_frames, frames, form, one_slice):
     cv2 = pytest.importorskip("cv2")
     f_codes, full_pel = VECTOR_FORMS[form]
-    es, types, order, stats = natural_clip(frames=frames, b_frames=b_frames, f_codes=f_codes, full_pel=full_pel)
+    es, types, order, stats = natural_clip(frames=frames, b_frames=b_frames, f_codes=f_codes, full_pel=full_pel, one_slice=one_slice)
     assert types.count(3) >= 4 and all(stats[k] > 0 for k in ("fwd", "bwd", "bi", "intra", "skipped")), stats
     got, _, d = helpers.decode_all(oracle_b, [(0, es)])
     w, h = d.width, d.height
@@ -243,6 +245,15 @@ def test_b_device_code_matches_the_oracle_on_a_natural_clip(oracle_b, form):
     es, types, order, stats = natural_clip(frames=13 if form == 0 else 10, f_codes=f_codes, full_pel=full_pel)
     checked, n_b = _emulated_b_pipeline(es, f"mini_enc 176x144 {f_codes} {full_pel}")
     assert checked == len(types) and n_b == types.count(3)
+
+
+def test_b_device_code_on_one_slice_pictures(oracle_b):
+    """One slice per picture (FFmpeg's layout): the I/P pictures take the lane-parallel walk proper (sub-sequences of
+    one long slice), the B pictures one long chain each, skipped runs cross macroblock rows."""
+    pytest.importorskip("cv2")
+    es, types, order, stats = natural_clip(frames=10, one_slice=True)
+    checked, n_b = _emulated_b_pipeline(es, "mini_enc 176x144, one slice per picture")
+    assert checked == len(types) and n_b == types.count(3) > 0
 
 
 FIXTURE_720P = os.path.join(HERE, "fixtures", "b_clip_1280x720.m1v")  # tools/mini_enc.py: make_b_clip(1280, 720, 13, 2, seed=1234)

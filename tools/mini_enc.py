@@ -76,7 +76,7 @@ def predict(ref, x, y, size, mx, my):
 
 class Encoder:
     def __init__(self, width, height, b_frames=2, gop_refs=4, qscale=(6, 8, 10), search=7, seed=1,
-                 f_codes=(3, 3), full_pel=(0, 0)):
+                 f_codes=(3, 3), full_pel=(0, 0), one_slice=False):
         assert width % 16 == 0 and height % 16 == 0
         self.w, self.h = width, height
         self.mbw, self.mbh = width // 16, height // 16
@@ -85,6 +85,7 @@ class Encoder:
         self.search = search
         self.f_codes = f_codes    # (forward_f_code, backward_f_code): vectors in [-16 f, 16 f - 1] of their unit
         self.full_pel = full_pel  # (full_pel_forward_vector, full_pel_backward_vector): unit = a whole sample
+        self.one_slice = one_slice  # one slice per picture (what FFmpeg writes) instead of one per macroblock row
         self.rng = np.random.default_rng(seed)
         self.out = BitWriter()
         self.stats = {"intra": 0, "fwd": 0, "bwd": 0, "bi": 0, "skipped": 0}
@@ -246,15 +247,19 @@ class Encoder:
         w.align()
         qs = self.qs[ptype]
         rec = [np.zeros_like(p) for p in cur]
+        sw = None
         for row in range(self.mbh):
-            sw = BitWriter()
-            sw.start_code(row + 1)
-            sw.put(qs, 5)
-            sw.put(0, 1)
-            pf, pb = [0, 0], [0, 0]
-            dc = [128, 128, 128]
-            last_mode = None
-            addr = row * self.mbw - 1
+            if sw is None:  # a slice starts: every predictor is reset (mpeg1.js:255-266)
+                sw = BitWriter()
+                sw.start_code(row + 1)
+                sw.put(qs, 5)
+                sw.put(0, 1)
+                pf, pb = [0, 0], [0, 0]
+                dc = [128, 128, 128]
+                last_mode = None
+                addr = row * self.mbw - 1
+            first_mb = 0 if self.one_slice else row * self.mbw                            # of the slice
+            last_mb = self.mbw * self.mbh - 1 if self.one_slice else (row + 1) * self.mbw - 1
             for col in range(self.mbw):
                 mb = row * self.mbw + col
                 src = (cur[0][row * 16:row * 16 + 16, col * 16:col * 16 + 16].astype(np.int32),
@@ -284,7 +289,7 @@ class Encoder:
                 cbp = 0x3F if intra else sum((0x20 >> k) for k in range(6) if np.any(levels[k]))
                 # skipped macroblock: nothing coded, not first / last of the slice, and -- P: zero vector,
                 # B: the same prediction and vectors as the macroblock before (which must not be intra)
-                can_skip = not intra and cbp == 0 and 0 < col < self.mbw - 1
+                can_skip = not intra and cbp == 0 and first_mb < mb < last_mb
                 if can_skip and ptype == 2:
                     can_skip = mvf == (0, 0)
                 elif can_skip:
@@ -306,6 +311,9 @@ class Encoder:
                     self.stats[mode] += 1
                     inc = mb - addr
                     mw = BitWriter()  # the macroblock's bits, appended to the slice below
+                    while inc > 33:  # macroblock_escape (a long skipped run in a one-slice picture)
+                        mw.code(MBA_CODE[35])
+                        inc -= 33
                     mw.code(MBA_CODE[inc])
                     addr = mb
                     if ptype == 1:
@@ -339,7 +347,7 @@ class Encoder:
                     # (buffer.js:141-150): a last macroblock whose bits all fit into the byte the
                     # previous one ended in would never be decoded by it (a conforming decoder decodes it).
                     # macroblock_stuffing in front pushes it over the byte boundary.
-                    if col == self.mbw - 1 and len(sw.bits) % 8 and len(sw.bits) % 8 + len(mw.bits) <= 8:
+                    if mb == last_mb and len(sw.bits) % 8 and len(sw.bits) % 8 + len(mw.bits) <= 8:
                         sw.code(MBA_CODE[34])
                     sw.bits.extend(mw.bits)
                     # closed loop: what a decoder rebuilds
@@ -352,8 +360,10 @@ class Encoder:
                 rec[0][row * 16:row * 16 + 16, col * 16:col * 16 + 16] = np.clip(np.rint(rec_mb[0]), 0, 255)
                 rec[1][row * 8:row * 8 + 8, col * 8:col * 8 + 8] = np.clip(np.rint(rec_mb[1]), 0, 255)
                 rec[2][row * 8:row * 8 + 8, col * 8:col * 8 + 8] = np.clip(np.rint(rec_mb[2]), 0, 255)
-            sw.align()
-            w.bits.extend(BitWriter_bits(sw.tobytes()))
+            if not self.one_slice or row == self.mbh - 1:
+                sw.align()
+                w.bits.extend(BitWriter_bits(sw.tobytes()))
+                sw = None
         return rec
 
     def encode(self, frames):
