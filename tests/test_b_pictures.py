@@ -310,7 +310,7 @@ def _random_knobs(rng):
 
 @pytest.mark.parametrize("seed", [101, 102])
 def test_random_streams_clean_and_damaged(oracle_b, seed):
-    """A slice of the randomised campaign run during development (320 random knob sets x (clean + 2 bit-flipped copies),
+    """A slice of the randomised campaign run during development (700 random knob sets x (clean + 2 bit-flipped copies),
     no difference): random sizes incl. non-multiples of 16, 1-3 B pictures between references, every f_code, full-pel,
     slice layouts, skipped runs, stuffing, escapes, custom matrices.  The B-picture device pipeline against the oracle
     (planes on clean streams; records, end_bit and error presence on damaged ones), and the three lane-parallel modes
